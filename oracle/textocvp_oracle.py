@@ -1,0 +1,317 @@
+"""
+CPU oracle for the TextOCVP rollout path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A functional fp32 (or fp64) restatement, in plain torch CPU ops, of the reference
+algorithm for the hot path named in BASELINE.json (SAVi corrector -> text-conditioned
+predictor -> spatial-broadcast decoder + compositing).  Every function takes a flat
+``state_dict`` that uses the reference's own parameter names, so
+the very same weights can be loaded into the reference modules, into this oracle and into
+the CUDA modules of ``textocvp_b200``.
+
+Parity status: PINNED.  ``oracle/make_golden.py`` imports the real reference from
+/root/reference (in the build container only), runs it on seeded inputs and stores its
+outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this restatement
+against those vectors.  PSNR is a restatement of piqa==1.2.2 (not installed) -> unpinned.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / --impl
+reference legs may import this file.  The product path (``textocvp_b200``) never does.
+
+All file:line citations are relative to /root/reference/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# configuration (the few numbers that are NOT derivable from tensor shapes)
+# --------------------------------------------------------------------------------------
+@dataclass
+class SAViCfg:
+    """src/configs/models/SAVi.json"""
+    num_slots: int = 8
+    slot_dim: int = 128
+    num_iterations_first: int = 3
+    num_iterations: int = 1
+    in_channels: int = 3
+    resolution: tuple = (64, 64)
+    transition_heads: int = 4
+    sa_eps: float = 1e-8          # attention.py:36 (epsilon)
+    sa_ln_eps: float = 1e-3       # attention.py:49-51
+    tf_ln_eps: float = 1e-6       # attention.py:361-362
+
+
+@dataclass
+class PredCfg:
+    """src/configs/predictors/TextOCVP_CustomTF.json + CONFIG.py:66-71"""
+    num_layers: int = 8
+    n_heads: int = 8
+    cross_heads: int = 8
+    cross_head_dim: int = 64
+    residual: bool = True
+    num_context: int = 1
+    num_preds: int = 19
+    input_buffer_size: int = 10
+    ln_eps: float = 1e-6          # attention.py:361-362, 427, 435-436
+
+
+def _sub(sd: SD, prefix: str) -> SD:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _ln(x: Tensor, sd: SD, name: str, eps: float) -> Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+def _lin(x: Tensor, sd: SD, name: str) -> Tensor:
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+# --------------------------------------------------------------------------------------
+# positional grid  (model_utils.py:12-34, model_blocks.py:186-226)
+# --------------------------------------------------------------------------------------
+def build_grid(resolution) -> Tensor:
+    """[1, 4, H, W] fp32 grid with channels (y, x, 1-y, 1-x), y,x in linspace(-1, 1)."""
+    ranges = [np.linspace(-1.0, 1.0, num=r) for r in resolution]
+    g = np.stack(np.meshgrid(*ranges, sparse=False, indexing="ij"), axis=-1)
+    g = g.reshape(resolution[0], resolution[1], -1)[None].astype(np.float32)
+    g = np.concatenate([g, 1.0 - g], axis=-1)                    # model_utils.py:33
+    return torch.from_numpy(g).permute(0, 3, 1, 2).contiguous()  # model_blocks.py:212
+
+
+def soft_pos_embed_table(sd: SD, prefix: str, resolution) -> Tensor:
+    """Conv1x1(4->C) of the grid: [H, W, C].  Batch independent (model_blocks.py:215-226)."""
+    grid = build_grid(resolution).to(sd[prefix + ".projection.weight"].dtype)
+    emb = F.conv2d(grid, sd[prefix + ".projection.weight"], sd[prefix + ".projection.bias"])
+    return emb[0].permute(1, 2, 0).contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# SAVi.encode  (SAVi.py:226-238; encoders.py:136-159; model_blocks.py:49-108)
+# --------------------------------------------------------------------------------------
+def savi_encode(sd: SD, x: Tensor, cfg: SAViCfg) -> Tensor:
+    """x [B,3,H,W] -> features [B, H*W, D]."""
+    i = 0
+    while f"encoder.encoder.{i}.block.0.weight" in sd:
+        w = sd[f"encoder.encoder.{i}.block.0.weight"]
+        b = sd[f"encoder.encoder.{i}.block.0.bias"]
+        x = F.relu(F.conv2d(x, w, b, stride=1, padding=w.shape[-1] // 2))
+        i += 1
+    x = x.permute(0, 2, 3, 1)                                              # SAVi.py:232
+    x = x + soft_pos_embed_table(sd, "encoder_pos_embedding", cfg.resolution)[None]
+    x = torch.flatten(x, 1, 2)                                             # SAVi.py:236
+    x = _ln(x, sd, "encoder_mlp.0", 1e-5)                                  # SAVi.py:116 (default eps)
+    x = F.relu(_lin(x, sd, "encoder_mlp.1"))
+    x = _lin(x, sd, "encoder_mlp.3")
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# SlotAttention.forward  (attention.py:67-112)
+# --------------------------------------------------------------------------------------
+def gru_cell(x: Tensor, h: Tensor, sd: SD, prefix: str) -> Tensor:
+    """torch.nn.GRUCell semantics (gate order r, z, n) -- SURVEY Appendix A.4."""
+    gi = F.linear(x, sd[prefix + ".weight_ih"], sd[prefix + ".bias_ih"])
+    gh = F.linear(h, sd[prefix + ".weight_hh"], sd[prefix + ".bias_hh"])
+    i_r, i_z, i_n = gi.chunk(3, -1)
+    h_r, h_z, h_n = gh.chunk(3, -1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return (1.0 - z) * n + z * h
+
+
+def slot_attention(sd: SD, inputs: Tensor, slots: Tensor, step: int, cfg: SAViCfg,
+                   prefix: str = "slot_attention", return_iters: bool = False):
+    """inputs [B,N,Df], slots [B,S,D] -> slots [B,S,D] (attention.py:67-112)."""
+    B, S, D = slots.shape
+    dim_feats = inputs.shape[-1]
+    scale = dim_feats ** -0.5                                              # attention.py:46
+    x = _ln(inputs, sd, prefix + ".norm_input", cfg.sa_ln_eps)            # :86
+    k = _lin(x, sd, prefix + ".to_k")                                      # :87
+    v = _lin(x, sd, prefix + ".to_v")
+    iters = cfg.num_iterations_first if step == 0 else cfg.num_iterations  # :90
+    hist = []
+    for _ in range(iters):
+        slots_prev = slots
+        q = _lin(_ln(slots, sd, prefix + ".norm_slot", cfg.sa_ln_eps), sd, prefix + ".to_q")
+        dots = torch.einsum("bid,bjd->bij", q, k) * scale                  # :99
+        attn = dots.softmax(dim=1) + cfg.sa_eps                            # :100 softmax over SLOTS
+        attn = attn / attn.sum(dim=-1, keepdim=True)                       # :102 renorm over locations
+        updates = torch.einsum("bij,bjd->bid", attn, v)                    # :103
+        slots = gru_cell(updates.reshape(-1, D), slots_prev.reshape(-1, D), sd, prefix + ".gru")
+        slots = slots.reshape(B, S, D)
+        h = _ln(slots, sd, prefix + ".norm_mlp", cfg.sa_ln_eps)
+        slots = slots + _lin(F.relu(_lin(h, sd, prefix + ".mlp.0")), sd, prefix + ".mlp.2")  # :110
+        hist.append(slots)
+    return (slots, hist) if return_iters else slots
+
+
+# --------------------------------------------------------------------------------------
+# multi-head attention helpers (attention.py:183-215, 245-265, 303-319)
+# --------------------------------------------------------------------------------------
+def _heads(x: Tensor, h: int) -> Tensor:
+    B, T, C = x.shape
+    return x.view(B, T, h, C // h).transpose(1, 2)          # [B,h,T,dh]  (contiguous head chunks)
+
+
+def _mha(q: Tensor, k: Tensor, v: Tensor, h: int) -> Tensor:
+    qh, kh, vh = _heads(q, h), _heads(k, h), _heads(v, h)
+    dh = qh.shape[-1]
+    att = (qh @ kh.transpose(-1, -2)) * dh ** -0.5           # attention.py:187-188
+    att = att.softmax(dim=-1)                                # no mask on this path
+    out = att @ vh
+    return out.transpose(1, 2).reshape(q.shape[0], q.shape[1], -1)
+
+
+def self_attention(x: Tensor, sd: SD, prefix: str, heads: int) -> Tensor:
+    q, k, v = (F.linear(x, sd[f"{prefix}.{n}.weight"]) for n in "qkv")    # no bias, attention.py:167-169
+    return F.linear(_mha(q, k, v, heads), sd[prefix + ".out_projection.0.weight"])
+
+
+# --------------------------------------------------------------------------------------
+# SAVi transition: post-norm TransformerBlock (attention.py:387-395; transition_models.py:26-31)
+# --------------------------------------------------------------------------------------
+def transition(sd: SD, slots: Tensor, cfg: SAViCfg, prefix: str = "transition_module") -> Tensor:
+    x = self_attention(slots, sd, prefix + ".attn", cfg.transition_heads)
+    y = _ln(x + slots, sd, prefix + ".layernorm_query", cfg.tf_ln_eps)
+    z = _lin(F.relu(_lin(y, sd, prefix + ".mlp.0")), sd, prefix + ".mlp.2")
+    return _ln(z + y, sd, prefix + ".layernorm_mlp", cfg.tf_ln_eps)
+
+
+# --------------------------------------------------------------------------------------
+# SAVi.decode + broadcast + ConvDecoder (SAVi.py:241-275; decoders.py:52-125)
+# --------------------------------------------------------------------------------------
+def savi_decoder_maps(sd: SD, slots: Tensor, cfg: SAViCfg) -> Tensor:
+    """slots [B',S,D] -> pre-softmax decoder maps [B'*S, 4, H, W]."""
+    D = slots.shape[-1]
+    H, W = cfg.resolution
+    x = slots.reshape(-1, 1, 1, D).expand(-1, H, W, D)
+    x = x + soft_pos_embed_table(sd, "decoder_pos_embedding", cfg.resolution)[None]
+    x = x.permute(0, 3, 1, 2)
+    i = 0
+    while f"decoder.decoder.{i}.block.0.weight" in sd:
+        w = sd[f"decoder.decoder.{i}.block.0.weight"]
+        b = sd[f"decoder.decoder.{i}.block.0.bias"]
+        x = F.relu(F.conv2d(x, w, b, stride=1, padding=w.shape[-1] // 2))
+        i += 1
+    w, b = sd[f"decoder.decoder.{i}.weight"], sd[f"decoder.decoder.{i}.bias"]
+    return F.conv2d(x, w, b, stride=1, padding=1)                          # decoders.py:110-116, no activation
+
+
+def savi_decode(sd: SD, slots: Tensor, cfg: SAViCfg) -> Dict[str, Tensor]:
+    B = slots.shape[0]
+    y = savi_decoder_maps(sd, slots, cfg)
+    y = y.reshape(B, -1, cfg.in_channels + 1, y.shape[2], y.shape[3])
+    recons, masks = y.split([cfg.in_channels, 1], dim=2)                   # SAVi.py:251-252 (RGB then mask)
+    masks = F.softmax(masks, dim=1)                                        # over slots
+    return {"recons_imgs": torch.sum(recons * masks, dim=1), "recons": recons, "masks": masks}
+
+
+# --------------------------------------------------------------------------------------
+# SAVi.forward_decomp (SAVi.py:152-223)
+# --------------------------------------------------------------------------------------
+def initial_slots(sd: SD, B: int, cfg: SAViCfg, noise: Optional[Tensor] = None) -> Tensor:
+    """LearnedRandom: mu + sigma * randn  (initializers.py:87-94; sigma NOT exponentiated)."""
+    mu, sigma = sd["initializer.slots_mu"], sd["initializer.slots_sigma"]
+    if noise is None:
+        noise = torch.randn(B, cfg.num_slots, cfg.slot_dim, dtype=mu.dtype)
+    return mu + sigma * noise
+
+
+def savi_decomp(sd: SD, x: Tensor, num_imgs: int, cfg: SAViCfg, init_slots: Tensor) -> Tensor:
+    """x [B,T,3,H,W] -> slot_history [B,num_imgs,S,D] (decode=False branch)."""
+    predicted = init_slots
+    hist = []
+    for t in range(num_imgs):
+        feats = savi_encode(sd, x[:, t], cfg)
+        slots = slot_attention(sd, feats, predicted, t, cfg)
+        predicted = transition(sd, slots, cfg)
+        hist.append(slots)
+    return torch.stack(hist, dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# Predictor: BaseTextOCVP.forward (text_cond_OCVP.py:79-105), AdaptedEncoderBlock
+# (attention.py:504-524), TransformerDecoderBlock (attention.py:445-463)
+# --------------------------------------------------------------------------------------
+def predictor_block(sd: SD, x: Tensor, text: Tensor, cfg: PredCfg, p: str) -> Tensor:
+    y = x + self_attention(_ln(x, sd, p + ".layernorm_query", cfg.ln_eps), sd, p + ".attn", cfg.n_heads)
+    c = p + ".cross_attention"
+    qe = _ln(y, sd, c + ".ln_cross_att_q", cfg.ln_eps)
+    kv = _ln(text, sd, c + ".ln_cross_att_kv", cfg.ln_eps)                 # every layer, raw text (:454)
+    q = F.linear(qe, sd[c + ".cross_attn.q.weight"])
+    k = F.linear(kv, sd[c + ".cross_attn.k.weight"])
+    v = F.linear(kv, sd[c + ".cross_attn.v.weight"])
+    z = _lin(_mha(q, k, v, cfg.cross_heads), sd, c + ".cross_attn.out_projection") + y   # out-proj HAS bias
+    h = _ln(z, sd, c + ".ln_mlp", cfg.ln_eps)
+    z = z + _lin(F.relu(_lin(h, sd, c + ".mlp.0")), sd, c + ".mlp.2")
+    h = _ln(z, sd, p + ".layernorm_mlp", cfg.ln_eps)
+    return y + _lin(F.relu(_lin(h, sd, p + ".mlp.0")), sd, p + ".mlp.2")  # skip is y (:521-523)
+
+
+def predictor_step(sd: SD, slots: Tensor, text: Tensor, cfg: PredCfg, return_layers: bool = False):
+    """slots [B,n,S,D], text [B,L,Dt] -> next slots [B,S,D]. ``sd`` keys relative to TextOCVP module."""
+    B, n, S, _ = slots.shape
+    tok = _lin(slots, sd, "mlp_in")
+    pe = sd["pe.pe"][:, :n]                                                # [1,n,1,Dt]
+    tok = tok + torch.flip(pe, dims=(1,))                                  # model_blocks.py:375-377
+    tok = tok.reshape(B, n * S, -1)
+    layers = []
+    for i in range(cfg.num_layers):
+        tok = predictor_block(sd, tok, text, cfg, f"predictor.{i}")
+        layers.append(tok)
+    tok = tok.reshape(B, n, S, -1)
+    out = _lin(tok[:, -1], sd, "mlp_out")
+    out = out + slots[:, -1] if cfg.residual else out
+    return (out, layers) if return_layers else out
+
+
+def predictor_rollout(sd: SD, slot_history: Tensor, text: Tensor, cfg: PredCfg,
+                      num_preds: Optional[int] = None) -> Tensor:
+    """PredictorWrapper.forward (predictor_wrapper.py:50-87), teacher_force=False."""
+    num_preds = cfg.num_preds if num_preds is None else num_preds
+    window = slot_history[:, :cfg.num_context].clone()
+    preds = []
+    for _ in range(num_preds):
+        cur = predictor_step(sd, window, text, cfg)
+        window = torch.cat([window, cur.unsqueeze(1)], dim=1)[:, -cfg.input_buffer_size:]
+        preds.append(cur)
+    return torch.stack(preds, dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# Evaluator.forward_eval composition (05_evaluate_predictor.py:82-96) and PSNR
+# --------------------------------------------------------------------------------------
+def rollout(savi_sd: SD, pred_sd: SD, videos: Tensor, text: Tensor, init_slots: Tensor,
+            scfg: SAViCfg, pcfg: PredCfg, num_imgs: Optional[int] = None) -> Dict[str, Tensor]:
+    B = videos.shape[0]
+    num_imgs = pcfg.num_context + pcfg.num_preds if num_imgs is None else num_imgs
+    sh = savi_decomp(savi_sd, videos, num_imgs, scfg, init_slots)
+    ps = predictor_rollout(pred_sd, sh, text, pcfg)
+    dec = savi_decode(savi_sd, ps.reshape(B * pcfg.num_preds, scfg.num_slots, scfg.slot_dim), scfg)
+    H, W = scfg.resolution
+    imgs = dec["recons_imgs"].view(B, pcfg.num_preds, scfg.in_channels, H, W).clamp(0, 1)
+    return {"slot_history": sh, "pred_slots": ps, "pred_imgs": imgs}
+
+
+def psnr(x: Tensor, y: Tensor, eps: float = 1e-8) -> Tensor:
+    """Per-image PSNR, value_range 1: 10*log10(1/(mse+eps)).  Restates piqa 1.2.2 (unpinned)."""
+    mse = ((x - y) ** 2).flatten(-3).mean(-1)
+    return 10.0 * torch.log10(1.0 / (mse + eps))
+
+
+def rel_err(a: Tensor, b: Tensor) -> float:
+    """Relative L2 error ||a-b|| / ||b|| in fp64 (the per-stage parity measure)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "cater_b2.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_weights(golden):
+    from textocvp_b200 import weights
+    m = golden["meta"]
+    savi_sd = weights.savi_state_dict(m["savi_seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
+    pred_sd = weights.predictor_state_dict(m["pred_seed"], mlp_out_scale=m["mlp_out_scale"],
+                                           ln_jitter=m["ln_jitter"])
+    videos, text, noise = weights.synthetic_inputs(m["B"], m["T"], m["L"], seed=m["input_seed"])
+    init = savi_sd["initializer.slots_mu"] + savi_sd["initializer.slots_sigma"] * noise
+    return dict(savi_sd=savi_sd, pred_sd=pred_sd, videos=videos, text=text, init=init)

@@ -1,0 +1,45 @@
+"""The CPU oracle (oracle/textocvp_oracle.py) against golden vectors produced by the REAL
+reference modules (oracle/make_golden.py).  This is what pins the oracle."""
+import torch
+
+from oracle import textocvp_oracle as O
+
+TOL = 2e-5   # fp32 vs fp32, different op order only
+
+
+def test_stage_vectors(golden, golden_weights):
+    g, w = golden, golden_weights
+    scfg, pcfg = O.SAViCfg(), O.PredCfg()
+    sd = w["savi_sd"]
+    feats = O.savi_encode(sd, w["videos"][:, 0], scfg)
+    assert O.rel_err(feats[:, ::g["meta"]["feat_stride"]], g["encode_feats_sub"]) < TOL
+    _, hist = O.slot_attention(sd, feats, w["init"], 0, scfg, return_iters=True)
+    for it in (1, 2, 3):
+        assert O.rel_err(hist[it - 1], g[f"sa_iter{it}"]) < TOL
+    assert O.rel_err(O.slot_attention(sd, feats, w["init"], 1, scfg), g["sa_step1"]) < TOL
+    assert O.rel_err(O.transition(sd, g["sa_iter3"], scfg), g["transition"]) < TOL
+
+
+def test_predictor_step(golden, golden_weights):
+    g, w = golden, golden_weights
+    pcfg = O.PredCfg()
+    sh = g["slot_history"]
+    assert O.rel_err(O.predictor_step(w["pred_sd"], sh[:, :10], w["text"], pcfg), g["pred_step_n10"]) < TOL
+    assert O.rel_err(O.predictor_step(w["pred_sd"], sh[:, :1], w["text"], pcfg), g["pred_step_n1"]) < TOL
+
+
+def test_decode(golden, golden_weights):
+    g, w = golden, golden_weights
+    dec = O.savi_decode(w["savi_sd"], g["pred_slots"][:1, -1], O.SAViCfg())
+    assert O.rel_err(dec["recons"], g["dec_recons"]) < TOL
+    assert O.rel_err(dec["masks"], g["dec_masks"]) < TOL
+    assert O.rel_err(dec["recons_imgs"], g["dec_img"]) < TOL
+
+
+def test_full_rollout(golden, golden_weights):
+    g, w = golden, golden_weights
+    out = O.rollout(w["savi_sd"], w["pred_sd"], w["videos"], w["text"], w["init"], O.SAViCfg(), O.PredCfg())
+    assert O.rel_err(out["slot_history"], g["slot_history"]) < 1e-4
+    assert O.rel_err(out["pred_slots"], g["pred_slots"]) < 1e-4
+    p = O.psnr(out["pred_imgs"], g["pred_imgs"])
+    assert p.min() > 70.0, p.min()   # eps=1e-8 caps PSNR at 80 dB

@@ -1,0 +1,167 @@
+"""
+Deterministic random-init state dicts with the reference's parameter names and shapes.
+
+There are no checkpoints offline, so benchmarks, tests and golden vectors all use weights
+drawn here (torch CPU generator, seeded) with the reference's init *distributions*
+(SURVEY.md Appendix A.20): xavier-uniform matrices / zero biases for SAVi, PyTorch-default
+Linear init for the predictor's cross block, mlp_in and mlp_out, pe = 512^-0.5 * randn.
+The key contract is SURVEY.md Appendix B (strict ``load_state_dict`` in the reference,
+src/lib/setup_model.py:224), so the dicts load into the reference modules, the oracle and
+the CUDA modules alike.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def _xavier(g, *shape) -> Tensor:
+    fan_out, fan_in = shape[0], shape[1]
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    a = math.sqrt(6.0 / ((fan_in + fan_out) * rf))
+    return (torch.rand(*shape, generator=g) * 2 - 1) * a
+
+
+def _default_linear(g, out_f, in_f, bias=True):
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=g) * 2 - 1) * bound if bias else None
+    return w, b
+
+
+def _ln(sd, name, dim, g, jitter):
+    # LayerNorm defaults are (1, 0); ``jitter`` perturbs them so that parity tests exercise
+    # the affine terms instead of multiplying by exactly one.
+    sd[name + ".weight"] = 1.0 + jitter * torch.randn(dim, generator=g)
+    sd[name + ".bias"] = jitter * torch.randn(dim, generator=g)
+
+
+def savi_state_dict(seed: int = 14, num_slots: int = 8, slot_dim: int = 128, in_channels: int = 3,
+                    enc_channels=(32, 32, 32, 32), dec_channels=(64, 64, 64, 64), kernel_size: int = 5,
+                    mlp_hidden: int = 256, mlp_encoder_dim: int = 128, transition_mlp: int = 512,
+                    bias_scale: float = 0.0, ln_jitter: float = 0.0) -> Dict[str, Tensor]:
+    """SAVi (src/models/SAVi.py) parameters.  ``bias_scale`` > 0 randomises the biases that the
+    reference initialises to zero, so that tests cover the bias paths."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    D, F = slot_dim, mlp_encoder_dim
+
+    def bias(n):
+        return bias_scale * torch.randn(n, generator=g)
+
+    lim = math.sqrt(6.0 / (1 + D))
+    sd["initializer.slots_mu"] = (torch.rand(1, 1, D, generator=g) * 2 - 1) * lim
+    sd["initializer.slots_sigma"] = (torch.rand(1, 1, D, generator=g) * 2 - 1) * lim
+    # transition: post-norm TransformerBlock
+    for n in "qkv":
+        sd[f"transition_module.attn.{n}.weight"] = _xavier(g, D, D)
+    sd["transition_module.attn.out_projection.0.weight"] = _xavier(g, D, D)
+    sd["transition_module.mlp.0.weight"] = _xavier(g, transition_mlp, D)
+    sd["transition_module.mlp.0.bias"] = bias(transition_mlp)
+    sd["transition_module.mlp.2.weight"] = _xavier(g, D, transition_mlp)
+    sd["transition_module.mlp.2.bias"] = bias(D)
+    _ln(sd, "transition_module.layernorm_query", D, g, ln_jitter)
+    _ln(sd, "transition_module.layernorm_mlp", D, g, ln_jitter)
+    # encoder
+    cin = in_channels
+    for i, c in enumerate(enc_channels):
+        sd[f"encoder.encoder.{i}.block.0.weight"] = _xavier(g, c, cin, kernel_size, kernel_size)
+        sd[f"encoder.encoder.{i}.block.0.bias"] = bias(c)
+        cin = c
+    sd["encoder_pos_embedding.projection.weight"] = _xavier(g, cin, 4, 1, 1)
+    sd["encoder_pos_embedding.projection.bias"] = bias(cin)
+    _ln(sd, "encoder_mlp.0", cin, g, ln_jitter)
+    sd["encoder_mlp.1.weight"] = _xavier(g, F, cin)
+    sd["encoder_mlp.1.bias"] = bias(F)
+    sd["encoder_mlp.3.weight"] = _xavier(g, F, F)
+    sd["encoder_mlp.3.bias"] = bias(F)
+    # decoder (ConvDecoder iterates hidden dims in reverse; all equal in the named config)
+    sd["decoder_pos_embedding.projection.weight"] = _xavier(g, D, 4, 1, 1)
+    sd["decoder_pos_embedding.projection.bias"] = bias(D)
+    cin = D
+    rev = list(dec_channels)[::-1]
+    for i, c in enumerate(rev):
+        sd[f"decoder.decoder.{i}.block.0.weight"] = _xavier(g, c, cin, kernel_size, kernel_size)
+        sd[f"decoder.decoder.{i}.block.0.bias"] = bias(c)
+        cin = c
+    n = len(rev)
+    sd[f"decoder.decoder.{n}.weight"] = _xavier(g, in_channels + 1, dec_channels[0], 3, 3)
+    sd[f"decoder.decoder.{n}.bias"] = bias(in_channels + 1)
+    # slot attention
+    for nm in ("norm_input",):
+        _ln(sd, f"slot_attention.{nm}", F, g, ln_jitter)
+    for nm in ("norm_slot", "norm_mlp"):
+        _ln(sd, f"slot_attention.{nm}", D, g, ln_jitter)
+    sd["slot_attention.to_q.weight"] = _xavier(g, D, D)
+    sd["slot_attention.to_q.bias"] = bias(D)
+    sd["slot_attention.to_k.weight"] = _xavier(g, D, F)
+    sd["slot_attention.to_k.bias"] = bias(D)
+    sd["slot_attention.to_v.weight"] = _xavier(g, D, F)
+    sd["slot_attention.to_v.bias"] = bias(D)
+    sd["slot_attention.gru.weight_ih"] = _xavier(g, 3 * D, D)
+    q, _ = torch.linalg.qr(torch.randn(3 * D, D, generator=g))               # orthogonal weight_hh
+    sd["slot_attention.gru.weight_hh"] = q.contiguous()
+    sd["slot_attention.gru.bias_ih"] = bias(3 * D)
+    sd["slot_attention.gru.bias_hh"] = bias(3 * D)
+    sd["slot_attention.mlp.0.weight"] = _xavier(g, mlp_hidden, D)
+    sd["slot_attention.mlp.0.bias"] = bias(mlp_hidden)
+    sd["slot_attention.mlp.2.weight"] = _xavier(g, D, mlp_hidden)
+    sd["slot_attention.mlp.2.bias"] = bias(D)
+    return sd
+
+
+def predictor_state_dict(seed: int = 15, slot_dim: int = 128, token_dim: int = 512, hidden_dim: int = 2048,
+                         num_layers: int = 8, cross_inner: int = 512, cross_mlp: int = 2048,
+                         input_buffer_size: int = 10, mlp_out_scale: float = 0.1,
+                         ln_jitter: float = 0.0) -> Dict[str, Tensor]:
+    """TextOCVP body (src/models/Predictors/text_cond_OCVP.py) parameters, keys relative to the
+    TextOCVP module (the PredictorWrapper adds a ``predictor.`` prefix, see Appendix B).
+
+    ``mlp_out_scale`` = 0.1 is the stable benchmark init of SURVEY.md 8(d): stock init makes the
+    19-step rollout diverge (slot std x1.3 per step) which no reduced-precision path can track
+    at 40 dB.  The same weights feed the oracle and the CUDA path."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    T = token_dim
+    sd["mlp_in.weight"], sd["mlp_in.bias"] = _default_linear(g, T, slot_dim)
+    w, b = _default_linear(g, slot_dim, T)
+    sd["mlp_out.weight"], sd["mlp_out.bias"] = w * mlp_out_scale, b * mlp_out_scale
+    sd["pe.pe"] = T ** -0.5 * torch.randn(1, input_buffer_size + 1, 1, T, generator=g)
+    for i in range(num_layers):
+        p = f"predictor.{i}"
+        for n in "qkv":
+            sd[f"{p}.attn.{n}.weight"] = _xavier(g, T, T)
+        sd[f"{p}.attn.out_projection.0.weight"] = _xavier(g, T, T)
+        sd[f"{p}.mlp.0.weight"] = _xavier(g, hidden_dim, T)
+        sd[f"{p}.mlp.0.bias"] = torch.zeros(hidden_dim)
+        sd[f"{p}.mlp.2.weight"] = _xavier(g, T, hidden_dim)
+        sd[f"{p}.mlp.2.bias"] = torch.zeros(T)
+        _ln(sd, f"{p}.layernorm_query", T, g, ln_jitter)
+        _ln(sd, f"{p}.layernorm_mlp", T, g, ln_jitter)
+        c = f"{p}.cross_attention"
+        for nm in ("ln_mlp", "ln_cross_att_q", "ln_cross_att_kv"):
+            _ln(sd, f"{c}.{nm}", T, g, ln_jitter)
+        sd[f"{c}.mlp.0.weight"], sd[f"{c}.mlp.0.bias"] = _default_linear(g, cross_mlp, T)
+        sd[f"{c}.mlp.2.weight"], sd[f"{c}.mlp.2.bias"] = _default_linear(g, T, cross_mlp)
+        for n in "qkv":
+            sd[f"{c}.cross_attn.{n}.weight"], _ = _default_linear(g, cross_inner, T, bias=False)
+        sd[f"{c}.cross_attn.out_projection.weight"], sd[f"{c}.cross_attn.out_projection.bias"] = \
+            _default_linear(g, T, cross_inner)
+    return sd
+
+
+def synthetic_inputs(B: int, T: int = 20, L: int = 32, token_dim: int = 512, num_slots: int = 8,
+                     slot_dim: int = 128, res=(64, 64), seed: int = 0):
+    """videos U[0,1) [B,T,3,H,W], text embeddings N(0,1) [B,L,512], slot-init noise N(0,1) [B,S,D]
+    (SURVEY.md 8(d) config 1).  The noise is injected into both paths (CPU and CUDA generators differ)."""
+    g = torch.Generator().manual_seed(seed)
+    videos = torch.rand(B, T, 3, res[0], res[1], generator=g)
+    text = torch.randn(B, L, token_dim, generator=g)
+    noise = torch.randn(B, num_slots, slot_dim, generator=g)
+    return videos, text, noise
