@@ -1,0 +1,64 @@
+"""GPU parity tests of the building-block kernels through the C ABI (run with -m gpu on a B200).
+Floating point -> compared against a plain torch fp32/fp64 reference of the same op; tolerances are
+written next to each check."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 512), (2048, 1536, 512), (1000, 2048, 512),
+                                   (4096, 512, 2048), (520, 128, 32), (333 * 8, 1600, 128), (64, 64, 128),
+                                   (20480, 512, 512)])
+def test_gemm_f16(M, N, K):
+    from textocvp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = a.double() @ w.double().t()
+    o32, o16 = ops.gemm_f16(a, w, out_f32=True, out_f16=True)
+    torch.cuda.synchronize()
+    assert _rel(o32, ref) < 1e-5          # exact f16 products, fp32 accumulation
+    assert _rel(o16, ref) < 1e-3          # + f16 output rounding
+    o32, _ = ops.gemm_f16(a, w, bias=bias, relu=True, residual=res)
+    ref2 = torch.relu(ref + bias.double()) + res.double()
+    assert _rel(o32, ref2) < 1e-5
+
+
+@pytest.mark.parametrize("rows,D,f16", [(1000, 512, False), (77, 128, False), (4096, 32, True), (300, 768, False)])
+def test_layernorm(rows, D, f16):
+    from textocvp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 1
+    if f16:
+        x = x.half()
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    add = torch.randn(64, D, device="cuda", generator=g)
+    o16, o32 = ops.layernorm(x, gamma, beta, 1e-6, out_f32=True)
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-6)
+    assert _rel(o32, ref) < 1e-5
+    assert _rel(o16, ref) < 1e-3
+    _, o32 = ops.layernorm(x, gamma, beta, 1e-3, add=add, out_f16=False, out_f32=True)
+    xa = x.double() + add.double().repeat((rows + 63) // 64, 1)[:rows]
+    ref = torch.nn.functional.layer_norm(xa, (D,), gamma.double(), beta.double(), 1e-3)
+    assert _rel(o32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("shift", [0, 1, 3, 8, 13, 68, 70, 127])
+def test_probe_shifted_sw128_operand(shift):
+    """The conv kernel's assumption: a SW128 K-major operand may start at any 128-byte row."""
+    from textocvp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(shift)
+    x = torch.randn(256, 64, device="cuda", generator=g).half()
+    w = torch.randn(64, 64, device="cuda", generator=g).half()
+    out = ops.probe_shifted_operand(x, w, shift, 0)
+    ref = x[shift:shift + 128].double() @ w.double().t()
+    assert _rel(out, ref) < 1e-5

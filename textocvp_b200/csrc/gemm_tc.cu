@@ -1,0 +1,254 @@
+// tcgen05 GEMM for the dense projections of the rollout path:
+//     C[M,N] = A[M,K] . W[N,K]^T  (+bias) (ReLU) (+residual)   -> fp32 and/or fp16
+// A and W are fp16, K-major (torch.nn.Linear weight layout [out,in] is already K-major), fp32 accumulate
+// in TMEM.  One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer (128B-swizzled 128x64 A tile + BNx64 W tile per stage)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
+//   warps 2..5  epilogue: tcgen05.ld -> bias/ReLU/residual -> global (double-buffered accumulators, so the
+//               epilogue of tile i overlaps the main loop of tile i+1)
+// Replaces the cuBLAS calls behind nn.Linear at reference src/models/Blocks/attention.py:167-175,255,296-300,
+// 352-356 and src/models/Predictors/text_cond_OCVP.py:47-48, src/models/SAVi.py:117-119.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 rows of length N (leading dim ldr) or null
+  int ldr;
+  int res_div, res_mod;   // residual row = res_mod ? (row / res_div) % res_mod : row
+  int relu;
+  float* out32;
+  int ld32;
+  __half* out16;
+  int ld16;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tfull = empty + S::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mb = t / tiles_n, nb = t % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], S::STAGE_BYTES);
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          tma_load_2d(&tmA, &full[s], st, kb * GEMM_BK, mb * GEMM_BM);
+          tma_load_2d(&tmB, &full[s], st + S::A_BYTES, kb * GEMM_BK, nb * BN);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t bph = (it >> 1) & 1;
+        mbar_wait(&tempty[b], bph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(b * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128(a0, 1024);
+          const uint64_t db = make_desc_sw128(a0 + S::A_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[s]);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int mb = t / tiles_n, nb = t % tiles_n;
+      const int b = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      mbar_wait(&tfull[b], bph);
+      tc_fence_after();
+      const int row = mb * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const float* res_row = nullptr;
+      if (g.residual != nullptr && row_ok) {
+        const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
+        res_row = g.residual + size_t(rr) * g.ldr;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + c * 32), v);
+        tmem_ld_wait();
+        const int n0 = nb * BN + c * 32;
+        if (row_ok && n0 < g.N) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int n = n0 + j8 * 8;
+            if (n < g.N) {  // N is a multiple of 8
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+              if (g.bias != nullptr) {
+                const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (g.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (res_row != nullptr) {
+                const float4 r0 = *reinterpret_cast<const float4*>(res_row + n);
+                const float4 r1 = *reinterpret_cast<const float4*>(res_row + n + 4);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+              }
+              if (g.out32 != nullptr) {
+                float* o = g.out32 + size_t(row) * g.ld32 + n;
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              }
+              if (g.out16 != nullptr) {
+                uint4 p;
+                p.x = pack_half2(f[0], f[1]);
+                p.y = pack_half2(f[2], f[3]);
+                p.z = pack_half2(f[4], f[5]);
+                p.w = pack_half2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(g.out16 + size_t(row) * g.ld16 + n) = p;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_f16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, g);
+  TOCVP_CUDA(cudaGetLastError());
+  return TOCVP_OK;
+}
+
+// Internal entry used by the stage drivers and by the public tocvp_gemm_f16.
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+             const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16,
+             int ld16, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(A != nullptr && W != nullptr);
+  TOCVP_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  TOCVP_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);
+  TOCVP_CHECK_ARG(out32 != nullptr || out16 != nullptr);
+  TOCVP_CHECK_ARG(out32 == nullptr || ld32 % 4 == 0);
+  TOCVP_CHECK_ARG(out16 == nullptr || ld16 % 8 == 0);
+  TOCVP_CHECK_ARG(residual == nullptr || ldr % 4 == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  // Tile width: wide tiles for wide outputs; 64 keeps enough tiles in flight for narrow / short problems.
+  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  int bn = 128;
+  if (N <= 64 || (N % 128 != 0 && N % 64 == 0 && N < 512)) bn = 64;
+  else if (tiles_m * ((N + 127) / 128) < num_sms() && N >= 128) bn = 64;
+  CUtensorMap tmA, tmB;
+  TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, GEMM_BM, GEMM_BK));
+  TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn, GEMM_BK));
+  GemmArgs g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16};
+  if (bn == 64) return launch_gemm<64>(tmA, tmB, g, stream);
+  return launch_gemm<128>(tmA, tmB, g, stream);
+}
+
+}  // namespace tocvp
+
+extern "C" int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                              int relu, const float* residual, int ldr, float* out_f32, int ld32, void* out_f16,
+                              int ld16, void* stream) {
+  return tocvp::gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N, K, bias, relu,
+                         residual, ldr, 1, 0, out_f32, ld32, static_cast<__half*>(out_f16), ld16,
+                         static_cast<cudaStream_t>(stream));
+}

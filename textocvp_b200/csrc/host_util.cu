@@ -1,0 +1,103 @@
+#include "host_util.h"
+
+#include <string.h>
+
+#include <mutex>
+
+namespace tocvp {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* file, int line, const char* msg) {
+  const char* base = strrchr(file, '/');
+  snprintf(g_err, sizeof(g_err), "%s:%d: %s", base ? base + 1 : file, line, msg);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return TOCVP_ERR_CUDA;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[5];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, dtype, cuuint32_t(rank), const_cast<void*>(base), gdims, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dim0 %llu box0 %u)", int(r), rank,
+             (unsigned long long)dims[0], box[0]);
+    set_last_error(__FILE__, __LINE__, msg);
+    return TOCVP_ERR_CUDA;
+  }
+  return TOCVP_OK;
+}
+
+int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld_elems * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace tocvp
+
+extern "C" const char* tocvp_last_error(void) { return tocvp::g_err; }
+
+extern "C" int tocvp_init(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    tocvp::set_last_error(__FILE__, __LINE__, "cudaGetDeviceProperties failed (no CUDA device)");
+    return TOCVP_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "device is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.major,
+             prop.minor);
+    tocvp::set_last_error(__FILE__, __LINE__, msg);
+    return TOCVP_ERR_ARCH;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return TOCVP_ERR_CUDA;
+  return TOCVP_OK;
+}
+
+extern "C" int tocvp_abi_version(void) { return TOCVP_ABI_VERSION; }

@@ -1,0 +1,48 @@
+// Host-side helpers shared by the C-ABI entry points: error codes, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tocvp.h"
+
+namespace tocvp {
+
+#define TOCVP_CHECK_ARG(cond)                                                      \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      tocvp::set_last_error(__FILE__, __LINE__, "bad argument: " #cond);           \
+      return TOCVP_ERR_BAD_ARG;                                                    \
+    }                                                                              \
+  } while (0)
+
+#define TOCVP_CUDA(call)                                                           \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      tocvp::set_last_error(__FILE__, __LINE__, cudaGetErrorString(e__));          \
+      return TOCVP_ERR_CUDA;                                                       \
+    }                                                                              \
+  } while (0)
+
+#define TOCVP_TRY(call)                                                            \
+  do {                                                                             \
+    int r__ = (call);                                                              \
+    if (r__ != TOCVP_OK) return r__;                                               \
+  } while (0)
+
+void set_last_error(const char* file, int line, const char* msg);
+
+// cuTensorMapEncodeTiled fetched through the runtime (no link-time dependency on libcuda).
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes /* rank-1 entries, dims 1.. */, const uint32_t* box,
+                CUtensorMapSwizzle swizzle);
+
+// 2D row-major fp16 matrix [rows, cols] (cols contiguous) with a {box_cols, box_rows} box, 128B swizzle.
+int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows, uint32_t box_cols);
+
+int num_sms();
+
+}  // namespace tocvp

@@ -1,0 +1,49 @@
+"""Thin tensor-level wrappers over the C ABI (device tensors in, device tensors out).
+Used by the nn.Module mirrors in ``modules.py`` and by the parity tests."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import c_float, c_int, ptr, stream
+
+
+def _chk_f16(t, name):
+    assert t.is_cuda and t.dtype == torch.float16 and t.stride(-1) == 1, f"{name}: need contiguous-cuda-f16"
+
+
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+             residual: Optional[torch.Tensor] = None, out_f32: bool = True, out_f16: bool = False):
+    """C = a @ w.T (+bias)(relu)(+residual).  a [M,K] f16, w [N,K] f16.  Returns (out32|None, out16|None)."""
+    L.init(a.device)
+    _chk_f16(a, "a"); _chk_f16(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    o32 = torch.empty(M, N, device=a.device, dtype=torch.float32) if out_f32 else None
+    o16 = torch.empty(M, N, device=a.device, dtype=torch.float16) if out_f16 else None
+    L.call("tocvp_gemm_f16", ptr(a), c_int(a.stride(0)), ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
+           ptr(bias), c_int(int(relu)), ptr(residual), c_int(residual.stride(0) if residual is not None else 0),
+           ptr(o32), c_int(N), ptr(o16), c_int(N), stream())
+    return o32, o16
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              add: Optional[torch.Tensor] = None, out_f16: bool = True, out_f32: bool = False):
+    """Row LayerNorm of a 2-D tensor [rows, D] (fp32 or f16 in)."""
+    L.init(x.device)
+    rows, D = x.shape
+    o16 = torch.empty(rows, D, device=x.device, dtype=torch.float16) if out_f16 else None
+    o32 = torch.empty(rows, D, device=x.device, dtype=torch.float32) if out_f32 else None
+    L.call("tocvp_layernorm", ptr(x), c_int(int(x.dtype == torch.float16)), c_int(x.stride(0)), ptr(add),
+           c_int(add.shape[0] if add is not None else 0), ptr(gamma), ptr(beta), c_float(eps), c_int(rows), c_int(D),
+           ptr(o16), c_int(D), ptr(o32), c_int(D), stream())
+    return o16, o32
+
+
+def probe_shifted_operand(x: torch.Tensor, w: torch.Tensor, shift: int, base_offset_mode: int):
+    L.init(x.device)
+    out = torch.zeros(128, 64, device=x.device, dtype=torch.float32)
+    L.call("tocvp_probe_shifted_operand", ptr(x), ptr(w), ptr(out), c_int(shift), c_int(base_offset_mode), stream())
+    return out
