@@ -65,6 +65,17 @@ int tocvp_layernorm(const void* x, int x_is_f16, int ldx, const float* add, int 
                     const float* beta, float eps, int rows, int D, void* out_f16, int ld16, float* out_f32,
                     int ld32, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 5x5 stride-1 zero-padded convolution + bias (+ReLU) as a tcgen05 implicit GEMM.
+ * x: f16 NHWC [n_img,H,W,cin]; w_packed: f16 [25,cout,cin] (tap-major, tap = ky*5+kx, i.e.
+ * torch weight[co,ci,ky,kx] permuted); bias fp32[cout]; out: f16 NHWC [n_img,H,W,cout].
+ * H % 16 == 0, W % 32 == 0; (cin,cout) in {(64,64),(32,32)}.
+ * Replaces nn.Conv2d -> cuDNN at src/models/Blocks/model_blocks.py:83-91 as used by
+ * src/models/EncodersDecoders/decoders.py:96-108 and encoders.py:141-153.
+ * ------------------------------------------------------------------------------------------ */
+int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H, int W,
+                      int cin, int cout, int relu, void* stream);
+
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
 int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,

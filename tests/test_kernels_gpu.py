@@ -62,3 +62,19 @@ def test_probe_shifted_sw128_operand(shift):
     out = ops.probe_shifted_operand(x, w, shift, 0)
     ref = x[shift:shift + 128].double() @ w.double().t()
     assert _rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("n,c", [(1, 64), (3, 64), (40, 64), (2, 32), (37, 32)])
+def test_conv5x5(n, c):
+    """tcgen05 implicit-GEMM conv vs torch conv2d (fp32) on f16-rounded operands."""
+    from textocvp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n * 100 + c)
+    x = torch.randn(n, 64, 64, c, device="cuda", generator=g).half()
+    w = (torch.randn(c, c, 5, 5, device="cuda", generator=g) / (25 * c) ** 0.5)
+    b = torch.randn(c, device="cuda", generator=g)
+    out = ops.conv5x5_f16(x, ops.pack_conv5x5_weight(w), b, relu=True)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=2))
+    ref = ref.permute(0, 2, 3, 1)
+    assert _rel(out, ref) < 1e-3      # f16 output rounding only (operands identical, fp32 accumulate)
+    assert (out.float() - ref).abs().max() < 2e-2

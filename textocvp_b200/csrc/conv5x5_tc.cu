@@ -1,0 +1,266 @@
+// 5x5 stride-1 "same" convolution + bias + ReLU as a tcgen05 implicit GEMM (NHWC f16 in/out, fp32 accumulate).
+//
+// The workhorse of the decoder (reference src/models/EncodersDecoders/decoders.py:96-119, 3 x conv5x5 64->64 per
+// slot-image = 2.5 GFLOP) and of the encoder (encoders.py:141-153, 3 x conv5x5 32->32).  Replaces cuDNN.
+//
+// Mapping.  A CTA owns an output tile of 16 rows x 8G columns of one image = G UMMA M-tiles of 128 pixels
+// (M index = row*8 + col inside a 16x8 sub-tile).  The input halo (20 rows x (8G+8) cols x CIN) is fetched ONCE
+// per tile by a single 4-D TMA box load -- out-of-image coordinates are zero-filled by the TMA unit, which is the
+// convolution's zero padding -- into a swizzled, pixel-major smem tile (one CIN*2-byte row per pixel).  Every filter
+// tap (ty,tx) then reads the SAME smem tile through a K-major UMMA descriptor whose start address is shifted by
+// (ty*WBUF + tx) pixel rows and whose 8-row-group stride (SBO) is one halo row: no im2col copy, 25x on-chip reuse.
+// The per-tap [COUT x CIN] weight slices stream through a small TMA ring (they are L2 resident).
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2..5: epilogue (bias+ReLU, f16 NHWC store)
+// Accumulators are double-buffered in TMEM (2 x G x COUT columns) so the epilogue overlaps the next tile.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+template <int CIN, int COUT, int G>
+struct ConvCfg {
+  static constexpr int KB = CIN * 2;                 // bytes per pixel row in smem (64 or 128)
+  static constexpr int TILE_H = 16;
+  static constexpr int TILE_W = 8 * G;
+  static constexpr int WBUF = TILE_W + 8;            // halo width, multiple of 8 (>= TILE_W + 4)
+  static constexpr int HROWS = TILE_H + 4;
+  static constexpr int A_BYTES = HROWS * WBUF * KB;  // multiple of 1024 for G in {2,4}
+  static constexpr int W_BYTES = COUT * KB;
+  static constexpr int WSTAGES = (CIN == 64) ? 3 : 8;
+  static constexpr int KSTEPS = CIN / 16;
+  static constexpr int ACC_COLS = G * COUT;          // per accumulator buffer
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
+  static constexpr int SMEM = 2 * A_BYTES + WSTAGES * W_BYTES + 256 + 1024;
+  static constexpr int LAYOUT = (KB == 128) ? 2 : 4;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  static_assert(KB == 128 || KB == 64, "CIN must be 32 or 64");
+  static_assert(A_BYTES % 1024 == 0, "halo tile must keep the second buffer 1024B aligned");
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+};
+
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, uint32_t sbo_bytes, int layout) {
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(layout) << 61);
+}
+
+struct ConvArgs {
+  int n_img, H, W;
+  const float* bias;  // [COUT]
+  __half* out;        // [n_img, H, W, COUT]
+  int relu;
+};
+
+template <int CIN, int COUT, int G>
+__global__ void __launch_bounds__(192, 1)
+conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
+  using C = ConvCfg<CIN, COUT, G>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                       // 2 halo buffers
+  uint8_t* sW = smem + 2 * C::A_BYTES;      // weight ring
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_BYTES);
+  uint64_t* w_empty = w_full + C::WSTAGES;
+  uint64_t* a_full = w_empty + C::WSTAGES;
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* t_full = a_empty + 2;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = a.W / C::TILE_W, tiles_y = a.H / C::TILE_H;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int num_tiles = a.n_img * tiles_per_img;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::WSTAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], 1);
+      mbar_init(&a_empty[b], 1);
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      auto load_halo = [&](int t, int it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int img = t / tiles_per_img, r = t % tiles_per_img;
+        const int y0 = (r / tiles_x) * C::TILE_H, x0 = (r % tiles_x) * C::TILE_W;
+        mbar_wait(&a_empty[buf], ph ^ 1);
+        mbar_expect_tx(&a_full[buf], C::A_BYTES);
+        tma_load_4d(&tmX, &a_full[buf], sA + buf * C::A_BYTES, 0, x0 - 2, y0 - 2, img);
+      };
+      int s = 0;
+      uint32_t wph = 0;
+      int it = 0;
+      if (int(blockIdx.x) < num_tiles) load_halo(blockIdx.x, 0);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        if (t + int(gridDim.x) < num_tiles) load_halo(t + gridDim.x, it + 1);  // prefetch the next tile's halo
+        for (int tap = 0; tap < 25; ++tap) {
+          mbar_wait(&w_empty[s], wph ^ 1);
+          mbar_expect_tx(&w_full[s], C::W_BYTES);
+          tma_load_2d(&tmW, &w_full[s], sW + s * C::W_BYTES, 0, tap * COUT);
+          if (++s == C::WSTAGES) { s = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, COUT, 0);
+      constexpr uint32_t SBO = C::WBUF * C::KB;
+      int s = 0;
+      uint32_t wph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], ph ^ 1);
+        mbar_wait(&a_full[buf], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + buf * C::A_BYTES);
+        const uint32_t d_base = tmem_base + uint32_t(buf * C::ACC_COLS);
+        for (int tap = 0; tap < 25; ++tap) {
+          const int ty = tap / 5, tx = tap % 5;
+          mbar_wait(&w_full[s], wph);
+          tc_fence_after();
+          const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_BYTES), 8 * C::KB, C::LAYOUT);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const uint32_t a_addr = a_base + uint32_t((ty * C::WBUF + tx + 8 * j) * C::KB);
+            const uint64_t da = make_desc_kmajor(a_addr, SBO, C::LAYOUT);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k) {
+              umma_f16(d_base + uint32_t(j * COUT), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                       (tap | k) != 0);
+            }
+          }
+          umma_commit(&w_empty[s]);
+          if (++s == C::WSTAGES) { s = 0; wph ^= 1; }
+        }
+        umma_commit(&a_empty[buf]);
+        umma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int m = q * 32 + lane;          // TMEM lane = pixel index inside the 16x8 sub-tile
+    const int pr = m >> 3, pc = m & 7;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int img = t / tiles_per_img, r = t % tiles_per_img;
+      const int y = (r / tiles_x) * C::TILE_H + pr;
+      const int x0 = (r % tiles_x) * C::TILE_W + pc;
+      mbar_wait(&t_full[buf], ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < G; ++j) {
+        __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
+#pragma unroll
+        for (int c = 0; c < COUT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int n = c * 32 + j8 * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j8 * 8 + e]);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 p;
+            p.x = pack_half2(f[0], f[1]);
+            p.y = pack_half2(f[2], f[3]);
+            p.z = pack_half2(f[4], f[5]);
+            p.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(o + n) = p;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int CIN, int COUT, int G>
+static int launch_conv(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
+                       int relu, cudaStream_t stream) {
+  using C = ConvCfg<CIN, COUT, G>;
+  TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(conv5x5_kernel<CIN, COUT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmX, tmW;
+  {
+    const uint64_t dims[4] = {uint64_t(CIN), uint64_t(W), uint64_t(H), uint64_t(n_img)};
+    const uint64_t str[3] = {uint64_t(CIN) * 2, uint64_t(W) * CIN * 2, uint64_t(H) * W * CIN * 2};
+    const uint32_t box[4] = {uint32_t(CIN), uint32_t(C::WBUF), uint32_t(C::HROWS), 1};
+    TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, sw));
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(CIN), uint64_t(25 * COUT)};
+    const uint64_t str[1] = {uint64_t(CIN) * 2};
+    const uint32_t box[2] = {uint32_t(CIN), uint32_t(COUT)};
+    TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
+  }
+  const int num_tiles = n_img * (H / C::TILE_H) * (W / C::TILE_W);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  ConvArgs a{n_img, H, W, bias, out, relu};
+  conv5x5_kernel<CIN, COUT, G><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
+  TOCVP_CUDA(cudaGetLastError());
+  return TOCVP_OK;
+}
+
+// x: f16 NHWC [n_img,H,W,cin]; wpacked: f16 [25, cout, cin] (tap-major, tap = ky*5+kx); out: f16 NHWC [n_img,H,W,cout]
+int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W, int cin,
+                int cout, int relu, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && wpacked && bias && out && n_img > 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (cin == 64 && cout == 64) return launch_conv<64, 64, 4>(x, wpacked, bias, out, n_img, H, W, relu, stream);
+  if (cin == 32 && cout == 32) return launch_conv<32, 32, 4>(x, wpacked, bias, out, n_img, H, W, relu, stream);
+  set_last_error(__FILE__, __LINE__, "conv5x5_f16: only 64->64 and 32->32 channels are instantiated");
+  return TOCVP_ERR_BAD_ARG;
+}
+
+}  // namespace tocvp
+
+extern "C" int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H,
+                                 int W, int cin, int cout, int relu, void* stream) {
+  return tocvp::conv5x5_f16(static_cast<const __half*>(x), static_cast<const __half*>(w_packed), bias,
+                            static_cast<__half*>(out), n_img, H, W, cin, cout, relu, static_cast<cudaStream_t>(stream));
+}

@@ -47,3 +47,21 @@ def probe_shifted_operand(x: torch.Tensor, w: torch.Tensor, shift: int, base_off
     out = torch.zeros(128, 64, device=x.device, dtype=torch.float32)
     L.call("tocvp_probe_shifted_operand", ptr(x), ptr(w), ptr(out), c_int(shift), c_int(base_offset_mode), stream())
     return out
+
+
+def pack_conv5x5_weight(w: torch.Tensor) -> torch.Tensor:
+    """torch conv weight [Cout,Cin,5,5] -> tap-major f16 [25, Cout, Cin] (tap = ky*5 + kx)."""
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().half()
+
+
+def conv5x5_f16(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, relu: bool = True):
+    """x f16 NHWC [N,H,W,Cin] -> f16 NHWC [N,H,W,Cout]."""
+    L.init(x.device)
+    _chk_f16(x, "x")
+    n, h, w_, ci = x.shape
+    co = w_packed.shape[1]
+    out = torch.empty(n, h, w_, co, device=x.device, dtype=torch.float16)
+    L.call("tocvp_conv5x5_f16", ptr(x), ptr(w_packed), ptr(bias), ptr(out), c_int(n), c_int(h), c_int(w_), c_int(ci),
+           c_int(co), c_int(int(relu)), stream())
+    return out
