@@ -76,6 +76,139 @@ int tocvp_layernorm(const void* x, int x_is_f16, int ldx, const float* add, int 
 int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H, int W,
                       int cin, int cout, int relu, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SAVi corrector: SlotAttention.forward (src/models/Blocks/attention.py:67-112) for 8 slots x 128-d
+ * over N locations of 128-d features, plus (optionally) the post-norm transition TransformerBlock
+ * (attention.py:387-395, built at src/models/Blocks/transition_models.py:26-31).
+ * All pointers are fp32 device arrays.  "_t" = transposed to [in][out]; wk is torch's [out][in].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_sa_weights {
+  const float *ln_in_g, *ln_in_b, *ln_slot_g, *ln_slot_b, *ln_mlp_g, *ln_mlp_b; /* norm_input / norm_slot / norm_mlp */
+  const float *wq_t, *bq, *wk, *bk, *wv_t, *bv;                                 /* to_q / to_k / to_v               */
+  const float *w_ih_t, *w_hh_t, *b_ih, *b_hh;                                   /* gru (gate order r,z,n)           */
+  const float *w1_t, *b1, *w2_t, *b2;                                           /* mlp.0 / mlp.2                    */
+  const float *t_wq_t, *t_wk_t, *t_wv_t, *t_wo_t;                               /* transition attn q,k,v,out (no bias) */
+  const float *t_ln1_g, *t_ln1_b, *t_ln2_g, *t_ln2_b;                           /* layernorm_query / layernorm_mlp  */
+  const float *t_w1_t, *t_b1, *t_w2_t, *t_b2;                                   /* transition mlp.0 / mlp.2         */
+  int mlp_hidden, t_heads, t_hidden;
+  float attn_eps, ln_eps_sa, ln_eps_tf, scale; /* 1e-8, 1e-3, 1e-6, dim_feats^-0.5 */
+} tocvp_sa_weights;
+
+size_t tocvp_sizeof_sa_weights(void);
+size_t tocvp_slot_attention_workspace_bytes(int B);
+/* feats fp32 or f16: sequence b's [N,128] block starts at feats + b*feats_seq_stride (elements), so the features of
+ * frame t inside a [B,T,N,128] encode batch are used in place; slots_in [B,8,128]; slots_out row b at
+ * slots_out + b*out_stride (floats), so results land straight in slot_history[:, t]; pred_out (optional) =
+ * transition(slots_out) [B,8,128].  iters = num_iterations_first for step 0, else num_iterations (attention.py:90). */
+int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats_f16, size_t feats_seq_stride, int B,
+                         int N,
+                         const float* slots_in, int iters, float* slots_out, int out_stride, float* pred_out,
+                         void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Short-sequence multi-head attention (head dim 64, <= 128 keys, fp32 softmax, no mask).
+ * q [B*Tq, ldq], k / v [B*Tk, ldkv] f16 with head h at column offset h*64; out [B*Tq, ldo] f16.
+ * Replaces MetaAttention.attention + split/merge_heads, src/models/Blocks/attention.py:183-215.
+ * ------------------------------------------------------------------------------------------ */
+int tocvp_mha_f16(const void* q, int ldq, const void* k, const void* v, int ldkv, int B, int Tq, int Tk, int heads,
+                  void* out, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Text-conditioned predictor (TextOCVP body).  f16 weight matrices are torch Linear weights
+ * [out,in] cast to f16; w_qkv = cat(attn.q, attn.k, attn.v), wc_kv = cat(cross_attn.k, cross_attn.v).
+ * Layer = AdaptedEncoderBlock, src/models/Blocks/attention.py:504-524 (+ TransformerDecoderBlock :445-463).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_pred_layer {
+  const float *ln_q_g, *ln_q_b;     /* layernorm_query                     */
+  const void* w_qkv;                /* f16 [3T, T]                          */
+  const void* w_o;                  /* f16 [T, T]   attn.out_projection.0   */
+  const float *ln_cq_g, *ln_cq_b;   /* cross_attention.ln_cross_att_q       */
+  const float *ln_ckv_g, *ln_ckv_b; /* cross_attention.ln_cross_att_kv      */
+  const void* wc_q;                 /* f16 [T, T]                           */
+  const void* wc_kv;                /* f16 [2T, T]                          */
+  const void* wc_o;                 /* f16 [T, T]   cross_attn.out_projection (with bias) */
+  const float* bc_o;
+  const float *ln_cm_g, *ln_cm_b;   /* cross_attention.ln_mlp               */
+  const void *wc_1, *wc_2;          /* f16 [Hc, T], [T, Hc]  cross_attention.mlp */
+  const float *bc_1, *bc_2;
+  const float *ln_m_g, *ln_m_b;     /* layernorm_mlp                        */
+  const void *w_1, *w_2;            /* f16 [H, T], [T, H]    mlp            */
+  const float *b_1, *b_2;
+} tocvp_pred_layer;
+
+typedef struct tocvp_pred_weights {
+  const tocvp_pred_layer* layers;   /* HOST array of num_layers entries     */
+  int num_layers, num_slots, slot_dim, token_dim, hidden_dim, cross_hidden, num_heads, cross_heads;
+  int buffer_size;                  /* input_buffer_size (max window, frames) */
+  int residual;
+  float ln_eps;                     /* 1e-6 */
+  const void* mlp_in_w;             /* f16 [T, D] */
+  const float* mlp_in_b;
+  const void* mlp_out_w;            /* f16 [D, T] */
+  const float* mlp_out_b;
+  const float* pe_flipped;          /* fp32 [buffer_size][buffer_size][T]: table n-1 row f = pe[n-1-f] (f < n) */
+} tocvp_pred_weights;
+
+size_t tocvp_sizeof_pred_weights(void);
+size_t tocvp_sizeof_pred_layer(void);
+size_t tocvp_predictor_workspace_bytes(const tocvp_pred_weights* w, int B, int L, int num_context, int num_preds);
+/* PredictorWrapper.forward (src/models/Predictors/predictor_wrapper.py:50-87), teacher_force = False:
+ * slot_history fp32 (sequence b at slot_history + b*hist_seq_stride, first num_context frames are read),
+ * text fp32 [B, L, T] (the text-encoder output), pred_slots fp32 [B, num_preds, S, D].  256B-aligned workspace. */
+int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float* slot_history, size_t hist_seq_stride,
+                            const float* text, int B, int L, int num_context, int num_preds, float* pred_slots,
+                            void* workspace, size_t ws_bytes, void* stream);
+/* BaseTextOCVP.forward (src/models/Predictors/text_cond_OCVP.py:79-105): slots [B,n,S,D] -> out [B,S,D].
+ * Workspace: tocvp_predictor_workspace_bytes(w, B, L, n, 1). */
+int tocvp_predictor_forward(const tocvp_pred_weights* w, const float* slots, const float* text, int B, int n, int L,
+                            float* out, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SAVi.encode (src/models/SAVi.py:226-238; SimpleConvEncoder src/models/EncodersDecoders/encoders.py:136-159;
+ * SoftPositionEmbed src/models/Blocks/model_blocks.py:215-226; encoder_mlp SAVi.py:115-120).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_enc_weights {
+  const float* w_conv1;      /* fp32 [25*3][32]: row (ky*5+kx)*3+ci, col co  (encoder.encoder.0.block.0.weight permuted) */
+  const float* b_conv1;
+  const void* w_conv[3];     /* f16 [25,32,32] tap-major (encoder.encoder.{1,2,3}) */
+  const float* b_conv[3];
+  const float* posemb;       /* fp32 [H*W, 32] = Conv1x1(build_grid) + bias, precomputed (batch independent) */
+  const float *ln_g, *ln_b;  /* encoder_mlp.0 */
+  const void* w_mlp1;        /* f16 [F, 32]   encoder_mlp.1 */
+  const float* b_mlp1;
+  const void* w_mlp2;        /* f16 [F, F]    encoder_mlp.3 */
+  const float* b_mlp2;
+  int H, W, in_channels, hidden, feat_dim;
+} tocvp_enc_weights;
+
+size_t tocvp_sizeof_enc_weights(void);
+size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img);
+/* frames fp32: image i = 3 planes of H x W at frames + i*img_stride (floats), so x[:, t] of a [B,T,3,H,W] video is
+ * addressed in place; feats [n_img, H*W, F] written as f16 and/or fp32 (either may be NULL, not both). */
+int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img, void* feats_f16,
+                      float* feats_f32, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SAVi.decode + broadcast + ConvDecoder + compositing (src/models/SAVi.py:241-275,
+ * src/models/EncodersDecoders/decoders.py:96-119).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_dec_weights {
+  const void* w1_taps;       /* f16 [25*64, D]: row tap*64+co, col ci  (decoder.decoder.0 weight, per-tap matrices) */
+  const float* p1;           /* fp32 [H*W, 64] = conv1(posemb map) + b1, precomputed (batch independent)            */
+  const void* w_conv[3];     /* f16 [25,64,64] tap-major (decoder.decoder.{1,2,3}) */
+  const float* b_conv[3];
+  const float* w_out;        /* fp32 [9][64][4]: (ky*3+kx, ci, co)  decoder.decoder.4 */
+  const float* b_out;        /* [4] */
+  int H, W, slot_dim, num_slots, hidden;
+} tocvp_dec_weights;
+
+size_t tocvp_sizeof_dec_weights(void);
+size_t tocvp_savi_decode_workspace_bytes(const tocvp_dec_weights* w, int n_frames);
+/* slots fp32 [n_frames, S, D] -> recons_imgs fp32 [n_frames,3,H,W]; optional recons [n_frames,S,3,H,W] and
+ * masks [n_frames,S,1,H,W] (NULL to skip: the evaluator only consumes recons_imgs). */
+int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots, int n_frames, float* recons_imgs, float* recons,
+                      float* masks, void* workspace, size_t ws_bytes, void* stream);
+
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
 int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,

@@ -1,0 +1,99 @@
+"""Stage-level and whole-rollout parity of the CUDA path (through the nn.Module mirrors -> C ABI) against
+the CPU oracle and the golden vectors produced by the real reference.  Tolerances (BASELINE.json north_star):
+per-stage relative L2 error <= 1e-3 on identical stage inputs; 19-step rollout >= 40 dB PSNR per frame.
+GEMM/conv operands are IEEE f16 (10-bit mantissa, same as TF32), fp32 accumulate, fp32 residual stream."""
+import pytest
+import torch
+
+from oracle import textocvp_oracle as O
+
+pytestmark = pytest.mark.gpu
+STAGE_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def models(golden_weights):
+    from textocvp_b200 import modules as M
+    ep = M.default_exp_params()
+    savi = M.setup_model(ep["model"])
+    pred = M.setup_predictor(ep)
+    savi.load_state_dict(golden_weights["savi_sd"], strict=True)
+    body_sd = dict(pred.predictor.state_dict())
+    body_sd.update(golden_weights["pred_sd"])
+    pred.predictor.load_state_dict(body_sd, strict=True)
+    return savi.cuda().eval(), pred.cuda().eval()
+
+
+def test_encode(models, golden, golden_weights):
+    savi, _ = models
+    x = golden_weights["videos"][:, 0].cuda()
+    feats = savi.encode(x)
+    ref = O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())
+    assert O.rel_err(feats, ref) < STAGE_TOL
+    st = golden["meta"]["feat_stride"]
+    assert O.rel_err(feats[:, ::st], golden["encode_feats_sub"]) < STAGE_TOL
+
+
+def test_slot_attention_iterations(models, golden, golden_weights):
+    savi, _ = models
+    sd, scfg = golden_weights["savi_sd"], O.SAViCfg()
+    feats = O.savi_encode(sd, golden_weights["videos"][:, 0], scfg)        # identical stage input (fp32 oracle features)
+    init = golden_weights["init"]
+    sa = savi.slot_attention
+    for it in (1, 2, 3):
+        sa.num_iters_first = it
+        out = sa(feats.cuda(), init.cuda(), step=0)
+        assert O.rel_err(out, golden[f"sa_iter{it}"]) < STAGE_TOL, it
+    sa.num_iters_first = 3
+    out = sa(feats.cuda(), init.cuda(), step=1)
+    assert O.rel_err(out, golden["sa_step1"]) < STAGE_TOL
+    out16 = sa(feats.cuda().half(), init.cuda(), step=0)                    # f16 features (the pipeline's format)
+    assert O.rel_err(out16, golden["sa_iter3"]) < STAGE_TOL
+
+
+def test_decomp_and_transition(models, golden, golden_weights):
+    savi, _ = models
+    v = golden_weights["videos"].cuda()
+    out = savi(mode="decomp", x=v, num_imgs=20, decode=False, init_slots=golden_weights["init"].cuda())
+    sh = out["slot_history"]
+    assert sh.shape == (2, 20, 8, 128)
+    assert O.rel_err(sh[:, 0], golden["slot_history"][:, 0]) < STAGE_TOL
+    # recurrent over 20 frames (encode -> correct -> transition): errors compound, allow 3x the single-stage budget
+    assert O.rel_err(sh, golden["slot_history"]) < 3 * STAGE_TOL
+
+
+def test_predictor_step(models, golden, golden_weights):
+    _, pred = models
+    sh = golden["slot_history"].cuda()
+    text = golden_weights["text"].cuda()
+    out = pred.predictor(slots=sh[:, :10], text_embeddings=text)
+    assert O.rel_err(out, golden["pred_step_n10"]) < STAGE_TOL
+    # the quantity the network adds (mlp_out branch) must itself be accurate, not just slots + small delta
+    d_ref = golden["pred_step_n10"] - golden["slot_history"][:, 9]
+    d_out = out.cpu() - golden["slot_history"][:, 9]
+    assert O.rel_err(d_out, d_ref) < 5e-3
+    out1 = pred.predictor(slots=sh[:, :1], text_embeddings=text)
+    assert O.rel_err(out1, golden["pred_step_n1"]) < STAGE_TOL
+
+
+def test_decode(models, golden, golden_weights):
+    savi, _ = models
+    slots = golden["pred_slots"][:1, -1].cuda()
+    out = savi(mode="decode", slots=slots)
+    assert O.rel_err(out["recons"], golden["dec_recons"]) < STAGE_TOL
+    assert O.rel_err(out["masks"], golden["dec_masks"]) < STAGE_TOL
+    assert O.rel_err(out["recons_imgs"], golden["dec_img"]) < STAGE_TOL
+
+
+def test_full_rollout_psnr(models, golden, golden_weights):
+    """Evaluator composition (05_evaluate_predictor.py:82-96) end to end vs the real reference's frames."""
+    savi, pred = models
+    v = golden_weights["videos"].cuda()
+    text = golden_weights["text"].cuda()
+    sh = savi(mode="decomp", x=v, num_imgs=20, decode=False, init_slots=golden_weights["init"].cuda())["slot_history"]
+    ps = pred(sh, text_embeddings=text)
+    assert ps.shape == (2, 19, 8, 128)
+    imgs = savi(mode="decode", slots=ps.reshape(2 * 19, 8, 128))["recons_imgs"].view(2, 19, 3, 64, 64).clamp(0, 1)
+    assert O.rel_err(ps, golden["pred_slots"]) < 5e-3
+    p = O.psnr(imgs.cpu(), golden["pred_imgs"])
+    assert p.min() >= 40.0, (p.min(), p.mean())

@@ -1,0 +1,133 @@
+// SAVi.encode (reference src/models/SAVi.py:226-238): SimpleConvEncoder (4 x conv5x5 + ReLU, encoders.py:136-159),
+// SoftPositionEmbed add (model_blocks.py:215-226), LayerNorm(32) and the 32 -> 128 -> 128 pointwise MLP (SAVi.py:115-120).
+//   conv 1 (3 -> 32, K = 75)  : direct fp32 SIMT convolution straight from the NCHW fp32 frame, writes NHWC f16
+//   conv 2-4 (32 -> 32)       : tcgen05 implicit GEMM (conv5x5_tc.cu)
+//   posemb + LN               : one fused bandwidth pass (norm.cu), the positional table is batch independent
+//   MLP                       : two tcgen05 GEMMs (bias+ReLU / bias epilogues)
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+             const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16,
+             int ld16, cudaStream_t stream);
+int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W, int cin,
+                int cout, int relu, cudaStream_t stream);
+int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_rows, const float* gamma,
+              const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
+              cudaStream_t stream);
+
+constexpr int E1_TH = 8, E1_TW = 32, E1_CO = 32;
+
+// x: fp32 [n, 3, H, W] with image i at x + i*img_stride; w: fp32 [75][32] ((ky*5+kx)*3+ci major); out: f16 NHWC [n,H,W,32]
+__global__ void __launch_bounds__(256)
+enc_conv1_kernel(const float* __restrict__ x, size_t img_stride, const float* __restrict__ w,
+                 const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
+  __shared__ float sIn[3][E1_TH + 4][E1_TW + 4 + 1];
+  __shared__ __align__(16) float sW[75 * E1_CO];
+  const int img = blockIdx.y;
+  const int tiles_x = W / E1_TW;
+  const int y0 = (blockIdx.x / tiles_x) * E1_TH, x0 = (blockIdx.x % tiles_x) * E1_TW;
+  for (int e = threadIdx.x; e < 75 * E1_CO; e += 256) sW[e] = w[e];
+  const float* xi = x + size_t(img) * img_stride;
+  for (int e = threadIdx.x; e < 3 * (E1_TH + 4) * (E1_TW + 4); e += 256) {
+    const int c = e / ((E1_TH + 4) * (E1_TW + 4)), r = e % ((E1_TH + 4) * (E1_TW + 4));
+    const int yy = r / (E1_TW + 4), xx = r % (E1_TW + 4);
+    const int gy = y0 - 2 + yy, gx = x0 - 2 + xx;
+    sIn[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xi[(size_t(c) * H + gy) * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[E1_CO];
+#pragma unroll
+  for (int o = 0; o < E1_CO; ++o) acc[o] = bias[o];
+#pragma unroll 1
+  for (int tap = 0; tap < 25; ++tap) {
+    const int ky = tap / 5, kx = tap % 5;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = sIn[c][ty + ky][tx + kx];
+      const float4* wr = reinterpret_cast<const float4*>(sW + (tap * 3 + c) * E1_CO);
+#pragma unroll
+      for (int o4 = 0; o4 < E1_CO / 4; ++o4) {
+        const float4 ww = wr[o4];
+        acc[o4 * 4 + 0] += v * ww.x; acc[o4 * 4 + 1] += v * ww.y;
+        acc[o4 * 4 + 2] += v * ww.z; acc[o4 * 4 + 3] += v * ww.w;
+      }
+    }
+  }
+  __half* o = out + ((size_t(img) * H + (y0 + ty)) * W + (x0 + tx)) * E1_CO;
+#pragma unroll
+  for (int o8 = 0; o8 < E1_CO / 8; ++o8) {
+    uint4 p;
+    p.x = pack_half2(fmaxf(acc[o8 * 8 + 0], 0.f), fmaxf(acc[o8 * 8 + 1], 0.f));
+    p.y = pack_half2(fmaxf(acc[o8 * 8 + 2], 0.f), fmaxf(acc[o8 * 8 + 3], 0.f));
+    p.z = pack_half2(fmaxf(acc[o8 * 8 + 4], 0.f), fmaxf(acc[o8 * 8 + 5], 0.f));
+    p.w = pack_half2(fmaxf(acc[o8 * 8 + 6], 0.f), fmaxf(acc[o8 * 8 + 7], 0.f));
+    *reinterpret_cast<uint4*>(o + o8 * 8) = p;
+  }
+}
+
+struct EncBuffers {
+  __half *actA, *actB, *h16, *mid16;
+};
+static size_t align256e(size_t n) { return (n + 255) & ~size_t(255); }
+static size_t enc_carve(const tocvp_enc_weights& w, int n, EncBuffers* eb, uint8_t* base) {
+  const size_t px = size_t(n) * w.H * w.W;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align256e(bytes);
+    return p;
+  };
+  EncBuffers t;
+  t.actA = reinterpret_cast<__half*>(take(px * w.hidden * 2));
+  t.actB = reinterpret_cast<__half*>(take(px * w.hidden * 2));
+  t.h16 = t.actA;   // LN output reuses actA (conv 4 lands in actB)
+  t.mid16 = reinterpret_cast<__half*>(take(px * w.feat_dim * 2));
+  if (eb) *eb = t;
+  return off;
+}
+
+}  // namespace tocvp
+
+using namespace tocvp;
+
+extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
+
+extern "C" size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img) {
+  if (!w || n_img <= 0) return 0;
+  return enc_carve(*w, n_img, nullptr, nullptr);
+}
+
+// frames: fp32, image i (3 x H x W, NCHW planes) at frames + i*img_stride floats; feats out: [n_img, H*W, feat_dim]
+extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img,
+                                 void* feats_f16, float* feats_f32, void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TOCVP_CHECK_ARG(w && frames && (feats_f16 || feats_f32) && workspace && n_img > 0);
+  TOCVP_CHECK_ARG(w->in_channels == 3 && w->hidden == 32 && w->feat_dim % 8 == 0);
+  TOCVP_CHECK_ARG(w->H % 16 == 0 && w->W % 32 == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  if (ws_bytes < enc_carve(*w, n_img, nullptr, nullptr)) {
+    set_last_error(__FILE__, __LINE__, "savi_encode: workspace too small");
+    return TOCVP_ERR_WORKSPACE;
+  }
+  EncBuffers eb;
+  enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
+  const int H = w->H, W = w->W, C = w->hidden, F = w->feat_dim;
+  const int M = n_img * H * W;
+  const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
+  enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
+  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], eb.actB, n_img, H, W, C, C, 1, st));
+  TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv[1]), w->b_conv[1], eb.actA, n_img, H, W, C, C, 1, st));
+  TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], eb.actB, n_img, H, W, C, C, 1, st));
+  // + positional embedding, LayerNorm(32) (eps 1e-5, SAVi.py:116)
+  TOCVP_TRY(layernorm(eb.actB, 1, C, w->posemb, H * W, w->ln_g, w->ln_b, 1e-5f, M, C, eb.h16, C, nullptr, 0, st));
+  TOCVP_TRY(gemm_f16(eb.h16, C, static_cast<const __half*>(w->w_mlp1), C, M, F, C, w->b_mlp1, 1, nullptr, 0, 1, 0, nullptr,
+                     0, eb.mid16, F, st));
+  TOCVP_TRY(gemm_f16(eb.mid16, F, static_cast<const __half*>(w->w_mlp2), F, M, F, F, w->b_mlp2, 0, nullptr, 0, 1, 0,
+                     feats_f32, F, static_cast<__half*>(feats_f16), F, st));
+  return TOCVP_OK;
+}

@@ -1,0 +1,475 @@
+// SAVi corrector: SlotAttention (reference src/models/Blocks/attention.py:67-112) and the post-norm transition
+// TransformerBlock (attention.py:387-395) as bandwidth-oriented fused kernels.
+//
+// K/V are never materialised.  With x_j the input feature of location j, LN(x_j) = (x_j - mu_j) * rstd_j * gamma + beta:
+//     q_i . k_j   = rstd_j * (g_i . x_j - mu_j * sum(g_i)) + (qt_i . beta + q_i . bk),     qt_i = Wk^T q_i,  g_i = qt_i * gamma
+//     updates_i   = Wv * ( gamma * (sum_j w_ij x_j - sum_j w_ij mu_j) + beta * A_i ) / A_i + bv
+// with a_ij = softmax_i(scale * q_i.k_j) + eps, A_i = sum_j a_ij, w_ij = a_ij * rstd_j  (sum_j a_ij / A_i = 1, so bv passes
+// through unchanged).  One iteration = one streaming pass over the features (`sa_stream_kernel`, the HBM-bound part: the
+// 8-way slot softmax lives in registers, location-axis sums use a warp reduce-scatter) + one small per-slot kernel
+// (`sa_update_kernel`: weighted-mean finalisation, V projection, GRUCell, LayerNorm, residual MLP, and the next
+// iteration's query / g vectors, or the transition block after the last iteration).  All of it fp32.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+constexpr int SA_S = 8;        // slots
+constexpr int SA_D = 128;      // slot dim == feature dim (named configs)
+constexpr int SA_CHUNKS = 8;   // location chunks per sequence (grid.x of the streaming kernel)
+constexpr int SA_GVEC = SA_S * SA_D + 2 * SA_S;   // g[8][128], sg[8], cb[8] per sequence
+constexpr int SA_PART = SA_S * SA_D + 2 * SA_S;   // Uacc[8][128], A[8], Mw[8] per (sequence, chunk)
+
+template <typename T>
+__device__ __forceinline__ float4 ldx4(const T* p);
+template <>
+__device__ __forceinline__ float4 ldx4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 ldx4<__half>(const __half* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Reduce-scatter of N per-lane values over the 32 lanes of a warp: afterwards v[0] of lane L is the warp-wide
+// total of value index (L >> log2(32/N))  (N = 32: index L).  N-1 shuffles instead of 5N.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
+#pragma unroll
+  for (int n = N, off = 16; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float send = upper ? v[k] : v[k + n / 2];
+      const float keep = upper ? v[k + n / 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming pass.  grid = (SA_CHUNKS, B), 256 threads.  Lane l of every warp owns channels 4l..4l+3;
+// a warp handles 4 locations per step.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+sa_stream_kernel(const T* __restrict__ feats, size_t seq_stride, int N, const float* __restrict__ gvec, float* __restrict__ partial,
+                 float ln_eps, float attn_eps) {
+  __shared__ __align__(16) float s_w[8][4][8];            // per warp: w[l][i]
+  __shared__ __align__(16) float s_red[8][SA_S][SA_D];    // cross-warp reduction of the update accumulators (32 KB)
+  __shared__ float s_am[8][2][SA_S];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int LC = N / SA_CHUNKS;
+  const T* x = feats + size_t(b) * seq_stride + size_t(chunk) * LC * SA_D + lane * 4;
+  const float* gv = gvec + size_t(b) * SA_GVEC;
+
+  float g[SA_S][4];
+#pragma unroll
+  for (int i = 0; i < SA_S; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(gv + i * SA_D + lane * 4);
+    g[i][0] = t.x; g[i][1] = t.y; g[i][2] = t.z; g[i][3] = t.w;
+  }
+  const int my_i = lane & 7, my_l = lane >> 3;
+  const float sg = gv[SA_S * SA_D + my_i];
+  const float cb = gv[SA_S * SA_D + SA_S + my_i];
+
+  float acc[SA_S][4];
+#pragma unroll
+  for (int i = 0; i < SA_S; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  float a_sum = 0.f, mw_sum = 0.f;
+
+  const int groups = LC / 4;
+  float4 xn[4];
+  if (warp < groups) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) xn[l] = ldx4<T>(x + size_t(warp * 4 + l) * SA_D);
+  }
+  for (int gi = warp; gi < groups; gi += 8) {
+    float4 xv[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) xv[l] = xn[l];
+    if (gi + 8 < groups) {  // software prefetch of the next group's features
+#pragma unroll
+      for (int l = 0; l < 4; ++l) xn[l] = ldx4<T>(x + size_t((gi + 8) * 4 + l) * SA_D);
+    }
+    float v[32], st[8];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+#pragma unroll
+      for (int i = 0; i < SA_S; ++i)
+        v[l * 8 + i] = g[i][0] * xv[l].x + g[i][1] * xv[l].y + g[i][2] * xv[l].z + g[i][3] * xv[l].w;
+      st[l] = (xv[l].x + xv[l].y) + (xv[l].z + xv[l].w);
+      st[4 + l] = xv[l].x * xv[l].x + xv[l].y * xv[l].y + xv[l].z * xv[l].z + xv[l].w * xv[l].w;
+    }
+    warp_reduce_scatter<32>(v, lane);   // lane (l,i) = 8l+i now holds g_i . x_l
+    warp_reduce_scatter<8>(st, lane);   // lane L holds stat index (L>>2)&7 summed over lanes with equal L&3 ...
+    float sv = st[0];
+    sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+    sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+    const float sum = __shfl_sync(0xffffffffu, sv, my_l * 4);
+    const float ssq = __shfl_sync(0xffffffffu, sv, (4 + my_l) * 4);
+    const float mu = sum * (1.f / SA_D);
+    const float var = fmaxf(ssq * (1.f / SA_D) - mu * mu, 0.f);
+    const float rstd = rsqrtf(var + ln_eps);
+    const float d = rstd * (v[0] - mu * sg) + cb;            // already multiplied by the attention scale
+    float m = d;
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    const float e = __expf(d - m);
+    float s = e;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float a = e / s + attn_eps;                        // softmax over SLOTS, + eps (attention.py:100)
+    const float w = a * rstd;
+    a_sum += a;
+    mw_sum += w * mu;
+    __syncwarp();
+    s_w[warp][my_l][my_i] = w;
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[warp][l][0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[warp][l][4]);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < SA_S; ++i) {
+        acc[i][0] += ww[i] * xv[l].x;
+        acc[i][1] += ww[i] * xv[l].y;
+        acc[i][2] += ww[i] * xv[l].z;
+        acc[i][3] += ww[i] * xv[l].w;
+      }
+    }
+  }
+  // ---- block reduction -> partial[b][chunk]
+  a_sum += __shfl_xor_sync(0xffffffffu, a_sum, 8);
+  a_sum += __shfl_xor_sync(0xffffffffu, a_sum, 16);
+  mw_sum += __shfl_xor_sync(0xffffffffu, mw_sum, 8);
+  mw_sum += __shfl_xor_sync(0xffffffffu, mw_sum, 16);
+  if (lane < 8) {
+    s_am[warp][0][lane] = a_sum;
+    s_am[warp][1][lane] = mw_sum;
+  }
+#pragma unroll
+  for (int i = 0; i < SA_S; ++i)
+    *reinterpret_cast<float4*>(&s_red[warp][i][lane * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  float* out = partial + (size_t(b) * SA_CHUNKS + chunk) * SA_PART;
+  for (int e = threadIdx.x; e < SA_S * SA_D; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += (&s_red[w8][0][0])[e];
+    out[e] = t;
+  }
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += (&s_am[w8][0][0])[threadIdx.x];
+    out[SA_S * SA_D + threadIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-slot update kernel.  Each CTA owns R = 16 slot rows (2 sequences); activations live in smem
+// transposed as [feature][row] so that a thread computing one output column reads the rows as float4.
+// ------------------------------------------------------------------------------------------------
+constexpr int UP_R = 16;
+constexpr int UP_THREADS = 256;
+
+using SaWeights = tocvp_sa_weights;  // include/tocvp.h
+
+// ys[o][r] = act(bias[o] + sum_k Wt[k][o] * xs[k][r])  for r < UP_R
+__device__ void linear_T(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+                         const float* xs, float* ys, bool relu) {
+  const int tid = threadIdx.x;
+  if (OUT >= UP_THREADS) {
+    for (int o = tid; o < OUT; o += UP_THREADS) {
+      float acc[UP_R];
+      const float bv = bias ? bias[o] : 0.f;
+#pragma unroll
+      for (int r = 0; r < UP_R; ++r) acc[r] = bv;
+#pragma unroll 4
+      for (int k = 0; k < IN; ++k) {
+        const float w = __ldg(Wt + size_t(k) * OUT + o);
+        const float4* xr = reinterpret_cast<const float4*>(xs + k * UP_R);
+#pragma unroll
+        for (int r4 = 0; r4 < UP_R / 4; ++r4) {
+          const float4 xx = xr[r4];
+          acc[r4 * 4 + 0] += w * xx.x; acc[r4 * 4 + 1] += w * xx.y;
+          acc[r4 * 4 + 2] += w * xx.z; acc[r4 * 4 + 3] += w * xx.w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < UP_R; ++r) ys[o * UP_R + r] = relu ? fmaxf(acc[r], 0.f) : acc[r];
+    }
+  } else {  // OUT == 128: two row-halves per column
+    const int o = tid % OUT, half = tid / OUT;  // half in {0,1}
+    constexpr int RP = UP_R / 2;
+    float acc[RP];
+    const float bv = bias ? bias[o] : 0.f;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) acc[r] = bv;
+#pragma unroll 4
+    for (int k = 0; k < IN; ++k) {
+      const float w = __ldg(Wt + size_t(k) * OUT + o);
+      const float4* xr = reinterpret_cast<const float4*>(xs + k * UP_R + half * RP);
+#pragma unroll
+      for (int r4 = 0; r4 < RP / 4; ++r4) {
+        const float4 xx = xr[r4];
+        acc[r4 * 4 + 0] += w * xx.x; acc[r4 * 4 + 1] += w * xx.y;
+        acc[r4 * 4 + 2] += w * xx.z; acc[r4 * 4 + 3] += w * xx.w;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r) ys[o * UP_R + half * RP + r] = relu ? fmaxf(acc[r], 0.f) : acc[r];
+  }
+  __syncthreads();
+}
+
+// LayerNorm over the feature axis of xs[D][R] -> ys[D][R] (one thread per row; rows are consecutive banks)
+__device__ void layernorm_T(const float* xs, float* ys, const float* __restrict__ g, const float* __restrict__ b,
+                            float eps, int D) {
+  const int r = threadIdx.x;
+  if (r < UP_R) {
+    float s = 0.f;
+    for (int k = 0; k < D; ++k) s += xs[k * UP_R + r];
+    const float mean = s / D;
+    float q = 0.f;
+    for (int k = 0; k < D; ++k) {
+      const float d = xs[k * UP_R + r] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(q / D + eps);
+    for (int k = 0; k < D; ++k) ys[k * UP_R + r] = (xs[k * UP_R + r] - mean) * rstd * g[k] + b[k];
+  }
+  __syncthreads();
+}
+
+// flags
+constexpr int UP_DO_C = 1;   // finish the iteration from the streaming partials (weighted mean, V, GRU, MLP)
+constexpr int UP_DO_T = 2;   // apply the transition block to the result -> pred_out
+constexpr int UP_DO_A = 4;   // emit g / sg / cb for the next streaming pass (from the result, or from pred if DO_T)
+
+__global__ void __launch_bounds__(UP_THREADS, 1)
+sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __restrict__ slots_in,
+                 const float* __restrict__ partial, float* __restrict__ slots_out, int slots_out_stride /* per seq */,
+                 float* __restrict__ pred_out, float* __restrict__ gvec) {
+  extern __shared__ float sm[];
+  float* cur = sm;                        // [128][R]  slots (prev, then new)
+  float* t0 = cur + SA_D * UP_R;          // [128][R]
+  float* t1 = t0 + SA_D * UP_R;           // [128][R]
+  float* big0 = t1 + SA_D * UP_R;         // [512][R]
+  float* big1 = big0 + 512 * UP_R;        // [512][R]
+  const int row0 = blockIdx.x * UP_R;
+  const int tid = threadIdx.x;
+  const int D = SA_D;
+
+  // load slots_in [rows][D] -> cur[D][R]
+  for (int e = tid; e < UP_R * D; e += UP_THREADS) {
+    const int r = e / D, k = e % D;
+    cur[k * UP_R + r] = (row0 + r < n_rows) ? slots_in[size_t(row0 + r) * D + k] : 0.f;
+  }
+  __syncthreads();
+
+  if (flags & UP_DO_C) {
+    // ---- weighted mean: uhat[f][r] = (gamma_f (U - Mw) + beta_f A) / A   (sum over chunks first)
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) {
+      const int r = e / D, f = e % D;
+      const int row = row0 + r;
+      float val = 0.f;
+      if (row < n_rows) {
+        const int b = row / SA_S, i = row % SA_S;
+        const float* p = partial + size_t(b) * SA_CHUNKS * SA_PART;
+        float U = 0.f, A = 0.f, Mw = 0.f;
+        for (int c = 0; c < SA_CHUNKS; ++c) {
+          U += p[c * SA_PART + i * D + f];
+          A += p[c * SA_PART + SA_S * D + i];
+          Mw += p[c * SA_PART + SA_S * D + SA_S + i];
+        }
+        val = (w.ln_in_g[f] * (U - Mw) + w.ln_in_b[f] * A) / A;
+      }
+      t0[f * UP_R + r] = val;
+    }
+    __syncthreads();
+    linear_T(w.wv_t, w.bv, D, D, t0, t1, false);                 // updates = Wv uhat + bv       -> t1
+    linear_T(w.w_ih_t, w.b_ih, D, 3 * D, t1, big0, false);       // gi                          -> big0 [384][R]
+    linear_T(w.w_hh_t, w.b_hh, D, 3 * D, cur, big1, false);      // gh (hidden = slots_prev)    -> big1
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) {           // GRUCell, gate order r,z,n
+      const int k = e / UP_R, r = e % UP_R;
+      const float ir = big0[k * UP_R + r], iz = big0[(D + k) * UP_R + r], in_ = big0[(2 * D + k) * UP_R + r];
+      const float hr = big1[k * UP_R + r], hz = big1[(D + k) * UP_R + r], hn = big1[(2 * D + k) * UP_R + r];
+      const float rg = 1.f / (1.f + __expf(-(ir + hr)));
+      const float zg = 1.f / (1.f + __expf(-(iz + hz)));
+      const float ng = tanhf(in_ + rg * hn);
+      const float h = cur[k * UP_R + r];
+      cur[k * UP_R + r] = (1.f - zg) * ng + zg * h;
+    }
+    __syncthreads();
+    layernorm_T(cur, t0, w.ln_mlp_g, w.ln_mlp_b, w.ln_eps_sa, D);
+    linear_T(w.w1_t, w.b1, D, w.mlp_hidden, t0, big0, true);
+    linear_T(w.w2_t, w.b2, w.mlp_hidden, D, big0, t1, false);
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) cur[e] += t1[e];   // slots + MLP(LN(slots))
+    __syncthreads();
+    if (slots_out) {
+      for (int e = tid; e < UP_R * D; e += UP_THREADS) {
+        const int r = e / D, k = e % D;
+        const int row = row0 + r;
+        if (row < n_rows) slots_out[size_t(row / SA_S) * slots_out_stride + size_t(row % SA_S) * D + k] = cur[k * UP_R + r];
+      }
+    }
+  }
+
+  if (flags & UP_DO_T) {
+    // ---- post-norm TransformerBlock: y = LN(MHSA(x) + x); z = LN(MLP(y) + y)   (attention.py:387-395)
+    linear_T(w.t_wq_t, nullptr, D, D, cur, t0, false);           // q -> t0
+    linear_T(w.t_wk_t, nullptr, D, D, cur, t1, false);           // k -> t1
+    linear_T(w.t_wv_t, nullptr, D, D, cur, big0, false);         // v -> big0[0..127]
+    float* att = big1;                                           // attention output [128][R]
+    const int H = w.t_heads, dh = D / H;
+    const float sc = rsqrtf(float(dh));
+    for (int e = tid; e < UP_R * H; e += UP_THREADS) {
+      const int r = e % UP_R, h = e / UP_R;                      // query row r (seq = r / S)
+      const int rs = (r / SA_S) * SA_S;
+      float sco[SA_S];
+      float mx = -1e30f;
+      for (int j = 0; j < SA_S; ++j) {
+        float d = 0.f;
+        for (int c = 0; c < dh; ++c) d += t0[(h * dh + c) * UP_R + r] * t1[(h * dh + c) * UP_R + rs + j];
+        sco[j] = d * sc;
+        mx = fmaxf(mx, sco[j]);
+      }
+      float den = 0.f;
+      for (int j = 0; j < SA_S; ++j) { sco[j] = __expf(sco[j] - mx); den += sco[j]; }
+      const float inv = 1.f / den;
+      for (int c = 0; c < dh; ++c) {
+        float o = 0.f;
+        for (int j = 0; j < SA_S; ++j) o += sco[j] * big0[(h * dh + c) * UP_R + rs + j];
+        att[(h * dh + c) * UP_R + r] = o * inv;
+      }
+    }
+    __syncthreads();
+    linear_T(w.t_wo_t, nullptr, D, D, att, t0, false);
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) t0[e] += cur[e];
+    __syncthreads();
+    layernorm_T(t0, t1, w.t_ln1_g, w.t_ln1_b, w.ln_eps_tf, D);   // y -> t1
+    linear_T(w.t_w1_t, w.t_b1, D, w.t_hidden, t1, big0, true);
+    linear_T(w.t_w2_t, w.t_b2, w.t_hidden, D, big0, t0, false);
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) t0[e] += t1[e];
+    __syncthreads();
+    layernorm_T(t0, cur, w.t_ln2_g, w.t_ln2_b, w.ln_eps_tf, D);  // z -> cur
+    if (pred_out) {
+      for (int e = tid; e < UP_R * D; e += UP_THREADS) {
+        const int r = e / D, k = e % D;
+        if (row0 + r < n_rows) pred_out[size_t(row0 + r) * D + k] = cur[k * UP_R + r];
+      }
+    }
+  }
+
+  if (flags & UP_DO_A) {
+    // ---- next pass: q = Wq LN(slots) + bq ; qt = Wk^T q ; g = scale*qt*gamma ; sg = sum g ; cb = scale*(qt.beta + q.bk)
+    layernorm_T(cur, t0, w.ln_slot_g, w.ln_slot_b, w.ln_eps_sa, D);
+    linear_T(w.wq_t, w.bq, D, D, t0, t1, false);                 // q  -> t1
+    linear_T(w.wk, nullptr, D, D, t1, t0, false);                // qt -> t0  (Wk as stored [d][f] is "in-major" here)
+    for (int e = tid; e < UP_R * D; e += UP_THREADS) {
+      const int r = e / D, f = e % D;
+      if (row0 + r < n_rows) {
+        const int b = (row0 + r) / SA_S, i = (row0 + r) % SA_S;
+        gvec[size_t(b) * SA_GVEC + i * D + f] = w.scale * t0[f * UP_R + r] * w.ln_in_g[f];
+      }
+    }
+    if (tid < UP_R && row0 + tid < n_rows) {
+      const int r = tid;
+      float sgv = 0.f, cbv = 0.f;
+      for (int f = 0; f < D; ++f) {
+        const float qt = t0[f * UP_R + r];
+        sgv += qt * w.ln_in_g[f];
+        cbv += qt * w.ln_in_b[f] + t1[f * UP_R + r] * w.bk[f];
+      }
+      const int b = (row0 + r) / SA_S, i = (row0 + r) % SA_S;
+      gvec[size_t(b) * SA_GVEC + SA_S * D + i] = w.scale * sgv;
+      gvec[size_t(b) * SA_GVEC + SA_S * D + SA_S + i] = w.scale * cbv;
+    }
+  }
+}
+
+constexpr int UP_SMEM = (3 * SA_D + 2 * 512) * UP_R * 4;   // 90112 B
+
+static int launch_update(const SaWeights& w, int B, int flags, const float* slots_in, const float* partial,
+                         float* slots_out, int out_stride, float* pred_out, float* gvec, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
+    attr_set = true;
+  }
+  const int rows = B * SA_S;
+  sa_update_kernel<<<(rows + UP_R - 1) / UP_R, UP_THREADS, UP_SMEM, stream>>>(w, rows, flags, slots_in, partial,
+                                                                             slots_out, out_stride, pred_out, gvec);
+  TOCVP_CUDA(cudaGetLastError());
+  return TOCVP_OK;
+}
+
+size_t slot_attention_workspace_bytes(int B) {
+  return (size_t(B) * SA_GVEC + size_t(B) * SA_CHUNKS * SA_PART + size_t(B) * SA_S * SA_D) * sizeof(float);
+}
+
+// feats [B,N,128] (fp32 or f16), slots_in [B,8,128] fp32 -> slots_out (row b at slots_out + b*out_stride), and,
+// if pred_out != null, pred_out = transition(slots_out) [B,8,128].
+int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t feats_seq_stride, int B, int N, const float* slots_in, int iters,
+                   float* slots_out, int out_stride, float* pred_out, void* workspace, size_t ws_bytes,
+                   cudaStream_t stream) {
+  TOCVP_CHECK_ARG(feats && slots_in && slots_out && workspace && B > 0 && iters >= 1);
+  TOCVP_CHECK_ARG(feats_seq_stride >= size_t(N) * SA_D && feats_seq_stride % 8 == 0);
+  TOCVP_CHECK_ARG(N % (SA_CHUNKS * 4) == 0 && w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
+  TOCVP_CHECK_ARG(pred_out == nullptr || (w.t_heads > 0 && SA_D % w.t_heads == 0 && w.t_hidden % 256 == 0));
+  if (ws_bytes < slot_attention_workspace_bytes(B)) {
+    set_last_error(__FILE__, __LINE__, "slot_attention: workspace too small");
+    return TOCVP_ERR_WORKSPACE;
+  }
+  float* gvec = static_cast<float*>(workspace);
+  float* partial = gvec + size_t(B) * SA_GVEC;
+  float* tmp_slots = partial + size_t(B) * SA_CHUNKS * SA_PART;   // [B,8,128] intermediate iterates
+  TOCVP_TRY(launch_update(w, B, UP_DO_A, slots_in, nullptr, nullptr, 0, nullptr, gvec, stream));
+  const float* cur = slots_in;
+  for (int it = 0; it < iters; ++it) {
+    const dim3 grid(SA_CHUNKS, B);
+    if (feats_f16)
+      sa_stream_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(feats), feats_seq_stride, N, gvec, partial,
+                                                         w.ln_eps_sa, w.attn_eps);
+    else
+      sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec, partial,
+                                                        w.ln_eps_sa, w.attn_eps);
+    TOCVP_CUDA(cudaGetLastError());
+    const bool last = (it == iters - 1);
+    if (!last) {
+      TOCVP_TRY(launch_update(w, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, SA_S * SA_D, nullptr, gvec, stream));
+      cur = tmp_slots;
+    } else {
+      TOCVP_TRY(launch_update(w, B, UP_DO_C | (pred_out ? UP_DO_T : 0), cur, partial, slots_out, out_stride, pred_out,
+                              gvec, stream));
+    }
+  }
+  return TOCVP_OK;
+}
+
+}  // namespace tocvp
+
+extern "C" size_t tocvp_slot_attention_workspace_bytes(int B) { return tocvp::slot_attention_workspace_bytes(B); }
+
+extern "C" int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats_f16,
+                                    size_t feats_seq_stride, int B, int N,
+                                    const float* slots_in, int iters, float* slots_out, int out_stride,
+                                    float* pred_out, void* workspace, size_t ws_bytes, void* stream) {
+  if (w == nullptr) {
+    tocvp::set_last_error(__FILE__, __LINE__, "null weights");
+    return TOCVP_ERR_BAD_ARG;
+  }
+  return tocvp::slot_attention(*w, feats, feats_f16, feats_seq_stride, B, N, slots_in, iters, slots_out, out_stride, pred_out, workspace,
+                               ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t tocvp_sizeof_sa_weights(void) { return sizeof(tocvp_sa_weights); }

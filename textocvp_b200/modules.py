@@ -1,0 +1,798 @@
+"""
+Host-side mirror of the reference's nn.Module interface for the rollout path.
+
+Same class names, constructor arguments, ``forward`` signatures, output dict keys and
+``state_dict`` key names/shapes as the reference, so the reference's
+``load_checkpoint`` (strict ``load_state_dict``) and ``05_evaluate_predictor.py`` work unchanged.
+The torch layers below (nn.Linear, nn.Conv2d, nn.LayerNorm, nn.GRUCell) are *parameter containers
+only*: their ``forward`` is never called.  All arithmetic of the path runs in libtocvp.so (hand-written
+sm_100a kernels) through the C ABI of include/tocvp.h.  There is no fallback: without the library or
+on a non-sm_100 device every forward raises.
+
+Reference classes mirrored (paths relative to the reference root):
+  SlotAttention, TransformerBlock, AdaptedEncoderBlock, TransformerDecoderBlock ... src/models/Blocks/attention.py
+  SoftPositionEmbed, TemporalPositionalEncoding, ConvBlock ..................... src/models/Blocks/model_blocks.py
+  LearnedRandom ................................................................ src/models/Blocks/initializers.py
+  SimpleConvEncoder / ConvDecoder ............................ src/models/EncodersDecoders/{encoders,decoders}.py
+  SAVi ......................................................................... src/models/SAVi.py
+  TextOCVP_CustomTF (BaseTextOCVP), PredictorWrapper ........................... src/models/Predictors/*.py
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from ._lib import c_int, c_size_t, ptr, stream
+
+_f = ctypes.c_void_p
+
+
+def _struct(name, ptr_fields, tail):
+    fields = [(n, _f) for n in ptr_fields] + tail
+    return type(name, (ctypes.Structure,), {"_fields_": fields})
+
+
+SaW = _struct("SaW", [
+    "ln_in_g", "ln_in_b", "ln_slot_g", "ln_slot_b", "ln_mlp_g", "ln_mlp_b",
+    "wq_t", "bq", "wk", "bk", "wv_t", "bv", "w_ih_t", "w_hh_t", "b_ih", "b_hh", "w1_t", "b1", "w2_t", "b2",
+    "t_wq_t", "t_wk_t", "t_wv_t", "t_wo_t", "t_ln1_g", "t_ln1_b", "t_ln2_g", "t_ln2_b",
+    "t_w1_t", "t_b1", "t_w2_t", "t_b2"],
+    [("mlp_hidden", ctypes.c_int), ("t_heads", ctypes.c_int), ("t_hidden", ctypes.c_int),
+     ("attn_eps", ctypes.c_float), ("ln_eps_sa", ctypes.c_float), ("ln_eps_tf", ctypes.c_float),
+     ("scale", ctypes.c_float)])
+
+PredLayer = _struct("PredLayer", [
+    "ln_q_g", "ln_q_b", "w_qkv", "w_o", "ln_cq_g", "ln_cq_b", "ln_ckv_g", "ln_ckv_b", "wc_q", "wc_kv", "wc_o", "bc_o",
+    "ln_cm_g", "ln_cm_b", "wc_1", "wc_2", "bc_1", "bc_2", "ln_m_g", "ln_m_b", "w_1", "w_2", "b_1", "b_2"], [])
+
+PredW = type("PredW", (ctypes.Structure,), {"_fields_": [
+    ("layers", ctypes.POINTER(PredLayer)),
+    ("num_layers", ctypes.c_int), ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int),
+    ("token_dim", ctypes.c_int), ("hidden_dim", ctypes.c_int), ("cross_hidden", ctypes.c_int),
+    ("num_heads", ctypes.c_int), ("cross_heads", ctypes.c_int), ("buffer_size", ctypes.c_int),
+    ("residual", ctypes.c_int), ("ln_eps", ctypes.c_float),
+    ("mlp_in_w", _f), ("mlp_in_b", _f), ("mlp_out_w", _f), ("mlp_out_b", _f), ("pe_flipped", _f)]})
+
+EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
+    ("w_conv1", _f), ("b_conv1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("posemb", _f),
+    ("ln_g", _f), ("ln_b", _f), ("w_mlp1", _f), ("b_mlp1", _f), ("w_mlp2", _f), ("b_mlp2", _f),
+    ("H", ctypes.c_int), ("W", ctypes.c_int), ("in_channels", ctypes.c_int), ("hidden", ctypes.c_int),
+    ("feat_dim", ctypes.c_int)]})
+
+DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
+    ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
+    ("H", ctypes.c_int), ("W", ctypes.c_int), ("slot_dim", ctypes.c_int), ("num_slots", ctypes.c_int),
+    ("hidden", ctypes.c_int)]})
+
+
+def check_struct_sizes():
+    lib = L.load()
+    for name, st in (("sa_weights", SaW), ("pred_weights", PredW), ("pred_layer", PredLayer),
+                     ("enc_weights", EncW), ("dec_weights", DecW)):
+        fn = getattr(lib, f"tocvp_sizeof_{name}")
+        fn.restype = ctypes.c_size_t
+        if fn() != ctypes.sizeof(st):
+            raise L.TocvpError(f"struct tocvp_{name}: C size {fn()} != ctypes size {ctypes.sizeof(st)}")
+
+
+def _dp(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class _Workspace:
+    """Grow-only byte buffer owned by a module (the library never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        off = (-self.buf.data_ptr()) % 256
+        return ctypes.c_void_p(self.buf.data_ptr() + off), c_size_t(self.buf.numel() - off)
+
+
+class _Packed(nn.Module):
+    """Mixin: device-side packed weight copies, rebuilt whenever a parameter changes (load_state_dict, .to())."""
+
+    def _sig(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+
+    def _ensure_packed(self):
+        sig = self._sig()
+        if getattr(self, "_pack_sig", None) != sig:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise L.TocvpError("textocvp_b200 modules run on a CUDA (sm_100) device only; no CPU path exists")
+            L.init(dev)
+            check_struct_sizes()
+            with torch.no_grad():
+                self._pack(dev)
+            self._pack_sig = sig
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _f16(t):
+    return t.detach().half().contiguous()
+
+
+def _tr(t):  # [out,in] -> [in,out] fp32
+    return t.detach().float().t().contiguous()
+
+
+# =====================================================================================================
+# building blocks (parameter containers with the reference's names)
+# =====================================================================================================
+def build_grid(resolution):
+    """model_utils.py:12-34 -> [1,4,H,W] fp32 (y, x, 1-y, 1-x)."""
+    ranges = [np.linspace(-1.0, 1.0, num=r) for r in resolution]
+    g = np.stack(np.meshgrid(*ranges, sparse=False, indexing="ij"), axis=-1)
+    g = g.reshape(resolution[0], resolution[1], -1)[None].astype(np.float32)
+    g = np.concatenate([g, 1.0 - g], axis=-1)
+    return torch.from_numpy(g).permute(0, 3, 1, 2).contiguous()
+
+
+class SoftPositionEmbed(nn.Module):
+    def __init__(self, hidden_size, resolution, vmin=-1., vmax=1.):
+        super().__init__()
+        self.projection = nn.Conv2d(4, hidden_size, kernel_size=1)
+        self.grid = build_grid(resolution)          # plain attribute, not a buffer (model_blocks.py:212)
+        self.resolution = tuple(resolution)
+
+    def table(self) -> torch.Tensor:
+        """[H*W, C] fp32 = projection(grid): a 4 -> C affine map per pixel, batch independent."""
+        w = self.projection.weight.detach().float()
+        g = self.grid.to(w.device)[0].permute(1, 2, 0).reshape(-1, 4)          # [HW,4]
+        return (g @ w.reshape(w.shape[0], 4).t() + self.projection.bias.detach().float()).contiguous()
+
+
+class ConvBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=None, **kw):
+        super().__init__()
+        padding = padding if padding is not None else kernel_size // 2
+        self.block = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding), nn.ReLU())
+
+
+class SimpleConvEncoder(nn.Module):
+    def __init__(self, in_channels=3, hidden_dims=(64, 64, 64, 64), kernel_size=5, **kw):
+        super().__init__()
+        mods, cin = [], in_channels
+        for h in hidden_dims:
+            mods.append(ConvBlock(cin, h, kernel_size))
+            cin = h
+        self.encoder = nn.Sequential(*mods)
+        self.out_features = hidden_dims[-1]
+        self.hidden_dims, self.kernel_size, self.in_channels = list(hidden_dims), kernel_size, in_channels
+
+
+class ConvDecoder(nn.Module):
+    def __init__(self, in_channels, hidden_dims, kernel_size=5, upsample=None, out_channels=4, **kw):
+        super().__init__()
+        if upsample is not None and upsample >= 2:
+            raise NotImplementedError("ConvDecoder with upsampling is outside the named configurations")
+        mods, cin = [], in_channels
+        for i in range(len(hidden_dims) - 1, -1, -1):
+            mods.append(ConvBlock(cin, hidden_dims[i], kernel_size))
+            cin = hidden_dims[i]
+        mods.append(nn.Conv2d(hidden_dims[0], out_channels, kernel_size=3, stride=1, padding=1))
+        self.decoder = nn.Sequential(*mods)
+        self.hidden_dims, self.kernel_size, self.out_channels = list(hidden_dims), kernel_size, out_channels
+
+
+class LearnedRandom(nn.Module):
+    def __init__(self, slot_dim, num_slots):
+        super().__init__()
+        self.slot_dim, self.num_slots = slot_dim, num_slots
+        lim = math.sqrt(6.0 / (1 + slot_dim))
+        self.slots_mu = nn.Parameter((torch.rand(1, 1, slot_dim) * 2 - 1) * lim)
+        self.slots_sigma = nn.Parameter((torch.rand(1, 1, slot_dim) * 2 - 1) * lim)
+
+    def forward(self, batch_size, **kwargs):
+        mu = self.slots_mu.expand(batch_size, self.num_slots, -1)
+        sigma = self.slots_sigma.expand(batch_size, self.num_slots, -1)
+        return mu + sigma * torch.randn(mu.shape, device=self.slots_mu.device)   # initializers.py:87-94
+
+
+class Learned(nn.Module):
+    def __init__(self, slot_dim, num_slots):
+        super().__init__()
+        lim = math.sqrt(6.0 / (1 + slot_dim))
+        self.slots = nn.Parameter((torch.rand(1, num_slots, slot_dim) * 2 - 1) * lim)
+
+    def forward(self, batch_size, **kwargs):
+        return self.slots.repeat(batch_size, 1, 1)
+
+
+class MultiHeadSelfAttention(nn.Module):
+    def __init__(self, emb_dim, num_heads=8, dropout=0.):
+        super().__init__()
+        self.emb_dim, self.num_heads = emb_dim, num_heads
+        self.q = nn.Linear(emb_dim, emb_dim, bias=False)
+        self.k = nn.Linear(emb_dim, emb_dim, bias=False)
+        self.v = nn.Linear(emb_dim, emb_dim, bias=False)
+        self.out_projection = nn.Sequential(nn.Linear(emb_dim, emb_dim, bias=False))
+
+
+class MultiHeadCrossAttention(nn.Module):
+    def __init__(self, emb_dim, dim_head, kv_dim, num_heads=8, dropout=0.):
+        super().__init__()
+        inner = dim_head * num_heads
+        self.emb_dim, self.num_heads, self.dim_head = emb_dim, num_heads, dim_head
+        self.q = nn.Linear(emb_dim, inner, bias=False)
+        self.k = nn.Linear(kv_dim, inner, bias=False)
+        self.v = nn.Linear(kv_dim, inner, bias=False)
+        self.out_projection = nn.Linear(inner, emb_dim)
+
+
+class TransformerDecoderBlock(nn.Module):
+    def __init__(self, embed_dim, head_dim, kv_dim, num_heads, mlp_size):
+        super().__init__()
+        self.ln_mlp = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.mlp = nn.Sequential(nn.Linear(embed_dim, mlp_size), nn.ReLU(), nn.Linear(mlp_size, embed_dim))
+        self.ln_cross_att_q = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.ln_cross_att_kv = nn.LayerNorm(kv_dim, eps=1e-6)
+        self.cross_attn = MultiHeadCrossAttention(embed_dim, head_dim, kv_dim, num_heads)
+
+
+class TransformerBlock(_Packed):
+    """attention.py:323-396.  Stand-alone forward is provided for the post-norm (transition) flavour."""
+
+    def __init__(self, embed_dim, num_heads, mlp_size, pre_norm=True):
+        super().__init__()
+        self.embed_dim, self.mlp_size, self.num_heads, self.pre_norm = embed_dim, mlp_size, num_heads, pre_norm
+        self.attn = MultiHeadSelfAttention(embed_dim, num_heads)
+        self.mlp = nn.Sequential(nn.Linear(embed_dim, mlp_size), nn.ReLU(), nn.Linear(mlp_size, embed_dim))
+        self.layernorm_query = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.layernorm_mlp = nn.LayerNorm(embed_dim, eps=1e-6)
+        with torch.no_grad():
+            for n, p in self.named_parameters():
+                if n.endswith(".bias"):
+                    p.zero_()
+                elif p.dim() > 1:
+                    nn.init.xavier_uniform_(p)
+
+
+class AdaptedEncoderBlock(TransformerBlock):
+    def __init__(self, embed_dim, num_heads, mlp_size, fusion_params):
+        super().__init__(embed_dim=embed_dim, num_heads=num_heads, mlp_size=mlp_size)
+        self.cross_attention = TransformerDecoderBlock(
+            embed_dim=embed_dim, kv_dim=embed_dim, head_dim=fusion_params.get("head_dim"),
+            num_heads=fusion_params.get("num_heads"), mlp_size=fusion_params.get("mlp_size"))
+
+
+class TemporalPositionalEncoding(nn.Module):
+    def __init__(self, d_model, dropout=0.0, max_len=50, mode="learned"):
+        super().__init__()
+        if mode != "learned":
+            raise NotImplementedError("only the learned PE is on the TextOCVP path (text_cond_OCVP.py:63-67)")
+        self.d_model, self.max_len = d_model, max_len
+        self.pe = nn.Parameter(d_model ** -0.5 * torch.randn(1, max_len, 1, d_model))
+
+
+# =====================================================================================================
+# SlotAttention (+ transition) -- corrector
+# =====================================================================================================
+class SlotAttention(_Packed):
+    """attention.py:12-112.  forward(inputs [B,N,Df], slots [B,S,D], step) -> [B,S,D]."""
+
+    def __init__(self, dim_feats, dim_slots, num_slots, num_iters_first=2, num_iters=2, mlp_hidden=128,
+                 epsilon=1e-8):
+        super().__init__()
+        self.dim_feats, self.dim_slots, self.num_slots = dim_feats, dim_slots, num_slots
+        self.num_iters_first, self.num_iters, self.epsilon = num_iters_first, num_iters, epsilon
+        self.scale = dim_feats ** -0.5
+        self.mlp_hidden = mlp_hidden
+        self.norm_input = nn.LayerNorm(dim_feats, eps=0.001)
+        self.norm_slot = nn.LayerNorm(dim_slots, eps=0.001)
+        self.norm_mlp = nn.LayerNorm(dim_slots, eps=0.001)
+        self.to_q = nn.Linear(dim_slots, dim_slots)
+        self.to_k = nn.Linear(dim_feats, dim_slots)
+        self.to_v = nn.Linear(dim_feats, dim_slots)
+        self.gru = nn.GRUCell(dim_slots, dim_slots)
+        self.mlp = nn.Sequential(nn.Linear(dim_slots, mlp_hidden), nn.ReLU(), nn.Linear(mlp_hidden, dim_slots))
+        self._ws = _Workspace()
+        object.__setattr__(self, "_transition", None)   # set by SAVi (unregistered) so one kernel chain covers both
+        self.attention_masks = None
+
+    def _pack(self, dev):
+        if self.dim_feats != 128 or self.dim_slots != 128 or self.num_slots != 8:
+            raise L.TocvpError("SlotAttention kernels are instantiated for 8 slots x 128-d features/slots")
+        k = {}
+        k["ln_in_g"], k["ln_in_b"] = _f32(self.norm_input.weight), _f32(self.norm_input.bias)
+        k["ln_slot_g"], k["ln_slot_b"] = _f32(self.norm_slot.weight), _f32(self.norm_slot.bias)
+        k["ln_mlp_g"], k["ln_mlp_b"] = _f32(self.norm_mlp.weight), _f32(self.norm_mlp.bias)
+        k["wq_t"], k["bq"] = _tr(self.to_q.weight), _f32(self.to_q.bias)
+        k["wk"], k["bk"] = _f32(self.to_k.weight), _f32(self.to_k.bias)
+        k["wv_t"], k["bv"] = _tr(self.to_v.weight), _f32(self.to_v.bias)
+        k["w_ih_t"], k["w_hh_t"] = _tr(self.gru.weight_ih), _tr(self.gru.weight_hh)
+        k["b_ih"], k["b_hh"] = _f32(self.gru.bias_ih), _f32(self.gru.bias_hh)
+        k["w1_t"], k["b1"] = _tr(self.mlp[0].weight), _f32(self.mlp[0].bias)
+        k["w2_t"], k["b2"] = _tr(self.mlp[2].weight), _f32(self.mlp[2].bias)
+        t = self._transition
+        t_heads = t_hidden = 0
+        if t is not None:
+            k["t_wq_t"], k["t_wk_t"], k["t_wv_t"] = _tr(t.attn.q.weight), _tr(t.attn.k.weight), _tr(t.attn.v.weight)
+            k["t_wo_t"] = _tr(t.attn.out_projection[0].weight)
+            k["t_ln1_g"], k["t_ln1_b"] = _f32(t.layernorm_query.weight), _f32(t.layernorm_query.bias)
+            k["t_ln2_g"], k["t_ln2_b"] = _f32(t.layernorm_mlp.weight), _f32(t.layernorm_mlp.bias)
+            k["t_w1_t"], k["t_b1"] = _tr(t.mlp[0].weight), _f32(t.mlp[0].bias)
+            k["t_w2_t"], k["t_b2"] = _tr(t.mlp[2].weight), _f32(t.mlp[2].bias)
+            t_heads, t_hidden = t.num_heads, t.mlp_size
+        self._keep = k
+        w = SaW()
+        for n, v in k.items():
+            setattr(w, n, v.data_ptr())
+        w.mlp_hidden, w.t_heads, w.t_hidden = self.mlp_hidden, t_heads, t_hidden
+        w.attn_eps, w.ln_eps_sa, w.ln_eps_tf, w.scale = self.epsilon, 1e-3, 1e-6, self.scale
+        self._w = w
+
+    def _sig(self):
+        extra = tuple((p.data_ptr(), p._version) for p in self._transition.parameters()) if self._transition is not None else ()
+        return super()._sig() + extra
+
+    def run(self, feats, feats_seq_stride, B, N, slots, iters, slots_out, out_stride, pred_out):
+        """Raw call.  feats: f16/fp32 device tensor holding sequence b's [N,128] block at b*feats_seq_stride."""
+        self._ensure_packed()
+        lib = L.load()
+        lib.tocvp_slot_attention_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_slot_attention_workspace_bytes(c_int(B)), slots.device)
+        L.call("tocvp_slot_attention", ctypes.byref(self._w), ptr(feats), c_int(int(feats.dtype == torch.float16)),
+               c_size_t(feats_seq_stride), c_int(B), c_int(N), ptr(slots), c_int(iters), ptr(slots_out),
+               c_int(out_stride), ptr(pred_out), ws, wsb, stream())
+
+    @torch.no_grad()
+    def forward(self, inputs, slots, step=0, **kwargs):
+        B, N, _ = inputs.shape
+        inputs = inputs.contiguous()
+        if inputs.dtype not in (torch.float16, torch.float32):
+            inputs = inputs.float()
+        slots = slots.float().contiguous()
+        out = torch.empty_like(slots)
+        iters = self.num_iters_first if step == 0 else self.num_iters
+        self.run(inputs, N * self.dim_feats, B, N, slots, iters, out, self.num_slots * self.dim_slots, None)
+        return out
+
+
+# =====================================================================================================
+# SAVi
+# =====================================================================================================
+class SAVi(_Packed):
+    """src/models/SAVi.py.  forward(mode="decomp"|"decode", ...), encode(x), decode(slots)."""
+
+    def __init__(self, num_slots, slot_dim, num_iterations=1, num_iterations_first=3, in_channels=3, mlp_hidden=128,
+                 mlp_encoder_dim=128, encoder={}, decoder={}, transition_module={}, initializer=None, **kwargs):
+        super().__init__()
+        self.num_slots, self.slot_dim, self.in_channels = num_slots, slot_dim, in_channels
+        self.mlp_encoder_dim = mlp_encoder_dim
+        if initializer == "LearnedRandom":
+            self.initializer = LearnedRandom(slot_dim, num_slots)
+        elif initializer == "Learned":
+            self.initializer = Learned(slot_dim, num_slots)
+        else:
+            raise ValueError(f"UPSI, mode = {initializer} is not a recongnized initializer...")
+        tm = dict(transition_module)
+        name = tm.pop("model_name", None)
+        if name in (None, ""):
+            self.transition_module = nn.Identity()
+        elif name == "TransformerBlock":
+            self.transition_module = TransformerBlock(embed_dim=slot_dim, pre_norm=False, **tm)
+        else:
+            raise ValueError(f"UPSI, model_name = {name} was not a recognized transition module...")
+        ep, dp = dict(encoder["encoder_params"]), dict(decoder["decoder_params"])
+        if encoder["encoder_name"] != "ConvEncoder" or decoder["decoder_name"] != "ConvDecoder":
+            raise NotImplementedError("SAVi path is built for ConvEncoder + ConvDecoder (src/configs/models/SAVi.json)")
+        self.encoder = SimpleConvEncoder(in_channels, ep["num_channels"], ep["kernel_size"])
+        self.out_features = self.encoder.out_features
+        self.encoder_pos_embedding = SoftPositionEmbed(self.out_features, ep.get("resolution"))
+        self.encoder_mlp = nn.Sequential(nn.LayerNorm(self.out_features), nn.Linear(self.out_features, mlp_encoder_dim),
+                                         nn.ReLU(), nn.Linear(mlp_encoder_dim, mlp_encoder_dim))
+        self.decoder_resolution = tuple(dp.get("resolution"))
+        self.decoder_pos_embedding = SoftPositionEmbed(slot_dim, self.decoder_resolution)
+        self.decoder = ConvDecoder(slot_dim, dp["num_channels"], dp["kernel_size"], dp.get("upsample", 1),
+                                   out_channels=in_channels + 1)
+        self.slot_attention = SlotAttention(dim_feats=mlp_encoder_dim, dim_slots=slot_dim, num_slots=num_slots,
+                                            num_iters_first=num_iterations_first, num_iters=num_iterations,
+                                            mlp_hidden=mlp_hidden)
+        if isinstance(self.transition_module, TransformerBlock):
+            object.__setattr__(self.slot_attention, "_transition", self.transition_module)   # not a submodule
+        self._init_model()
+        self._ws_enc, self._ws_dec = _Workspace(), _Workspace()
+        self.max_encode_images = 8192     # images encoded per library call (bounds the activation workspace)
+
+    @torch.no_grad()
+    def _init_model(self):
+        for n, p in self.named_parameters():               # init_xavier_ (model_utils.py:65-79)
+            if n.endswith(".bias"):
+                p.zero_()
+            elif p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        nn.init.zeros_(self.slot_attention.gru.bias_ih)
+        nn.init.zeros_(self.slot_attention.gru.bias_hh)
+        nn.init.orthogonal_(self.slot_attention.gru.weight_hh)
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self, dev):
+        H, W = self.encoder_pos_embedding.resolution
+        enc = [m.block[0] for m in self.encoder.encoder]
+        if len(enc) != 4 or enc[0].weight.shape[:2] != (32, 3) or any(m.weight.shape[:2] != (32, 32) for m in enc[1:]) \
+                or self.encoder.kernel_size != 5:
+            raise L.TocvpError("encoder kernels are instantiated for 4 x conv5x5 (3->32->32->32->32)")
+        k = {}
+        k["w_conv1"] = _f32(enc[0].weight.permute(2, 3, 1, 0).reshape(75, 32))
+        k["b_conv1"] = _f32(enc[0].bias)
+        for i in range(3):
+            k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
+            k[f"bc{i}"] = _f32(enc[i + 1].bias)
+        k["posemb"] = self.encoder_pos_embedding.table()
+        k["ln_g"], k["ln_b"] = _f32(self.encoder_mlp[0].weight), _f32(self.encoder_mlp[0].bias)
+        k["w_mlp1"], k["b_mlp1"] = _f16(self.encoder_mlp[1].weight), _f32(self.encoder_mlp[1].bias)
+        k["w_mlp2"], k["b_mlp2"] = _f16(self.encoder_mlp[3].weight), _f32(self.encoder_mlp[3].bias)
+        ew = EncW()
+        ew.w_conv1, ew.b_conv1, ew.posemb = k["w_conv1"].data_ptr(), k["b_conv1"].data_ptr(), k["posemb"].data_ptr()
+        for i in range(3):
+            ew.w_conv[i], ew.b_conv[i] = k[f"wc{i}"].data_ptr(), k[f"bc{i}"].data_ptr()
+        for n in ("ln_g", "ln_b", "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2"):
+            setattr(ew, n, k[n].data_ptr())
+        ew.H, ew.W, ew.in_channels, ew.hidden, ew.feat_dim = H, W, self.in_channels, 32, self.mlp_encoder_dim
+        self._enc_keep, self._enc_w = k, ew
+
+        # ---- decoder
+        dH, dW = self.decoder_resolution
+        convs = [m.block[0] for m in list(self.decoder.decoder)[:-1]]
+        last = self.decoder.decoder[-1]
+        if len(convs) != 4 or convs[0].weight.shape[0] != 64 or any(c.weight.shape[:2] != (64, 64) for c in convs[1:]) \
+                or last.weight.shape != (4, 64, 3, 3) or self.decoder.kernel_size != 5:
+            raise L.TocvpError("decoder kernels are instantiated for conv5x5 D->64, 3 x conv5x5 64->64, conv3x3 64->4")
+        d = {}
+        w1 = convs[0].weight.detach().float()                                   # [64, D, 5, 5]
+        d["w1_taps"] = _f16(w1.permute(2, 3, 0, 1).reshape(25 * 64, self.slot_dim))
+        # P = conv1(posemb map) + b1 : batch-independent, computed once in fp32 (weight preparation, not the hot path)
+        pos = self.decoder_pos_embedding.table().reshape(dH, dW, self.slot_dim).permute(2, 0, 1)[None]
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        p1 = torch.nn.functional.conv2d(pos.double(), w1.double(), convs[0].bias.detach().double(), padding=2)
+        torch.backends.cudnn.allow_tf32 = prev
+        d["p1"] = p1[0].permute(1, 2, 0).reshape(dH * dW, 64).float().contiguous()
+        for i in range(3):
+            d[f"wc{i}"] = _f16(convs[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 64, 64))
+            d[f"bc{i}"] = _f32(convs[i + 1].bias)
+        d["w_out"] = _f32(last.weight.permute(2, 3, 1, 0).reshape(9, 64, 4))
+        d["b_out"] = _f32(last.bias)
+        dw = DecW()
+        dw.w1_taps, dw.p1, dw.w_out, dw.b_out = (d[n].data_ptr() for n in ("w1_taps", "p1", "w_out", "b_out"))
+        for i in range(3):
+            dw.w_conv[i], dw.b_conv[i] = d[f"wc{i}"].data_ptr(), d[f"bc{i}"].data_ptr()
+        dw.H, dw.W, dw.slot_dim, dw.num_slots, dw.hidden = dH, dW, self.slot_dim, self.num_slots, 64
+        self._dec_keep, self._dec_w = d, dw
+
+    # ------------------------------------------------------------------ forward API (SAVi.py:139-149)
+    def forward(self, mode="decomp", *args, **kwargs):
+        if mode == "decomp":
+            return self.forward_decomp(*args, **kwargs)
+        elif mode == "decode":
+            return self.decode(*args, **kwargs)
+        raise NameError(f"mode = {mode!r} not recognized. Use ['decomp', 'decode']")
+
+    def _encode_raw(self, frames: torch.Tensor, n_img: int, img_stride: int, want_f32: bool):
+        """frames: fp32 device tensor; returns feats (f16 [n_img,N,F], fp32 or None)."""
+        self._ensure_packed()
+        lib = L.load()
+        H, W = self.encoder_pos_embedding.resolution
+        F = self.mlp_encoder_dim
+        f16 = torch.empty(n_img, H * W, F, device=frames.device, dtype=torch.float16)
+        f32 = torch.empty(n_img, H * W, F, device=frames.device, dtype=torch.float32) if want_f32 else None
+        lib.tocvp_savi_encode_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws_enc.get(lib.tocvp_savi_encode_workspace_bytes(ctypes.byref(self._enc_w), c_int(n_img)),
+                                   frames.device)
+        L.call("tocvp_savi_encode", ctypes.byref(self._enc_w), ptr(frames), c_size_t(img_stride), c_int(n_img),
+               ptr(f16), ptr(f32), ws, wsb, stream())
+        return f16, f32
+
+    @torch.no_grad()
+    def encode(self, x):
+        """x [B,3,H,W] -> [B, H*W, D] fp32 (SAVi.py:226-238)."""
+        x = x.float().contiguous()
+        _, f32 = self._encode_raw(x, x.shape[0], x[0].numel(), want_f32=True)
+        return f32
+
+    @torch.no_grad()
+    def forward_decomp(self, x, num_imgs=10, decode=True, init_slots=None, **kwargs):
+        """SAVi.py:152-223.  ``init_slots`` (optional, not in the reference) injects the sampled initial slots so that
+        parity runs do not depend on the device RNG."""
+        B, T = x.shape[0], x.shape[1]
+        S, D = self.num_slots, self.slot_dim
+        H, W = self.encoder_pos_embedding.resolution
+        N = H * W
+        x = x.float()
+        init = (self.initializer(batch_size=B, **kwargs) if init_slots is None else init_slots).float()
+        cur = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
+        cur.copy_(init)
+        slot_history = torch.empty(B, num_imgs, S, D, device=x.device, dtype=torch.float32)
+        has_t = isinstance(self.transition_module, TransformerBlock)
+        nxt = torch.empty_like(cur) if has_t else None
+        chunk = max(1, min(num_imgs, self.max_encode_images // max(B, 1)))
+        recs, objs, msks = [], [], []
+        for t0 in range(0, num_imgs, chunk):
+            t1 = min(num_imgs, t0 + chunk)
+            nt = t1 - t0
+            xs = x[:, t0:t1].contiguous()                                        # [B,nt,3,H,W]
+            feats, _ = self._encode_raw(xs, B * nt, xs[0, 0].numel(), want_f32=False)   # image index b*nt + (t-t0)
+            for t in range(t0, t1):
+                ft = feats[(t - t0):]                                            # sequence stride nt*N*F
+                iters = self.slot_attention.num_iters_first if t == 0 else self.slot_attention.num_iters
+                out_t = slot_history[:, t]
+                self.slot_attention.run(ft, nt * N * self.mlp_encoder_dim, B, N, cur, iters, out_t,
+                                        num_imgs * S * D, nxt)
+                if has_t:
+                    cur, nxt = nxt, cur
+                else:
+                    cur.copy_(out_t)
+                if decode:
+                    o = self.decode(out_t.contiguous())
+                    recs.append(o["recons_imgs"]); objs.append(o["recons"]); msks.append(o["masks"])
+        if decode:
+            return {"recons_imgs": torch.stack(recs, 1), "recons_objs": torch.stack(objs, 1),
+                    "masks": torch.stack(msks, 1), "slot_history": slot_history}
+        empty = torch.zeros(0, num_imgs)                                          # torch.stack of empty tensors
+        return {"recons_imgs": empty, "recons_objs": empty.clone(), "masks": empty.clone(), "slot_history": slot_history}
+
+    @torch.no_grad()
+    def decode(self, slots, only_imgs: bool = False):
+        """slots [B',S,D] -> recons_imgs [B',3,H,W], recons [B',S,3,H,W], masks [B',S,1,H,W] (SAVi.py:241-261)."""
+        self._ensure_packed()
+        lib = L.load()
+        slots = slots.float().contiguous()
+        n = slots.shape[0]
+        H, W = self.decoder_resolution
+        dev = slots.device
+        imgs = torch.empty(n, self.in_channels, H, W, device=dev, dtype=torch.float32)
+        recons = None if only_imgs else torch.empty(n, self.num_slots, self.in_channels, H, W, device=dev)
+        masks = None if only_imgs else torch.empty(n, self.num_slots, 1, H, W, device=dev)
+        lib.tocvp_savi_decode_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws_dec.get(lib.tocvp_savi_decode_workspace_bytes(ctypes.byref(self._dec_w), c_int(n)), dev)
+        L.call("tocvp_savi_decode", ctypes.byref(self._dec_w), ptr(slots), c_int(n), ptr(imgs), ptr(recons), ptr(masks),
+               ws, wsb, stream())
+        return {"recons_imgs": imgs, "recons": recons, "masks": masks}
+
+
+# =====================================================================================================
+# Predictor
+# =====================================================================================================
+class TransformerTextEncoder(nn.Module):
+    """text_encoders.py:14-138.  NOT on the accelerated path: it runs once per rollout and the benchmark replaces
+    its output by synthetic embeddings (BASELINE.json north_star).  Kept as a plain torch module (the reference's own
+    composition of torch layers) so that checkpoints load strictly and captions can be encoded."""
+
+    def __init__(self, input_dim, num_layers, num_heads, output_dim, vocab_size, context_length=50, dropout=0.1):
+        super().__init__()
+        self.vocab_size, self.padding_idx = vocab_size, 0
+        layer = nn.TransformerEncoderLayer(d_model=input_dim, nhead=num_heads, dim_feedforward=input_dim * 4,
+                                           dropout=dropout, activation="gelu")
+        self.transformer = nn.TransformerEncoder(layer, num_layers, enable_nested_tensor=False)
+        self.token_embedding = nn.Embedding(vocab_size, input_dim)
+        self.position_embedding = nn.Embedding(context_length, input_dim)
+        self.layer_norm = nn.LayerNorm(input_dim, eps=1e-8)
+        self.dropout = nn.Dropout(p=dropout)
+        self.text_out_projection = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, output_dim))
+
+    def forward(self, text, text_length):
+        pos = torch.arange(text.shape[1], dtype=text.dtype, device=text.device)[None].repeat(text.shape[0], 1)
+        tok = self.layer_norm(self.token_embedding(text) + self.position_embedding(pos))
+        tok = self.dropout(tok) * (text != self.padding_idx).unsqueeze(-1).type(tok.dtype)
+        cap_mask = text_length.unsqueeze(1) < torch.ones_like(text).cumsum(dim=1)
+        emb = self.transformer(tok.permute(1, 0, 2), mask=None, src_key_padding_mask=cap_mask).permute(1, 0, 2)
+        return self.text_out_projection(emb)
+
+
+class BaseTextOCVP(_Packed):
+    """text_cond_OCVP.py:22-121.  forward(slots [B,n,S,D], text_embeddings [B,L,T]) -> [B,S,D]."""
+
+    def __init__(self, slot_dim, predictor_params, fusion_params, text_encoder_params):
+        super().__init__()
+        self.predictor_params, self.fusion_params, self.text_encoder_params = predictor_params, fusion_params, text_encoder_params
+        self.slot_dim = slot_dim
+        self.token_dim = predictor_params.get("token_dim")
+        self.num_heads = predictor_params.get("n_heads")
+        self.hidden_dim = predictor_params.get("hidden_dim")
+        self.num_layers = predictor_params.get("num_layers")
+        self.residual = predictor_params.get("residual")
+        self.input_buffer_size = predictor_params.get("input_buffer_size")
+        self.mlp_in = nn.Linear(self.slot_dim, self.token_dim)
+        self.mlp_out = nn.Linear(self.token_dim, self.slot_dim)
+        self.predictor = nn.ModuleList([AdaptedEncoderBlock(self.token_dim, self.num_heads, self.hidden_dim, fusion_params)
+                                        for _ in range(self.num_layers)])
+        self._instantiate_text_encoder()
+        self.pe = TemporalPositionalEncoding(d_model=self.token_dim, max_len=self.input_buffer_size + 1, mode="learned")
+        self._ws = _Workspace()
+        self.num_slots_hint = None
+
+    def _instantiate_text_encoder(self):
+        raise NotImplementedError("'BaseTextOCVP' does not implement '_instantiate_text_encoder'...")
+
+    def _pack(self, dev, num_slots=None):
+        T, keep, layers = self.token_dim, [], (PredLayer * self.num_layers)()
+        for i, blk in enumerate(self.predictor):
+            c = blk.cross_attention
+            t = dict(
+                ln_q_g=_f32(blk.layernorm_query.weight), ln_q_b=_f32(blk.layernorm_query.bias),
+                w_qkv=_f16(torch.cat([blk.attn.q.weight, blk.attn.k.weight, blk.attn.v.weight], 0)),
+                w_o=_f16(blk.attn.out_projection[0].weight),
+                ln_cq_g=_f32(c.ln_cross_att_q.weight), ln_cq_b=_f32(c.ln_cross_att_q.bias),
+                ln_ckv_g=_f32(c.ln_cross_att_kv.weight), ln_ckv_b=_f32(c.ln_cross_att_kv.bias),
+                wc_q=_f16(c.cross_attn.q.weight),
+                wc_kv=_f16(torch.cat([c.cross_attn.k.weight, c.cross_attn.v.weight], 0)),
+                wc_o=_f16(c.cross_attn.out_projection.weight), bc_o=_f32(c.cross_attn.out_projection.bias),
+                ln_cm_g=_f32(c.ln_mlp.weight), ln_cm_b=_f32(c.ln_mlp.bias),
+                wc_1=_f16(c.mlp[0].weight), wc_2=_f16(c.mlp[2].weight), bc_1=_f32(c.mlp[0].bias), bc_2=_f32(c.mlp[2].bias),
+                ln_m_g=_f32(blk.layernorm_mlp.weight), ln_m_b=_f32(blk.layernorm_mlp.bias),
+                w_1=_f16(blk.mlp[0].weight), w_2=_f16(blk.mlp[2].weight), b_1=_f32(blk.mlp[0].bias), b_2=_f32(blk.mlp[2].bias))
+            keep.append(t)
+            for n, v in t.items():
+                setattr(layers[i], n, v.data_ptr())
+        nb = self.input_buffer_size
+        pe = self.pe.pe.detach().float().reshape(-1, T)                       # [max_len, T]
+        pef = torch.zeros(nb, nb, T, device=dev)
+        for n in range(1, nb + 1):
+            pef[n - 1, :n] = torch.flip(pe[:n], dims=(0,))                     # model_blocks.py:375-377
+        g = dict(mlp_in_w=_f16(self.mlp_in.weight), mlp_in_b=_f32(self.mlp_in.bias), mlp_out_w=_f16(self.mlp_out.weight),
+                 mlp_out_b=_f32(self.mlp_out.bias), pe_flipped=pef.contiguous())
+        w = PredW()
+        w.layers = ctypes.cast(layers, ctypes.POINTER(PredLayer))
+        w.num_layers, w.slot_dim, w.token_dim, w.hidden_dim = self.num_layers, self.slot_dim, T, self.hidden_dim
+        w.cross_hidden = self.fusion_params.get("mlp_size")
+        w.num_heads, w.cross_heads = self.num_heads, self.fusion_params.get("num_heads")
+        w.buffer_size, w.residual, w.ln_eps = nb, int(bool(self.residual)), 1e-6
+        for n, v in g.items():
+            setattr(w, n, v.data_ptr())
+        self._keep, self._layers, self._w = (keep, g), layers, w
+
+    def _weights(self, num_slots):
+        self._ensure_packed()
+        self._w.num_slots = num_slots
+        return self._w
+
+    @torch.no_grad()
+    def forward(self, slots, text_embeddings, **kwargs):
+        B, n, S, D = slots.shape
+        w = self._weights(S)
+        lib = L.load()
+        slots = slots.float().contiguous()
+        text = text_embeddings.float().contiguous()
+        Lt = text.shape[1]
+        out = torch.empty(B, S, D, device=slots.device, dtype=torch.float32)
+        lib.tocvp_predictor_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_predictor_workspace_bytes(ctypes.byref(w), c_int(B), c_int(Lt), c_int(n), c_int(1)),
+                               slots.device)
+        L.call("tocvp_predictor_forward", ctypes.byref(w), ptr(slots), ptr(text), c_int(B), c_int(n), c_int(Lt), ptr(out),
+               ws, wsb, stream())
+        return out
+
+    @torch.no_grad()
+    def rollout(self, slot_history, text_embeddings, num_context, num_preds):
+        """The whole autoregressive loop in one library call (all kernels enqueued from C++)."""
+        B, _, S, D = slot_history.shape
+        w = self._weights(S)
+        lib = L.load()
+        sh = slot_history.float()
+        if sh.stride(-1) != 1 or sh.stride(2) != D or sh.stride(1) != S * D:
+            sh = sh.contiguous()
+        text = text_embeddings.float().contiguous()
+        Lt = text.shape[1]
+        out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
+        lib.tocvp_predictor_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_predictor_workspace_bytes(ctypes.byref(w), c_int(B), c_int(Lt), c_int(num_context),
+                                                                   c_int(num_preds)), sh.device)
+        L.call("tocvp_predictor_rollout", ctypes.byref(w), ptr(sh), c_size_t(sh.stride(0)), ptr(text), c_int(B), c_int(Lt),
+               c_int(num_context), c_int(num_preds), ptr(out), ws, wsb, stream())
+        return out
+
+
+class TextOCVP_CustomTF(BaseTextOCVP):
+    def _instantiate_text_encoder(self):
+        p = self.text_encoder_params
+        self.text_encoder = TransformerTextEncoder(input_dim=p.get("input_dim"), num_layers=p.get("num_layers"),
+                                                   num_heads=p.get("num_heads"), output_dim=self.token_dim,
+                                                   vocab_size=p.get("vocab_size"))
+
+    def _sig(self):   # the text encoder is not packed; ignore its parameters
+        return tuple((p.data_ptr(), p._version, str(p.device)) for n, p in self.named_parameters()
+                     if not n.startswith("text_encoder."))
+
+
+class PredictorWrapper(nn.Module):
+    """predictor_wrapper.py:18-153."""
+
+    def __init__(self, exp_params, predictor):
+        super().__init__()
+        self.exp_params, self.predictor = exp_params, predictor
+        self.predictor_name = exp_params["predictor"]["predictor_name"]
+        self.predictor_params = exp_params["predictor"]["predictor_params"]
+        pp = exp_params["prediction_params"]
+        self.num_context, self.num_preds = pp["num_context"], pp["num_preds"]
+        self.teacher_force, self.input_buffer_size = pp["teacher_force"], pp["input_buffer_size"]
+        if self.input_buffer_size is None:
+            self.input_buffer_size = self.num_context
+
+    def encode_text_caption(self, **kwargs):
+        """predictor_wrapper.py:90-127; additionally accepts precomputed ``text_embeddings`` [B,L,T]."""
+        if kwargs.get("text_embeddings") is not None:
+            return kwargs["text_embeddings"]
+        caption = kwargs.get("caption_tokens", None)
+        if caption is None:
+            raise KeyError("'caption_tokens' must be provided for the text-encoder.")
+        device = next(self.parameters()).device
+        if "CustomTF" in self.predictor_name:
+            lengths = kwargs.get("caption_lengths", None)
+            if lengths is None:
+                raise KeyError("'caption_lengths' must be provided for CustomTF Pred.")
+            return self.predictor.text_encoder(text=caption.to(device), text_length=lengths.to(device))
+        raise NotImplementedError("only the CustomTF text encoder is available offline (T5 weights need network)")
+
+    @torch.no_grad()
+    def forward(self, slot_history, num_preds=None, **kwargs):
+        num_preds = num_preds if num_preds is not None else self.num_preds
+        teacher_force = self.exp_params["prediction_params"]["teacher_force"]      # see Appendix A.12
+        text = self.encode_text_caption(**kwargs)
+        if not teacher_force and self.predictor.input_buffer_size == self.input_buffer_size:
+            return self.predictor.rollout(slot_history, text, self.num_context, num_preds)
+        # generic loop (teacher forcing): same composition as the reference, one library call per step
+        window = slot_history[:, :self.num_context].clone()
+        preds = []
+        for t in range(num_preds):
+            cur = self.predictor(slots=window, time_step=t, text_embeddings=text)
+            nxt = slot_history[:, self.num_context + t] if teacher_force else cur
+            window = torch.cat([window, nxt.unsqueeze(1)], dim=1)[:, -self.input_buffer_size:]
+            preds.append(cur)
+        return torch.stack(preds, dim=1)
+
+
+# =====================================================================================================
+# factories mirroring lib/setup_model.py:22-132
+# =====================================================================================================
+def setup_model(model_params: Dict):
+    import copy
+    if model_params["model_name"] != "SAVi":
+        raise NotImplementedError("only SAVi is built in this round (ExtendedDINOSAUR: SURVEY.md 8(a) a18-a19, next)")
+    return SAVi(**copy.deepcopy(model_params["model_params"]))
+
+
+def setup_predictor(exp_params: Dict):
+    import copy
+    pp = copy.deepcopy(exp_params["predictor"]["predictor_params"])
+    pp["predictor_params"]["input_buffer_size"] = exp_params["prediction_params"]["input_buffer_size"]
+    name = exp_params["predictor"]["predictor_name"]
+    if name != "TextOCVP_CustomTF":
+        raise NotImplementedError(f"predictor {name}: only TextOCVP_CustomTF is available offline")
+    body = TextOCVP_CustomTF(slot_dim=exp_params["model"]["model_params"]["slot_dim"], **pp)
+    return PredictorWrapper(exp_params=exp_params, predictor=body)
+
+
+def default_exp_params(num_context=1, num_preds=19, input_buffer_size=10):
+    """src/configs/models/SAVi.json + src/configs/predictors/TextOCVP_CustomTF.json + CONFIG.py:66-71."""
+    return {
+        "model": {"model_name": "SAVi", "model_params": {
+            "num_slots": 8, "slot_dim": 128, "num_iterations_first": 3, "num_iterations": 1, "in_channels": 3,
+            "mlp_hidden": 256, "mlp_encoder_dim": 128, "initializer": "LearnedRandom",
+            "transition_module": {"model_name": "TransformerBlock", "num_heads": 4, "mlp_size": 512},
+            "encoder": {"encoder_name": "ConvEncoder", "encoder_params": {
+                "num_channels": [32, 32, 32, 32], "kernel_size": 5, "resolution": [64, 64],
+                "downsample_encoder": False, "downsample": 2}},
+            "decoder": {"decoder_name": "ConvDecoder", "decoder_params": {
+                "num_channels": [64, 64, 64, 64], "kernel_size": 5, "resolution": [64, 64],
+                "downsample_decoder": False, "upsample": 1}}}},
+        "predictor": {"predictor_name": "TextOCVP_CustomTF", "predictor_params": {
+            "predictor_params": {"token_dim": 512, "n_heads": 8, "hidden_dim": 2048, "num_layers": 8, "residual": True},
+            "fusion_params": {"num_heads": 8, "head_dim": 64, "mlp_size": 2048},
+            "text_encoder_params": {"input_dim": 128, "num_layers": 2, "num_heads": 4, "vocab_size": 50}}},
+        "prediction_params": {"num_context": num_context, "num_preds": num_preds, "teacher_force": False,
+                              "input_buffer_size": input_buffer_size},
+    }
