@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""
+bench.py -- predicted frames/s of the TextOCVP 19-step rollout (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W           our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...           the reference algorithm on the host CPU (oracle port)
+
+A "step" = one evaluator pass (src/05_evaluate_predictor.py:82-103) over one batch of B sequences per GPU:
+SAVi decomp over 20 frames -> 19-step text-conditioned rollout -> decode + composite 19 frames -> clamp -> PSNR/MSE.
+`value` times it with the inputs resident in HBM; `e2e` times the same call with host (pinned) inputs, H2D copies of
+videos + text embeddings and a D2H read of the per-frame metrics inside the timed region.  Weak scaling: B per GPU is
+fixed, ranks are independent (no collective in the step); the metric sums are all-reduced once after the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_CONTEXT, NUM_PREDS, T_FRAMES, L_TEXT = 1, 19, 20, 32
+# decoder-conv FLOPs actually executed by one conv5x5 64->64 launch over n slot-images (2*H*W*25*64*64 each)
+CONV_FLOP_PER_SLOTIMG = 2 * 64 * 64 * 25 * 64 * 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU (BASELINE config 3: 256)")
+    ap.add_argument("--cpu-batch", type=int, default=1, help="sequences per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU (reference algorithm)
+def cpu_rollout_time(batch, reps):
+    """Oracle port (oracle/textocvp_oracle.py = the reference's algorithm in plain torch CPU ops, fp32, all host threads)."""
+    import torch
+    from oracle import textocvp_oracle as O
+    from textocvp_b200 import weights
+    torch.set_num_threads(os.cpu_count())
+    ssd, psd = weights.savi_state_dict(14), weights.predictor_state_dict(15, mlp_out_scale=0.1)
+    videos, text, noise = weights.synthetic_inputs(batch, T_FRAMES, L_TEXT, seed=0)
+    init = ssd["initializer.slots_mu"] + ssd["initializer.slots_sigma"] * noise
+    scfg, pcfg = O.SAViCfg(), O.PredCfg(num_context=NUM_CONTEXT, num_preds=NUM_PREDS)
+    times = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.rollout(ssd, psd, videos, text, init, scfg, pcfg)
+            times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = max(1, args.cpu_batch)
+    times, cores = cpu_rollout_time(b, args.warmup + args.steps)
+    t = times[args.warmup:]
+    total = sum(t)
+    fps = b * NUM_PREDS * len(t) / total
+    line = {
+        "impl": "reference", "metric": "predicted frames/sec (19-step rollout)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(t),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CATER-shape TextOCVP rollout, 20-frame decomp + 19 preds + decode, L={L_TEXT}",
+                   "batch_per_step": b, "note": "reference algorithm (oracle port, torch CPU fp32) on host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"B={b} sequences x 19 predicted frames per step, {len(t)} timed steps"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from textocvp_b200 import _lib, rollout, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: there is no CPU fallback for this path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    savi, pred, _ = rollout.build_models(dev, num_context=NUM_CONTEXT, num_preds=NUM_PREDS)
+    videos_h, text_h, noise = weights.synthetic_inputs(B, T_FRAMES, L_TEXT, seed=100 + rank)
+    videos_h, text_h = videos_h.pin_memory(), text_h.pin_memory()
+    ssd = weights.savi_state_dict(14)
+    init = (ssd["initializer.slots_mu"] + ssd["initializer.slots_sigma"] * noise).to(dev)
+    videos_d, text_d = videos_h.to(dev), text_h.to(dev)
+    lib = _lib.load()
+    lib.tocvp_kernel_launches.restype = __import__("ctypes").c_ulonglong
+    metrics = rollout.MetricSums(NUM_PREDS, dev)
+
+    def step_resident(events=None):
+        return rollout.forward_eval(savi, pred, videos_d, text_d, NUM_CONTEXT, NUM_PREDS, init_slots=init,
+                                    conv_events=events)
+
+    vbuf = torch.empty_like(videos_d)
+    tbuf = torch.empty_like(text_d)
+
+    def step_e2e():
+        vbuf.copy_(videos_h, non_blocking=True)
+        tbuf.copy_(text_h, non_blocking=True)
+        out = rollout.forward_eval(savi, pred, vbuf, tbuf, NUM_CONTEXT, NUM_PREDS, init_slots=init)
+        return torch.stack([out["psnr"], out["mse"]]).cpu()      # D2H of the step's metrics (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    # ---- timed region 1: resident inputs, CUDA events, conv kernel timed live inside the steps
+    n_chunks = (B * NUM_PREDS + 255) // 256
+    conv_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * 3 * n_chunks)] for _ in range(args.steps)]
+    for evs in conv_evs:          # torch creates the cudaEvent_t lazily: record once so the handles exist
+        for e in evs:
+            e.record()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.tocvp_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        out = step_resident(conv_evs[k])
+        metrics.accumulate(out["psnr"], out["mse"])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.tocvp_kernel_launches() - l0
+    ms_total = e0.elapsed_time(e1)
+    conv_ms = [a.elapsed_time(b) for evs in conv_evs for a, b in zip(evs[0::2], evs[1::2])]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+
+    # ---- timed region 2: end to end through the public module API with host inputs
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e3.record()
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = t2.item()
+
+    metrics.all_reduce()          # the ONLY collective of the path: NCCL all-reduce of the metric sums
+    res_metrics = metrics.results()
+
+    frames_per_step = world * B * NUM_PREDS
+    value = frames_per_step * args.steps / (ms_total / 1e3)
+    e2e_value = frames_per_step * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+            "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        # one conv launch covers min(256, remaining) frames x 8 slot-images
+        per_launch = []
+        for k in range(args.steps):
+            for c in range(n_chunks):
+                nf = min(256, B * NUM_PREDS - c * 256)
+                per_launch += [nf * 8 * CONV_FLOP_PER_SLOTIMG] * 3
+        conv_avg_ms = sum(conv_ms) / len(conv_ms)
+        achieved = sum(per_launch) / (sum(conv_ms) / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv5x5_kernel<64,64,4> (decoder layers 2-4)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": conv_avg_ms,
+                    "share_of_step": sum(conv_ms) / ms_total,
+                    "flops_note": "FLOPs executed (layer 1 is computed algebraically, not as a convolution); "
+                                  "operands f16 (kind::f16, same tensor rate as bf16), fp32 accumulate"}
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            times, cores = cpu_rollout_time(args.cpu_batch, 4)
+            tt = times[1:]
+            cpu_fps = args.cpu_batch * NUM_PREDS * len(tt) / sum(tt)
+            cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"B={args.cpu_batch} sequence(s), full 20-frame decomp + 19-step rollout + decode, "
+                                      f"{len(tt)} timed reps after 1 warm-up (oracle port, torch CPU fp32)"}
+        line = {
+            "metric": "predicted frames/sec (19-step rollout)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": "Full CATER-shape TextOCVP rollout (configs[2]): 64x64 RGB, 8 slots x 128-d, 1 seed + 19 "
+                                   "predicted frames, 20-frame decomp (evaluator-faithful), L=32 synthetic text embeddings, "
+                                   "random init (mlp_out x0.1)",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch-sharded x{world}",
+                       "l2": "inputs (251 MB video / step) and activations exceed the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": videos_h.numel() * 4 + text_h.numel() * 4,
+                    "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "quality": {"psnr_vs_synthetic_targets_mean": res_metrics["psnr_mean"], "count": res_metrics["count"]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

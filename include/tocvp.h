@@ -41,6 +41,8 @@ int tocvp_abi_version(void);
 /* Checks that `device` is an sm_100 part and makes it current. */
 int tocvp_init(int device);
 const char* tocvp_last_error(void);
+/* Statistics: number of kernels this library has launched so far in this process (monotonic). */
+unsigned long long tocvp_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projection: C[M,N] = A[M,K] . W[N,K]^T (+bias) (ReLU) (+residual), tcgen05 / TMEM / TMA.
@@ -206,8 +208,12 @@ size_t tocvp_sizeof_dec_weights(void);
 size_t tocvp_savi_decode_workspace_bytes(const tocvp_dec_weights* w, int n_frames);
 /* slots fp32 [n_frames, S, D] -> recons_imgs fp32 [n_frames,3,H,W]; optional recons [n_frames,S,3,H,W] and
  * masks [n_frames,S,1,H,W] (NULL to skip: the evaluator only consumes recons_imgs). */
+#define TOCVP_DECODE_CHUNK_FRAMES 256 /* frames decoded per internal pass (bounds the activation workspace) */
+/* conv_events (optional, may be NULL): cudaEvent_t handles; pair (2i, 2i+1) is recorded around the i-th conv5x5
+ * launch (3 per chunk of TOCVP_DECODE_CHUNK_FRAMES frames) so a caller can time the dominant kernel inside a step. */
 int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots, int n_frames, float* recons_imgs, float* recons,
-                      float* masks, void* workspace, size_t ws_bytes, void* stream);
+                      float* masks, void* workspace, size_t ws_bytes, void* stream, void* const* conv_events,
+                      int n_conv_events);
 
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */

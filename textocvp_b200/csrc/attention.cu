@@ -91,7 +91,7 @@ int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv
   TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && Tk > 0 && Tk <= ATT_MAXK && heads > 0);
   TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0);
   mha_kernel<<<B * heads, ATT_THREADS, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, 0.125f, out, ldo);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 

@@ -242,7 +242,7 @@ static int launch_conv(const __half* x, const __half* wpacked, const float* bias
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   ConvArgs a{n_img, H, W, bias, out, relu};
   conv5x5_kernel<CIN, COUT, G><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 

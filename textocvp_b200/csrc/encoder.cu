@@ -119,7 +119,7 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   const int M = n_img * H * W;
   const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
   enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], eb.actB, n_img, H, W, C, C, 1, st));
   TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv[1]), w->b_conv[1], eb.actA, n_img, H, W, C, C, 1, st));
   TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], eb.actB, n_img, H, W, C, C, 1, st));

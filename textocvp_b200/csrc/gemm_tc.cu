@@ -214,7 +214,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_f16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, g);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 

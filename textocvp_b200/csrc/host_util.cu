@@ -2,11 +2,16 @@
 
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace tocvp {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(); }
 
 void set_last_error(const char* file, int line, const char* msg) {
   const char* base = strrchr(file, '/');
@@ -101,3 +106,6 @@ extern "C" int tocvp_init(int device) {
 }
 
 extern "C" int tocvp_abi_version(void) { return TOCVP_ABI_VERSION; }
+
+// Statistics only (monotonic counter of kernels this library has launched in this process).
+extern "C" unsigned long long tocvp_kernel_launches(void) { return tocvp::launch_count(); }

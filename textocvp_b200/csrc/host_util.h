@@ -33,6 +33,16 @@ namespace tocvp {
   } while (0)
 
 void set_last_error(const char* file, int line, const char* msg);
+void count_launch();
+unsigned long long launch_count();
+
+// after every kernel launch: surface launch errors and count the launch (tocvp_kernel_launches)
+#define TOCVP_LAUNCHED()                 \
+  do {                                   \
+    TOCVP_CUDA(cudaGetLastError());      \
+    tocvp::count_launch();               \
+  } while (0)
+
 
 // cuTensorMapEncodeTiled fetched through the runtime (no link-time dependency on libcuda).
 int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,

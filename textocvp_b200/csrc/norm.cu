@@ -94,7 +94,7 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
   else
     layernorm_kernel<float><<<grid, wpb * 32, 0, stream>>>(static_cast<const float*>(x), ldx, add, add_rows, gamma,
                                                            beta, eps, rows, D, out16, ld16, out32, ld32);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 

@@ -129,7 +129,7 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   const int M = B * n * S;
   const size_t seq_stride = size_t(ftot) * S * D;
   window_to_f16_kernel<<<ew_grid(size_t(M) * D / 4), 256, 0, st>>>(pb.frames, seq_stride, f0, n, S * D, B, pb.tok16);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   // tokens = mlp_in(slots) + flip(pe[:n])   (text_cond_OCVP.py:86-91, model_blocks.py:375-377): the pre-flipped
   // table for window length n is added in the GEMM epilogue, row -> frame index (row / S) % n.
   const float* pe_n = w.pe_flipped + size_t(n - 1) * w.buffer_size * T;
@@ -167,7 +167,7 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   }
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
   last_frame_to_f16_kernel<<<ew_grid(size_t(B) * S * T / 4), 256, 0, st>>>(pb.x32, n, S, T, B, pb.last16);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   TOCVP_TRY(gemm_f16(pb.last16, T, static_cast<const __half*>(w.mlp_out_w), T, B * S, D, T, w.mlp_out_b, 0, nullptr, 0,
                      1, 0, pb.pred32, D, nullptr, 0, st));
   return TOCVP_OK;
@@ -227,7 +227,7 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
   const size_t seq_stride = size_t(ftot) * SD;
   copy_context_kernel<<<ew_grid(size_t(B) * num_context * SD), 256, 0, st>>>(slot_history, hist_seq_stride, pb.frames,
                                                                             seq_stride, num_context, SD, B);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   for (int t = 0; t < num_preds; ++t) {
     const int have = num_context + t;                                   // frames available
@@ -237,7 +237,7 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
     commit_prediction_kernel<<<ew_grid(size_t(B) * SD), 256, 0, st>>>(pb.pred32, pb.frames, seq_stride, have - 1, have,
                                                                      w->residual, pred_slots, size_t(num_preds) * SD, t,
                                                                      SD, B);
-    TOCVP_CUDA(cudaGetLastError());
+    TOCVP_LAUNCHED();
   }
   return TOCVP_OK;
 }
@@ -259,11 +259,11 @@ extern "C" int tocvp_predictor_forward(const tocvp_pred_weights* w, const float*
   const int SD = w->num_slots * w->slot_dim;
   const size_t seq_stride = size_t(n + 1) * SD;
   copy_context_kernel<<<ew_grid(size_t(B) * n * SD), 256, 0, st>>>(slots, size_t(n) * SD, pb.frames, seq_stride, n, SD, B);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   TOCVP_TRY(predictor_step(*w, pb, B, L, 0, n, n + 1, st));
   commit_prediction_kernel<<<ew_grid(size_t(B) * SD), 256, 0, st>>>(pb.pred32, pb.frames, seq_stride, n - 1, n,
                                                                    w->residual, out, size_t(SD), 0, SD, B);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }

@@ -75,6 +75,6 @@ extern "C" int tocvp_probe_shifted_operand(const void* X, const void* W, float* 
   const int smem = 256 * 128 + 64 * 128 + 64 + 1024;
   TOCVP_CUDA(cudaFuncSetAttribute(probe_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   probe_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, out, shift, base_offset_mode);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }

@@ -409,7 +409,7 @@ static int launch_update(const SaWeights& w, int B, int flags, const float* slot
   const int rows = B * SA_S;
   sa_update_kernel<<<(rows + UP_R - 1) / UP_R, UP_THREADS, UP_SMEM, stream>>>(w, rows, flags, slots_in, partial,
                                                                              slots_out, out_stride, pred_out, gvec);
-  TOCVP_CUDA(cudaGetLastError());
+  TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 
@@ -443,7 +443,7 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
     else
       sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec, partial,
                                                         w.ln_eps_sa, w.attn_eps);
-    TOCVP_CUDA(cudaGetLastError());
+    TOCVP_LAUNCHED();
     const bool last = (it == iters - 1);
     if (!last) {
       TOCVP_TRY(launch_update(w, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, SA_S * SA_D, nullptr, gvec, stream));

@@ -546,7 +546,7 @@ class SAVi(_Packed):
         return {"recons_imgs": empty, "recons_objs": empty.clone(), "masks": empty.clone(), "slot_history": slot_history}
 
     @torch.no_grad()
-    def decode(self, slots, only_imgs: bool = False):
+    def decode(self, slots, only_imgs: bool = False, conv_events=None):
         """slots [B',S,D] -> recons_imgs [B',3,H,W], recons [B',S,3,H,W], masks [B',S,1,H,W] (SAVi.py:241-261)."""
         self._ensure_packed()
         lib = L.load()
@@ -559,8 +559,13 @@ class SAVi(_Packed):
         masks = None if only_imgs else torch.empty(n, self.num_slots, 1, H, W, device=dev)
         lib.tocvp_savi_decode_workspace_bytes.restype = ctypes.c_size_t
         ws, wsb = self._ws_dec.get(lib.tocvp_savi_decode_workspace_bytes(ctypes.byref(self._dec_w), c_int(n)), dev)
+        if conv_events:
+            evs = (ctypes.c_void_p * len(conv_events))(*[e.cuda_event for e in conv_events])
+            n_ev = len(conv_events)
+        else:
+            evs, n_ev = None, 0
         L.call("tocvp_savi_decode", ctypes.byref(self._dec_w), ptr(slots), c_int(n), ptr(imgs), ptr(recons), ptr(masks),
-               ws, wsb, stream())
+               ws, wsb, stream(), evs, c_int(n_ev))
         return {"recons_imgs": imgs, "recons": recons, "masks": masks}
 
 

@@ -1,0 +1,74 @@
+"""Evaluator composition of the rollout path (reference src/05_evaluate_predictor.py:53-104) and the metric
+accumulators that are all-reduced across ranks (src/lib/metrics.py:207-212 semantics: global mean + per-frame mean).
+
+The path shards by sequence (batch): one process per GPU, no collective inside the step; the only collective is the
+final all-reduce (SUM) of the accumulator vector."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import modules as M
+from . import weights
+
+
+def build_models(device, savi_seed=14, pred_seed=15, mlp_out_scale=0.1, num_context=1, num_preds=19,
+                 input_buffer_size=10):
+    """Named architectures (SAVi.json + TextOCVP_CustomTF.json), random init from seeds, on `device`."""
+    ep = M.default_exp_params(num_context, num_preds, input_buffer_size)
+    savi = M.setup_model(ep["model"])
+    pred = M.setup_predictor(ep)
+    savi.load_state_dict(weights.savi_state_dict(savi_seed), strict=True)
+    body = dict(pred.predictor.state_dict())
+    body.update(weights.predictor_state_dict(pred_seed, mlp_out_scale=mlp_out_scale))
+    pred.predictor.load_state_dict(body, strict=True)
+    return savi.to(device).eval(), pred.to(device).eval(), ep
+
+
+@torch.no_grad()
+def forward_eval(savi, pred, videos, text_embeddings, num_context, num_preds, init_slots=None, num_imgs=None,
+                 conv_events=None, only_imgs=False) -> Dict[str, torch.Tensor]:
+    """videos [B,L,3,H,W] (device) -> clamped predicted frames [B,num_preds,3,H,W] + PSNR/MSE per frame.
+    Mirrors Evaluator.forward_eval: decomp over num_context+num_preds frames (the reference encodes them all although
+    only the seed frames are consumed when teacher_force=False), predict, decode all B*num_preds frames, clamp."""
+    B, L_, C, H, W = videos.shape
+    if L_ < num_context + num_preds:
+        raise ValueError(f"Seq. length {L_} smaller that num_context = {num_context} + num_preds = {num_preds}")
+    num_imgs = num_context + num_preds if num_imgs is None else num_imgs
+    out = savi(mode="decomp", x=videos, num_imgs=num_imgs, decode=False, init_slots=init_slots)
+    slot_history = out["slot_history"]
+    pred_slots = pred(slot_history, text_embeddings=text_embeddings)
+    dec = savi.decode(pred_slots.reshape(B * num_preds, savi.num_slots, savi.slot_dim), only_imgs=only_imgs,
+                      conv_events=conv_events)
+    pred_imgs = dec["recons_imgs"].view(B, num_preds, C, H, W).clamp(0, 1)
+    targets = videos[:, num_context:num_context + num_preds].clamp(0, 1)
+    mse = ((pred_imgs - targets) ** 2).flatten(2).mean(-1)                       # [B, num_preds]
+    psnr = 10.0 * torch.log10(1.0 / (mse + 1e-8))                                # piqa-style, value_range 1 (unpinned)
+    return {"slot_history": slot_history, "pred_slots": pred_slots, "pred_imgs": pred_imgs, "mse": mse, "psnr": psnr}
+
+
+class MetricSums:
+    """[sum_b psnr[b,f] (F), sum_b mse[b,f] (F), count] in fp64; all-reduced once at the end."""
+
+    def __init__(self, num_preds, device):
+        self.F = num_preds
+        self.acc = torch.zeros(2 * num_preds + 1, dtype=torch.float64, device=device)
+
+    def accumulate(self, psnr, mse):
+        self.acc[:self.F] += psnr.double().sum(0)
+        self.acc[self.F:2 * self.F] += mse.double().sum(0)
+        self.acc[-1] += psnr.shape[0]
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        return self
+
+    def results(self):
+        n = self.acc[-1].item()
+        pf = (self.acc[:self.F] / n).tolist()
+        mf = (self.acc[self.F:2 * self.F] / n).tolist()
+        return {"count": int(n), "psnr_mean": sum(pf) / len(pf), "psnr_per_frame": pf, "mse_mean": sum(mf) / len(mf),
+                "mse_per_frame": mf}
