@@ -78,3 +78,30 @@ def test_conv5x5(n, c):
     ref = ref.permute(0, 2, 3, 1)
     assert _rel(out, ref) < 1e-3      # f16 output rounding only (operands identical, fp32 accumulate)
     assert (out.float() - ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("B,Tq,Tk,cross", [(3, 80, 80, False), (2, 8, 8, False), (5, 24, 24, False), (4, 80, 32, True),
+                                           (2, 72, 16, True), (2, 100, 100, False)])
+def test_mha(B, Tq, Tk, cross):
+    """mma.sync attention vs torch (fp32 softmax) on the same f16 q/k/v."""
+    from textocvp_b200 import _lib as L
+    from textocvp_b200._lib import c_int, ptr, stream
+    H, dh = 8, 64
+    g = torch.Generator(device="cuda").manual_seed(Tq * 7 + Tk)
+    if cross:
+        q = torch.randn(B * Tq, H * dh, device="cuda", generator=g).half()
+        kv = torch.randn(B * Tk, 2 * H * dh, device="cuda", generator=g).half()
+        k, v, ldq, ldkv = kv, kv[:, H * dh:], H * dh, 2 * H * dh
+    else:
+        qkv = torch.randn(B * Tq, 3 * H * dh, device="cuda", generator=g).half()
+        q, k, v, ldq, ldkv = qkv, qkv[:, H * dh:], qkv[:, 2 * H * dh:], 3 * H * dh, 3 * H * dh
+    out = torch.empty(B * Tq, H * dh, device="cuda", dtype=torch.float16)
+    L.init(out.device)
+    L.call("tocvp_mha_f16", ptr(q), c_int(ldq), ptr(k), ptr(v), c_int(ldkv), c_int(B), c_int(Tq), c_int(Tk), c_int(H),
+           ptr(out), c_int(H * dh), stream())
+    qf = q[:, :H * dh].double().view(B, Tq, H, dh).transpose(1, 2)
+    kf = k[:, :H * dh].double().view(B, Tk, H, dh).transpose(1, 2)
+    vf = v[:, :H * dh].double().view(B, Tk, H, dh).transpose(1, 2)
+    ref = ((qf @ kf.transpose(-1, -2)) * dh ** -0.5).softmax(-1) @ vf
+    ref = ref.transpose(1, 2).reshape(B * Tq, H * dh)
+    assert _rel(out, ref) < 2e-3      # P and the output are rounded to f16

@@ -1,10 +1,13 @@
 // Multi-head attention for the predictor's short sequences (<= 128 keys, head dim 64), fp32 softmax.
-// One CTA per (sequence, head); K/V of the head are staged once in shared memory (K rows padded to 33 words so that
-// lanes reading different keys hit different banks); each warp then owns query rows: lanes split the keys for
-// Q.K^T, warp-shuffle max/sum for the softmax, and split the 64 output dims for P.V.
-// Serves both the unmasked self-attention over the <= 10-frame slot window (reference
-// src/models/Blocks/attention.py:245-265, 183-193) and the text cross-attention (attention.py:303-319): q, k, v
-// are addressed as (base + row*ld + head*64) so the fused QKV GEMM output and the hoisted text K|V are used in place.
+// One CTA per (sequence, head).  K and V^T of the head are staged once in shared memory (row strides padded to
+// 4 (mod 32) words so every fragment load is bank-conflict free); each warp owns 16-query tiles and runs
+//     S = Q K^T  ->  softmax in registers (quad shuffles)  ->  O = P V
+// on mma.sync.m16n8k16 (f16 operands, fp32 accumulate) with the S accumulator fragments re-used directly as the
+// A operand of the second product (no smem round trip).  The problem per CTA (<= 80 x 80 x 64) is far too small to
+// amortise a tcgen05/TMEM pipeline, and the kernel is a few % of the step.
+// Serves the unmasked self-attention over the <= 10-frame slot window (reference
+// src/models/Blocks/attention.py:245-265, 183-193) and the text cross-attention (attention.py:303-319): q, k, v are
+// addressed as (base + row*ld + head*64), so the fused QKV GEMM output and the hoisted text K|V are used in place.
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -13,75 +16,129 @@ namespace tocvp {
 constexpr int ATT_DH = 64;
 constexpr int ATT_MAXK = 128;
 constexpr int ATT_THREADS = 128;
+constexpr int ATT_KS = 72;    // K row stride (halfs): 36 words
+constexpr int ATT_VS = 136;   // V^T row stride (halfs): 68 words
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(ATT_THREADS)
 mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, const __half* __restrict__ v, int ldkv,
-           int Tq, int Tk, int heads, float scale, __half* __restrict__ out, int ldo) {
-  __shared__ __align__(16) uint32_t sK[ATT_MAXK * 33];      // half2 words, row stride 33
-  __shared__ __align__(16) uint32_t sV[ATT_MAXK * 32];      // half2 words, row stride 32
-  __shared__ float sQ[ATT_THREADS / 32][ATT_DH];
-  __shared__ float sP[ATT_THREADS / 32][ATT_MAXK];
+           int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out, int ldo) {
+  __shared__ __align__(16) __half sK[ATT_MAXK * ATT_KS];
+  __shared__ __align__(16) __half sVt[ATT_DH * ATT_VS];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int TkP = (Tk + 15) & ~15;
   const __half* kb = k + size_t(b) * Tk * ldkv + h * ATT_DH;
   const __half* vb = v + size_t(b) * Tk * ldkv + h * ATT_DH;
-  // stage K, V: 8 x 16-byte chunks per row
-  for (int e = threadIdx.x; e < Tk * 8; e += ATT_THREADS) {
+  for (int e = threadIdx.x; e < TkP * 8; e += ATT_THREADS) {
     const int r = e >> 3, c = e & 7;
-    const uint4 kk = *reinterpret_cast<const uint4*>(kb + size_t(r) * ldkv + c * 8);
-    const uint4 vv = *reinterpret_cast<const uint4*>(vb + size_t(r) * ldkv + c * 8);
-    uint32_t* dk = sK + r * 33 + c * 4;
-    dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
-    *reinterpret_cast<uint4*>(sV + r * 32 + c * 4) = vv;
+    uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (r < Tk) {
+      kk = *reinterpret_cast<const uint4*>(kb + size_t(r) * ldkv + c * 8);
+      vv = *reinterpret_cast<const uint4*>(vb + size_t(r) * ldkv + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + r * ATT_KS + c * 8) = kk;
+    const __half* vh = reinterpret_cast<const __half*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sVt[(c * 8 + j) * ATT_VS + r] = vh[j];
   }
   __syncthreads();
+  const int n_tiles = TkP / 8;    // key tiles of 8
   const __half* qb = q + size_t(b) * Tq * ldq + h * ATT_DH;
   __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
-  for (int i = warp; i < Tq; i += ATT_THREADS / 32) {
-    const __half2 q2 = *reinterpret_cast<const __half2*>(qb + size_t(i) * ldq + lane * 2);
-    const float2 qf = __half22float2(q2);
-    __syncwarp();
-    sQ[warp][lane * 2] = qf.x * scale;
-    sQ[warp][lane * 2 + 1] = qf.y * scale;
-    __syncwarp();
-    float sc[ATT_MAXK / 32];
-    float mx = -1e30f;
+  for (int m0 = warp * 16; m0 < Tq; m0 += (ATT_THREADS / 32) * 16) {
+    const int r0 = m0 + g, r1 = m0 + g + 8;
+    const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
+    uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
 #pragma unroll
-    for (int t = 0; t < ATT_MAXK / 32; ++t) {
-      const int j = lane + t * 32;
-      float d = -1e30f;
-      if (j < Tk) {
-        d = 0.f;
-        const uint32_t* kr = sK + j * 33;
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c) : 0u;
+      qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c) : 0u;
+      qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c + 8) : 0u;
+      qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c + 8) : 0u;
+    }
+    float s[ATT_MAXK / 8][4];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kr[c]));
-          d += sQ[warp][2 * c] * kf.x + sQ[warp][2 * c + 1] * kf.y;
+    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt < n_tiles) {
+        const __half* kr = sK + (nt * 8 + g) * ATT_KS + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
+          mma_16816(s[nt], qa[ks], b0, b1);
         }
       }
-      sc[t] = d;
-      mx = fmaxf(mx, d);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
+    // softmax over keys (rows g and g+8 of this tile; a row lives in the 4 lanes of a quad)
+    float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
-    for (int t = 0; t < ATT_MAXK / 32; ++t) {
-      const int j = lane + t * 32;
-      const float p = (j < Tk) ? __expf(sc[t] - mx) : 0.f;
-      sum += p;
-      if (j < Tk) sP[warp][j] = p;
+    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+      if (nt < n_tiles) {
+        const int c = nt * 8 + 2 * t;
+        if (c >= Tk) s[nt][0] = s[nt][2] = -1e30f;
+        if (c + 1 >= Tk) s[nt][1] = s[nt][3] = -1e30f;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
     }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < Tk; ++j) {
-      const float p = sP[warp][j];
-      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&sV[j * 32 + lane]));
-      o0 += p * vf.x;
-      o1 += p * vf.y;
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+      if (nt < n_tiles) {
+        s[nt][0] = exp2f((s[nt][0] - mx0) * scale_log2e);
+        s[nt][1] = exp2f((s[nt][1] - mx0) * scale_log2e);
+        s[nt][2] = exp2f((s[nt][2] - mx1) * scale_log2e);
+        s[nt][3] = exp2f((s[nt][3] - mx1) * scale_log2e);
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
     }
-    const float inv = 1.f / sum;
-    *reinterpret_cast<__half2*>(ob + size_t(i) * ldo + lane * 2) = __floats2half2_rn(o0 * inv, o1 * inv);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V : the S fragments of key tiles (2kk, 2kk+1) are exactly the A fragment of k-step kk
+    float o[ATT_DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < ATT_DH / 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < ATT_MAXK / 16; ++kk) {
+      if (kk * 2 < n_tiles) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < ATT_DH / 8; ++nd) {
+          const __half* vr = sVt + (nd * 8 + g) * ATT_VS + kk * 16 + 2 * t;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
+          mma_16816(o[nd], pa, b0, b1);
+        }
+      }
+    }
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+#pragma unroll
+    for (int nd = 0; nd < ATT_DH / 8; ++nd) {
+      const int c = nd * 8 + 2 * t;
+      if (ok0) *reinterpret_cast<__half2*>(ob + size_t(r0) * ldo + c) = __floats2half2_rn(o[nd][0] * inv0, o[nd][1] * inv0);
+      if (ok1) *reinterpret_cast<__half2*>(ob + size_t(r1) * ldo + c) = __floats2half2_rn(o[nd][2] * inv1, o[nd][3] * inv1);
+    }
   }
 }
 
@@ -90,7 +147,8 @@ int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv
             __half* out, int ldo, cudaStream_t stream) {
   TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && Tk > 0 && Tk <= ATT_MAXK && heads > 0);
   TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0);
-  mha_kernel<<<B * heads, ATT_THREADS, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, 0.125f, out, ldo);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (attention.py:187) * log2(e)
+  mha_kernel<<<B * heads, ATT_THREADS, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }

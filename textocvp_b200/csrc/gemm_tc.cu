@@ -4,7 +4,7 @@
 // in TMEM.  One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer (128B-swizzled 128x64 A tile + BNx64 W tile per stage)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
-//   warps 2..5  epilogue: tcgen05.ld -> bias/ReLU/residual -> global (double-buffered accumulators, so the
+//   warps 2..9  epilogue: tcgen05.ld -> bias/ReLU/residual -> global (double-buffered accumulators, so the
 //               epilogue of tile i overlaps the main loop of tile i+1)
 // Replaces the cuBLAS calls behind nn.Linear at reference src/models/Blocks/attention.py:167-175,255,296-300,
 // 352-356 and src/models/Predictors/text_cond_OCVP.py:47-48, src/models/SAVi.py:117-119.
@@ -15,7 +15,7 @@ namespace tocvp {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmArgs {
   int M, N, K;
@@ -36,7 +36,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + 2 * BN * 4;   // mbarriers + tmem slot, then bias staging [2][BN]
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
@@ -51,6 +51,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = empty + S::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
@@ -68,7 +69,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[b], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -126,28 +127,60 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter, each owning half of the tile's columns.  Everything that does not depend on the
+    // accumulator (bias -> smem, the fp32 residual row segment -> registers) is fetched BEFORE waiting for the MMA,
+    // and the residual of chunk c+1 is in flight while chunk c is processed: for K = 512 the main loop of a tile is
+    // only ~2k cycles, so an epilogue that exposes global-load latency would set the pace of the whole kernel.
+    const int ew = warp - 2;
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = ew >> 2;             // which half of the BN columns
+    const int et = threadIdx.x - 64;      // 0..255
+    constexpr int CW = BN / 2;            // columns per warp
+    constexpr int NCH = CW / 32;          // 32-column chunks per warp
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mb = t / tiles_n, nb = t % tiles_n;
       const int b = it & 1;
       const uint32_t bph = (it >> 1) & 1;
-      mbar_wait(&tfull[b], bph);
-      tc_fence_after();
+      if (g.bias != nullptr && et < BN) {
+        const int n = nb * BN + et;
+        sbias[b * BN + et] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
+      }
       const int row = mb * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < g.M;
+      const int ncol0 = nb * BN + half * CW;
       const float* res_row = nullptr;
       if (g.residual != nullptr && row_ok) {
         const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
         res_row = g.residual + size_t(rr) * g.ldr;
       }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + c * 32), v);
-        tmem_ld_wait();
-        const int n0 = nb * BN + c * 32;
+      float4 rbuf[2][8];
+      auto load_res = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = ncol0 + c * 32 + j * 4;
+          dst[j] = (res_row != nullptr && n < g.N) ? __ldg(reinterpret_cast<const float4*>(res_row + n))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_res(0, rbuf[0]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // bias staged (epilogue warps only)
+      mbar_wait(&tfull[b], bph);
+      tc_fence_after();
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + half * CW + c * 32), v[c]);
+      tmem_ld_wait();
+      // accumulators are in registers: release the TMEM buffer to the MMA warp as early as possible
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c + 1 < NCH) load_res(c + 1, rbuf[(c + 1) & 1]);
+        const int n0 = ncol0 + c * 32;
         if (row_ok && n0 < g.N) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
@@ -155,10 +188,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (n < g.N) {  // N is a multiple of 8
               float f[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c][j8 * 8 + j]);
               if (g.bias != nullptr) {
-                const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
-                const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8 + 4]);
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
@@ -167,8 +200,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
               }
               if (res_row != nullptr) {
-                const float4 r0 = *reinterpret_cast<const float4*>(res_row + n);
-                const float4 r1 = *reinterpret_cast<const float4*>(res_row + n + 4);
+                const float4 r0 = rbuf[c & 1][j8 * 2], r1 = rbuf[c & 1][j8 * 2 + 1];
                 f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
                 f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
               }
@@ -189,9 +221,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[b]);
     }
   }
 

@@ -80,12 +80,71 @@ layernorm_kernel(const TIN* __restrict__ x, int ldx, const float* __restrict__ a
   }
 }
 
+
+// Narrow rows (D = 4*LPR <= 64): LPR lanes per row, 32/LPR rows per warp, one float4 per lane -- keeps all 32 lanes busy
+// for the encoder's LayerNorm(32) over B*T*4096 pixels (SAVi.py:116).
+template <typename TIN, int LPR>
+__global__ void __launch_bounds__(256)
+layernorm_narrow_kernel(const TIN* __restrict__ x, int ldx, const float* __restrict__ add, int add_rows,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows,
+                        __half* __restrict__ out16, int ld16, float* __restrict__ out32, int ld32) {
+  constexpr int D = 4 * LPR;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const float4 g = *reinterpret_cast<const float4*>(gamma + sub * 4);
+  const float4 bt = *reinterpret_cast<const float4*>(beta + sub * 4);
+  const long long warp0 = (long long)(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)(gridDim.x) * (blockDim.x >> 5);
+  for (long long base = warp0 * RPW; base < rows; base += nwarps * RPW) {   // warp-uniform trip count (shuffles inside)
+    const long long row = base + lane / LPR;
+    const bool valid = row < rows;
+    float4 v = valid ? load4<TIN>(x + size_t(row) * ldx + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add && valid) {
+      const float4 a = *reinterpret_cast<const float4*>(add + size_t(row % add_rows) * D + sub * 4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / D);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    float q = (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / D) + eps);
+    const float y0 = a * rstd * g.x + bt.x, y1 = b * rstd * g.y + bt.y, y2 = c * rstd * g.z + bt.z,
+                y3 = d * rstd * g.w + bt.w;
+    if (out16 && valid) {
+      uint2 p;
+      p.x = pack_half2(y0, y1);
+      p.y = pack_half2(y2, y3);
+      *reinterpret_cast<uint2*>(out16 + size_t(row) * ld16 + sub * 4) = p;
+    }
+    if (out32 && valid) *reinterpret_cast<float4*>(out32 + size_t(row) * ld32 + sub * 4) = make_float4(y0, y1, y2, y3);
+  }
+}
+
 int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_rows, const float* gamma,
               const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
               cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && gamma && beta && rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_CHUNKS * 128);
   TOCVP_CHECK_ARG(ldx % 4 == 0 && (out16 || out32));
   TOCVP_CHECK_ARG(!add || add_rows > 0);
+  if (D == 32 || D == 64) {
+    const int rpw = 128 / D;
+    long long warps = (rows + rpw - 1) / rpw;
+    long long blocks = (warps + 7) / 8;
+    const int grid = int(blocks > 148 * 32 ? 148 * 32 : blocks);
+#define LN_NARROW(TIN, LPR)                                                                                         \
+  layernorm_narrow_kernel<TIN, LPR><<<grid, 256, 0, stream>>>(static_cast<const TIN*>(x), ldx, add, add_rows, gamma, \
+                                                              beta, eps, rows, out16, ld16, out32, ld32)
+    if (x_is_f16) { if (D == 32) LN_NARROW(__half, 8); else LN_NARROW(__half, 16); }
+    else          { if (D == 32) LN_NARROW(float, 8);  else LN_NARROW(float, 16); }
+#undef LN_NARROW
+    TOCVP_LAUNCHED();
+    return TOCVP_OK;
+  }
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   if (x_is_f16)
