@@ -241,7 +241,7 @@ def run_ours(args):
                 per_launch += [nf * 8 * CONV_FLOP_PER_SLOTIMG] * 3
         conv_avg_ms = sum(conv_ms) / len(conv_ms)
         achieved = sum(per_launch) / (sum(conv_ms) / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv5x5_kernel<64,64,4> (decoder layers 2-4)",
+        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<64,64,4,5,0> = conv5x5 64->64 (decoder layers 2-4)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": None, "peak_source": peak_src, "avg_launch_ms": conv_avg_ms,
                     "share_of_step": sum(conv_ms) / ms_total,

@@ -199,7 +199,7 @@ typedef struct tocvp_dec_weights {
   const float* p1;           /* fp32 [H*W, 64] = conv1(posemb map) + b1, precomputed (batch independent)            */
   const void* w_conv[3];     /* f16 [25,64,64] tap-major (decoder.decoder.{1,2,3}) */
   const float* b_conv[3];
-  const float* w_out;        /* fp32 [9][64][4]: (ky*3+kx, ci, co)  decoder.decoder.4 */
+  const void* w_out;         /* f16 [9][16][64]: (ky*3+kx, co zero-padded 4 -> 16, ci)  decoder.decoder.4 */
   const float* b_out;        /* [4] */
   int H, W, slot_dim, num_slots, hidden;
 } tocvp_dec_weights;

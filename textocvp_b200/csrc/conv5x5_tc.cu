@@ -17,23 +17,24 @@
 
 namespace tocvp {
 
-template <int CIN, int COUT, int G>
+template <int CIN, int COUT, int G, int KS>
 struct ConvCfg {
   static constexpr int KB = CIN * 2;                 // bytes per pixel row in smem (64 or 128)
   static constexpr int TILE_H = 16;
   static constexpr int TILE_W = 8 * G;
   static constexpr int WBUF = TILE_W + 8;            // halo width, multiple of 8 (>= TILE_W + 4)
-  static constexpr int HROWS = TILE_H + 4;
+  static constexpr int HROWS = TILE_H + KS - 1;
+  static constexpr int TAPS = KS * KS;
   static constexpr int A_BYTES = HROWS * WBUF * KB;  // multiple of 1024 for G in {2,4}
   static constexpr int W_BYTES = COUT * KB;
-  static constexpr int WSTAGES = (CIN == 64) ? 3 : 8;
+  static constexpr int WSTAGES = (W_BYTES >= 8192) ? 3 : 8;
   static constexpr int KSTEPS = CIN / 16;
   static constexpr int ACC_COLS = G * COUT;          // per accumulator buffer
   static constexpr int TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
-  static constexpr int SMEM = 2 * A_BYTES + WSTAGES * W_BYTES + 256 + 1024;
+  static constexpr int SMEM = 2 * ((HROWS * WBUF * KB + 1023) & ~1023) + WSTAGES * W_BYTES + 256 + 1024;
   static constexpr int LAYOUT = (KB == 128) ? 2 : 4;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
   static_assert(KB == 128 || KB == 64, "CIN must be 32 or 64");
-  static_assert(A_BYTES % 1024 == 0, "halo tile must keep the second buffer 1024B aligned");
+  static constexpr int A_STRIDE = (A_BYTES + 1023) & ~1023;   // keeps the second buffer 1024B aligned
   static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
 };
 
@@ -45,18 +46,19 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, uint32_t sb
 struct ConvArgs {
   int n_img, H, W;
   const float* bias;  // [COUT]
-  __half* out;        // [n_img, H, W, COUT]
+  __half* out;        // EPI 0: f16 NHWC [n_img, H, W, COUT]
+  float* out4;        // EPI 1: fp32 NHWC [n_img, H, W, 4] (first 4 output channels, no activation)
   int relu;
 };
 
-template <int CIN, int COUT, int G>
+template <int CIN, int COUT, int G, int KS, int EPI>
 __global__ void __launch_bounds__(192, 1)
-conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
-  using C = ConvCfg<CIN, COUT, G>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
+  using C = ConvCfg<CIN, COUT, G, KS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                       // 2 halo buffers
-  uint8_t* sW = smem + 2 * C::A_BYTES;      // weight ring
+  uint8_t* sW = smem + 2 * C::A_STRIDE;     // weight ring
   uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_BYTES);
   uint64_t* w_empty = w_full + C::WSTAGES;
   uint64_t* a_full = w_empty + C::WSTAGES;
@@ -101,7 +103,7 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int y0 = (r / tiles_x) * C::TILE_H, x0 = (r % tiles_x) * C::TILE_W;
         mbar_wait(&a_empty[buf], ph ^ 1);
         mbar_expect_tx(&a_full[buf], C::A_BYTES);
-        tma_load_4d(&tmX, &a_full[buf], sA + buf * C::A_BYTES, 0, x0 - 2, y0 - 2, img);
+        tma_load_4d(&tmX, &a_full[buf], sA + buf * C::A_STRIDE, 0, x0 - KS / 2, y0 - KS / 2, img);
       };
       int s = 0;
       uint32_t wph = 0;
@@ -109,7 +111,7 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (int(blockIdx.x) < num_tiles) load_halo(blockIdx.x, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         if (t + int(gridDim.x) < num_tiles) load_halo(t + gridDim.x, it + 1);  // prefetch the next tile's halo
-        for (int tap = 0; tap < 25; ++tap) {
+        for (int tap = 0; tap < C::TAPS; ++tap) {
           mbar_wait(&w_empty[s], wph ^ 1);
           mbar_expect_tx(&w_full[s], C::W_BYTES);
           tma_load_2d(&tmW, &w_full[s], sW + s * C::W_BYTES, 0, tap * COUT);
@@ -118,10 +120,12 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp converged, one elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_f16(128, COUT, 0);
       constexpr uint32_t SBO = C::WBUF * C::KB;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+      const uint32_t leader = elect_one_sync();
       int s = 0;
       uint32_t wph = 0;
       int it = 0;
@@ -131,10 +135,11 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_wait(&t_empty[buf], ph ^ 1);
         mbar_wait(&a_full[buf], ph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + buf * C::A_BYTES);
-        const uint32_t d_base = tmem_base + uint32_t(buf * C::ACC_COLS);
-        for (int tap = 0; tap < 25; ++tap) {
-          const int ty = tap / 5, tx = tap % 5;
+        const uint32_t a_base = smem_u32(sA + buf * C::A_STRIDE);
+        const uint32_t d_base = tmem_u + uint32_t(buf * C::ACC_COLS);
+#pragma unroll 1
+        for (int tap = 0; tap < C::TAPS; ++tap) {
+          const int ty = tap / KS, tx = tap % KS;
           mbar_wait(&w_full[s], wph);
           tc_fence_after();
           const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_BYTES), 8 * C::KB, C::LAYOUT);
@@ -145,14 +150,14 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < C::KSTEPS; ++k) {
               umma_f16(d_base + uint32_t(j * COUT), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                       (tap | k) != 0);
+                       (tap | k) != 0, leader);
             }
           }
-          umma_commit(&w_empty[s]);
+          umma_commit(&w_empty[s], leader);
           if (++s == C::WSTAGES) { s = 0; wph ^= 1; }
         }
-        umma_commit(&a_empty[buf]);
-        umma_commit(&t_full[buf]);
+        umma_commit(&a_empty[buf], leader);
+        umma_commit(&t_full[buf], leader);
       }
     }
   } else {
@@ -169,35 +174,49 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int x0 = (r % tiles_x) * C::TILE_W + pc;
       mbar_wait(&t_full[buf], ph);
       tc_fence_after();
+      if constexpr (EPI == 0) {
 #pragma unroll 1
-      for (int j = 0; j < G; ++j) {
-        __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
+        for (int j = 0; j < G; ++j) {
+          __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
 #pragma unroll
-        for (int c = 0; c < COUT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
-          tmem_ld_wait();
+          for (int c = 0; c < COUT / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const int n = c * 32 + j8 * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-            float f[8];
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int n = c * 32 + j8 * 8;
+              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+              float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j8 * 8 + e]);
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            if (a.relu) {
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j8 * 8 + e]);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              if (a.relu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              uint4 p;
+              p.x = pack_half2(f[0], f[1]);
+              p.y = pack_half2(f[2], f[3]);
+              p.z = pack_half2(f[4], f[5]);
+              p.w = pack_half2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(o + n) = p;
             }
-            uint4 p;
-            p.x = pack_half2(f[0], f[1]);
-            p.y = pack_half2(f[2], f[3]);
-            p.z = pack_half2(f[4], f[5]);
-            p.w = pack_half2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(o + n) = p;
           }
+        }
+      } else {
+        // narrow head (COUT = 16, 4 real channels): one float4 per pixel, no activation
+        const float4 b0 = *reinterpret_cast<const float4*>(a.bias);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          uint32_t v[4];
+          tmem_ld4(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT), v);
+          tmem_ld_wait();
+          float* o = a.out4 + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * 4;
+          *reinterpret_cast<float4*>(o) = make_float4(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y,
+                                                      __uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
         }
       }
       tc_fence_before();
@@ -214,14 +233,15 @@ conv5x5_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
-template <int CIN, int COUT, int G>
-static int launch_conv(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
-                       int relu, cudaStream_t stream) {
-  using C = ConvCfg<CIN, COUT, G>;
+template <int CIN, int COUT, int G, int KS, int EPI>
+static int launch_conv(const __half* x, const __half* wpacked, const float* bias, __half* out, float* out4, int n_img,
+                       int H, int W, int relu, cudaStream_t stream) {
+  using C = ConvCfg<CIN, COUT, G, KS>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv5x5_kernel<CIN, COUT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, G, KS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM));
     attr_set = true;
   }
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -233,15 +253,15 @@ static int launch_conv(const __half* x, const __half* wpacked, const float* bias
     TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, sw));
   }
   {
-    const uint64_t dims[2] = {uint64_t(CIN), uint64_t(25 * COUT)};
+    const uint64_t dims[2] = {uint64_t(CIN), uint64_t(C::TAPS * COUT)};
     const uint64_t str[1] = {uint64_t(CIN) * 2};
     const uint32_t box[2] = {uint32_t(CIN), uint32_t(COUT)};
     TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
   }
   const int num_tiles = n_img * (H / C::TILE_H) * (W / C::TILE_W);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  ConvArgs a{n_img, H, W, bias, out, relu};
-  conv5x5_kernel<CIN, COUT, G><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
+  ConvArgs a{n_img, H, W, bias, out, out4, relu};
+  conv_tc_kernel<CIN, COUT, G, KS, EPI><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -251,10 +271,19 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && wpacked && bias && out && n_img > 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (cin == 64 && cout == 64) return launch_conv<64, 64, 4>(x, wpacked, bias, out, n_img, H, W, relu, stream);
-  if (cin == 32 && cout == 32) return launch_conv<32, 32, 4>(x, wpacked, bias, out, n_img, H, W, relu, stream);
+  if (cin == 64 && cout == 64) return launch_conv<64, 64, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
+  if (cin == 32 && cout == 32) return launch_conv<32, 32, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
   set_last_error(__FILE__, __LINE__, "conv5x5_f16: only 64->64 and 32->32 channels are instantiated");
   return TOCVP_ERR_BAD_ARG;
+}
+
+// Decoder head: conv3x3 64 -> 4 (weights zero-padded to 16 output channels: the narrowest UMMA N for M = 128), no
+// activation.  wpacked: f16 [9, 16, 64]; bias fp32 [4]; out4: fp32 NHWC [n_img, H, W, 4].
+int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, float* out4, int n_img, int H, int W,
+                     cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && wpacked && bias && out4 && n_img > 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out4) & 15) == 0);
+  return launch_conv<64, 16, 4, 3, 1>(x, wpacked, bias, nullptr, out4, n_img, H, W, 0, stream);
 }
 
 }  // namespace tocvp

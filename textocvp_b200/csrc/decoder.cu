@@ -9,9 +9,9 @@
 //      NHWC activation -- a pure bandwidth kernel replacing 40% of the decoder FLOPs (the broadcast tensor of
 //      SAVi.py:264-275 is never materialised).
 //  layers 2-4: tcgen05 implicit-GEMM conv5x5 64->64 (conv5x5_tc.cu).
-//  final conv3x3 64->4 + softmax over slots + weighted sum (SAVi.py:251-255): `conv3x3_composite_kernel`, all 8 slots
-//      of a pixel tile handled by one CTA with an online softmax, so the [B',8,4,H,W] maps never hit HBM unless the
-//      caller asks for `recons` / `masks`.
+//  final conv3x3 64->4 (decoders.py:110-116): the same tcgen05 implicit-GEMM kernel with a 3x3 tap set and the output
+//      channels zero-padded to N = 16; it writes one float4 (RGB + mask logit) per pixel and slot.
+//  compositing (SAVi.py:251-255): `composite_kernel`, softmax over the slot axis + weighted sum, one thread per pixel.
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -22,6 +22,8 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
              int ld16, cudaStream_t stream);
 int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W, int cin,
                 int cout, int relu, cudaStream_t stream);
+int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, float* out4, int n_img, int H, int W,
+                     cudaStream_t stream);
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4) {
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n4; e += size_t(gridDim.x) * blockDim.x) {
@@ -77,94 +79,35 @@ dec_l1_kernel(const float* __restrict__ taps, const float* __restrict__ P, __hal
   }
 }
 
-// ------------------------------------------------------------------------------------------------ conv3x3 + compositing
-constexpr int C3_TH = 16, C3_TW = 32, C3_C = 64, C3_CP = 72;   // 72 halfs = 144 B per pixel: conflict-free LDS.128
-constexpr int C3_HALO = (C3_TH + 2) * (C3_TW + 2);
-constexpr int C3_SMEM = C3_HALO * C3_CP * 2 + 9 * C3_C * 4 * 4;
-
-// act: f16 NHWC [n_frames*S, H, W, 64]; w: fp32 [9][64][4]; imgs: fp32 [n_frames,3,H,W];
-// recons (opt) fp32 [n_frames,S,3,H,W]; masks (opt) fp32 [n_frames,S,1,H,W]
-__global__ void __launch_bounds__(256, 2)
-conv3x3_composite_kernel(const __half* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
-                         float* __restrict__ imgs, float* __restrict__ recons, float* __restrict__ masks, int S, int H,
-                         int W) {
-  extern __shared__ __align__(16) uint8_t c3_smem[];
-  __half* sIn = reinterpret_cast<__half*>(c3_smem);
-  float4* sW = reinterpret_cast<float4*>(c3_smem + C3_HALO * C3_CP * 2);
-  const int frame = blockIdx.y;
-  const int tiles_x = W / C3_TW;
-  const int y0 = (blockIdx.x / tiles_x) * C3_TH, x0 = (blockIdx.x % tiles_x) * C3_TW;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // pixels (ty, tx) and (ty + 8, tx)
-  for (int e = threadIdx.x; e < 9 * C3_C; e += 256) sW[e] = reinterpret_cast<const float4*>(w)[e];
-  const float4 b4 = *reinterpret_cast<const float4*>(bias);
-  float mx[2] = {-1e30f, -1e30f}, den[2] = {0.f, 0.f}, rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  const size_t plane = size_t(H) * W;
+// ------------------------------------------------------------------------------------------------ compositing
+// maps: fp32 [n_frames*S, H*W, 4] (RGB + mask logit, SAVi.py:251-252) from the tcgen05 conv3x3 head.
+// imgs fp32 [n_frames,3,H,W]; recons (opt) [n_frames,S,3,H,W]; masks (opt) [n_frames,S,1,H,W].
+// One thread per pixel: softmax over the slot axis + weighted sum in registers, fully coalesced 16-byte reads.
+__global__ void __launch_bounds__(256)
+composite_kernel(const float4* __restrict__ maps, float* __restrict__ imgs, float* __restrict__ recons,
+                 float* __restrict__ masks, int S, int plane, int n_frames) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(n_frames) * plane) return;
+  const int frame = int(idx / plane), pix = int(idx % plane);
+  const float4* m = maps + size_t(frame) * S * plane + pix;
+  float mx = -1e30f;
+  for (int s = 0; s < S; ++s) mx = fmaxf(mx, __ldg(m + size_t(s) * plane).w);
+  float den = 0.f, r = 0.f, g = 0.f, b = 0.f;
   for (int s = 0; s < S; ++s) {
-    const __half* a = act + (size_t(frame) * S + s) * plane * C3_C;
-    __syncthreads();   // previous slot's tile fully consumed (also orders the sW fill on the first pass)
-    for (int e = threadIdx.x; e < C3_HALO * 8; e += 256) {
-      const int p = e >> 3, c = e & 7;
-      const int gy = y0 - 1 + p / (C3_TW + 2), gx = x0 - 1 + p % (C3_TW + 2);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(reinterpret_cast<const uint4*>(a + (size_t(gy) * W + gx) * C3_C + c * 8));
-      *reinterpret_cast<uint4*>(sIn + p * C3_CP + c * 8) = v;
-    }
-    __syncthreads();
-    float acc[2][4] = {{b4.x, b4.y, b4.z, b4.w}, {b4.x, b4.y, b4.z, b4.w}};
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ky = tap / 3, kx = tap % 3;
-      const __half* pa = sIn + ((ty + ky) * (C3_TW + 2) + tx + kx) * C3_CP;
-      const __half* pb = pa + 8 * (C3_TW + 2) * C3_CP;
-      const float4* wt = sW + tap * C3_C;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const uint4 ua = *reinterpret_cast<const uint4*>(pa + c8 * 8);
-        const uint4 ub = *reinterpret_cast<const uint4*>(pb + c8 * 8);
-        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&wa[h]));
-          const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&wb[h]));
-          const float4 w0 = wt[c8 * 8 + h * 2], w1 = wt[c8 * 8 + h * 2 + 1];
-          acc[0][0] += fa.x * w0.x + fa.y * w1.x; acc[0][1] += fa.x * w0.y + fa.y * w1.y;
-          acc[0][2] += fa.x * w0.z + fa.y * w1.z; acc[0][3] += fa.x * w0.w + fa.y * w1.w;
-          acc[1][0] += fb.x * w0.x + fb.y * w1.x; acc[1][1] += fb.x * w0.y + fb.y * w1.y;
-          acc[1][2] += fb.x * w0.z + fb.y * w1.z; acc[1][3] += fb.x * w0.w + fb.y * w1.w;
-        }
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int gy = y0 + ty + 8 * p, gx = x0 + tx;
-      const float logit = acc[p][3];                          // channel order RGB then mask (SAVi.py:251-252)
-      const float nm = fmaxf(mx[p], logit);
-      const float corr = __expf(mx[p] - nm), e = __expf(logit - nm);
-      den[p] = den[p] * corr + e;
-      rgb[p][0] = rgb[p][0] * corr + e * acc[p][0];
-      rgb[p][1] = rgb[p][1] * corr + e * acc[p][1];
-      rgb[p][2] = rgb[p][2] * corr + e * acc[p][2];
-      mx[p] = nm;
-      if (recons) {
-        float* r = recons + ((size_t(frame) * S + s) * 3) * plane + size_t(gy) * W + gx;
-        r[0] = acc[p][0]; r[plane] = acc[p][1]; r[2 * plane] = acc[p][2];
-      }
-      if (masks) masks[(size_t(frame) * S + s) * plane + size_t(gy) * W + gx] = logit;
+    const float4 v = __ldg(m + size_t(s) * plane);
+    const float e = __expf(v.w - mx);
+    den += e; r += e * v.x; g += e * v.y; b += e * v.z;
+    if (recons) {
+      float* o = recons + (size_t(frame) * S + s) * 3 * plane + pix;
+      o[0] = v.x; o[plane] = v.y; o[2 * size_t(plane)] = v.z;
     }
   }
-#pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const int gy = y0 + ty + 8 * p, gx = x0 + tx;
-    const float inv = 1.f / den[p];
-    float* o = imgs + size_t(frame) * 3 * plane + size_t(gy) * W + gx;
-    o[0] = rgb[p][0] * inv; o[plane] = rgb[p][1] * inv; o[2 * plane] = rgb[p][2] * inv;
-    if (masks) {
-      for (int s = 0; s < S; ++s) {
-        float* m = masks + (size_t(frame) * S + s) * plane + size_t(gy) * W + gx;
-        *m = __expf(*m - mx[p]) * inv;
-      }
-    }
+  const float inv = 1.f / den;
+  float* o = imgs + size_t(frame) * 3 * plane + pix;
+  o[0] = r * inv; o[plane] = g * inv; o[2 * size_t(plane)] = b * inv;
+  if (masks) {
+    for (int s = 0; s < S; ++s)
+      masks[(size_t(frame) * S + s) * plane + pix] = __expf(__ldg(m + size_t(s) * plane).w - mx) * inv;
   }
 }
 
@@ -174,6 +117,7 @@ struct DecBuffers {
   __half* slots16;
   float* taps32;
   __half *actA, *actB;
+  float* maps4;
 };
 
 static size_t align256d(size_t n) { return (n + 255) & ~size_t(255); }
@@ -192,6 +136,7 @@ static size_t dec_carve(const tocvp_dec_weights& w, int n_frames, DecBuffers* db
   t.taps32 = reinterpret_cast<float*>(take(nsi * 25 * w.hidden * 4));
   t.actA = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
   t.actB = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
+  t.maps4 = reinterpret_cast<float*>(take(nsi * w.H * w.W * 4 * 4));
   if (db) *db = t;
   return off;
 }
@@ -212,16 +157,11 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
                                  void* const* conv_events, int n_conv_events) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && slots && recons_imgs && workspace && n_frames > 0);
-  TOCVP_CHECK_ARG(w->hidden == 64 && w->slot_dim % 8 == 0 && w->H % C3_TH == 0 && w->W % C3_TW == 0 && w->H >= 5 && w->W >= 5);
+  TOCVP_CHECK_ARG(w->hidden == 64 && w->slot_dim % 8 == 0 && w->H % 16 == 0 && w->W % 32 == 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   if (ws_bytes < dec_carve(*w, n_frames, nullptr, nullptr)) {
     set_last_error(__FILE__, __LINE__, "savi_decode: workspace too small");
     return TOCVP_ERR_WORKSPACE;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv3x3_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
-    attr_set = true;
   }
   DecBuffers db;
   dec_carve(*w, n_frames, &db, static_cast<uint8_t*>(workspace));
@@ -247,10 +187,13 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
                             W, C, C, 1, st));
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev + 1]), st));
     }
-    const dim3 grid((H / C3_TH) * (W / C3_TW), nf);
-    conv3x3_composite_kernel<<<grid, 256, C3_SMEM, st>>>(
-        db.actB, w->w_out, w->b_out, recons_imgs + size_t(f0) * 3 * plane,
-        recons ? recons + size_t(f0) * S * 3 * plane : nullptr, masks ? masks + size_t(f0) * S * plane : nullptr, S, H, W);
+    // conv3x3 64 -> 4 head on the tensor cores (N padded to 16), then softmax-over-slots compositing
+    TOCVP_TRY(conv3x3_head_f16(db.actB, static_cast<const __half*>(w->w_out), w->b_out, db.maps4, nsi, H, W, st));
+    const size_t npix = size_t(nf) * plane;
+    composite_kernel<<<int((npix + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(db.maps4), recons_imgs + size_t(f0) * 3 * plane,
+        recons ? recons + size_t(f0) * S * 3 * plane : nullptr, masks ? masks + size_t(f0) * S * plane : nullptr, S,
+        int(plane), nf);
     TOCVP_LAUNCHED();
   }
   return TOCVP_OK;

@@ -97,9 +97,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t leader = elect_one_sync();
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -108,7 +110,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t bph = (it >> 1) & 1;
         mbar_wait(&tempty[b], bph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(b * BN);
+        const uint32_t d_tmem = tmem_u + uint32_t(b * BN);
+#pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -118,12 +121,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0, leader);
           }
-          umma_commit(&empty[s]);
+          umma_commit(&empty[s], leader);
           if (++s == S::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[b]);
+        umma_commit(&tfull[b], leader);
       }
     }
   } else {

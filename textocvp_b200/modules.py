@@ -465,7 +465,9 @@ class SAVi(_Packed):
         for i in range(3):
             d[f"wc{i}"] = _f16(convs[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 64, 64))
             d[f"bc{i}"] = _f32(convs[i + 1].bias)
-        d["w_out"] = _f32(last.weight.permute(2, 3, 1, 0).reshape(9, 64, 4))
+        wo = torch.zeros(9, 16, 64, device=dev)                                  # N padded 4 -> 16 (UMMA minimum for M=128)
+        wo[:, :4] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
+        d["w_out"] = _f16(wo)
         d["b_out"] = _f32(last.bias)
         dw = DecW()
         dw.w1_taps, dw.p1, dw.w_out, dw.b_out = (d[n].data_ptr() for n in ("w1_taps", "p1", "w_out", "b_out"))
