@@ -193,7 +193,7 @@ __device__ void linear_T(const float* __restrict__ Wt, const float* __restrict__
       const float bv = bias ? bias[o] : 0.f;
 #pragma unroll
       for (int r = 0; r < UP_R; ++r) acc[r] = bv;
-#pragma unroll 4
+#pragma unroll 16
       for (int k = 0; k < IN; ++k) {
         const float w = __ldg(Wt + size_t(k) * OUT + o);
         const float4* xr = reinterpret_cast<const float4*>(xs + k * UP_R);
@@ -214,7 +214,7 @@ __device__ void linear_T(const float* __restrict__ Wt, const float* __restrict__
     const float bv = bias ? bias[o] : 0.f;
 #pragma unroll
     for (int r = 0; r < RP; ++r) acc[r] = bv;
-#pragma unroll 4
+#pragma unroll 16
     for (int k = 0; k < IN; ++k) {
       const float w = __ldg(Wt + size_t(k) * OUT + o);
       const float4* xr = reinterpret_cast<const float4*>(xs + k * UP_R + half * RP);

@@ -72,3 +72,11 @@ class MetricSums:
         mf = (self.acc[self.F:2 * self.F] / n).tolist()
         return {"count": int(n), "psnr_mean": sum(pf) / len(pf), "psnr_per_frame": pf, "mse_mean": sum(mf) / len(mf),
                 "mse_per_frame": mf}
+
+
+def shard_range(rank: int, world: int, total: int):
+    """Sequences [lo, hi) owned by `rank` when `total` sequences are sharded by batch over `world` ranks
+    (rank r <- sequences [r*B/G, (r+1)*B/G); remainders go to the first ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
