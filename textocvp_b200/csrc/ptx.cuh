@@ -132,6 +132,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt) 
   return (1u << 4) | (uint32_t(ab_fmt) << 7) | (uint32_t(ab_fmt) << 10) | (uint32_t(N >> 3) << 17) |
          (uint32_t(M >> 4) << 24);
 }
+// Same with explicit operand majors (0 = K-major, 1 = MN-major).
+__host__ __device__ constexpr uint32_t make_idesc_f16_ex(int M, int N, int ab_fmt, int a_mn_major, int b_mn_major) {
+  return make_idesc_f16(M, N, ab_fmt) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16);
+}
+// Generic 128B-swizzle descriptor: for K-major operands lbo is ignored and sbo = stride between 8-row groups; for
+// MN-major operands lbo = stride between 64-element (128 B) blocks along M/N, sbo = stride between 8-deep K groups.
+__device__ __forceinline__ uint64_t make_desc_sw128_ex(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B.
 // sbo_bytes = distance between consecutive 8-row groups.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
@@ -149,6 +159,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

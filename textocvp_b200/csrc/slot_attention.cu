@@ -11,14 +11,13 @@
 // iteration's query / g vectors, or the transition block after the last iteration).  All of it fp32.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "slot_attention.h"
 
 namespace tocvp {
 
-constexpr int SA_S = 8;        // slots
-constexpr int SA_D = 128;      // slot dim == feature dim (named configs)
-constexpr int SA_CHUNKS = 8;   // location chunks per sequence (grid.x of the streaming kernel)
-constexpr int SA_GVEC = SA_S * SA_D + 2 * SA_S;   // g[8][128], sg[8], cb[8] per sequence
-constexpr int SA_PART = SA_S * SA_D + 2 * SA_S;   // Uacc[8][128], A[8], Mw[8] per (sequence, chunk)
+int sa_stream_tc(const __half* feats, size_t seq_stride, int B, int N, const float* gvec, float* partial, float ln_eps,
+                 float attn_eps, cudaStream_t stream);
+
 
 template <typename T>
 __device__ __forceinline__ float4 ldx4(const T* p);
@@ -424,7 +423,7 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
                    cudaStream_t stream) {
   TOCVP_CHECK_ARG(feats && slots_in && slots_out && workspace && B > 0 && iters >= 1);
   TOCVP_CHECK_ARG(feats_seq_stride >= size_t(N) * SA_D && feats_seq_stride % 8 == 0);
-  TOCVP_CHECK_ARG(N % (SA_CHUNKS * 4) == 0 && w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
+  TOCVP_CHECK_ARG(N % (SA_CHUNKS * 128) == 0 && w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
   TOCVP_CHECK_ARG(pred_out == nullptr || (w.t_heads > 0 && SA_D % w.t_heads == 0 && w.t_hidden % 256 == 0));
   if (ws_bytes < slot_attention_workspace_bytes(B)) {
     set_last_error(__FILE__, __LINE__, "slot_attention: workspace too small");
@@ -437,13 +436,16 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
   const float* cur = slots_in;
   for (int it = 0; it < iters; ++it) {
     const dim3 grid(SA_CHUNKS, B);
-    if (feats_f16)
-      sa_stream_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(feats), feats_seq_stride, N, gvec, partial,
-                                                         w.ln_eps_sa, w.attn_eps);
-    else
-      sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec, partial,
-                                                        w.ln_eps_sa, w.attn_eps);
-    TOCVP_LAUNCHED();
+    if (feats_f16) {
+      // pipeline format: tcgen05 streaming kernel (slot_attention_tc.cu)
+      TOCVP_TRY(sa_stream_tc(static_cast<const __half*>(feats), feats_seq_stride, B, N, gvec, partial, w.ln_eps_sa,
+                             w.attn_eps, stream));
+    } else {
+      // fp32 features (the reference dtype at the module boundary): all-fp32 SIMT kernel
+      sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec,
+                                                        partial, w.ln_eps_sa, w.attn_eps);
+      TOCVP_LAUNCHED();
+    }
     const bool last = (it == iters - 1);
     if (!last) {
       TOCVP_TRY(launch_update(w, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, SA_S * SA_D, nullptr, gvec, stream));
