@@ -14,7 +14,8 @@
 //   end: U (hi + lo columns) -> partial[b][chunk][slot][ch]; A_i = sum a, Mw_i = sum w*mu reduced from registers.
 //
 // warp 0: TMA producer (3-stage ring)   warp 1: TMEM alloc + MMA issue (MMA1 of tile t+1 is issued before MMA2 of tile t)
-// warps 2-5: softmax / epilogue.  ~113 KB smem and 128 TMEM columns per CTA -> 2 CTAs per SM.
+// warps 2-5 / 6-9: two softmax groups working on even / odd tiles (each owns one D1 and one Wt buffer), so the
+// per-tile register-level latency chain of one group overlaps the other's.  ~113 KB smem, 128 TMEM columns -> 2 CTAs / SM.
 #include "host_util.h"
 #include "ptx.cuh"
 #include "slot_attention.h"
@@ -29,7 +30,7 @@ constexpr int ST_W_BYTES = 2 * 16 * 128;        // Wt: two location halves of [1
 constexpr int ST_OFF_G = ST_STAGES * ST_X_BYTES;
 constexpr int ST_OFF_W = ST_OFF_G + ST_G_BYTES;
 constexpr int ST_OFF_BAR = ST_OFF_W + 2 * ST_W_BYTES;
-constexpr int ST_SMEM = ST_OFF_BAR + 256 + 1024;
+constexpr int ST_SMEM = ST_OFF_BAR + 1024 + 1024;   // barriers + reduction scratch, alignment slack
 constexpr int ST_TMEM_COLS = 128;               // D1: 2 x 32 columns, U: 16 columns at column 64
 
 // byte offset of element (row r, k-element e) in a K-major 128B-swizzled operand stored as halves of 64 k-elements
@@ -38,7 +39,9 @@ __device__ __forceinline__ uint32_t sw128_kmajor_off(int r, int e, int rows_per_
   return uint32_t(half * rows_per_half * 128 + r * 128 + ((((ee >> 3) ^ (r & 7)) << 4) | ((ee & 7) << 1)));
 }
 
-__global__ void __launch_bounds__(192, 2)
+constexpr int ST_THREADS = 320;   // TMA warp, MMA warp, 2 softmax groups of 4 warps (even / odd tiles)
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
 sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ gvec, float* __restrict__ partial,
                     int tiles_per_chunk, float ln_eps, float attn_eps) {
   extern __shared__ uint8_t smem_raw[];
@@ -52,7 +55,7 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
   uint64_t* w_empty = w_full + 2;           // [2]
   uint64_t* u_full = w_empty + 2;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
-  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][16]
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][16]
 
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,18 +76,29 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, ST_TMEM_COLS);
-  // ---- Gt operand: rows 0-7 g_hi, 8-15 g_lo, 16 ones, 17-31 zero (K-major, swizzled exactly as TMA would write it)
-  for (int e = threadIdx.x; e < 32 * SA_D; e += blockDim.x) {
-    const int r = e / SA_D, ch = e % SA_D;
-    __half val = __float2half_rn(0.f);
-    if (r < 16) {
-      const float g = gv[(r & 7) * SA_D + ch];
-      const __half hi = __float2half_rn(g);
-      val = (r < 8) ? hi : __float2half_rn(g - __half2float(hi));
-    } else if (r == 16) {
-      val = __float2half_rn(1.f);
+  // ---- Gt operand: rows 0-7 g_hi, 8-15 g_lo, 16 ones, 17-31 zero (K-major, swizzled exactly as TMA would write it);
+  //      one 16-byte chunk (8 channels) per item
+  for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
+    const int r = e >> 4, c16 = e & 15;                 // row, 8-channel chunk
+    const int half = c16 >> 3, c = c16 & 7;
+    uint8_t* dst = sG + half * 32 * 128 + r * 128 + ((c ^ (r & 7)) << 4);
+    if (r < 8) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gv + r * SA_D + c16 * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gv + r * SA_D + c16 * 8 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half h0 = __float2half_rn(g[2 * j]), h1 = __float2half_rn(g[2 * j + 1]);
+        hi[j] = pack_half2(__half2float(h0), __half2float(h1));
+        lo[j] = pack_half2(g[2 * j] - __half2float(h0), g[2 * j + 1] - __half2float(h1));
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + 8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);   // row r+8: same swizzle phase
+    } else if (r >= 16) {
+      const uint32_t one2 = (r == 16) ? 0x3C003C00u : 0u;   // half2(1, 1)
+      *reinterpret_cast<uint4*>(dst) = make_uint4(one2, one2, one2, one2);
     }
-    *reinterpret_cast<__half*>(sG + sw128_kmajor_off(r, ch, 32)) = val;
   }
   fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
@@ -150,6 +164,7 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
   } else {
     // ---------------------------------------------------------------- softmax warps: thread = location / channel
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;        // 0: even tiles, 1: odd tiles
     const int row = q * 32 + lane;          // TMEM lane
     float sg[SA_S], cb[SA_S], a_acc[SA_S], mw_acc[SA_S];
 #pragma unroll
@@ -159,11 +174,11 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
       a_acc[i] = 0.f;
       mw_acc[i] = 0.f;
     }
-    for (int t = 0; t < tiles_per_chunk; ++t) {
+    for (int t = grp; t < tiles_per_chunk; t += 2) {
       const int s = t % ST_STAGES;
       mbar_wait(&x_full[s], (t / ST_STAGES) & 1);      // acquire the TMA-written tile for generic loads
       const uint8_t* xr = smem + s * ST_X_BYTES + row * 128;
-      float ssq = 0.f;
+      float sq[4] = {0.f, 0.f, 0.f, 0.f};               // independent chains (ILP)
 #pragma unroll
       for (int hc = 0; hc < 16; ++hc) {
         const int half = hc >> 3, c = hc & 7;
@@ -172,9 +187,10 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-          ssq += f.x * f.x + f.y * f.y;
+          sq[j] += f.x * f.x + f.y * f.y;
         }
       }
+      const float ssq = (sq[0] + sq[1]) + (sq[2] + sq[3]);
       mbar_wait(&d_full[t & 1], (t >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
@@ -198,7 +214,10 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
       const float inv = 1.f / den;
       // Wt buffer (t & 1) is free once MMA2 of tile t-2 has completed
       mbar_wait(&w_empty[t & 1], ((t >> 1) & 1) ^ 1);
-      uint8_t* wdst = sW + (t & 1) * ST_W_BYTES;
+      // element (slot row i, location `row`): half = row / 64, 16-byte chunk (row % 64) / 8 XOR i, halfword row % 8;
+      // the lo row 8+i has the same swizzle phase, 1024 B further
+      uint8_t* wdst = sW + (t & 1) * ST_W_BYTES + (row >> 6) * 16 * 128 + ((row & 7) << 1);
+      const int wc = (row & 63) >> 3;
 #pragma unroll
       for (int i = 0; i < SA_S; ++i) {
         const float a = d[i] * inv + attn_eps;         // softmax over SLOTS, + eps (attention.py:100)
@@ -207,22 +226,24 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
         mw_acc[i] += w * mu;
         const __half hi = __float2half_rn(w);
         const __half lo = __float2half_rn(w - __half2float(hi));
-        *reinterpret_cast<__half*>(wdst + sw128_kmajor_off(i, row, 16)) = hi;
-        *reinterpret_cast<__half*>(wdst + sw128_kmajor_off(8 + i, row, 16)) = lo;
+        *reinterpret_cast<__half*>(wdst + i * 128 + ((wc ^ i) << 4)) = hi;
+        *reinterpret_cast<__half*>(wdst + i * 128 + ((wc ^ i) << 4) + 1024) = lo;
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&w_full[t & 1]);
     }
-    // ---- results: U^T[ch = row][16] (hi + lo)  ->  partial[b][chunk][slot][ch]
-    mbar_wait(u_full, 0);
-    tc_fence_after();
-    uint32_t u[16];
-    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + 64, u);
-    tmem_ld_wait();
+    // ---- results: U^T[ch = row][16] (hi + lo)  ->  partial[b][chunk][slot][ch]   (group 0 reads TMEM)
     float* out = partial + (size_t(b) * SA_CHUNKS + chunk) * SA_PART;
+    if (grp == 0) {
+      mbar_wait(u_full, 0);
+      tc_fence_after();
+      uint32_t u[16];
+      tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + 64, u);
+      tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < SA_S; ++i) out[i * SA_D + row] = __uint_as_float(u[i]) + __uint_as_float(u[8 + i]);
+      for (int i = 0; i < SA_S; ++i) out[i * SA_D + row] = __uint_as_float(u[i]) + __uint_as_float(u[8 + i]);
+    }
 #pragma unroll
     for (int i = 0; i < SA_S; ++i) {
       a_acc[i] = warp_sum(a_acc[i]);
@@ -231,14 +252,17 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < SA_S; ++i) {
-        s_red[q * 16 + i] = a_acc[i];
-        s_red[q * 16 + 8 + i] = mw_acc[i];
+        s_red[(warp - 2) * 16 + i] = a_acc[i];
+        s_red[(warp - 2) * 16 + 8 + i] = mw_acc[i];
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x - 64 < 16) {
       const int i = threadIdx.x - 64;
-      out[SA_S * SA_D + i] = s_red[i] + s_red[16 + i] + s_red[32 + i] + s_red[48 + i];
+      float t8 = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t8 += s_red[w8 * 16 + i];
+      out[SA_S * SA_D + i] = t8;
     }
   }
 
@@ -264,7 +288,7 @@ int sa_stream_tc(const __half* feats, size_t seq_stride, int B, int N, const flo
   const uint32_t box[3] = {64, uint32_t(ST_TILE), 1};
   TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, feats, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   const dim3 grid(SA_CHUNKS, B);
-  sa_stream_tc_kernel<<<grid, 192, ST_SMEM, stream>>>(tmX, gvec, partial, N / (SA_CHUNKS * ST_TILE), ln_eps, attn_eps);
+  sa_stream_tc_kernel<<<grid, ST_THREADS, ST_SMEM, stream>>>(tmX, gvec, partial, N / (SA_CHUNKS * ST_TILE), ln_eps, attn_eps);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
