@@ -74,6 +74,34 @@ def build_reference(num_preds: int = 19, num_context: int = 1, savi_overrides=No
     return savi, pred
 
 
+def build_reference_dino(img_size: int = 128, num_patches: int = 81, num_preds: int = 29, num_context: int = 1):
+    """Reference ExtendedDINOSAUR (frozen ViT backbone replaced by identity: it is fed patch features directly, SURVEY.md
+    Appendix C) and PredictorWrapper(TextOCVP_CustomTF), from the reference's own JSONs with the BASELINE.json geometry."""
+    _prepare()
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import torch
+            import lib.setup_model as sm
+            import models.ExtendedDINOSAUR as ED
+            from CONFIG import DEFAULTS
+            ED.get_encoder = lambda **kw: torch.nn.Identity()
+            mp = json.load(open("src/configs/models/ExtendedDINOSAUR.json"))
+            mp["img_size"] = img_size
+            mp["decoder"]["decoder_params"]["num_patches"] = num_patches
+            pp = json.load(open("src/configs/predictors/TextOCVP_CustomTF.json"))
+            exp = {"model": {"model_name": "ExtendedDINOSAUR", "model_params": mp},
+                   "predictor": pp,
+                   "prediction_params": {**DEFAULTS["prediction_params"],
+                                         "num_context": num_context, "num_preds": num_preds}}
+            dino = sm.setup_model(copy.deepcopy(exp["model"])).eval()
+            pred = sm.setup_predictor(copy.deepcopy(exp)).eval()
+    finally:
+        os.chdir(cwd)
+    return dino, pred
+
+
 def _deep_update(d, u):
     d = copy.deepcopy(d)
     for k, v in u.items():
@@ -86,7 +114,8 @@ def _deep_update(d, u):
 
 def load_weights(savi, pred, savi_sd, pred_sd):
     """Strict load of our generated dicts into the reference modules (proves the key contract)."""
-    savi.load_state_dict(savi_sd, strict=True)
+    if savi is not None:
+        savi.load_state_dict(savi_sd, strict=True)
     body = pred.predictor
     full = dict(body.state_dict())
     for k, v in pred_sd.items():

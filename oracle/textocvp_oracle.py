@@ -291,6 +291,112 @@ def predictor_rollout(sd: SD, slot_history: Tensor, text: Tensor, cfg: PredCfg,
 
 
 # --------------------------------------------------------------------------------------
+# ExtendedDINOSAUR (src/models/ExtendedDINOSAUR.py:97-102, 139-214) with MLPPatchDecoder
+# (src/models/EncodersDecoders/decoders.py:129-365).  The frozen ViT backbone is replaced by
+# synthetic patch features [B,T,N,768] (north star), i.e. ``encoder`` = identity.
+# --------------------------------------------------------------------------------------
+@dataclass
+class DinoCfg:
+    """src/configs/models/ExtendedDINOSAUR.json (img_size / num_patches per BASELINE.json config 4)"""
+    num_slots: int = 10
+    slot_dim: int = 128
+    num_iterations_first: int = 3
+    num_iterations: int = 1
+    in_channels: int = 3
+    img_size: int = 128
+    num_patches: int = 81
+    transition_heads: int = 4
+    sa_eps: float = 1e-8
+    sa_ln_eps: float = 1e-3
+    tf_ln_eps: float = 1e-6
+    bn_eps: float = 1e-5          # nn.BatchNorm2d default (model_blocks.py:93)
+
+
+def dino_project(sd: SD, feats: Tensor) -> Tensor:
+    """linear_feat_proj (ExtendedDINOSAUR.py:97-102): LN(768) -> Linear -> ReLU -> Linear(->slot_dim)."""
+    x = _ln(feats, sd, "linear_feat_proj.0", 1e-5)
+    x = F.relu(_lin(x, sd, "linear_feat_proj.1"))
+    return _lin(x, sd, "linear_feat_proj.3")
+
+
+def dino_decomp(sd: SD, feats: Tensor, num_imgs: int, cfg: DinoCfg, init_slots: Tensor) -> Tensor:
+    """feats [B,T,N,768] (ViT patch features) -> slot_history [B,num_imgs,S,D] (ExtendedDINOSAUR.py:176-205)."""
+    predicted = init_slots
+    hist = []
+    for t in range(num_imgs):
+        proj = dino_project(sd, feats[:, t])
+        slots = slot_attention(sd, proj, predicted, t, cfg)
+        predicted = transition(sd, slots, cfg)
+        hist.append(slots)
+    return torch.stack(hist, dim=1)
+
+
+def patch_mlp(sd: SD, slots: Tensor, prefix: str = "decoder") -> Tensor:
+    """broadcast + pos_embed + MLP (decoders.py:244-249, 309-322): slots [B,S,D] -> [B,S,N,out_dim]."""
+    pos = sd[prefix + ".pos_embed"]                                        # [1,1,N,D]
+    x = slots.unsqueeze(2) + pos                                           # decoders.py:152-199
+    i = 0
+    if f"{prefix}.mlp.0.weight" in sd and sd[f"{prefix}.mlp.0.weight"].dim() == 1:   # initial_layer_norm
+        x = _ln(x, sd, f"{prefix}.mlp.0", 1e-5)
+        i = 1
+    while f"{prefix}.mlp.{i}.weight" in sd:
+        x = _lin(x, sd, f"{prefix}.mlp.{i}")
+        i += 1
+        if f"{prefix}.mlp.{i + 1}.weight" in sd:                           # ReLU between linears only
+            x = F.relu(x)
+        i += 1
+    return x
+
+
+def patch_cnn(sd: SD, x: Tensor, cfg: DinoCfg, prefix: str = "decoder.conv_patch_decoder") -> Tensor:
+    """conv_patch_decoder (decoders.py:325-365): [ConvBlock(3x3,BN,ReLU) (+ nearest x2)]* + conv3x3 -> 3.
+    The upsampling rule is re-derived from the layer index exactly as the builder does (patch_size 14)."""
+    idxs = sorted({int(k[len(prefix) + 1:].split(".")[0]) for k in sd if k.startswith(prefix + ".")})
+    for j, i in enumerate(idxs):
+        p = f"{prefix}.{i}"
+        if f"{p}.block.0.weight" in sd:
+            x = F.conv2d(x, sd[f"{p}.block.0.weight"], sd[f"{p}.block.0.bias"], padding=1)
+            x = F.batch_norm(x, sd[f"{p}.block.1.running_mean"], sd[f"{p}.block.1.running_var"],
+                             sd[f"{p}.block.1.weight"], sd[f"{p}.block.1.bias"], False, 0.0, cfg.bn_eps)
+            x = F.relu(x)
+            nxt = idxs[j + 1] if j + 1 < len(idxs) else i + 1
+            if nxt == i + 2:                                               # an Upsample module sits between (no params)
+                x = F.interpolate(x.contiguous(), scale_factor=2, mode="nearest")
+        else:
+            x = F.conv2d(x, sd[f"{p}.weight"], sd[f"{p}.bias"], padding=1)
+    return x
+
+
+def mlp_patch_decode(sd: SD, slots: Tensor, cfg: DinoCfg) -> Dict[str, Tensor]:
+    """MLPPatchDecoder.forward (decoders.py:232-282)."""
+    B, S, _ = slots.shape
+    dec = patch_mlp(sd, slots)
+    feats, alpha = dec[..., :-1], dec[..., -1:]
+    alpha = F.softmax(alpha, dim=1)                                        # over slots
+    recons_feats = torch.sum(feats * alpha, dim=1)                         # [B,N,768]
+    g = int(cfg.num_patches ** 0.5)
+    masks = alpha.reshape(B, S, 1, g, g)
+    x = recons_feats.permute(0, 2, 1).reshape(B, feats.shape[-1], g, g)
+    imgs = patch_cnn(sd, x, cfg)
+    if imgs.shape[-1] != cfg.img_size:
+        imgs = F.interpolate(imgs, size=(cfg.img_size, cfg.img_size), mode="bilinear", align_corners=False)
+    return {"recons_imgs": imgs, "recons_feats": recons_feats, "masks": masks}
+
+
+def dino_rollout(dino_sd: SD, pred_sd: SD, feats: Tensor, text: Tensor, init_slots: Tensor, dcfg: DinoCfg,
+                 pcfg: PredCfg, num_imgs: Optional[int] = None) -> Dict[str, Tensor]:
+    """Evaluator composition for the CLIPort / ExtendedDINOSAUR shape (05_evaluate_predictor.py:82-96)."""
+    B = feats.shape[0]
+    num_imgs = pcfg.num_context + pcfg.num_preds if num_imgs is None else num_imgs
+    sh = dino_decomp(dino_sd, feats, num_imgs, dcfg, init_slots)
+    ps = predictor_rollout(pred_sd, sh, text, pcfg)
+    dec = mlp_patch_decode(dino_sd, ps.reshape(B * pcfg.num_preds, dcfg.num_slots, dcfg.slot_dim), dcfg)
+    imgs = dec["recons_imgs"].view(B, pcfg.num_preds, dcfg.in_channels, dcfg.img_size, dcfg.img_size).clamp(0, 1)
+    return {"slot_history": sh, "pred_slots": ps, "pred_imgs": imgs,
+            "pred_feats": dec["recons_feats"].view(B, pcfg.num_preds, dcfg.num_patches, -1)}
+
+
+# --------------------------------------------------------------------------------------
 # Evaluator.forward_eval composition (05_evaluate_predictor.py:82-96) and PSNR
 # --------------------------------------------------------------------------------------
 def rollout(savi_sd: SD, pred_sd: SD, videos: Tensor, text: Tensor, init_slots: Tensor,

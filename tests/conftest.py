@@ -28,3 +28,21 @@ def golden_weights(golden):
     videos, text, noise = weights.synthetic_inputs(m["B"], m["T"], m["L"], seed=m["input_seed"])
     init = savi_sd["initializer.slots_mu"] + savi_sd["initializer.slots_sigma"] * noise
     return dict(savi_sd=savi_sd, pred_sd=pred_sd, videos=videos, text=text, init=init)
+
+
+@pytest.fixture(scope="session")
+def golden_dino():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "cliport_b2.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_dino_weights(golden_dino):
+    from textocvp_b200 import weights
+    m = golden_dino["meta"]
+    dsd = weights.dino_state_dict(m["dino_seed"], img_size=m["img_size"], num_patches=m["N"],
+                                  bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"], bn_jitter=m["bn_jitter"])
+    psd = weights.predictor_state_dict(m["pred_seed"], mlp_out_scale=m["mlp_out_scale"], ln_jitter=m["ln_jitter"])
+    feats, text, noise = weights.synthetic_dino_inputs(m["B"], m["T"], m["N"], L=m["L"], seed=m["input_seed"])
+    init = dsd["initializer.slots_mu"] + dsd["initializer.slots_sigma"] * noise
+    return dict(dino_sd=dsd, pred_sd=psd, feats=feats, text=text, init=init)

@@ -43,3 +43,36 @@ def test_full_rollout(golden, golden_weights):
     assert O.rel_err(out["pred_slots"], g["pred_slots"]) < 1e-4
     p = O.psnr(out["pred_imgs"], g["pred_imgs"])
     assert p.min() > 70.0, p.min()   # eps=1e-8 caps PSNR at 80 dB
+
+
+# ---------------------------------------------------------------- CLIPort / ExtendedDINOSAUR shape (configs[3])
+def test_dino_stage_vectors(golden_dino, golden_dino_weights):
+    g, w = golden_dino, golden_dino_weights
+    cfg = O.DinoCfg(img_size=g["meta"]["img_size"], num_patches=g["meta"]["N"])
+    sd = w["dino_sd"]
+    proj = O.dino_project(sd, w["feats"][:, 0])
+    assert O.rel_err(proj, g["proj_feats"]) < TOL
+    assert O.rel_err(O.slot_attention(sd, proj, w["init"], 0, cfg), g["sa_step0"]) < TOL
+    assert O.rel_err(O.slot_attention(sd, proj, w["init"], 1, cfg), g["sa_step1"]) < TOL
+    assert O.rel_err(O.transition(sd, g["sa_step0"], cfg), g["transition"]) < TOL
+
+
+def test_dino_decode(golden_dino, golden_dino_weights):
+    g, w = golden_dino, golden_dino_weights
+    cfg = O.DinoCfg(img_size=g["meta"]["img_size"], num_patches=g["meta"]["N"])
+    dec = O.mlp_patch_decode(w["dino_sd"], g["pred_slots"].reshape(-1, 10, 128), cfg)
+    assert O.rel_err(dec["recons_feats"], g["pred_feats"]) < TOL
+    assert O.rel_err(dec["masks"], g["pred_masks"]) < TOL
+    assert O.rel_err(dec["recons_imgs"], g["pred_imgs"]) < 1e-4
+
+
+def test_dino_rollout(golden_dino, golden_dino_weights):
+    g, w = golden_dino, golden_dino_weights
+    m = g["meta"]
+    cfg = O.DinoCfg(img_size=m["img_size"], num_patches=m["N"])
+    pcfg = O.PredCfg(num_context=m["num_context"], num_preds=m["num_preds"])
+    out = O.dino_rollout(w["dino_sd"], w["pred_sd"], w["feats"], w["text"], w["init"], cfg, pcfg, num_imgs=m["T"])
+    assert O.rel_err(out["slot_history"], g["slot_history"]) < 1e-4
+    assert O.rel_err(out["pred_slots"], g["pred_slots"]) < 1e-4
+    p = O.psnr(out["pred_imgs"], g["pred_imgs"].view_as(out["pred_imgs"]).clamp(0, 1))
+    assert p.min() > 70.0, p.min()

@@ -165,3 +165,103 @@ def synthetic_inputs(B: int, T: int = 20, L: int = 32, token_dim: int = 512, num
     text = torch.randn(B, L, token_dim, generator=g)
     noise = torch.randn(B, num_slots, slot_dim, generator=g)
     return videos, text, noise
+
+
+def dino_cnn_plan(img_size: int, num_patches: int, hidden_dim: int = 1024, in_dim: int = 768, num_layers: int = 4,
+                  patch_size: int = 14):
+    """Channel / upsampling plan of MLPPatchDecoder._build_conv_patch_decoder (reference
+    src/models/EncodersDecoders/decoders.py:325-365): list of (cin, cout, upsample_after) + module indices."""
+    plan, idx, cur, h = [], 0, int(num_patches ** 0.5), hidden_dim
+    for i in range(num_layers):
+        cin = in_dim if i == 0 else h
+        if i > 0 and (i + 1) * 2 < patch_size and cur < img_size:
+            h = h // 2
+        up = (i + 1) * 2 < patch_size and cur < img_size
+        plan.append(dict(index=idx, cin=cin, cout=h, up=up))
+        idx += 2 if up else 1
+        if up:
+            cur *= 2
+    return plan, idx, h, cur          # conv blocks, index of the final conv, its input channels, final spatial size
+
+
+def dino_state_dict(seed: int = 16, num_slots: int = 10, slot_dim: int = 128, feat_dim: int = 768,
+                    img_size: int = 128, num_patches: int = 81, mlp_hidden: int = 512, transition_mlp: int = 512,
+                    dec_hidden: int = 1024, dec_layers: int = 4, cnn_layers: int = 4, patch_size: int = 14,
+                    bias_scale: float = 0.0, ln_jitter: float = 0.0, bn_jitter: float = 0.0) -> Dict[str, Tensor]:
+    """ExtendedDINOSAUR (src/models/ExtendedDINOSAUR.py, configs/models/ExtendedDINOSAUR.json) parameters without the
+    frozen ViT backbone (replaced by synthetic patch features).  init_xavier_ on linear_feat_proj / transition /
+    slot_attention / decoder (ExtendedDINOSAUR.py:222-236); BatchNorm running statistics default to (0, 1) and are
+    perturbed by ``bn_jitter`` so that tests exercise the eval-mode BN folding."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    D = slot_dim
+
+    def bias(n):
+        return bias_scale * torch.randn(n, generator=g)
+
+    lim = math.sqrt(6.0 / (1 + D))
+    sd["initializer.slots_mu"] = (torch.rand(1, 1, D, generator=g) * 2 - 1) * lim
+    sd["initializer.slots_sigma"] = (torch.rand(1, 1, D, generator=g) * 2 - 1) * lim
+    for n in "qkv":
+        sd[f"transition_module.attn.{n}.weight"] = _xavier(g, D, D)
+    sd["transition_module.attn.out_projection.0.weight"] = _xavier(g, D, D)
+    sd["transition_module.mlp.0.weight"] = _xavier(g, transition_mlp, D)
+    sd["transition_module.mlp.0.bias"] = bias(transition_mlp)
+    sd["transition_module.mlp.2.weight"] = _xavier(g, D, transition_mlp)
+    sd["transition_module.mlp.2.bias"] = bias(D)
+    _ln(sd, "transition_module.layernorm_query", D, g, ln_jitter)
+    _ln(sd, "transition_module.layernorm_mlp", D, g, ln_jitter)
+    _ln(sd, "linear_feat_proj.0", feat_dim, g, ln_jitter)
+    sd["linear_feat_proj.1.weight"] = _xavier(g, feat_dim, feat_dim)
+    sd["linear_feat_proj.1.bias"] = bias(feat_dim)
+    sd["linear_feat_proj.3.weight"] = _xavier(g, D, feat_dim)
+    sd["linear_feat_proj.3.bias"] = bias(D)
+    # MLPPatchDecoder
+    sd["decoder.pos_embed"] = torch.randn(1, 1, num_patches, D, generator=g) / (D ** 0.5)
+    _ln(sd, "decoder.mlp.0", D, g, ln_jitter)
+    out_dim = feat_dim + 1
+    for i in range(dec_layers):
+        d1 = dec_hidden if i > 0 else D
+        d2 = dec_hidden if i < dec_layers - 1 else out_dim
+        sd[f"decoder.mlp.{1 + 2 * i}.weight"] = _xavier(g, d2, d1)
+        sd[f"decoder.mlp.{1 + 2 * i}.bias"] = bias(d2)
+    plan, last_idx, last_c, _ = dino_cnn_plan(img_size, num_patches, dec_hidden, feat_dim, cnn_layers, patch_size)
+    for blk in plan:
+        p = f"decoder.conv_patch_decoder.{blk['index']}.block"
+        c = blk["cout"]
+        sd[f"{p}.0.weight"] = _xavier(g, c, blk["cin"], 3, 3)
+        sd[f"{p}.0.bias"] = bias(c)
+        sd[f"{p}.1.weight"] = 1.0 + bn_jitter * torch.randn(c, generator=g)
+        sd[f"{p}.1.bias"] = bn_jitter * torch.randn(c, generator=g)
+        sd[f"{p}.1.running_mean"] = bn_jitter * torch.randn(c, generator=g)
+        sd[f"{p}.1.running_var"] = 1.0 + bn_jitter * (torch.rand(c, generator=g) - 0.5)
+        sd[f"{p}.1.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    sd[f"decoder.conv_patch_decoder.{last_idx}.weight"] = _xavier(g, 3, last_c, 3, 3)
+    sd[f"decoder.conv_patch_decoder.{last_idx}.bias"] = bias(3)
+    # slot attention
+    _ln(sd, "slot_attention.norm_input", D, g, ln_jitter)
+    _ln(sd, "slot_attention.norm_slot", D, g, ln_jitter)
+    _ln(sd, "slot_attention.norm_mlp", D, g, ln_jitter)
+    for nm in ("to_q", "to_k", "to_v"):
+        sd[f"slot_attention.{nm}.weight"] = _xavier(g, D, D)
+        sd[f"slot_attention.{nm}.bias"] = bias(D)
+    sd["slot_attention.gru.weight_ih"] = _xavier(g, 3 * D, D)
+    q, _ = torch.linalg.qr(torch.randn(3 * D, D, generator=g))
+    sd["slot_attention.gru.weight_hh"] = q.contiguous()
+    sd["slot_attention.gru.bias_ih"] = bias(3 * D)
+    sd["slot_attention.gru.bias_hh"] = bias(3 * D)
+    sd["slot_attention.mlp.0.weight"] = _xavier(g, mlp_hidden, D)
+    sd["slot_attention.mlp.0.bias"] = bias(mlp_hidden)
+    sd["slot_attention.mlp.2.weight"] = _xavier(g, D, mlp_hidden)
+    sd["slot_attention.mlp.2.bias"] = bias(D)
+    return sd
+
+
+def synthetic_dino_inputs(B: int, T: int = 30, N: int = 81, feat_dim: int = 768, L: int = 16, token_dim: int = 512,
+                          num_slots: int = 10, slot_dim: int = 128, seed: int = 0):
+    """ViT patch features N(0,1) [B,T,N,768] (stand-in for the frozen DINOv2 backbone), text [B,L,512], slot noise."""
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, T, N, feat_dim, generator=g)
+    text = torch.randn(B, L, token_dim, generator=g)
+    noise = torch.randn(B, num_slots, slot_dim, generator=g)
+    return feats, text, noise
