@@ -79,8 +79,9 @@ int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, vo
                       int cin, int cout, int relu, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * SAVi corrector: SlotAttention.forward (src/models/Blocks/attention.py:67-112) for 8 slots x 128-d
- * over N locations of 128-d features, plus (optionally) the post-norm transition TransformerBlock
+ * SAVi / ExtendedDINOSAUR corrector: SlotAttention.forward (src/models/Blocks/attention.py:67-112) for
+ * num_slots x 128-d slots over N locations of 128-d features (tcgen05 streaming kernel for 8 slots and
+ * N % 512 == 0 with f16 features, generic SIMT kernel otherwise), plus (optionally) the post-norm transition TransformerBlock
  * (attention.py:387-395, built at src/models/Blocks/transition_models.py:26-31).
  * All pointers are fp32 device arrays.  "_t" = transposed to [in][out]; wk is torch's [out][in].
  * ------------------------------------------------------------------------------------------ */
@@ -94,14 +95,15 @@ typedef struct tocvp_sa_weights {
   const float *t_w1_t, *t_b1, *t_w2_t, *t_b2;                                   /* transition mlp.0 / mlp.2         */
   int mlp_hidden, t_heads, t_hidden;
   float attn_eps, ln_eps_sa, ln_eps_tf, scale; /* 1e-8, 1e-3, 1e-6, dim_feats^-0.5 */
+  int num_slots;                               /* 4..11: 8 (SAVi.json) and 10 (ExtendedDINOSAUR.json) are the named ones */
 } tocvp_sa_weights;
 
 size_t tocvp_sizeof_sa_weights(void);
 size_t tocvp_slot_attention_workspace_bytes(int B);
 /* feats fp32 or f16: sequence b's [N,128] block starts at feats + b*feats_seq_stride (elements), so the features of
- * frame t inside a [B,T,N,128] encode batch are used in place; slots_in [B,8,128]; slots_out row b at
+ * frame t inside a [B,T,N,128] encode batch are used in place; slots_in [B,S,128]; slots_out row b at
  * slots_out + b*out_stride (floats), so results land straight in slot_history[:, t]; pred_out (optional) =
- * transition(slots_out) [B,8,128].  iters = num_iterations_first for step 0, else num_iterations (attention.py:90). */
+ * transition(slots_out) [B,S,128].  iters = num_iterations_first for step 0, else num_iterations (attention.py:90). */
 int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats_f16, size_t feats_seq_stride, int B,
                          int N,
                          const float* slots_in, int iters, float* slots_out, int out_stride, float* pred_out,
@@ -214,6 +216,66 @@ size_t tocvp_savi_decode_workspace_bytes(const tocvp_dec_weights* w, int n_frame
 int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots, int n_frames, float* recons_imgs, float* recons,
                       float* masks, void* workspace, size_t ws_bytes, void* stream, void* const* conv_events,
                       int n_conv_events);
+
+/* ------------------------------------------------------------------------------------------
+ * ExtendedDINOSAUR.linear_feat_proj (src/models/ExtendedDINOSAUR.py:97-102, applied at :186):
+ * LayerNorm(F) -> Linear(F,Hd) -> ReLU -> Linear(Hd,D) over rows of ViT patch features.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_proj_weights {
+  const float *ln_g, *ln_b; /* linear_feat_proj.0 [F]                */
+  const void* w1;           /* f16 [Hd, F]   linear_feat_proj.1      */
+  const float* b1;
+  const void* w2;           /* f16 [D, Hd]   linear_feat_proj.3      */
+  const float* b2;
+  int feat_dim, hidden_dim, slot_dim;
+  float ln_eps;             /* 1e-5 (nn.LayerNorm default)           */
+} tocvp_proj_weights;
+
+size_t tocvp_sizeof_proj_weights(void);
+size_t tocvp_dino_project_workspace_bytes(const tocvp_proj_weights* w, int rows);
+/* feats fp32 [rows, F] -> projected features [rows, D] as f16 and/or fp32 (either may be NULL, not both). */
+int tocvp_dino_project(const tocvp_proj_weights* w, const float* feats, int rows, void* out_f16, float* out_f32,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MLPPatchDecoder.forward (src/models/EncodersDecoders/decoders.py:232-282; MLP built at :309-322,
+ * CNN at :325-365; BasePatchDecoder.broadcast_slots / add_positional_encoding :152-199).
+ * Weight packing (done once per load by the host module):
+ *   mlp_w[i]  f16 [out_i, in_i] = torch Linear weight; the last layer (out = feat_dim + 1, alpha last) is zero-padded
+ *             to a multiple of 8 rows, its bias likewise.
+ *   cnn_w[i]  ConvBlock i with eval-mode BatchNorm folded in (w' = w * gamma/sqrt(var+eps), b' = (b-mean)*scale+beta):
+ *             cnn_up[i] == 0: f16 [cout, 9*cin], K index = (ky*3+kx)*cin + ci;
+ *             cnn_up[i] == 1 (an Upsample(2) precedes the conv: it is folded into 4 phase convolutions on the
+ *             low-resolution input): f16 [4*cout, 4*cin], row = (py*2+px)*cout + co, K index = (dy*2+dx)*cin + ci,
+ *             weight = sum of the 3x3 taps that land on low-res offset (dy+py-1, dx+px-1); bias repeated per phase.
+ *   out_w     final conv3x3 -> 3 channels, padded to 4: out_up == 1: f16 [64 rows allocated, 16 used; 9*cin], row =
+ *             phase*4 + c, K index = (oy*3+ox)*cin + ci over the low-res 3x3 neighbourhood (zeros where a phase does not
+ *             see a tap); out_up == 0: rows = c (8 used).  out_b fp32 [16] / [8].
+ * ------------------------------------------------------------------------------------------ */
+#define TOCVP_PATCH_MAX_MLP 6
+#define TOCVP_PATCH_MAX_CNN 6
+typedef struct tocvp_patch_weights {
+  const float* pos_embed;   /* fp32 [N, D]  decoder.pos_embed                    */
+  const float *ln_g, *ln_b; /* decoder.mlp.0 (initial_layer_norm)                */
+  const void* mlp_w[TOCVP_PATCH_MAX_MLP];
+  const float* mlp_b[TOCVP_PATCH_MAX_MLP];
+  const void* cnn_w[TOCVP_PATCH_MAX_CNN];
+  const float* cnn_b[TOCVP_PATCH_MAX_CNN];
+  const void* out_w;
+  const float* out_b;
+  int mlp_out[TOCVP_PATCH_MAX_MLP];
+  int cnn_cin[TOCVP_PATCH_MAX_CNN], cnn_cout[TOCVP_PATCH_MAX_CNN], cnn_up[TOCVP_PATCH_MAX_CNN];
+  int n_mlp, n_cnn, out_cin, out_up, reconstruct_images;
+  int num_slots, slot_dim, num_patches, grid, feat_dim, img_size;
+  float ln_eps;             /* 1e-5 */
+} tocvp_patch_weights;
+
+size_t tocvp_sizeof_patch_weights(void);
+size_t tocvp_patch_decode_workspace_bytes(const tocvp_patch_weights* w, int n_frames);
+/* slots fp32 [n_frames, S, D] -> recons_imgs fp32 [n_frames,3,I,I], recons_feats fp32 [n_frames,N,F],
+ * masks fp32 [n_frames,S,1,g,g]; any output may be NULL (recons_imgs == NULL skips the CNN). */
+int tocvp_patch_decode(const tocvp_patch_weights* w, const float* slots, int n_frames, float* recons_imgs,
+                       float* recons_feats, float* masks, void* workspace, size_t ws_bytes, void* stream);
 
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */

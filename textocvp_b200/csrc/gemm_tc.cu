@@ -8,6 +8,7 @@
 //               epilogue of tile i overlaps the main loop of tile i+1)
 // Replaces the cuBLAS calls behind nn.Linear at reference src/models/Blocks/attention.py:167-175,255,296-300,
 // 352-356 and src/models/Predictors/text_cond_OCVP.py:47-48, src/models/SAVi.py:117-119.
+#include "gemm.h"
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -28,6 +29,7 @@ struct GemmArgs {
   int ld32;
   __half* out16;
   int ld16;
+  ConvMap cm;             // implicit-convolution mode (CONV instantiations only)
 };
 
 template <int BN>
@@ -40,9 +42,10 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
-template <int BN>
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ GemmArgs g) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,13 +89,31 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int mb = t / tiles_n, nb = t % tiles_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], S::STAGE_BYTES);
-          uint8_t* st = smem + s * S::STAGE_BYTES;
-          tma_load_2d(&tmA, &full[s], st, kb * GEMM_BK, mb * GEMM_BM);
-          tma_load_2d(&tmB, &full[s], st + S::A_BYTES, kb * GEMM_BK, nb * BN);
-          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        if constexpr (CONV) {
+          // K-blocks are grouped by filter tap; the A tile of a tap is the same pixel rows shifted by a constant
+          const int phase = g.cm.tiles_per_phase > 0 ? nb / g.cm.tiles_per_phase : 0;
+          const int kpt = g.cm.cin / GEMM_BK;
+          int kb = 0;
+          for (int tap = 0; tap < g.cm.taps; ++tap) {
+            const int arow = mb * GEMM_BM + g.cm.off[phase][tap];
+            for (int kc = 0; kc < kpt; ++kc, ++kb) {
+              mbar_wait(&empty[s], ph ^ 1);
+              mbar_expect_tx(&full[s], S::STAGE_BYTES);
+              uint8_t* st = smem + s * S::STAGE_BYTES;
+              tma_load_2d(&tmA, &full[s], st, kc * GEMM_BK, arow);
+              tma_load_2d(&tmB, &full[s], st + S::A_BYTES, kb * GEMM_BK, nb * BN);
+              if (++s == S::STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], S::STAGE_BYTES);
+            uint8_t* st = smem + s * S::STAGE_BYTES;
+            tma_load_2d(&tmA, &full[s], st, kb * GEMM_BK, mb * GEMM_BM);
+            tma_load_2d(&tmB, &full[s], st + S::A_BYTES, kb * GEMM_BK, nb * BN);
+            if (++s == S::STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -151,9 +172,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         sbias[b * BN + et] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
       }
       const int row = mb * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < g.M;
+      bool row_ok = row < g.M;
       const int ncol0 = nb * BN + half * CW;
       const float* res_row = nullptr;
+      size_t cbase = 0;       // CONV: output pixel index of phase (0,0) for this row
+      if constexpr (CONV) {
+        const int hw = g.cm.Hp * g.cm.Wp;
+        const int img = row / hw, rem = row - img * hw;
+        const int yp = rem / g.cm.Wp, xp = rem - yp * g.cm.Wp;
+        row_ok = row_ok && yp >= 1 && yp <= g.cm.Hp - 2 && xp >= 1 && xp <= g.cm.Wp - 2;   // border rows: not stored
+        const int sc = g.cm.up ? 2 : 1;
+        cbase = (size_t(img) * g.cm.Hop + size_t((yp - 1) * sc + g.cm.pad)) * g.cm.Wop + size_t((xp - 1) * sc + g.cm.pad);
+      }
       if (g.residual != nullptr && row_ok) {
         const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
         res_row = g.residual + size_t(rr) * g.ldr;
@@ -207,6 +237,27 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
                 f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
               }
+              if constexpr (CONV) {
+                // column n -> (phase, channel); a 4-column group never straddles a phase (cpp % 4 == 0)
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {
+                  const int n4 = n + 4 * h4;
+                  const int phs = g.cm.up ? n4 / g.cm.cpp : 0;
+                  const int c = n4 - phs * g.cm.cpp;
+                  const size_t pix = cbase + size_t(phs >> 1) * g.cm.Wop + size_t(phs & 1);
+                  if (phs < 4) {
+                    if (g.out32 != nullptr)
+                      *reinterpret_cast<float4*>(g.out32 + pix * g.ld32 + c) =
+                          make_float4(f[4 * h4], f[4 * h4 + 1], f[4 * h4 + 2], f[4 * h4 + 3]);
+                    if (g.out16 != nullptr) {
+                      uint2 p2;
+                      p2.x = pack_half2(f[4 * h4], f[4 * h4 + 1]);
+                      p2.y = pack_half2(f[4 * h4 + 2], f[4 * h4 + 3]);
+                      *reinterpret_cast<uint2*>(g.out16 + pix * g.ld16 + c) = p2;
+                    }
+                  }
+                }
+              } else {
               if (g.out32 != nullptr) {
                 float* o = g.out32 + size_t(row) * g.ld32 + n;
                 *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -219,6 +270,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 p.z = pack_half2(f[4], f[5]);
                 p.w = pack_half2(f[6], f[7]);
                 *reinterpret_cast<uint4*>(g.out16 + size_t(row) * g.ld16 + n) = p;
+              }
               }
             }
           }
@@ -235,17 +287,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN>
+template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    TOCVP_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_f16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, g);
+  gemm_f16_kernel<BN, CONV><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, g);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -270,9 +322,28 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, GEMM_BM, GEMM_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn, GEMM_BK));
-  GemmArgs g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16};
-  if (bn == 64) return launch_gemm<64>(tmA, tmB, g, stream);
-  return launch_gemm<128>(tmA, tmB, g, stream);
+  GemmArgs g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{}};
+  if (bn == 64) return launch_gemm<64, false>(tmA, tmB, g, stream);
+  return launch_gemm<128, false>(tmA, tmB, g, stream);
+}
+
+int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const ConvMap& cm, const float* bias, int relu,
+                  float* out32, __half* out16, int ldo, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(X && W && n_img > 0 && N > 0 && N % 8 == 0 && (out32 || out16));
+  TOCVP_CHECK_ARG(cm.taps >= 1 && cm.taps <= 9 && cm.cin % GEMM_BK == 0 && cm.cpp % 4 == 0 && ldo % 4 == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  const long long M64 = (long long)n_img * cm.Hp * cm.Wp;
+  TOCVP_CHECK_ARG(M64 < (1ll << 31));
+  const int M = int(M64), K = cm.taps * cm.cin;
+  const int bn = (N >= 128 && (cm.tiles_per_phase == 0 || cm.cpp % 128 == 0)) ? 128 : 64;
+  TOCVP_CHECK_ARG(cm.tiles_per_phase == 0 || (cm.cpp % bn == 0 && cm.tiles_per_phase == cm.cpp / bn));
+  CUtensorMap tmA, tmB;
+  TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, GEMM_BM, GEMM_BK));
+  // W must be allocated with at least `bn` rows (narrow heads are zero-padded by the packer)
+  TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N < bn ? bn : N, K, K, bn, GEMM_BK));
+  GemmArgs g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm};
+  if (bn == 64) return launch_gemm<64, true>(tmA, tmB, g, stream);
+  return launch_gemm<128, true>(tmA, tmB, g, stream);
 }
 
 }  // namespace tocvp

@@ -26,13 +26,13 @@ __device__ __forceinline__ float4 load4<__half>(const __half* p) {
 
 template <typename TIN>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const TIN* __restrict__ x, int ldx, const float* __restrict__ add, int add_rows,
+layernorm_kernel(const TIN* __restrict__ x, int ldx, int x_div, const float* __restrict__ add, int add_rows,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int D,
                  __half* __restrict__ out16, int ld16, float* __restrict__ out32, int ld32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const TIN* xr = x + size_t(warp) * ldx;
+  const TIN* xr = x + size_t(warp / x_div) * ldx;   // x_div > 1: each input row is broadcast to x_div output rows
   const float* ar = add ? add + size_t(warp % add_rows) * D : nullptr;
   float4 v[LN_MAX_CHUNKS];
   float s = 0.f;
@@ -125,13 +125,25 @@ layernorm_narrow_kernel(const TIN* __restrict__ x, int ldx, const float* __restr
   }
 }
 
+int layernorm_bcast(const void* x, int x_is_f16, int ldx, int x_div, const float* add, int add_rows, const float* gamma,
+                    const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
+                    cudaStream_t stream);
+
 int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_rows, const float* gamma,
               const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
               cudaStream_t stream) {
-  TOCVP_CHECK_ARG(x && gamma && beta && rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_CHUNKS * 128);
+  return layernorm_bcast(x, x_is_f16, ldx, 1, add, add_rows, gamma, beta, eps, rows, D, out16, ld16, out32, ld32, stream);
+}
+
+// y[row] = LN(x[row / x_div] + add[row % add_rows]): with x_div = add_rows = N this is the broadcast-slots + positional
+// embedding + LayerNorm front of MLPPatchDecoder (reference src/models/EncodersDecoders/decoders.py:152-199, 314).
+int layernorm_bcast(const void* x, int x_is_f16, int ldx, int x_div, const float* add, int add_rows, const float* gamma,
+                    const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
+                    cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && gamma && beta && rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_CHUNKS * 128 && x_div >= 1);
   TOCVP_CHECK_ARG(ldx % 4 == 0 && (out16 || out32));
   TOCVP_CHECK_ARG(!add || add_rows > 0);
-  if (D == 32 || D == 64) {
+  if ((D == 32 || D == 64) && x_div == 1) {
     const int rpw = 128 / D;
     long long warps = (rows + rpw - 1) / rpw;
     long long blocks = (warps + 7) / 8;
@@ -148,10 +160,10 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   if (x_is_f16)
-    layernorm_kernel<__half><<<grid, wpb * 32, 0, stream>>>(static_cast<const __half*>(x), ldx, add, add_rows, gamma,
+    layernorm_kernel<__half><<<grid, wpb * 32, 0, stream>>>(static_cast<const __half*>(x), ldx, x_div, add, add_rows, gamma,
                                                             beta, eps, rows, D, out16, ld16, out32, ld32);
   else
-    layernorm_kernel<float><<<grid, wpb * 32, 0, stream>>>(static_cast<const float*>(x), ldx, add, add_rows, gamma,
+    layernorm_kernel<float><<<grid, wpb * 32, 0, stream>>>(static_cast<const float*>(x), ldx, x_div, add, add_rows, gamma,
                                                            beta, eps, rows, D, out16, ld16, out32, ld32);
   TOCVP_LAUNCHED();
   return TOCVP_OK;

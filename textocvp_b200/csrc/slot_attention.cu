@@ -174,6 +174,90 @@ sa_stream_kernel(const T* __restrict__ feats, size_t seq_stride, int N, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic streaming pass (any slot count 4 <= S <= 11, any N, fp32 or f16 features): the CLIPort / ExtendedDINOSAUR shape
+// (10 slots over 81..576 patch tokens, reference src/models/ExtendedDINOSAUR.py:188-194) and any shape the two
+// specialised kernels do not cover.  grid = (chunks, B), 256 threads; one warp per location, lane l owns channels
+// 4l..4l+3, every lane holds the full S-way softmax.  Same folded-K/V algebra and the same partial[] layout.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+sa_stream_generic_kernel(const T* __restrict__ feats, size_t seq_stride, int N, int chunks, const float* __restrict__ gvec,
+                         float* __restrict__ partial, float ln_eps, float attn_eps) {
+  constexpr int PART = S * SA_D + 2 * S;
+  __shared__ __align__(16) float s_red[8][S][SA_D];
+  __shared__ float s_am[8][2][S];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int LC = (N + chunks - 1) / chunks;
+  const int l0 = chunk * LC, l1 = min(N, l0 + LC);
+  const T* x = feats + size_t(b) * seq_stride + lane * 4;
+  const float* gv = gvec + size_t(b) * PART;
+  float g[S][4], sg[S], cb[S], acc[S][4], a_acc[S], mw_acc[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(gv + i * SA_D + lane * 4);
+    g[i][0] = t.x; g[i][1] = t.y; g[i][2] = t.z; g[i][3] = t.w;
+    sg[i] = gv[S * SA_D + i];
+    cb[i] = gv[S * SA_D + S + i];
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    a_acc[i] = 0.f;
+    mw_acc[i] = 0.f;
+  }
+  for (int l = l0 + warp; l < l1; l += 8) {
+    const float4 xv = ldx4<T>(x + size_t(l) * SA_D);
+    const float sum = warp_sum((xv.x + xv.y) + (xv.z + xv.w));
+    const float ssq = warp_sum(xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w);
+    const float mu = sum * (1.f / SA_D);
+    const float rstd = rsqrtf(fmaxf(ssq * (1.f / SA_D) - mu * mu, 0.f) + ln_eps);
+    float d[S];
+    float m = -1e30f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const float dot = warp_sum(g[i][0] * xv.x + g[i][1] * xv.y + g[i][2] * xv.z + g[i][3] * xv.w);
+      d[i] = rstd * (dot - mu * sg[i]) + cb[i];                // already multiplied by the attention scale
+      m = fmaxf(m, d[i]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      d[i] = __expf(d[i] - m);
+      den += d[i];
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const float a = d[i] * inv + attn_eps;                   // softmax over SLOTS, + eps (attention.py:100)
+      const float w = a * rstd;
+      a_acc[i] += a;
+      mw_acc[i] += w * mu;
+      acc[i][0] += w * xv.x; acc[i][1] += w * xv.y; acc[i][2] += w * xv.z; acc[i][3] += w * xv.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    *reinterpret_cast<float4*>(&s_red[warp][i][lane * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (lane == 0) {
+      s_am[warp][0][i] = a_acc[i];
+      s_am[warp][1][i] = mw_acc[i];
+    }
+  }
+  __syncthreads();
+  float* out = partial + (size_t(b) * chunks + chunk) * PART;
+  for (int e = threadIdx.x; e < S * SA_D; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += (&s_red[w8][0][0])[e];
+    out[e] = t;
+  }
+  if (threadIdx.x < 2 * S) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += (&s_am[w8][0][0])[threadIdx.x];
+    out[S * SA_D + threadIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-slot update kernel.  Each CTA owns R = 16 slot rows (2 sequences); activations live in smem
 // transposed as [feature][row] so that a thread computing one output column reads the rows as float4.
 // ------------------------------------------------------------------------------------------------
@@ -255,7 +339,7 @@ constexpr int UP_DO_T = 2;   // apply the transition block to the result -> pred
 constexpr int UP_DO_A = 4;   // emit g / sg / cb for the next streaming pass (from the result, or from pred if DO_T)
 
 __global__ void __launch_bounds__(UP_THREADS, 1)
-sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __restrict__ slots_in,
+sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags, const float* __restrict__ slots_in,
                  const float* __restrict__ partial, float* __restrict__ slots_out, int slots_out_stride /* per seq */,
                  float* __restrict__ pred_out, float* __restrict__ gvec) {
   extern __shared__ float sm[];
@@ -264,9 +348,13 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
   float* t1 = t0 + SA_D * UP_R;           // [128][R]
   float* big0 = t1 + SA_D * UP_R;         // [512][R]
   float* big1 = big0 + 512 * UP_R;        // [512][R]
-  const int row0 = blockIdx.x * UP_R;
+  // a CTA owns whole sequences: RPC = floor(16 / S) * S slot rows (16 for 8 slots, 10 for 10 slots); rows >= RPC are padding
+  const int RPC = (UP_R / S) * S;
+  const int row0 = blockIdx.x * RPC;
   const int tid = threadIdx.x;
   const int D = SA_D;
+  const int PART = S * D + 2 * S;
+  n_rows = min(n_rows, row0 + RPC);   // rows of the next CTA are not ours
 
   // load slots_in [rows][D] -> cur[D][R]
   for (int e = tid; e < UP_R * D; e += UP_THREADS) {
@@ -282,13 +370,13 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
       const int row = row0 + r;
       float val = 0.f;
       if (row < n_rows) {
-        const int b = row / SA_S, i = row % SA_S;
-        const float* p = partial + size_t(b) * SA_CHUNKS * SA_PART;
+        const int b = row / S, i = row % S;
+        const float* p = partial + size_t(b) * chunks * PART;
         float U = 0.f, A = 0.f, Mw = 0.f;
-        for (int c = 0; c < SA_CHUNKS; ++c) {
-          U += p[c * SA_PART + i * D + f];
-          A += p[c * SA_PART + SA_S * D + i];
-          Mw += p[c * SA_PART + SA_S * D + SA_S + i];
+        for (int c = 0; c < chunks; ++c) {
+          U += p[c * PART + i * D + f];
+          A += p[c * PART + S * D + i];
+          Mw += p[c * PART + S * D + S + i];
         }
         val = (w.ln_in_g[f] * (U - Mw) + w.ln_in_b[f] * A) / A;
       }
@@ -318,7 +406,7 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
       for (int e = tid; e < UP_R * D; e += UP_THREADS) {
         const int r = e / D, k = e % D;
         const int row = row0 + r;
-        if (row < n_rows) slots_out[size_t(row / SA_S) * slots_out_stride + size_t(row % SA_S) * D + k] = cur[k * UP_R + r];
+        if (row < n_rows) slots_out[size_t(row / S) * slots_out_stride + size_t(row % S) * D + k] = cur[k * UP_R + r];
       }
     }
   }
@@ -333,21 +421,22 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
     const float sc = rsqrtf(float(dh));
     for (int e = tid; e < UP_R * H; e += UP_THREADS) {
       const int r = e % UP_R, h = e / UP_R;                      // query row r (seq = r / S)
-      const int rs = (r / SA_S) * SA_S;
-      float sco[SA_S];
+      const int rs = (r / S) * S;
+      float sco[16];
       float mx = -1e30f;
-      for (int j = 0; j < SA_S; ++j) {
+      if (r >= RPC) continue;                                    // padding rows
+      for (int j = 0; j < S; ++j) {
         float d = 0.f;
         for (int c = 0; c < dh; ++c) d += t0[(h * dh + c) * UP_R + r] * t1[(h * dh + c) * UP_R + rs + j];
         sco[j] = d * sc;
         mx = fmaxf(mx, sco[j]);
       }
       float den = 0.f;
-      for (int j = 0; j < SA_S; ++j) { sco[j] = __expf(sco[j] - mx); den += sco[j]; }
+      for (int j = 0; j < S; ++j) { sco[j] = __expf(sco[j] - mx); den += sco[j]; }
       const float inv = 1.f / den;
       for (int c = 0; c < dh; ++c) {
         float o = 0.f;
-        for (int j = 0; j < SA_S; ++j) o += sco[j] * big0[(h * dh + c) * UP_R + rs + j];
+        for (int j = 0; j < S; ++j) o += sco[j] * big0[(h * dh + c) * UP_R + rs + j];
         att[(h * dh + c) * UP_R + r] = o * inv;
       }
     }
@@ -377,8 +466,8 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
     for (int e = tid; e < UP_R * D; e += UP_THREADS) {
       const int r = e / D, f = e % D;
       if (row0 + r < n_rows) {
-        const int b = (row0 + r) / SA_S, i = (row0 + r) % SA_S;
-        gvec[size_t(b) * SA_GVEC + i * D + f] = w.scale * t0[f * UP_R + r] * w.ln_in_g[f];
+        const int b = (row0 + r) / S, i = (row0 + r) % S;
+        gvec[size_t(b) * PART + i * D + f] = w.scale * t0[f * UP_R + r] * w.ln_in_g[f];
       }
     }
     if (tid < UP_R && row0 + tid < n_rows) {
@@ -389,70 +478,111 @@ sa_update_kernel(SaWeights w, int n_rows /* B*S */, int flags, const float* __re
         sgv += qt * w.ln_in_g[f];
         cbv += qt * w.ln_in_b[f] + t1[f * UP_R + r] * w.bk[f];
       }
-      const int b = (row0 + r) / SA_S, i = (row0 + r) % SA_S;
-      gvec[size_t(b) * SA_GVEC + SA_S * D + i] = w.scale * sgv;
-      gvec[size_t(b) * SA_GVEC + SA_S * D + SA_S + i] = w.scale * cbv;
+      const int b = (row0 + r) / S, i = (row0 + r) % S;
+      gvec[size_t(b) * PART + S * D + i] = w.scale * sgv;
+      gvec[size_t(b) * PART + S * D + S + i] = w.scale * cbv;
     }
   }
 }
 
 constexpr int UP_SMEM = (3 * SA_D + 2 * 512) * UP_R * 4;   // 90112 B
 
-static int launch_update(const SaWeights& w, int B, int flags, const float* slots_in, const float* partial,
+static int launch_update(const SaWeights& w, int S, int chunks, int B, int flags, const float* slots_in, const float* partial,
                          float* slots_out, int out_stride, float* pred_out, float* gvec, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     TOCVP_CUDA(cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
     attr_set = true;
   }
-  const int rows = B * SA_S;
-  sa_update_kernel<<<(rows + UP_R - 1) / UP_R, UP_THREADS, UP_SMEM, stream>>>(w, rows, flags, slots_in, partial,
-                                                                             slots_out, out_stride, pred_out, gvec);
+  const int rows = B * S;
+  const int rpc = (UP_R / S) * S;
+  sa_update_kernel<<<(rows + rpc - 1) / rpc, UP_THREADS, UP_SMEM, stream>>>(w, S, chunks, rows, flags, slots_in, partial,
+                                                                           slots_out, out_stride, pred_out, gvec);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
 
-size_t slot_attention_workspace_bytes(int B) {
-  return (size_t(B) * SA_GVEC + size_t(B) * SA_CHUNKS * SA_PART + size_t(B) * SA_S * SA_D) * sizeof(float);
+constexpr int SA_MAX_S = 11;   // generic path: cross-warp reduction buffer [8][S][128] floats must fit static smem
+
+size_t slot_attention_workspace_bytes(int B) {   // sized for the largest supported slot count
+  constexpr size_t part = SA_MAX_S * SA_D + 2 * SA_MAX_S;
+  return (size_t(B) * part + size_t(B) * SA_CHUNKS * part + size_t(B) * SA_MAX_S * SA_D) * sizeof(float);
 }
 
-// feats [B,N,128] (fp32 or f16), slots_in [B,8,128] fp32 -> slots_out (row b at slots_out + b*out_stride), and,
-// if pred_out != null, pred_out = transition(slots_out) [B,8,128].
+template <int S>
+static int launch_generic(const void* feats, int feats_f16, size_t seq_stride, int B, int N, int chunks, const float* gvec,
+                          float* partial, float ln_eps, float attn_eps, cudaStream_t stream) {
+  const dim3 grid(chunks, B);
+  if (feats_f16)
+    sa_stream_generic_kernel<__half, S><<<grid, 256, 0, stream>>>(static_cast<const __half*>(feats), seq_stride, N, chunks,
+                                                                  gvec, partial, ln_eps, attn_eps);
+  else
+    sa_stream_generic_kernel<float, S><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), seq_stride, N, chunks,
+                                                                 gvec, partial, ln_eps, attn_eps);
+  TOCVP_LAUNCHED();
+  return TOCVP_OK;
+}
+
+// feats [B,N,128] (fp32 or f16), slots_in [B,S,128] fp32 -> slots_out (row b at slots_out + b*out_stride), and,
+// if pred_out != null, pred_out = transition(slots_out) [B,S,128].
 int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t feats_seq_stride, int B, int N, const float* slots_in, int iters,
                    float* slots_out, int out_stride, float* pred_out, void* workspace, size_t ws_bytes,
                    cudaStream_t stream) {
-  TOCVP_CHECK_ARG(feats && slots_in && slots_out && workspace && B > 0 && iters >= 1);
+  const int S = w.num_slots;
+  TOCVP_CHECK_ARG(feats && slots_in && slots_out && workspace && B > 0 && iters >= 1 && N >= 1);
+  TOCVP_CHECK_ARG(S >= 1 && S <= SA_MAX_S);
   TOCVP_CHECK_ARG(feats_seq_stride >= size_t(N) * SA_D && feats_seq_stride % 8 == 0);
-  TOCVP_CHECK_ARG(N % (SA_CHUNKS * 128) == 0 && w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
+  TOCVP_CHECK_ARG(w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
   TOCVP_CHECK_ARG(pred_out == nullptr || (w.t_heads > 0 && SA_D % w.t_heads == 0 && w.t_hidden % 256 == 0));
   if (ws_bytes < slot_attention_workspace_bytes(B)) {
     set_last_error(__FILE__, __LINE__, "slot_attention: workspace too small");
     return TOCVP_ERR_WORKSPACE;
   }
+  // kernel choice: the two specialised streaming kernels cover 8 slots over N % 512 == 0 locations (SAVi / CATER);
+  // everything else (10 slots over 81 / 576 patch tokens for ExtendedDINOSAUR) takes the generic kernel
+  const bool fast = (S == SA_S) && (N % (SA_CHUNKS * 128) == 0);
+  const int chunks = fast ? SA_CHUNKS : (N >= 1024 ? 4 : (N >= 256 ? 2 : 1));
+  const int part = S * SA_D + 2 * S;
   float* gvec = static_cast<float*>(workspace);
-  float* partial = gvec + size_t(B) * SA_GVEC;
-  float* tmp_slots = partial + size_t(B) * SA_CHUNKS * SA_PART;   // [B,8,128] intermediate iterates
-  TOCVP_TRY(launch_update(w, B, UP_DO_A, slots_in, nullptr, nullptr, 0, nullptr, gvec, stream));
+  float* partial = gvec + size_t(B) * part;
+  float* tmp_slots = partial + size_t(B) * chunks * part;   // [B,S,128] intermediate iterates
+  TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_A, slots_in, nullptr, nullptr, 0, nullptr, gvec, stream));
   const float* cur = slots_in;
   for (int it = 0; it < iters; ++it) {
-    const dim3 grid(SA_CHUNKS, B);
-    if (feats_f16) {
+    if (fast && feats_f16) {
       // pipeline format: tcgen05 streaming kernel (slot_attention_tc.cu)
       TOCVP_TRY(sa_stream_tc(static_cast<const __half*>(feats), feats_seq_stride, B, N, gvec, partial, w.ln_eps_sa,
                              w.attn_eps, stream));
-    } else {
+    } else if (fast) {
       // fp32 features (the reference dtype at the module boundary): all-fp32 SIMT kernel
+      const dim3 grid(SA_CHUNKS, B);
       sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec,
                                                         partial, w.ln_eps_sa, w.attn_eps);
       TOCVP_LAUNCHED();
+    } else {
+      int r = TOCVP_ERR_BAD_ARG;
+      switch (S) {
+#define SA_GENERIC_CASE(SS)                                                                                        \
+  case SS:                                                                                                         \
+    r = launch_generic<SS>(feats, feats_f16, feats_seq_stride, B, N, chunks, gvec, partial, w.ln_eps_sa, w.attn_eps, \
+                           stream);                                                                                \
+    break;
+        SA_GENERIC_CASE(4) SA_GENERIC_CASE(5) SA_GENERIC_CASE(6) SA_GENERIC_CASE(7) SA_GENERIC_CASE(8)
+        SA_GENERIC_CASE(9) SA_GENERIC_CASE(10) SA_GENERIC_CASE(11)
+#undef SA_GENERIC_CASE
+        default:
+          set_last_error(__FILE__, __LINE__, "slot_attention: num_slots must be in 4..11");
+          return TOCVP_ERR_BAD_ARG;
+      }
+      TOCVP_TRY(r);
     }
     const bool last = (it == iters - 1);
     if (!last) {
-      TOCVP_TRY(launch_update(w, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, SA_S * SA_D, nullptr, gvec, stream));
+      TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, S * SA_D, nullptr, gvec, stream));
       cur = tmp_slots;
     } else {
-      TOCVP_TRY(launch_update(w, B, UP_DO_C | (pred_out ? UP_DO_T : 0), cur, partial, slots_out, out_stride, pred_out,
-                              gvec, stream));
+      TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_C | (pred_out ? UP_DO_T : 0), cur, partial, slots_out, out_stride,
+                              pred_out, gvec, stream));
     }
   }
   return TOCVP_OK;

@@ -45,7 +45,7 @@ SaW = _struct("SaW", [
     "t_w1_t", "t_b1", "t_w2_t", "t_b2"],
     [("mlp_hidden", ctypes.c_int), ("t_heads", ctypes.c_int), ("t_hidden", ctypes.c_int),
      ("attn_eps", ctypes.c_float), ("ln_eps_sa", ctypes.c_float), ("ln_eps_tf", ctypes.c_float),
-     ("scale", ctypes.c_float)])
+     ("scale", ctypes.c_float), ("num_slots", ctypes.c_int)])
 
 PredLayer = _struct("PredLayer", [
     "ln_q_g", "ln_q_b", "w_qkv", "w_o", "ln_cq_g", "ln_cq_b", "ln_ckv_g", "ln_ckv_b", "wc_q", "wc_kv", "wc_o", "bc_o",
@@ -71,10 +71,28 @@ DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("hidden", ctypes.c_int)]})
 
 
+ProjW = type("ProjW", (ctypes.Structure,), {"_fields_": [
+    ("ln_g", _f), ("ln_b", _f), ("w1", _f), ("b1", _f), ("w2", _f), ("b2", _f),
+    ("feat_dim", ctypes.c_int), ("hidden_dim", ctypes.c_int), ("slot_dim", ctypes.c_int), ("ln_eps", ctypes.c_float)]})
+
+PATCH_MAX_MLP = PATCH_MAX_CNN = 6
+PatchW = type("PatchW", (ctypes.Structure,), {"_fields_": [
+    ("pos_embed", _f), ("ln_g", _f), ("ln_b", _f),
+    ("mlp_w", _f * PATCH_MAX_MLP), ("mlp_b", _f * PATCH_MAX_MLP),
+    ("cnn_w", _f * PATCH_MAX_CNN), ("cnn_b", _f * PATCH_MAX_CNN), ("out_w", _f), ("out_b", _f),
+    ("mlp_out", ctypes.c_int * PATCH_MAX_MLP),
+    ("cnn_cin", ctypes.c_int * PATCH_MAX_CNN), ("cnn_cout", ctypes.c_int * PATCH_MAX_CNN),
+    ("cnn_up", ctypes.c_int * PATCH_MAX_CNN),
+    ("n_mlp", ctypes.c_int), ("n_cnn", ctypes.c_int), ("out_cin", ctypes.c_int), ("out_up", ctypes.c_int),
+    ("reconstruct_images", ctypes.c_int),
+    ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int), ("num_patches", ctypes.c_int), ("grid", ctypes.c_int),
+    ("feat_dim", ctypes.c_int), ("img_size", ctypes.c_int), ("ln_eps", ctypes.c_float)]})
+
+
 def check_struct_sizes():
     lib = L.load()
     for name, st in (("sa_weights", SaW), ("pred_weights", PredW), ("pred_layer", PredLayer),
-                     ("enc_weights", EncW), ("dec_weights", DecW)):
+                     ("enc_weights", EncW), ("dec_weights", DecW), ("proj_weights", ProjW), ("patch_weights", PatchW)):
         fn = getattr(lib, f"tocvp_sizeof_{name}")
         fn.restype = ctypes.c_size_t
         if fn() != ctypes.sizeof(st):
@@ -156,10 +174,25 @@ class SoftPositionEmbed(nn.Module):
 
 
 class ConvBlock(nn.Module):
-    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=None, **kw):
+    """model_blocks.py:49-108 (conv - [BatchNorm] - ReLU); parameter container."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=None, batch_norm=False, **kw):
         super().__init__()
         padding = padding if padding is not None else kernel_size // 2
-        self.block = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding), nn.ReLU())
+        layers = [nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding)]
+        if batch_norm:
+            layers.append(nn.BatchNorm2d(out_channels))
+        layers.append(nn.ReLU())
+        self.block = nn.Sequential(*layers)
+
+
+class Upsample(nn.Module):
+    """model_blocks.py:22-46 (nearest, scale 2).  Parameter-free placeholder that keeps the reference's Sequential indices;
+    the CUDA path folds it into the following convolution (four 2x2 phase convolutions on the low-resolution input)."""
+
+    def __init__(self, scale_factor):
+        super().__init__()
+        self.scale_factor = scale_factor
 
 
 class SimpleConvEncoder(nn.Module):
@@ -304,8 +337,8 @@ class SlotAttention(_Packed):
         self.attention_masks = None
 
     def _pack(self, dev):
-        if self.dim_feats != 128 or self.dim_slots != 128 or self.num_slots != 8:
-            raise L.TocvpError("SlotAttention kernels are instantiated for 8 slots x 128-d features/slots")
+        if self.dim_feats != 128 or self.dim_slots != 128 or not 4 <= self.num_slots <= 11:
+            raise L.TocvpError("SlotAttention kernels are instantiated for 4..11 slots x 128-d features/slots")
         k = {}
         k["ln_in_g"], k["ln_in_b"] = _f32(self.norm_input.weight), _f32(self.norm_input.bias)
         k["ln_slot_g"], k["ln_slot_b"] = _f32(self.norm_slot.weight), _f32(self.norm_slot.bias)
@@ -333,6 +366,7 @@ class SlotAttention(_Packed):
             setattr(w, n, v.data_ptr())
         w.mlp_hidden, w.t_heads, w.t_hidden = self.mlp_hidden, t_heads, t_hidden
         w.attn_eps, w.ln_eps_sa, w.ln_eps_tf, w.scale = self.epsilon, 1e-3, 1e-6, self.scale
+        w.num_slots = self.num_slots
         self._w = w
 
     def _sig(self):
@@ -572,6 +606,288 @@ class SAVi(_Packed):
 
 
 # =====================================================================================================
+# ExtendedDINOSAUR + MLPPatchDecoder (CLIPort shape)
+# =====================================================================================================
+class MLPPatchDecoder(_Packed):
+    """decoders.py:129-365.  forward(slots [B',S,D]) -> {"recons_imgs" [B',3,I,I], "recons_feats" [B',N,F],
+    "masks" [B',S,1,g,g]}."""
+
+    def __init__(self, num_patches, in_dim, hidden_dim, out_dim, num_layers=4, initial_layer_norm=False,
+                 reconstruct_images=False, **kwargs):
+        super().__init__()
+        self.num_patches, self.in_dim, self.hidden_dim, self.out_dim = num_patches, in_dim, hidden_dim, out_dim
+        self.num_layers, self.initial_layer_norm, self.reconstruct_images = num_layers, initial_layer_norm, reconstruct_images
+        self.patch_grid = (int(num_patches ** 0.5), int(num_patches ** 0.5))
+        self.pos_embed = nn.Parameter(torch.randn(1, 1, num_patches, in_dim) / (in_dim ** 0.5))
+        mlp = [nn.LayerNorm(in_dim)] if initial_layer_norm else []
+        for i in range(num_layers):
+            d1 = hidden_dim if i > 0 else in_dim
+            d2 = hidden_dim if i < num_layers - 1 else out_dim
+            mlp.append(nn.Linear(d1, d2))
+            if i < num_layers - 1:
+                mlp.append(nn.ReLU())
+        self.mlp = nn.Sequential(*mlp)
+        if reconstruct_images:
+            self.patch_size, self.image_size = kwargs.get("patch_size"), kwargs.get("img_size")
+            self.num_layers_cnn = kwargs.get("num_layers_cnn")
+            mods, cur, h = [], self.patch_grid[0], hidden_dim                       # decoders.py:325-365
+            for i in range(self.num_layers_cnn):
+                cin = out_dim - 1 if i == 0 else h
+                if i > 0 and (i + 1) * 2 < self.patch_size and cur < self.image_size:
+                    h = h // 2
+                mods.append(ConvBlock(cin, h, 3, 1, 1, batch_norm=True))
+                if (i + 1) * 2 < self.patch_size and cur < self.image_size:
+                    mods.append(Upsample(scale_factor=2))
+                    cur *= 2
+            mods.append(nn.Conv2d(h, 3, kernel_size=3, stride=1, padding=1))
+            self.conv_patch_decoder = nn.Sequential(*mods)
+        self._ws = _Workspace()
+        object.__setattr__(self, "_num_slots", None)
+
+    def _sig(self):   # BatchNorm running statistics are buffers: include them
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in list(self.parameters()) + list(self.buffers()))
+
+    @staticmethod
+    def _phase_rows(p, d):
+        """3x3 taps (ky) of an Upsample(2)->conv3x3 pair that land on low-res offset d + p - 1 for output phase p."""
+        return ([0], [1, 2])[d] if p == 0 else ([0, 1], [2])[d]
+
+    def _pack(self, dev):
+        if not self.initial_layer_norm:
+            raise L.TocvpError("MLPPatchDecoder kernels expect initial_layer_norm = true (ExtendedDINOSAUR.json)")
+        k = {"pos_embed": _f32(self.pos_embed.reshape(self.num_patches, self.in_dim)),
+             "ln_g": _f32(self.mlp[0].weight), "ln_b": _f32(self.mlp[0].bias)}
+        w = PatchW()
+        lins = [m for m in self.mlp if isinstance(m, nn.Linear)]
+        if len(lins) > PATCH_MAX_MLP:
+            raise L.TocvpError("too many MLP layers")
+        for i, lin in enumerate(lins):
+            wt, b = lin.weight.detach().float(), lin.bias.detach().float()
+            if i == len(lins) - 1:                                       # pad 769 -> 776 rows (GEMM N % 8 == 0)
+                pad = (-wt.shape[0]) % 8
+                wt = torch.cat([wt, wt.new_zeros(pad, wt.shape[1])], 0)
+                b = torch.cat([b, b.new_zeros(pad)], 0)
+            k[f"mlp_w{i}"], k[f"mlp_b{i}"] = _f16(wt), _f32(b)
+            w.mlp_w[i], w.mlp_b[i], w.mlp_out[i] = k[f"mlp_w{i}"].data_ptr(), k[f"mlp_b{i}"].data_ptr(), lin.weight.shape[0]
+        w.n_mlp = len(lins)
+        w.reconstruct_images = int(bool(self.reconstruct_images))
+        if self.reconstruct_images:
+            mods = list(self.conv_patch_decoder)
+            up_before, ci = False, 0
+            for m in mods:
+                if isinstance(m, Upsample):
+                    up_before = True
+                    continue
+                if isinstance(m, ConvBlock):
+                    conv, bn = m.block[0], m.block[1]
+                    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                    wt = conv.weight.detach().float() * scale[:, None, None, None]             # fold eval-mode BN
+                    b = (conv.bias.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+                    co, cin = wt.shape[:2]
+                    if not up_before:
+                        packed = wt.permute(0, 2, 3, 1).reshape(co, 9 * cin)
+                    else:
+                        packed = wt.new_zeros(4, co, 4, cin)
+                        for py in range(2):
+                            for px in range(2):
+                                for dy in range(2):
+                                    for dx in range(2):
+                                        acc = 0
+                                        for ky in self._phase_rows(py, dy):
+                                            for kx in self._phase_rows(px, dx):
+                                                acc = acc + wt[:, :, ky, kx]
+                                        packed[py * 2 + px, :, dy * 2 + dx] = acc
+                        packed = packed.reshape(4 * co, 4 * cin)
+                        b = b.repeat(4)
+                    k[f"cnn_w{ci}"], k[f"cnn_b{ci}"] = _f16(packed), _f32(b)
+                    w.cnn_w[ci], w.cnn_b[ci] = k[f"cnn_w{ci}"].data_ptr(), k[f"cnn_b{ci}"].data_ptr()
+                    w.cnn_cin[ci], w.cnn_cout[ci], w.cnn_up[ci] = cin, co, int(up_before)
+                    ci += 1
+                    up_before = False
+                else:                                                    # final nn.Conv2d -> 3 channels
+                    wt, b = m.weight.detach().float(), m.bias.detach().float()
+                    cin = wt.shape[1]
+                    packed = wt.new_zeros(64, 9, cin)                    # >= one N-tile of rows allocated
+                    bias = wt.new_zeros(16)
+                    if up_before:
+                        for py in range(2):
+                            for px in range(2):
+                                ph = py * 2 + px
+                                bias[ph * 4:ph * 4 + 3] = b
+                                for dy in range(2):
+                                    for dx in range(2):
+                                        tap = (dy + py) * 3 + (dx + px)     # low-res offset (dy+py-1, dx+px-1) + 1
+                                        for ky in self._phase_rows(py, dy):
+                                            for kx in self._phase_rows(px, dx):
+                                                packed[ph * 4:ph * 4 + 3, tap] += wt[:, :, ky, kx]
+                    else:
+                        packed[:3] = wt.permute(0, 2, 3, 1).reshape(3, 9, cin)
+                        bias[:3] = b
+                    k["out_w"], k["out_b"] = _f16(packed.reshape(64, 9 * cin)), _f32(bias)
+                    w.out_w, w.out_b, w.out_cin, w.out_up = k["out_w"].data_ptr(), k["out_b"].data_ptr(), cin, int(up_before)
+            w.n_cnn = ci
+        for n in ("pos_embed", "ln_g", "ln_b"):
+            setattr(w, n, k[n].data_ptr())
+        w.slot_dim, w.num_patches, w.grid = self.in_dim, self.num_patches, self.patch_grid[0]
+        w.feat_dim, w.img_size, w.ln_eps = self.out_dim - 1, int(self.image_size or 0) if self.reconstruct_images else 0, 1e-5
+        self._keep, self._w = k, w
+
+    @torch.no_grad()
+    def forward(self, slots, only_imgs: bool = False):
+        self._ensure_packed()
+        lib = L.load()
+        slots = slots.float().contiguous()
+        n, S, _ = slots.shape
+        self._w.num_slots = S
+        dev, g, F = slots.device, self.patch_grid[0], self.out_dim - 1
+        imgs = torch.empty(n, 3, self.image_size, self.image_size, device=dev) if self.reconstruct_images else None
+        feats = None if only_imgs else torch.empty(n, self.num_patches, F, device=dev)
+        masks = None if only_imgs else torch.empty(n, S, 1, g, g, device=dev)
+        lib.tocvp_patch_decode_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_patch_decode_workspace_bytes(ctypes.byref(self._w), c_int(n)), dev)
+        L.call("tocvp_patch_decode", ctypes.byref(self._w), ptr(slots), c_int(n), ptr(imgs), ptr(feats), ptr(masks),
+               ws, wsb, stream())
+        return {"recons_imgs": imgs if imgs is not None else torch.tensor([]), "recons_feats": feats, "masks": masks}
+
+
+class ExtendedDINOSAUR(_Packed):
+    """src/models/ExtendedDINOSAUR.py.  forward(mode="decomp"|"decode", ...).  The frozen ViT backbone
+    (timm vit_base_patch14_dinov2, third-party and weight-gated) is NOT part of the accelerated path: ``x`` carries its
+    output, the patch features [B, T, N, mlp_encoder_dim] (BASELINE.json north star: synthetic inputs of the named shape).
+    A backbone callable mapping images [B,3,H,W] -> [B,N,F] can be attached with ``set_backbone``."""
+
+    def __init__(self, img_size, num_slots, slot_dim, num_iterations=1, num_iterations_first=3, in_channels=3,
+                 mlp_hidden=128, mlp_encoder_dim=128, initializer=None, encoder=None, decoder=None,
+                 transition_module=None, **kwargs):
+        super().__init__()
+        self.img_size, self.num_slots, self.slot_dim, self.in_channels = img_size, num_slots, slot_dim, in_channels
+        self.mlp_hidden, self.mlp_encoder_dim = mlp_hidden, mlp_encoder_dim
+        if initializer == "LearnedRandom":
+            self.initializer = LearnedRandom(slot_dim, num_slots)
+        elif initializer == "Learned":
+            self.initializer = Learned(slot_dim, num_slots)
+        else:
+            raise ValueError(f"UPSI, mode = {initializer} is not a recongnized initializer...")
+        tm = dict(transition_module or {})
+        name = tm.pop("model_name", None)
+        if name in (None, ""):
+            self.transition_module = nn.Identity()
+        elif name == "TransformerBlock":
+            self.transition_module = TransformerBlock(embed_dim=slot_dim, pre_norm=False, **tm)
+        else:
+            raise ValueError(f"UPSI, model_name = {name} was not a recognized transition module...")
+        if self.img_size is None:
+            raise KeyError("'img_size' must be provided in model parameters in order to instanciate ViT-based image encoder.")
+        if encoder is not None and "vit" not in encoder.get("encoder_name", "vit"):
+            raise NameError("Extended-DINOSAUR expects a ViT-Based encoder...")
+        self.encoder = nn.Identity()
+        self.linear_feat_proj = nn.Sequential(nn.LayerNorm(mlp_encoder_dim), nn.Linear(mlp_encoder_dim, mlp_encoder_dim),
+                                              nn.ReLU(), nn.Linear(mlp_encoder_dim, slot_dim))
+        if decoder["decoder_name"] != "MLPPatchDecoder":
+            raise NameError("Extended-DINOSAUR expects a 'MLPPatchDecoder'...")
+        dp = dict(decoder["decoder_params"])
+        dp["img_size"] = self.img_size
+        self.decoder = MLPPatchDecoder(**dp)
+        self.slot_attention = SlotAttention(dim_feats=slot_dim, dim_slots=slot_dim, num_slots=num_slots,
+                                            num_iters_first=num_iterations_first, num_iters=num_iterations,
+                                            mlp_hidden=mlp_hidden)
+        if isinstance(self.transition_module, TransformerBlock):
+            object.__setattr__(self.slot_attention, "_transition", self.transition_module)
+        self._init_model()
+        self._ws = _Workspace()
+
+    @torch.no_grad()
+    def _init_model(self):
+        for mod in (self.linear_feat_proj, self.transition_module, self.slot_attention, self.decoder):
+            for n, p in mod.named_parameters():
+                if n.endswith(".bias"):
+                    p.zero_()
+                elif p.dim() > 1 and "pos_embed" not in n:
+                    nn.init.xavier_uniform_(p)
+        nn.init.zeros_(self.slot_attention.gru.bias_ih)
+        nn.init.zeros_(self.slot_attention.gru.bias_hh)
+        nn.init.orthogonal_(self.slot_attention.gru.weight_hh)
+
+    def set_backbone(self, fn):
+        object.__setattr__(self, "_backbone", fn)
+
+    def _sig(self):   # only the projection is packed here (sub-modules pack themselves)
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.linear_feat_proj.parameters())
+
+    def _pack(self, dev):
+        p = self.linear_feat_proj
+        k = dict(ln_g=_f32(p[0].weight), ln_b=_f32(p[0].bias), w1=_f16(p[1].weight), b1=_f32(p[1].bias),
+                 w2=_f16(p[3].weight), b2=_f32(p[3].bias))
+        w = ProjW()
+        for n, v in k.items():
+            setattr(w, n, v.data_ptr())
+        w.feat_dim, w.hidden_dim, w.slot_dim, w.ln_eps = p[1].weight.shape[1], p[1].weight.shape[0], self.slot_dim, 1e-5
+        self._keep, self._w = k, w
+
+    def forward(self, mode="decomp", *args, **kwargs):
+        if mode == "decomp":
+            return self.forward_decomp(*args, **kwargs)
+        elif mode == "decode":
+            return self.decode(*args, **kwargs)
+        raise NameError(f"mode = {mode!r} not recognized. Use ['decomp', 'decode']")
+
+    @torch.no_grad()
+    def project(self, feats, want_f32=False):
+        """linear_feat_proj on patch features [..., F] -> [..., D] (f16 pipeline format, or fp32)."""
+        self._ensure_packed()
+        lib = L.load()
+        F = feats.shape[-1]
+        x = feats.float().contiguous().reshape(-1, F)
+        rows = x.shape[0]
+        out = torch.empty(rows, self.slot_dim, device=x.device, dtype=torch.float32 if want_f32 else torch.float16)
+        lib.tocvp_dino_project_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_dino_project_workspace_bytes(ctypes.byref(self._w), c_int(rows)), x.device)
+        L.call("tocvp_dino_project", ctypes.byref(self._w), ptr(x), c_int(rows), ptr(None if want_f32 else out),
+               ptr(out if want_f32 else None), ws, wsb, stream())
+        return out.reshape(*feats.shape[:-1], self.slot_dim)
+
+    @torch.no_grad()
+    def forward_decomp(self, x, num_imgs=10, decode=True, init_slots=None, **kwargs):
+        """ExtendedDINOSAUR.py:139-214.  x: patch features [B,T,N,F] (or images [B,T,3,H,W] with a backbone attached)."""
+        if x.dim() == 5:
+            bb = getattr(self, "_backbone", None)
+            if bb is None:
+                raise L.TocvpError("ExtendedDINOSAUR got images but no ViT backbone is attached (set_backbone); the "
+                                   "accelerated path starts at the patch features [B,T,N,F]")
+            x = torch.stack([bb(x[:, t]) for t in range(num_imgs)], dim=1)
+        B, T, N, F = x.shape
+        S, D = self.num_slots, self.slot_dim
+        feats_in = x[:, :num_imgs]
+        proj = self.project(feats_in)                                             # [B,num_imgs,N,D] f16
+        init = (self.initializer(batch_size=B, **kwargs) if init_slots is None else init_slots).float()
+        cur = torch.empty(B, S, D, device=x.device, dtype=torch.float32)
+        cur.copy_(init)
+        slot_history = torch.empty(B, num_imgs, S, D, device=x.device, dtype=torch.float32)
+        has_t = isinstance(self.transition_module, TransformerBlock)
+        nxt = torch.empty_like(cur) if has_t else None
+        outs = []
+        for t in range(num_imgs):
+            iters = self.slot_attention.num_iters_first if t == 0 else self.slot_attention.num_iters
+            out_t = slot_history[:, t]
+            self.slot_attention.run(proj[:, t:], num_imgs * N * D, B, N, cur, iters, out_t, num_imgs * S * D, nxt)
+            if has_t:
+                cur, nxt = nxt, cur
+            else:
+                cur.copy_(out_t)
+            if decode:
+                outs.append(self.decode(out_t.contiguous()))
+        res = {"encoded_img_feats": feats_in, "slot_history": slot_history}
+        if decode:
+            for key in outs[0]:
+                res[key] = torch.stack([o[key] for o in outs], dim=1)
+        return res
+
+    @torch.no_grad()
+    def decode(self, slots, only_imgs: bool = False):
+        return self.decoder(slots, only_imgs=only_imgs)
+
+
+# =====================================================================================================
 # Predictor
 # =====================================================================================================
 class TransformerTextEncoder(nn.Module):
@@ -767,9 +1083,12 @@ class PredictorWrapper(nn.Module):
 # =====================================================================================================
 def setup_model(model_params: Dict):
     import copy
-    if model_params["model_name"] != "SAVi":
-        raise NotImplementedError("only SAVi is built in this round (ExtendedDINOSAUR: SURVEY.md 8(a) a18-a19, next)")
-    return SAVi(**copy.deepcopy(model_params["model_params"]))
+    name = model_params["model_name"]
+    if name == "SAVi":
+        return SAVi(**copy.deepcopy(model_params["model_params"]))
+    if name == "ExtendedDINOSAUR":
+        return ExtendedDINOSAUR(**copy.deepcopy(model_params["model_params"]))
+    raise NotImplementedError(f"UPSI, model_name = {name} is not a recognized decomposition model (SAVi, ExtendedDINOSAUR)")
 
 
 def setup_predictor(exp_params: Dict):
@@ -781,6 +1100,21 @@ def setup_predictor(exp_params: Dict):
         raise NotImplementedError(f"predictor {name}: only TextOCVP_CustomTF is available offline")
     body = TextOCVP_CustomTF(slot_dim=exp_params["model"]["model_params"]["slot_dim"], **pp)
     return PredictorWrapper(exp_params=exp_params, predictor=body)
+
+
+def dino_exp_params(num_context=1, num_preds=29, input_buffer_size=10, img_size=128, num_patches=81):
+    """src/configs/models/ExtendedDINOSAUR.json (img_size / num_patches per BASELINE.json configs[3]; the reference JSON
+    says 336 / 576) + src/configs/predictors/TextOCVP_CustomTF.json."""
+    ep = default_exp_params(num_context, num_preds, input_buffer_size)
+    ep["model"] = {"model_name": "ExtendedDINOSAUR", "model_params": {
+        "img_size": img_size, "in_channels": 3, "num_slots": 10, "slot_dim": 128, "num_iterations_first": 3,
+        "num_iterations": 1, "mlp_hidden": 512, "mlp_encoder_dim": 768, "initializer": "LearnedRandom",
+        "transition_module": {"model_name": "TransformerBlock", "num_heads": 4, "mlp_size": 512},
+        "encoder": {"encoder_name": "vit_base_patch14_dinov2", "encoder_params": {"encoder_num_blocks": 12}},
+        "decoder": {"decoder_name": "MLPPatchDecoder", "decoder_params": {
+            "patch_size": 14, "num_patches": num_patches, "in_dim": 128, "hidden_dim": 1024, "out_dim": 769,
+            "num_layers": 4, "initial_layer_norm": True, "reconstruct_images": True, "num_layers_cnn": 4}}}}
+    return ep
 
 
 def default_exp_params(num_context=1, num_preds=19, input_buffer_size=10):
