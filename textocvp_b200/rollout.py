@@ -26,6 +26,35 @@ def build_models(device, savi_seed=14, pred_seed=15, mlp_out_scale=0.1, num_cont
     return savi.to(device).eval(), pred.to(device).eval(), ep
 
 
+def build_dino_models(device, dino_seed=16, pred_seed=17, mlp_out_scale=0.1, num_context=1, num_preds=29,
+                      input_buffer_size=10, img_size=128, num_patches=81):
+    """CLIPort shape (BASELINE.json configs[3]): ExtendedDINOSAUR.json with the ViT backbone replaced by synthetic patch
+    features + TextOCVP_CustomTF.json, random init from seeds."""
+    ep = M.dino_exp_params(num_context, num_preds, input_buffer_size, img_size, num_patches)
+    dino = M.setup_model(ep["model"])
+    pred = M.setup_predictor(ep)
+    dino.load_state_dict(weights.dino_state_dict(dino_seed, img_size=img_size, num_patches=num_patches), strict=True)
+    body = dict(pred.predictor.state_dict())
+    body.update(weights.predictor_state_dict(pred_seed, mlp_out_scale=mlp_out_scale))
+    pred.predictor.load_state_dict(body, strict=True)
+    return dino.to(device).eval(), pred.to(device).eval(), ep
+
+
+@torch.no_grad()
+def forward_eval_dino(dino, pred, feats, text_embeddings, num_context, num_preds, init_slots=None, num_imgs=None,
+                      only_imgs=True) -> Dict[str, torch.Tensor]:
+    """Evaluator composition (05_evaluate_predictor.py:82-96) for ExtendedDINOSAUR: feats [B,T,N,F] are the frozen
+    backbone's patch features; returns predicted slots and clamped predicted frames [B,num_preds,3,I,I]."""
+    B = feats.shape[0]
+    num_imgs = num_context + num_preds if num_imgs is None else num_imgs
+    sh = dino(mode="decomp", x=feats, num_imgs=num_imgs, decode=False, init_slots=init_slots)["slot_history"]
+    ps = pred(sh, text_embeddings=text_embeddings)
+    dec = dino.decode(ps.reshape(B * num_preds, dino.num_slots, dino.slot_dim), only_imgs=only_imgs)
+    I = dino.img_size
+    imgs = dec["recons_imgs"].view(B, num_preds, 3, I, I).clamp(0, 1)
+    return {"slot_history": sh, "pred_slots": ps, "pred_imgs": imgs, "recons_feats": dec["recons_feats"]}
+
+
 @torch.no_grad()
 def forward_eval(savi, pred, videos, text_embeddings, num_context, num_preds, init_slots=None, num_imgs=None,
                  conv_events=None, only_imgs=False) -> Dict[str, torch.Tensor]:
