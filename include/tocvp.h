@@ -56,6 +56,10 @@ int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
                    int relu, const float* residual, int ldr, float* out_f32, int ld32, void* out_f16, int ld16,
                    void* stream);
 
+/* Tuning / test knob (process-wide): 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) GEMM
+ * kernels (default), 1 = single-CTA kernel only, 128 / 256 = pair kernel with that tile width wherever applicable. */
+int tocvp_set_gemm_mode(int mode);
+
 /* ------------------------------------------------------------------------------------------
  * Row LayerNorm (fp32 statistics): y = LN(x (+ add[row % add_rows])) * gamma + beta.
  * x: fp32 or f16 [rows, ldx]; add: optional fp32 table [add_rows, D] (the batch-independent

@@ -32,6 +32,35 @@ def test_gemm_f16(M, N, K):
     assert _rel(o32, ref2) < 1e-5
 
 
+@pytest.mark.parametrize("mode", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (20480, 512, 512), (1000, 2048, 512), (4096, 512, 2048),
+                                   (300, 768, 128), (2048, 1536, 512)])
+def test_gemm_pair_kernel(mode, M, N, K):
+    """CTA-pair (cta_group::2) kernel forced on, both tile widths: ragged M tails, both outputs at once (TMA-store
+    epilogue through shared staging tiles), bias + ReLU + residual."""
+    from textocvp_b200 import ops
+    if N % mode:
+        pytest.skip("tile width does not divide N")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = a.double() @ w.double().t()
+    ops.set_gemm_mode(mode)
+    try:
+        o32, o16 = ops.gemm_f16(a, w, out_f32=True, out_f16=True)
+        o32b, _ = ops.gemm_f16(a, w, bias=bias, relu=True, residual=res)
+        _, o16c = ops.gemm_f16(a, w, bias=bias, relu=True, out_f32=False, out_f16=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode(0)
+    assert _rel(o32, ref) < 1e-5
+    assert _rel(o16, ref) < 1e-3
+    assert _rel(o32b, torch.relu(ref + bias.double()) + res.double()) < 1e-5
+    assert _rel(o16c, torch.relu(ref + bias.double())) < 1e-3
+
+
 @pytest.mark.parametrize("rows,D,f16", [(1000, 512, False), (77, 128, False), (4096, 32, True), (300, 768, False)])
 def test_layernorm(rows, D, f16):
     from textocvp_b200 import ops

@@ -22,7 +22,7 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
 struct ConvMap {
   int taps;             // K-blocks are grouped by tap: K = taps * cin
   int cin;              // multiple of 64
-  int tiles_per_phase;  // N-tiles per phase when each phase has its own tap set; 0 = one tap set for all columns
+  int tiles_per_phase;  // != 0: each phase (cpp columns) has its own tap set (the GEMM fills in the tile count); 0 = one tap set
   int off[4][9];        // A row offset of (phase, tap)
   int Hp, Wp;           // padded input geometry; M = n_img * Hp * Wp
   int up;               // output is the 2x-upsampled grid, column n -> phase n / cpp

@@ -1,0 +1,486 @@
+// CTA-pair tcgen05 GEMM (cta_group::2): 256 x BN output tiles, one tile per pair of SMs at a time.
+//     C[M,N] = A[M,K] . W[N,K]^T  (+bias) (ReLU) (+residual)   -> fp32 and/or fp16          (and the implicit-conv mode)
+//
+// Why: with 128 x 128 single-CTA tiles every SM pulls 32 KB of operands per 256 tensor-clocks = 128 B/clk/SM, and the
+// L2 -> SM fabric of the chip sustains ~42 B/clk/SM, so that kernel plateaus near 600-900 TFLOP/s (ncu r1: lts-bound).
+// A CTA pair sharing one 256 x 256 tile halves the operand traffic twice over: each CTA loads only its 128 rows of A
+// and HALF of the W tile (the tensor core reads the other half from the peer's shared memory), 32 KB per 512 clocks
+// = 64 B/clk/SM.
+//
+// Structure (both CTAs run the same code; rank 0 is the leader):
+//   warp 0   TMA producer: own A half (128 x 64) + own W half (BN/2 x 64) per stage, completion bytes are signalled on
+//            the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1   TMEM allocator (cta_group::2, both CTAs); in the leader: the single-thread tcgen05.mma.cta_group::2 issuer;
+//            tcgen05.commit ... multicast releases the smem stage in BOTH CTAs and publishes the accumulator to BOTH
+//   warps 2..9  epilogue on the CTA's own 128 accumulator rows (TMEM lanes); the peer's warps arrive remotely on the
+//            leader's tmem-empty barrier.  Results leave through per-warp 128B-swizzled staging tiles and TMA STORES
+//            (cp.async.bulk.tensor global <- shared): a thread owns a row, so direct stores would touch 32 different
+//            rows per instruction and half-fill every 32-byte sector; with K = 512 the output is as large as the
+//            operands and that store pattern, not the tensor pipe, set the kernel's pace (r1 measurement).
+#include "gemm.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+constexpr int G2_BM = 128;          // rows per CTA (256 per pair)
+constexpr int G2_BK = 64;
+constexpr int G2_THREADS = 320;
+
+struct Gemm2Args {
+  int M, N, K;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  int res_div, res_mod;
+  int relu;
+  float* out32;
+  int ld32;
+  __half* out16;
+  int ld16;
+  ConvMap cm;
+};
+
+template <int BN>
+struct G2Smem {
+  static constexpr int A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;       // 16 KB (BN = 256) / 8 KB (BN = 128)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STG_BYTES = 8 * 2 * 4096;            // 8 epilogue warps x 2 staging tiles of 32 rows x 128 B
+  static constexpr int BAR_BYTES = 256 + 2 * BN * 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+};
+
+// ---- cluster / pair PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, pl;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 pl, %5, 0;\n\t"
+      "@pl tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// arrive (once) on the barrier at this smem offset in BOTH CTAs of the pair when all prior MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred pl;\n\t"
+      "setp.ne.b32 pl, %1, 0;\n\t"
+      "@pl tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "r"(leader), "h"(uint16_t(3))
+      : "memory");
+}
+
+// TMA store of one staging tile (32 rows x 128 B, 128B-swizzled) to global; clipped at the tensor bounds by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int BN, bool CONV>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
+                 const __grid_constant__ Gemm2Args g) {
+  using S = G2Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + S::STAGES * S::STAGE_BYTES;                              // 1024B aligned
+  smem += S::STG_BYTES;   // barrier block follows the staging tiles (the stage ring is addressed from stage_base)
+  uint8_t* stage_base = smem - S::STG_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);   // used in the leader only
+  uint64_t* empty = full + S::STAGES;                                                 // per CTA (multicast commit)
+  uint64_t* tfull = empty + S::STAGES;                                                // per CTA (multicast commit)
+  uint64_t* tempty = tfull + 2;                                                       // leader only, 16 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 256);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_m = (g.M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (g.K + G2_BK - 1) / G2_BK;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 16);   // 8 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();              // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (each CTA loads its halves)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int mb = t / tiles_n, nb = t % tiles_n;
+        const int m0 = mb * 2 * G2_BM + int(rank) * G2_BM;
+        const int n0 = nb * BN + int(rank) * (BN / 2);
+        const int phase = (CONV && g.cm.tiles_per_phase > 0) ? nb / g.cm.tiles_per_phase : 0;
+        const int kpt = CONV ? g.cm.cin / G2_BK : num_kb;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          int arow = m0, acol = kb * G2_BK;
+          if constexpr (CONV) {
+            const int tap = kb / kpt;
+            arow = m0 + g.cm.off[phase][tap];
+            acol = (kb - tap * kpt) * G2_BK;
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t full_leader = mapa_rank(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
+          uint8_t* st = stage_base + s * S::STAGE_BYTES;
+          tma_load_2d_pair(&tmA, full_leader, st, acol, arow);
+          tma_load_2d_pair(&tmB, full_leader, st + S::A_BYTES, kb * G2_BK, n0);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * G2_BM, BN, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t leader = elect_one_sync();
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += npairs, ++it) {
+        const int b = it & 1;
+        const uint32_t bph = (it >> 1) & 1;
+        mbar_wait(&tempty[b], bph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + uint32_t(b * BN);
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(stage_base + s * S::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128(a0, 1024);
+          const uint64_t db = make_desc_sw128(a0 + S::A_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k)
+            umma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0, leader);
+          umma_commit_pair(&empty[s], leader);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(&tfull[b], leader);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9) on this CTA's 128 rows
+    const int ew = warp - 2;
+    const int q = warp & 3;               // TMEM lane quarter
+    const int half = ew >> 2;             // column half of the tile
+    const int et = threadIdx.x - 64;      // 0..255
+    constexpr int CW = BN / 2;            // columns per warp
+    constexpr int NCH = CW / 32;
+    uint8_t* stg = stg_base + ew * 8192;  // this warp's two staging tiles
+    int sbuf = 0;
+    const uint32_t sw = uint32_t(lane & 7);
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int mb = t / tiles_n, nb = t % tiles_n;
+      const int b = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      if (g.bias != nullptr) {
+        for (int e = et; e < BN; e += 256) {
+          const int n = nb * BN + e;
+          sbias[b * BN + e] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
+        }
+      }
+      const int row = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32 + lane;
+      bool row_ok = row < g.M;
+      const int ncol0 = nb * BN + half * CW;
+      const float* res_row = nullptr;
+      size_t cbase = 0;
+      if constexpr (CONV) {
+        const int hw = g.cm.Hp * g.cm.Wp;
+        const int img = row / hw, rem = row - img * hw;
+        const int yp = rem / g.cm.Wp, xp = rem - yp * g.cm.Wp;
+        row_ok = row_ok && yp >= 1 && yp <= g.cm.Hp - 2 && xp >= 1 && xp <= g.cm.Wp - 2;
+        const int sc = g.cm.up ? 2 : 1;
+        cbase = (size_t(img) * g.cm.Hop + size_t((yp - 1) * sc + g.cm.pad)) * g.cm.Wop + size_t((xp - 1) * sc + g.cm.pad);
+      }
+      if (g.residual != nullptr && row_ok) {
+        const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
+        res_row = g.residual + size_t(rr) * g.ldr;
+      }
+      float4 rbuf[2][8];
+      auto load_res = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = ncol0 + c * 32 + j * 4;
+          dst[j] = (res_row != nullptr && n < g.N) ? __ldg(reinterpret_cast<const float4*>(res_row + n))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_res(0, rbuf[0]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // bias staged (epilogue warps only)
+      mbar_wait(&tfull[b], bph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + half * CW);
+      uint32_t v[2][32];
+      uint4 hold[4];
+      tmem_ld32(t_addr, v[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld_wait();                                            // chunk c is in v[c & 1]
+        if (c + 1 < NCH) {
+          tmem_ld32(t_addr + uint32_t((c + 1) * 32), v[(c + 1) & 1]);   // next chunk in flight while this one is stored
+          load_res(c + 1, rbuf[(c + 1) & 1]);
+        } else {
+          // all accumulator columns of this warp are in registers: hand the TMEM buffer back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[b]), 0));
+        }
+        const int n0 = ncol0 + c * 32;
+        if constexpr (!CONV) {
+          // ---- bias / ReLU / residual in registers, then out through swizzled staging tiles + TMA stores
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[c & 1][j]);
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j4 * 4]);
+              f[4 * j4] += bb.x; f[4 * j4 + 1] += bb.y; f[4 * j4 + 2] += bb.z; f[4 * j4 + 3] += bb.w;
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (g.residual != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 r = rbuf[c & 1][j4];
+              f[4 * j4] += r.x; f[4 * j4 + 1] += r.y; f[4 * j4 + 2] += r.z; f[4 * j4 + 3] += r.w;
+            }
+          }
+          const int trow = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32;
+          if (g.out32 != nullptr) {
+            if (lane == 0) bulk_wait_read<1>();          // the store that last read this staging tile has drained
+            __syncwarp();
+            uint8_t* dst = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(dst + ((uint32_t(j4) ^ sw) << 4)) =
+                  make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC32, stg + sbuf * 4096, n0, trow);
+              bulk_commit();
+            }
+            sbuf ^= 1;
+          }
+          if (g.out16 != nullptr) {
+            // two 32-column chunks make one 64-column (128 B) staging row: the even chunk waits in registers
+            uint4 p[4];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              p[j8].x = pack_half2(f[8 * j8], f[8 * j8 + 1]);
+              p[j8].y = pack_half2(f[8 * j8 + 2], f[8 * j8 + 3]);
+              p[j8].z = pack_half2(f[8 * j8 + 4], f[8 * j8 + 5]);
+              p[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
+            }
+            if ((c & 1) == 0) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) hold[j8] = p[j8];
+            } else {
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+              uint8_t* dst = stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                *reinterpret_cast<uint4*>(dst + ((uint32_t(j8) ^ sw) << 4)) = hold[j8];
+                *reinterpret_cast<uint4*>(dst + ((uint32_t(4 + j8) ^ sw) << 4)) = p[j8];
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmC16, stg + sbuf * 4096, n0 - 32, trow);
+                bulk_commit();
+              }
+              sbuf ^= 1;
+            }
+          }
+        } else if (row_ok && n0 < g.N) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int n = n0 + j8 * 8;
+            if (n < g.N) {  // N is a multiple of 8
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c & 1][j8 * 8 + j]);
+              if (g.bias != nullptr) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8 + 4]);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (g.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              // column n -> (phase, channel); a 4-column group never straddles a phase (cpp % 4 == 0)
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4) {
+                const int n4 = n + 4 * h4;
+                const int phs = g.cm.up ? n4 / g.cm.cpp : 0;
+                const int cc = n4 - phs * g.cm.cpp;
+                const size_t pix = cbase + size_t(phs >> 1) * g.cm.Wop + size_t(phs & 1);
+                if (phs < 4) {
+                  if (g.out32 != nullptr)
+                    *reinterpret_cast<float4*>(g.out32 + pix * g.ld32 + cc) =
+                        make_float4(f[4 * h4], f[4 * h4 + 1], f[4 * h4 + 2], f[4 * h4 + 3]);
+                  if (g.out16 != nullptr) {
+                    uint2 p2;
+                    p2.x = pack_half2(f[4 * h4], f[4 * h4 + 1]);
+                    p2.y = pack_half2(f[4 * h4 + 2], f[4 * h4 + 3]);
+                    *reinterpret_cast<uint2*>(g.out16 + pix * g.ld16 + cc) = p2;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();   // staging tiles must outlive the TMA stores that read them
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();              // both CTAs done with TMEM and with each other's barriers / shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, bool CONV>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
+  // output maps for the TMA-store epilogue: 32-row x 128-byte boxes (64 f16 / 32 fp32 columns), 128B swizzle
+  CUtensorMap tmC16 = tmA, tmC32 = tmA;     // placeholders when an output is absent (never dereferenced)
+  if (!CONV && g.out16 != nullptr) {
+    const uint64_t dims[2] = {uint64_t(g.N), uint64_t(g.M)};
+    const uint64_t str[1] = {uint64_t(g.ld16) * 2};
+    const uint32_t box[2] = {64, 32};
+    TOCVP_TRY(encode_tmap(&tmC16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.out16, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  if (!CONV && g.out32 != nullptr) {
+    const uint64_t dims[2] = {uint64_t(g.N), uint64_t(g.M)};
+    const uint64_t str[1] = {uint64_t(g.ld32) * 4};
+    const uint32_t box[2] = {32, 32};
+    TOCVP_TRY(encode_tmap(&tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.out32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  using S = G2Smem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((g.N + BN - 1) / BN);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm2_f16_kernel<BN, CONV><<<grid, G2_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, g);
+  TOCVP_LAUNCHED();
+  return TOCVP_OK;
+}
+
+// Tile width for the pair kernel, or 0 if the problem should stay on the single-CTA kernel.
+// cost model: waves of pair-tiles x tile width, with the narrower tile paying ~10% for its higher L2 traffic per FLOP
+// (measured r1: N = 512 -> 128-wide tiles (5 waves beat 3 of twice the width), N = 1536 / 2048 -> 256-wide).
+int gemm2_pick_bn(int M, int N, int force) {
+  if (force == 128 || force == 256) return force;
+  if (M < 1024 || N < 128 || N % 128 != 0) return 0;
+  const int pairs = num_sms() / 2;
+  const int tm = (M + 255) / 256;
+  auto waves = [&](int bn) { return (tm * ((N + bn - 1) / bn) + pairs - 1) / pairs; };
+  const double c256 = (N % 256 == 0) ? waves(256) * 256.0 : 1e30;
+  const double c128 = waves(128) * 128.0 * 1.1;
+  return c256 <= c128 ? 256 : 128;
+}
+
+int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+              const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16, int ld16,
+              cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, G2_BM, G2_BK));
+  TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn / 2, G2_BK));
+  Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{}};
+  if (bn == 256) return launch_gemm2<256, false>(tmA, tmB, g, stream);
+  return launch_gemm2<128, false>(tmA, tmB, g, stream);
+}
+
+int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
+                   int relu, float* out32, __half* out16, int ldo, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, G2_BM, G2_BK));
+  TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, K, bn / 2, G2_BK));
+  Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm};
+  if (bn == 256) return launch_gemm2<256, true>(tmA, tmB, g, stream);
+  return launch_gemm2<128, true>(tmA, tmB, g, stream);
+}
+
+}  // namespace tocvp

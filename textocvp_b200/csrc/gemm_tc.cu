@@ -302,6 +302,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return TOCVP_OK;
 }
 
+int gemm2_pick_bn(int M, int N, int force);
+int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+              const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16, int ld16,
+              cudaStream_t stream);
+int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
+                   int relu, float* out32, __half* out16, int ldo, cudaStream_t stream);
+
+// Tuning / test knob (tocvp_set_gemm_mode): 0 = automatic kernel choice, 1 = single-CTA kernel only,
+// 128 / 256 = CTA-pair kernel with that tile width wherever it is applicable.
+static int g_gemm_mode = 0;
+
 // Internal entry used by the stage drivers and by the public tocvp_gemm_f16.
 int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
              const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16,
@@ -314,6 +325,14 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   TOCVP_CHECK_ARG(out16 == nullptr || ld16 % 8 == 0);
   TOCVP_CHECK_ARG(residual == nullptr || ldr % 4 == 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (g_gemm_mode != 1) {
+    // CTA-pair kernel (256-row tiles, half the L2 operand traffic) for everything large enough to fill the chip
+    const int bn2 = (g_gemm_mode >= 128 && N % g_gemm_mode == 0 && N >= g_gemm_mode) ? g_gemm_mode
+                                                                                       : gemm2_pick_bn(M, N, 0);
+    if (bn2 != 0)
+      return gemm2_f16(bn2, A, lda, W, ldw, M, N, K, bias, relu, residual, ldr, res_div, res_mod, out32, ld32, out16, ld16,
+                       stream);
+  }
   // Tile width: wide tiles for wide outputs; 64 keeps enough tiles in flight for narrow / short problems.
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   int bn = 128;
@@ -335,18 +354,37 @@ int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const Conv
   const long long M64 = (long long)n_img * cm.Hp * cm.Wp;
   TOCVP_CHECK_ARG(M64 < (1ll << 31));
   const int M = int(M64), K = cm.taps * cm.cin;
-  const int bn = (N >= 128 && (cm.tiles_per_phase == 0 || cm.cpp % 128 == 0)) ? 128 : 64;
-  TOCVP_CHECK_ARG(cm.tiles_per_phase == 0 || (cm.cpp % bn == 0 && cm.tiles_per_phase == cm.cpp / bn));
+  const bool phased = cm.tiles_per_phase != 0;     // each phase (cpp columns) has its own tap set: tiles must not straddle
+  ConvMap cmx = cm;
+  if (g_gemm_mode != 1 && M >= 1024 && N >= 128) {
+    int bn2 = 0;
+    const int unit = phased ? cm.cpp : N;
+    if (unit % 256 == 0 && gemm2_pick_bn(M, N, 0) == 256 && g_gemm_mode != 128) bn2 = 256;
+    else if (unit % 128 == 0) bn2 = 128;
+    if (bn2 != 0) {
+      cmx.tiles_per_phase = phased ? cm.cpp / bn2 : 0;
+      return gemm2_conv_f16(bn2, X, W, M, N, K, cmx, bias, relu, out32, out16, ldo, stream);
+    }
+  }
+  const int bn = (N >= 128 && (!phased || cm.cpp % 128 == 0)) ? 128 : 64;
+  TOCVP_CHECK_ARG(!phased || cm.cpp % bn == 0);
+  cmx.tiles_per_phase = phased ? cm.cpp / bn : 0;
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, GEMM_BM, GEMM_BK));
   // W must be allocated with at least `bn` rows (narrow heads are zero-padded by the packer)
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N < bn ? bn : N, K, K, bn, GEMM_BK));
-  GemmArgs g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm};
+  GemmArgs g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cmx};
   if (bn == 64) return launch_gemm<64, true>(tmA, tmB, g, stream);
   return launch_gemm<128, true>(tmA, tmB, g, stream);
 }
 
 }  // namespace tocvp
+
+extern "C" int tocvp_set_gemm_mode(int mode) {
+  if (mode != 0 && mode != 1 && mode != 128 && mode != 256) return TOCVP_ERR_BAD_ARG;
+  tocvp::g_gemm_mode = mode;
+  return TOCVP_OK;
+}
 
 extern "C" int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                               int relu, const float* residual, int ldr, float* out_f32, int ld32, void* out_f16,

@@ -304,8 +304,7 @@ extern "C" int tocvp_patch_decode(const tocvp_patch_weights* w, const float* slo
       cm.cin = w->cnn_cin[i];
       cm.cpp = w->cnn_cout[i];
       cm.up = up;
-      const int bn = (cm.cpp % 128 == 0) ? 128 : 64;
-      cm.tiles_per_phase = up ? cm.cpp / bn : 0;
+      cm.tiles_per_phase = up ? 1 : 0;     // "phased": the GEMM derives the tile count from its tile width
       cm.Hp = cm.Wp = pb.sp[i] + 2;
       cm.Hop = cm.Wop = pb.sp[i + 1] + 2;
       cm.pad = 1;

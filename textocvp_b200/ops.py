@@ -65,3 +65,8 @@ def conv5x5_f16(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, rel
     L.call("tocvp_conv5x5_f16", ptr(x), ptr(w_packed), ptr(bias), ptr(out), c_int(n), c_int(h), c_int(w_), c_int(ci),
            c_int(co), c_int(int(relu)), stream())
     return out
+
+
+def set_gemm_mode(mode: int):
+    """0 = automatic, 1 = single-CTA GEMM kernel only, 128 / 256 = CTA-pair kernel with that tile width (tests, tuning)."""
+    L.call("tocvp_set_gemm_mode", c_int(mode))
