@@ -81,6 +81,9 @@ int tocvp_layernorm(const void* x, int x_is_f16, int ldx, const float* add, int 
  * ------------------------------------------------------------------------------------------ */
 int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H, int W,
                       int cin, int cout, int relu, void* stream);
+/* Tuning / test knob (process-wide): 0 = CTA-pair (cta_group::2) conv kernel whenever the tile count is even (default),
+ * 1 = single-CTA kernel only. */
+int tocvp_set_conv_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * SAVi / ExtendedDINOSAUR corrector: SlotAttention.forward (src/models/Blocks/attention.py:67-112) for

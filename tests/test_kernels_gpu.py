@@ -94,14 +94,21 @@ def test_probe_shifted_sw128_operand(shift):
 
 
 @pytest.mark.parametrize("n,c", [(1, 64), (3, 64), (40, 64), (2, 32), (37, 32)])
-def test_conv5x5(n, c):
-    """tcgen05 implicit-GEMM conv vs torch conv2d (fp32) on f16-rounded operands."""
+@pytest.mark.parametrize("mode", [0, 1])
+def test_conv5x5(n, c, mode):
+    """tcgen05 implicit-GEMM conv (mode 0: CTA-pair kernel when the tile count is even, mode 1: single-CTA kernel)
+    vs torch conv2d (fp32) on f16-rounded operands."""
     from textocvp_b200 import ops
+    ops.set_conv_mode(mode)
     g = torch.Generator(device="cuda").manual_seed(n * 100 + c)
     x = torch.randn(n, 64, 64, c, device="cuda", generator=g).half()
     w = (torch.randn(c, c, 5, 5, device="cuda", generator=g) / (25 * c) ** 0.5)
     b = torch.randn(c, device="cuda", generator=g)
-    out = ops.conv5x5_f16(x, ops.pack_conv5x5_weight(w), b, relu=True)
+    try:
+        out = ops.conv5x5_f16(x, ops.pack_conv5x5_weight(w), b, relu=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_mode(0)
     torch.backends.cudnn.allow_tf32 = False
     ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=2))
     ref = ref.permute(0, 2, 3, 1)

@@ -233,6 +233,229 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster own two different output tiles and the leader issues
+// M = 256 MMAs covering sub-tile j of both.  Each CTA stages only HALF of a tap's weight slice (the tensor core reads the
+// peer's half from the peer's shared memory): per 128x64x16 MMA-half the smem operand read drops from 4 KB (A) + 2 KB (B)
+// to 4 KB + 1 KB per SM -- the smem read port is what bounds the single-CTA kernel at N = 64 (ncu, profiles/) -- and
+// the per-SM L2 traffic for weights halves as well.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int G, int KS>
+struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
+  using Base = ConvCfg<CIN, COUT, G, KS>;
+  static constexpr int W_HALF = (COUT / 2) * Base::KB;
+  static constexpr int WSTAGES = (W_HALF >= 4096) ? 6 : 12;
+  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + 512 + 1024;
+};
+
+template <int CIN, int COUT, int G, int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
+  using C = ConvCfg2<CIN, COUT, G, KS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 2 * C::A_STRIDE;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_HALF);   // leader: bytes of both halves
+  uint64_t* w_empty = w_full + C::WSTAGES;                                        // per CTA (multicast commit)
+  uint64_t* a_full = w_empty + C::WSTAGES;                                        // leader: both halos
+  uint64_t* a_empty = a_full + 2;                                                 // per CTA
+  uint64_t* t_full = a_empty + 2;                                                 // per CTA
+  uint64_t* t_empty = t_full + 2;                                                 // leader: 4 warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_x = a.W / C::TILE_W, tiles_y = a.H / C::TILE_H;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int num_ptiles = (a.n_img * tiles_per_img) / 2;   // pair-tiles: tile 2*pt + rank belongs to CTA `rank`
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::WSTAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], 1);
+      mbar_init(&a_empty[b], 1);
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (own halo, own half of the weights)
+    if (lane == 0) {
+      auto load_halo = [&](int pt, int it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int t = 2 * pt + int(rank);
+        const int img = t / tiles_per_img, r = t % tiles_per_img;
+        const int y0 = (r / tiles_x) * C::TILE_H, x0 = (r % tiles_x) * C::TILE_W;
+        mbar_wait(&a_empty[buf], ph ^ 1);
+        if (rank == 0) mbar_expect_tx(&a_full[buf], 2 * C::A_BYTES);
+        tma_load_4d_pair(&tmX, mapa_rank(smem_u32(&a_full[buf]), 0), sA + buf * C::A_STRIDE, 0, x0 - KS / 2, y0 - KS / 2,
+                         img);
+      };
+      int s = 0;
+      uint32_t wph = 0;
+      int it = 0;
+      if (pair < num_ptiles) load_halo(pair, 0);
+      for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+        if (pt + npairs < num_ptiles) load_halo(pt + npairs, it + 1);
+        for (int tap = 0; tap < C::TAPS; ++tap) {
+          mbar_wait(&w_empty[s], wph ^ 1);
+          if (rank == 0) mbar_expect_tx(&w_full[s], 2 * C::W_HALF);
+          tma_load_2d_pair(&tmW, mapa_rank(smem_u32(&w_full[s]), 0), sW + s * C::W_HALF, 0,
+                           tap * COUT + int(rank) * (COUT / 2));
+          if (++s == C::WSTAGES) { s = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader CTA)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, COUT, 0);
+      constexpr uint32_t SBO = C::WBUF * C::KB;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t leader = elect_one_sync();
+      int s = 0;
+      uint32_t wph = 0;
+      int it = 0;
+      for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], ph ^ 1);
+        mbar_wait(&a_full[buf], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + buf * C::A_STRIDE);
+        const uint32_t d_base = tmem_u + uint32_t(buf * C::ACC_COLS);
+#pragma unroll 1
+        for (int tap = 0; tap < C::TAPS; ++tap) {
+          const int ty = tap / KS, tx = tap % KS;
+          mbar_wait(&w_full[s], wph);
+          tc_fence_after();
+          const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_HALF), 8 * C::KB, C::LAYOUT);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const uint32_t a_addr = a_base + uint32_t((ty * C::WBUF + tx + 8 * j) * C::KB);
+            const uint64_t da = make_desc_kmajor(a_addr, SBO, C::LAYOUT);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma_f16_pair(d_base + uint32_t(j * COUT), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (tap | k) != 0,
+                            leader);
+          }
+          umma_commit_pair(&w_empty[s], leader);
+          if (++s == C::WSTAGES) { s = 0; wph ^= 1; }
+        }
+        umma_commit_pair(&a_empty[buf], leader);
+        umma_commit_pair(&t_full[buf], leader);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (own tile)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int pr = m >> 3, pc = m & 7;
+    int it = 0;
+    for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int t = 2 * pt + int(rank);
+      const int img = t / tiles_per_img, r = t % tiles_per_img;
+      const int y = (r / tiles_x) * C::TILE_H + pr;
+      const int x0 = (r % tiles_x) * C::TILE_W + pc;
+      mbar_wait(&t_full[buf], ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < G; ++j) {
+        __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
+#pragma unroll
+        for (int c = 0; c < COUT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int n = c * 32 + j8 * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j8 * 8 + e]);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 p;
+            p.x = pack_half2(f[0], f[1]);
+            p.y = pack_half2(f[2], f[3]);
+            p.z = pack_half2(f[4], f[5]);
+            p.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(o + n) = p;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&t_empty[buf]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int CIN, int COUT, int G, int KS>
+static int launch_conv2(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
+                        int relu, cudaStream_t stream) {
+  using C = ConvCfg2<CIN, COUT, G, KS>;
+  TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmX, tmW;
+  {
+    const uint64_t dims[4] = {uint64_t(CIN), uint64_t(W), uint64_t(H), uint64_t(n_img)};
+    const uint64_t str[3] = {uint64_t(CIN) * 2, uint64_t(W) * CIN * 2, uint64_t(H) * W * CIN * 2};
+    const uint32_t box[4] = {uint32_t(CIN), uint32_t(C::WBUF), uint32_t(C::HROWS), 1};
+    TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, sw));
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(CIN), uint64_t(C::TAPS * COUT)};
+    const uint64_t str[1] = {uint64_t(CIN) * 2};
+    const uint32_t box[2] = {uint32_t(CIN), uint32_t(COUT / 2)};
+    TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
+  }
+  const int num_ptiles = n_img * (H / C::TILE_H) * (W / C::TILE_W) / 2;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
+  ConvArgs a{n_img, H, W, bias, out, nullptr, relu};
+  conv_tc2_kernel<CIN, COUT, G, KS><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
+  TOCVP_LAUNCHED();
+  return TOCVP_OK;
+}
+
+static int g_conv_mode = 0;   // 0 = automatic (pair kernel when the tile count is even), 1 = single-CTA kernel only
+
 template <int CIN, int COUT, int G, int KS, int EPI>
 static int launch_conv(const __half* x, const __half* wpacked, const float* bias, __half* out, float* out4, int n_img,
                        int H, int W, int relu, cudaStream_t stream) {
@@ -271,8 +494,15 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && wpacked && bias && out && n_img > 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (cin == 64 && cout == 64) return launch_conv<64, 64, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
-  if (cin == 32 && cout == 32) return launch_conv<32, 32, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
+  const bool pair_ok = g_conv_mode == 0 && H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
+  if (cin == 64 && cout == 64) {
+    if (pair_ok) return launch_conv2<64, 64, 4, 5>(x, wpacked, bias, out, n_img, H, W, relu, stream);
+    return launch_conv<64, 64, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
+  }
+  if (cin == 32 && cout == 32) {
+    if (pair_ok) return launch_conv2<32, 32, 4, 5>(x, wpacked, bias, out, n_img, H, W, relu, stream);
+    return launch_conv<32, 32, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
+  }
   set_last_error(__FILE__, __LINE__, "conv5x5_f16: only 64->64 and 32->32 channels are instantiated");
   return TOCVP_ERR_BAD_ARG;
 }
@@ -287,6 +517,12 @@ int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, 
 }
 
 }  // namespace tocvp
+
+extern "C" int tocvp_set_conv_mode(int mode) {
+  if (mode != 0 && mode != 1) return TOCVP_ERR_BAD_ARG;
+  tocvp::g_conv_mode = mode;
+  return TOCVP_OK;
+}
 
 extern "C" int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H,
                                  int W, int cin, int cout, int relu, void* stream) {

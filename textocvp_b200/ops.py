@@ -70,3 +70,8 @@ def conv5x5_f16(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, rel
 def set_gemm_mode(mode: int):
     """0 = automatic, 1 = single-CTA GEMM kernel only, 128 / 256 = CTA-pair kernel with that tile width (tests, tuning)."""
     L.call("tocvp_set_gemm_mode", c_int(mode))
+
+
+def set_conv_mode(mode: int):
+    """0 = CTA-pair conv kernel when applicable (default), 1 = single-CTA kernel only (tests, tuning)."""
+    L.call("tocvp_set_conv_mode", c_int(mode))

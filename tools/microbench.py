@@ -48,9 +48,12 @@ def bench_conv():
         x = torch.randn(n, 64, 64, c, device="cuda").half()
         w = ops.pack_conv5x5_weight(torch.randn(c, c, 5, 5, device="cuda") * 0.02)
         b = torch.zeros(c, device="cuda")
-        ms = timeit(lambda: ops.conv5x5_f16(x, w, b))
         fl = 2 * n * 4096 * 25 * c * c
-        print(f"conv5x5 {c}->{c} n={n}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s")
+        for mode in (1, 0):
+            ops.set_conv_mode(mode)
+            ms = timeit(lambda: ops.conv5x5_f16(x, w, b))
+            print(f"conv5x5 {c}->{c} n={n} mode{mode}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        ops.set_conv_mode(0)
 
 
 if __name__ == "__main__":
