@@ -166,7 +166,7 @@ def run_ours(args):
         vbuf.copy_(videos_h, non_blocking=True)
         tbuf.copy_(text_h, non_blocking=True)
         out = rollout.forward_eval(savi, pred, vbuf, tbuf, NUM_CONTEXT, NUM_PREDS, init_slots=init)
-        return torch.stack([out["psnr"], out["mse"]]).cpu()      # D2H of the step's metrics (synchronises)
+        return torch.stack([out["psnr"], out["mse"], out["ssim"]]).cpu()      # D2H of the step's metrics (synchronises)
 
     def barrier():
         if world > 1:
@@ -190,7 +190,7 @@ def run_ours(args):
     e0.record()
     for k in range(args.steps):
         out = step_resident(conv_evs[k])
-        metrics.accumulate(out["psnr"], out["mse"])
+        metrics.accumulate(out["psnr"], out["mse"], out["ssim"])
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -271,7 +271,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "quality": {"psnr_vs_synthetic_targets_mean": res_metrics["psnr_mean"], "count": res_metrics["count"]},
+            "quality": {"psnr_vs_synthetic_targets_mean": res_metrics["psnr_mean"],
+                        "ssim_vs_synthetic_targets_mean": res_metrics["ssim_mean"], "count": res_metrics["count"]},
         }
         print(json.dumps(line))
     if world > 1:

@@ -284,6 +284,19 @@ size_t tocvp_patch_decode_workspace_bytes(const tocvp_patch_weights* w, int n_fr
 int tocvp_patch_decode(const tocvp_patch_weights* w, const float* slots, int n_frames, float* recons_imgs,
                        float* recons_feats, float* masks, void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluator metrics on the device (src/05_evaluate_predictor.py:96-103 -> src/lib/metrics.py:181-270, piqa 1.2.2):
+ * optional clamp of both images to [0,1], then per image MSE, PSNR = 10 log10(1/(mse + 1e-8)) and SSIM (11-tap Gaussian
+ * window, sigma 1.5, k1 = 0.01, k2 = 0.03, value range 1, valid convolution, mean over channels and positions).
+ * pred fp32 [n_img, C, H, W]; the target of image i is read IN PLACE from a video tensor:
+ *   target + (i / frames_per_seq) * target_seq_stride + (target_frame0 + i % frames_per_seq) * C*H*W   (floats),
+ * i.e. videos[:, num_context : num_context + num_preds] needs no copy.  Outputs fp32 [n_img], any may be NULL.
+ * n_img, C <= 65535.
+ * ------------------------------------------------------------------------------------------ */
+int tocvp_frame_metrics(const float* pred, const float* target, size_t target_seq_stride, int frames_per_seq,
+                        int target_frame0, int n_img, int C, int H, int W, int clamp, float* mse, float* psnr, float* ssim,
+                        void* stream);
+
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
 int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,

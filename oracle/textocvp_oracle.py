@@ -417,6 +417,28 @@ def psnr(x: Tensor, y: Tensor, eps: float = 1e-8) -> Tensor:
     return 10.0 * torch.log10(1.0 / (mse + eps))
 
 
+def ssim(x: Tensor, y: Tensor, window_size: int = 11, sigma: float = 1.5, k1: float = 0.01, k2: float = 0.03,
+         value_range: float = 1.0) -> Tensor:
+    """Per-image SSIM [..., C, H, W] -> [...].  Restates piqa 1.2.2 `ssim` as called by src/lib/metrics.py:223-243
+    (SSIM(window_size=11, sigma=1.5, n_channels=3, reduction=None)): channel-wise valid convolution with a normalised
+    separable Gaussian window, cs = (2 s_xy + c2)/(s_xx + s_yy + c2), ss = (2 mu_x mu_y + c1)/(mu_x^2 + mu_y^2 + c1) * cs,
+    mean over channels and positions.  piqa is not installed -> unpinned restatement."""
+    lead = x.shape[:-3]
+    C, H, W = x.shape[-3:]
+    x, y = x.reshape(-1, C, H, W).double(), y.reshape(-1, C, H, W).double()
+    g = torch.exp(-(torch.arange(window_size, dtype=torch.float64) - (window_size - 1) / 2) ** 2 / (2 * sigma ** 2))
+    g = g / g.sum()
+    k = (g[:, None] * g[None, :]).expand(C, 1, window_size, window_size)
+    f = lambda t: F.conv2d(t, k, groups=C)
+    c1, c2 = (k1 * value_range) ** 2, (k2 * value_range) ** 2
+    mx, my = f(x), f(y)
+    mxx, myy, mxy = mx * mx, my * my, mx * my
+    sxx, syy, sxy = f(x * x) - mxx, f(y * y) - myy, f(x * y) - mxy
+    cs = (2 * sxy + c2) / (sxx + syy + c2)
+    ss = (2 * mxy + c1) / (mxx + myy + c1) * cs
+    return ss.flatten(1).mean(-1).reshape(lead).float()
+
+
 def rel_err(a: Tensor, b: Tensor) -> float:
     """Relative L2 error ||a-b|| / ||b|| in fp64 (the per-stage parity measure)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

@@ -141,3 +141,20 @@ def test_mha(B, Tq, Tk, cross):
     ref = ((qf @ kf.transpose(-1, -2)) * dh ** -0.5).softmax(-1) @ vf
     ref = ref.transpose(1, 2).reshape(B * Tq, H * dh)
     assert _rel(out, ref) < 2e-3      # P and the output are rounded to f16
+
+
+@pytest.mark.parametrize("B,F,H,W,T,f0", [(3, 4, 64, 64, 6, 1), (2, 3, 128, 128, 4, 1), (1, 2, 40, 72, 2, 0)])
+def test_frame_metrics(B, F, H, W, T, f0):
+    """clamp + MSE / PSNR / SSIM kernels vs the oracle's restatement of piqa 1.2.2 (tolerance: fp32 reductions, 1e-4
+    relative on MSE/SSIM, 1e-3 dB on PSNR); targets are read in place from the video tensor."""
+    from oracle import textocvp_oracle as O
+    from textocvp_b200 import rollout
+    g = torch.Generator().manual_seed(B * 100 + H)
+    videos = torch.rand(B, T, 3, H, W, generator=g)
+    pred = videos[:, f0:f0 + F] + 0.3 * torch.randn(B, F, 3, H, W, generator=g)       # leaves [0,1]: clamp matters
+    m = rollout.frame_metrics(pred.cuda(), videos.cuda(), f0)
+    p, t = pred.clamp(0, 1), videos[:, f0:f0 + F].clamp(0, 1)
+    mse = ((p - t) ** 2).flatten(2).mean(-1)
+    assert _rel(m["mse"].cpu(), mse) < 1e-4
+    assert (m["psnr"].cpu() - O.psnr(p, t)).abs().max() < 1e-3
+    assert (m["ssim"].cpu() - O.ssim(p, t)).abs().max() < 1e-4

@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, psnr, mse, out):
+def _worker(rank, world, port, psnr, mse, ssim, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -25,7 +25,7 @@ def _worker(rank, world, port, psnr, mse, out):
     lo, hi = rollout.shard_range(rank, world, psnr.shape[0])
     m = rollout.MetricSums(psnr.shape[1], torch.device("cpu"))
     for s in range(lo, hi, 3):                       # several "batches" per rank
-        m.accumulate(psnr[s:min(hi, s + 3)], mse[s:min(hi, s + 3)])
+        m.accumulate(psnr[s:min(hi, s + 3)], mse[s:min(hi, s + 3)], ssim[s:min(hi, s + 3)])
     res = m.all_reduce().results()
     if rank == 0:
         out.put(res)
@@ -45,10 +45,11 @@ def test_metric_allreduce_two_ranks():
     g = torch.Generator().manual_seed(0)
     psnr = torch.rand(11, 19, generator=g) * 40
     mse = torch.rand(11, 19, generator=g)
+    ssim = torch.rand(11, 19, generator=g)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, psnr, mse, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, psnr, mse, ssim, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = q.get(timeout=120)
@@ -59,3 +60,5 @@ def test_metric_allreduce_two_ranks():
     assert abs(res["psnr_mean"] - psnr.double().mean().item()) < 1e-9
     assert torch.allclose(torch.tensor(res["psnr_per_frame"], dtype=torch.float64), psnr.double().mean(0), atol=1e-9)
     assert torch.allclose(torch.tensor(res["mse_per_frame"], dtype=torch.float64), mse.double().mean(0), atol=1e-9)
+    assert torch.allclose(torch.tensor(res["ssim_per_frame"], dtype=torch.float64), ssim.double().mean(0), atol=1e-9)
+    assert res["lpips_mean"] == 0.0          # slot reserved, never filled offline

@@ -9,8 +9,31 @@ from typing import Dict, Optional
 
 import torch
 
+import ctypes
+
+from . import _lib as L
 from . import modules as M
 from . import weights
+
+
+@torch.no_grad()
+def frame_metrics(pred_imgs: torch.Tensor, videos: torch.Tensor, frame0: int, clamp: bool = True, want_ssim: bool = True):
+    """Evaluator metrics on the device (05_evaluate_predictor.py:96-103, lib/metrics.py:181-270): pred_imgs [B,F,C,H,W]
+    (unclamped) against videos[:, frame0:frame0+F] read in place; both are clamped to [0,1] inside the kernels.
+    Returns dict of [B,F] tensors: mse, psnr, ssim."""
+    B, F_, C, H, W = pred_imgs.shape
+    pred = pred_imgs.float().contiguous()
+    vid = videos.float()
+    if not vid.is_contiguous():
+        vid = vid.contiguous()
+    n = B * F_
+    mse = torch.empty(B, F_, device=pred.device, dtype=torch.float32)
+    psnr = torch.empty_like(mse)
+    ssim = torch.empty_like(mse) if want_ssim else None
+    L.call("tocvp_frame_metrics", L.ptr(pred), L.ptr(vid), L.c_size_t(vid.stride(0)), L.c_int(F_), L.c_int(frame0),
+           L.c_int(n), L.c_int(C), L.c_int(H), L.c_int(W), L.c_int(int(clamp)), L.ptr(mse), L.ptr(psnr), L.ptr(ssim),
+           L.stream())
+    return {"mse": mse, "psnr": psnr, "ssim": ssim}
 
 
 def build_models(device, savi_seed=14, pred_seed=15, mlp_out_scale=0.1, num_context=1, num_preds=19,
@@ -57,7 +80,7 @@ def forward_eval_dino(dino, pred, feats, text_embeddings, num_context, num_preds
 
 @torch.no_grad()
 def forward_eval(savi, pred, videos, text_embeddings, num_context, num_preds, init_slots=None, num_imgs=None,
-                 conv_events=None, only_imgs=False) -> Dict[str, torch.Tensor]:
+                 conv_events=None, only_imgs=False, want_ssim=True, clamp_output=True) -> Dict[str, torch.Tensor]:
     """videos [B,L,3,H,W] (device) -> clamped predicted frames [B,num_preds,3,H,W] + PSNR/MSE per frame.
     Mirrors Evaluator.forward_eval: decomp over num_context+num_preds frames (the reference encodes them all although
     only the seed frames are consumed when teacher_force=False), predict, decode all B*num_preds frames, clamp."""
@@ -70,23 +93,29 @@ def forward_eval(savi, pred, videos, text_embeddings, num_context, num_preds, in
     pred_slots = pred(slot_history, text_embeddings=text_embeddings)
     dec = savi.decode(pred_slots.reshape(B * num_preds, savi.num_slots, savi.slot_dim), only_imgs=only_imgs,
                       conv_events=conv_events)
-    pred_imgs = dec["recons_imgs"].view(B, num_preds, C, H, W).clamp(0, 1)
-    targets = videos[:, num_context:num_context + num_preds].clamp(0, 1)
-    mse = ((pred_imgs - targets) ** 2).flatten(2).mean(-1)                       # [B, num_preds]
-    psnr = 10.0 * torch.log10(1.0 / (mse + 1e-8))                                # piqa-style, value_range 1 (unpinned)
-    return {"slot_history": slot_history, "pred_slots": pred_slots, "pred_imgs": pred_imgs, "mse": mse, "psnr": psnr}
+    raw = dec["recons_imgs"].view(B, num_preds, C, H, W)
+    # clamp + MSE / PSNR / SSIM in the metric kernels (targets = videos[:, num_context:num_context+num_preds], in place)
+    m = frame_metrics(raw, videos, num_context, clamp=True, want_ssim=want_ssim)
+    pred_imgs = raw.clamp_(0, 1) if clamp_output else raw
+    return {"slot_history": slot_history, "pred_slots": pred_slots, "pred_imgs": pred_imgs, "mse": m["mse"],
+            "psnr": m["psnr"], "ssim": m["ssim"]}
 
 
 class MetricSums:
-    """[sum_b psnr[b,f] (F), sum_b mse[b,f] (F), count] in fp64; all-reduced once at the end."""
+    """[sum_b psnr[b,f] (F), sum_b mse[b,f] (F), sum_b ssim[b,f] (F), sum_b lpips[b,f] (F), count] in fp64; all-reduced
+    once at the end.  The LPIPS slot stays zero: its AlexNet weights need network access."""
+
+    NAMES = ("psnr", "mse", "ssim", "lpips")
 
     def __init__(self, num_preds, device):
         self.F = num_preds
-        self.acc = torch.zeros(2 * num_preds + 1, dtype=torch.float64, device=device)
+        self.acc = torch.zeros(len(self.NAMES) * num_preds + 1, dtype=torch.float64, device=device)
 
-    def accumulate(self, psnr, mse):
-        self.acc[:self.F] += psnr.double().sum(0)
-        self.acc[self.F:2 * self.F] += mse.double().sum(0)
+    def accumulate(self, psnr, mse, ssim=None, lpips=None):
+        F_ = self.F
+        for k, v in enumerate((psnr, mse, ssim, lpips)):
+            if v is not None:
+                self.acc[k * F_:(k + 1) * F_] += v.double().sum(0)
         self.acc[-1] += psnr.shape[0]
 
     def all_reduce(self):
@@ -97,10 +126,12 @@ class MetricSums:
 
     def results(self):
         n = self.acc[-1].item()
-        pf = (self.acc[:self.F] / n).tolist()
-        mf = (self.acc[self.F:2 * self.F] / n).tolist()
-        return {"count": int(n), "psnr_mean": sum(pf) / len(pf), "psnr_per_frame": pf, "mse_mean": sum(mf) / len(mf),
-                "mse_per_frame": mf}
+        out = {"count": int(n)}
+        for k, name in enumerate(self.NAMES):
+            pf = (self.acc[k * self.F:(k + 1) * self.F] / n).tolist()
+            out[f"{name}_mean"] = sum(pf) / len(pf)
+            out[f"{name}_per_frame"] = pf
+        return out
 
 
 def shard_range(rank: int, world: int, total: int):
