@@ -145,6 +145,11 @@ typedef struct tocvp_pred_layer {
   const float *ln_m_g, *ln_m_b;     /* layernorm_mlp                        */
   const void *w_1, *w_2;            /* f16 [H, T], [T, H]    mlp            */
   const float *b_1, *b_2;
+  /* LayerNorm folded into the projection that consumes it (used for M >= 1024 rows, where the CTA-pair GEMM applies
+   * LN(x).W^T = rstd*(x.(W*gamma)^T - mu*c) + d in its epilogue from row statistics emitted by the producing GEMM):
+   * *_f = f16(W * gamma[None,:]) with W the matrix above, c = row sums of *_f (fp32), d = W.beta (+ bias). */
+  const void *w_qkv_f, *wc_q_f, *wc_1_f, *w_1_f;
+  const float *c_qkv, *d_qkv, *c_cq, *d_cq, *c_c1, *d_c1, *c_1, *d_1;
 } tocvp_pred_layer;
 
 typedef struct tocvp_pred_weights {

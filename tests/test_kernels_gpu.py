@@ -34,13 +34,13 @@ def test_gemm_f16(M, N, K):
 
 @pytest.mark.parametrize("mode", [128, 256])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (20480, 512, 512), (1000, 2048, 512), (4096, 512, 2048),
-                                   (300, 768, 128), (2048, 1536, 512)])
+                                   (300, 768, 128), (2048, 1536, 512), (1300, 776, 1024), (700, 264, 64)])
 def test_gemm_pair_kernel(mode, M, N, K):
     """CTA-pair (cta_group::2) kernel forced on, both tile widths: ragged M tails, both outputs at once (TMA-store
     epilogue through shared staging tiles), bias + ReLU + residual."""
     from textocvp_b200 import ops
-    if N % mode:
-        pytest.skip("tile width does not divide N")
+    if N < mode:
+        pytest.skip("narrower than one tile")
     g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
     a = torch.randn(M, K, device="cuda", generator=g).half()
     w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()

@@ -97,3 +97,30 @@ def test_full_rollout_psnr(models, golden, golden_weights):
     assert O.rel_err(ps, golden["pred_slots"]) < 5e-3
     p = O.psnr(imgs.cpu(), golden["pred_imgs"])
     assert p.min() >= 40.0, (p.min(), p.mean())
+
+
+def test_predictor_step_folded_layernorm(models, golden, golden_weights):
+    """M = B*n*S >= 1024 rows takes the CTA-pair GEMMs with LayerNorm folded into the projections (row statistics from
+    the producing GEMM, gamma-folded weights, rstd / mu applied in the epilogue).  Checked against the fp32 oracle on
+    identical inputs, and against the unfolded path (single-CTA kernels + explicit LayerNorm) of the same library."""
+    from textocvp_b200 import ops
+    _, pred = models
+    B = 16
+    g = torch.Generator().manual_seed(9)
+    base = golden["slot_history"][:, :10]                                   # realistic slot statistics
+    slots = base[torch.randint(0, base.shape[0], (B,), generator=g)] + 0.1 * torch.randn(B, 10, 8, 128, generator=g)
+    text = torch.randn(B, 32, 512, generator=g)
+    ref = O.predictor_step(golden_weights["pred_sd"], slots, text, O.PredCfg())
+    out = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())
+    assert O.rel_err(out, ref) < STAGE_TOL
+    d_ref, d_out = ref - slots[:, -1], out.cpu() - slots[:, -1]
+    assert O.rel_err(d_out, d_ref) < 5e-3
+    ops.set_gemm_mode(1)
+    try:
+        out_unfolded = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode(0)
+    assert O.rel_err(out_unfolded, ref) < STAGE_TOL
+    print(f"folded-LN predictor step: rel err {O.rel_err(out, ref):.2e} (delta {O.rel_err(d_out, d_ref):.2e}); "
+          f"unfolded {O.rel_err(out_unfolded, ref):.2e}")

@@ -1,6 +1,8 @@
 // Multi-head attention for the predictor's short sequences (<= 128 keys, head dim 64), fp32 softmax.
-// One CTA per (sequence, head).  K and V^T of the head are staged once in shared memory (row strides padded to
-// 4 (mod 32) words so every fragment load is bank-conflict free); each warp owns 16-query tiles and runs
+// One CTA per (sequence, head) with one warp per 16-query tile (ceil(Tq/16) warps, so the 80-token window of the named
+// config is ONE pass of 5 warps).  K and V of the head are staged once in shared memory, both row-major with the row
+// stride padded to 4 (mod 32) words: K fragments are plain 32-bit loads, V fragments come from ldmatrix.trans (no
+// transposing scalar stores).  Each warp runs
 //     S = Q K^T  ->  softmax in registers (quad shuffles)  ->  O = P V
 // on mma.sync.m16n8k16 (f16 operands, fp32 accumulate) with the S accumulator fragments re-used directly as the
 // A operand of the second product (no smem round trip).  The problem per CTA (<= 80 x 80 x 64) is far too small to
@@ -15,9 +17,15 @@ namespace tocvp {
 
 constexpr int ATT_DH = 64;
 constexpr int ATT_MAXK = 128;
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_KS = 72;    // K row stride (halfs): 36 words
-constexpr int ATT_VS = 136;   // V^T row stride (halfs): 68 words
+constexpr int ATT_MAX_WARPS = 8;
+constexpr int ATT_KS = 72;    // K / V row stride (halfs): 36 words = 144 B (16-byte aligned rows for ldmatrix)
+
+// two transposed 8x8 b16 tiles x 2: B fragments (k = key, n = head-dim column) of two adjacent 8-column blocks
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -26,34 +34,32 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_MAX_WARPS * 32)
 mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, const __half* __restrict__ v, int ldkv,
            int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out, int ldo) {
   __shared__ __align__(16) __half sK[ATT_MAXK * ATT_KS];
-  __shared__ __align__(16) __half sVt[ATT_DH * ATT_VS];
+  __shared__ __align__(16) __half sV[ATT_MAXK * ATT_KS];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int TkP = (Tk + 15) & ~15;
   const __half* kb = k + size_t(b) * Tk * ldkv + h * ATT_DH;
   const __half* vb = v + size_t(b) * Tk * ldkv + h * ATT_DH;
-  for (int e = threadIdx.x; e < TkP * 8; e += ATT_THREADS) {
+  for (int e = threadIdx.x; e < TkP * 8; e += blockDim.x) {
     const int r = e >> 3, c = e & 7;
     uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
     if (r < Tk) {
-      kk = *reinterpret_cast<const uint4*>(kb + size_t(r) * ldkv + c * 8);
-      vv = *reinterpret_cast<const uint4*>(vb + size_t(r) * ldkv + c * 8);
+      kk = __ldg(reinterpret_cast<const uint4*>(kb + size_t(r) * ldkv + c * 8));
+      vv = __ldg(reinterpret_cast<const uint4*>(vb + size_t(r) * ldkv + c * 8));
     }
     *reinterpret_cast<uint4*>(sK + r * ATT_KS + c * 8) = kk;
-    const __half* vh = reinterpret_cast<const __half*>(&vv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sVt[(c * 8 + j) * ATT_VS + r] = vh[j];
+    *reinterpret_cast<uint4*>(sV + r * ATT_KS + c * 8) = vv;    // padded keys are zero rows (their P is exactly 0)
   }
   __syncthreads();
   const int n_tiles = TkP / 8;    // key tiles of 8
   const __half* qb = q + size_t(b) * Tq * ldq + h * ATT_DH;
   __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
-  for (int m0 = warp * 16; m0 < Tq; m0 += (ATT_THREADS / 32) * 16) {
+  for (int m0 = warp * 16; m0 < Tq; m0 += (blockDim.x >> 5) * 16) {
     const int r0 = m0 + g, r1 = m0 + g + 8;
     const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
     uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
@@ -123,12 +129,14 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
         pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
         pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
         pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        // lane l supplies the row address of key kk*16 + (l & 15), column block nd2*16 + 8*(l >> 4)
+        const __half* vrow = sV + (kk * 16 + (lane & 15)) * ATT_KS + ((lane >> 4) << 3);
 #pragma unroll
-        for (int nd = 0; nd < ATT_DH / 8; ++nd) {
-          const __half* vr = sVt + (nd * 8 + g) * ATT_VS + kk * 16 + 2 * t;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
-          mma_16816(o[nd], pa, b0, b1);
+        for (int nd2 = 0; nd2 < ATT_DH / 16; ++nd2) {
+          uint32_t vb4[4];
+          ldmatrix_x4_trans(vb4, vrow + nd2 * 16);
+          mma_16816(o[2 * nd2], pa, vb4[0], vb4[1]);
+          mma_16816(o[2 * nd2 + 1], pa, vb4[2], vb4[3]);
         }
       }
     }
@@ -148,7 +156,9 @@ int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv
   TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && Tk > 0 && Tk <= ATT_MAXK && heads > 0);
   TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0);
   const float scale_log2e = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (attention.py:187) * log2(e)
-  mha_kernel<<<B * heads, ATT_THREADS, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo);
+  int warps = (Tq + 15) / 16;
+  warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
+  mha_kernel<<<B * heads, warps * 32, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }

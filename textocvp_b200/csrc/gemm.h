@@ -9,6 +9,25 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
              const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16,
              int ld16, cudaStream_t stream);
 
+// LayerNorm folded into a pair of GEMMs (CTA-pair kernel only, M >= 1024):
+//   producer  (stats_out != null): C = A.W^T (+bias) + residual in fp32, PLUS an f16 copy of C (out16) and per-row
+//             partial [sum, sum of squares] pairs of C: stats_out[M][N/64][2], one pair per 64 output columns (each
+//             written by exactly one warp: no atomics, nothing to zero);
+//   consumer  (stats != null): A is that f16 copy, W holds W*gamma, and the epilogue applies
+//             y = rstd*(acc - mu*c_n) + d_n with mu, rstd from the `slots` partial pairs, c_n = sum_k W'[n,k], d_n passed
+//             as `bias`.
+struct GemmLn {
+  const float* stats;
+  int slots;
+  const float* c;
+  float inv_k, eps;
+  float* stats_out;
+};
+bool gemm_ln_supported(int M, int N);   // true when gemm_f16_ln will take the CTA-pair kernel for this shape
+int gemm_f16_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+                const float* residual, int ldr, float* out32, int ld32, __half* out16, int ld16, const GemmLn& ln,
+                cudaStream_t stream);
+
 // 3x3 convolution over a zero-bordered NHWC f16 activation [n_img, Hp, Wp, Cin] (Hp = H+2, Wp = W+2) run as a GEMM over
 // the FLATTENED padded pixel index p: a filter tap is a constant row offset dy*Wp + dx of the A operand, so the A tile
 // of tap t is one 2-D TMA box at row m0 + off[t] (rows outside the tensor are zero-filled by the TMA unit) and no

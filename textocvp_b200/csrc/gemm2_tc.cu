@@ -39,6 +39,13 @@ struct Gemm2Args {
   __half* out16;
   int ld16;
   ConvMap cm;
+  // LayerNorm folded into the GEMM (LN(x).W^T = rstd*(x.(W*gamma)^T - mu*c) + d, see predictor.cu):
+  const float* ln_stats;  // consumer: per-row partial [sum, sumsq] pairs (ln_slots of them) of the fp32 tensor whose f16
+                          // copy is A, or null
+  int ln_slots;           // partial pairs per row = (producer N) / 64: one per (128-wide tile, 64-column warp half)
+  const float* ln_c;      // consumer: per-column c_n = sum_k W'[n,k] (bias then holds d_n)
+  float ln_inv_k, ln_eps; // 1 / (LayerNorm width), eps
+  float* stats_out;       // producer: writes its [sum, sumsq] of 64 output columns to slot n/64 of the row (no atomics)
 };
 
 template <int BN>
@@ -46,9 +53,10 @@ struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;       // 16 KB (BN = 256) / 8 KB (BN = 128)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int STG_BYTES = 8 * 2 * 4096;            // 8 epilogue warps x 2 staging tiles of 32 rows x 128 B
-  static constexpr int BAR_BYTES = 256 + 2 * BN * 4;
+  static constexpr int STAGES = (BN == 256) ? 4 : 5;
+  static constexpr int STG_TILES = (BN == 128) ? 3 : 2;     // staging tiles (32 rows x 128 B) per epilogue warp
+  static constexpr int STG_BYTES = 8 * STG_TILES * 4096;
+  static constexpr int BAR_BYTES = 512 + 4 * BN * 4;        // barriers, then [2 buffers][bias | ln_c][BN] floats
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
 };
 
@@ -69,7 +77,7 @@ template <int BN, bool CONV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
-                 const __grid_constant__ Gemm2Args g) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ Gemm2Args g) {
   using S = G2Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,7 +89,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = empty + S::STAGES;                                                // per CTA (multicast commit)
   uint64_t* tempty = tfull + 2;                                                       // leader only, 16 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 256);   // [2][BN]
+  uint64_t* resbar = tempty + 4;                                                      // [8 warps][2]: residual tiles landed
+  float* sbias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 512);   // [2][2][BN]: bias, ln_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -103,6 +112,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 16);   // 8 epilogue warps x 2 CTAs
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
@@ -178,8 +188,12 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;      // 0..255
     constexpr int CW = BN / 2;            // columns per warp
     constexpr int NCH = CW / 32;
-    uint8_t* stg = stg_base + ew * 8192;  // this warp's two staging tiles
+    uint8_t* stg = stg_base + ew * (S::STG_TILES * 4096);  // this warp's staging tiles
     int sbuf = 0;
+    // fp32 residual + fp32 output with two chunks per warp (the N = 512 projections of the predictor): the residual
+    // tiles are TMA-LOADED into the staging tiles while the main loop of the tile runs, the accumulator is added in
+    // place and the same tile is TMA-stored -- both directions in full 128-byte lines instead of 16 bytes per row
+    const bool tma_res = !CONV && NCH == 2 && g.residual != nullptr && g.res_mod == 0 && g.out32 != nullptr;
     const uint32_t sw = uint32_t(lane & 7);
     int it = 0;
     for (int t = pair; t < num_tiles; t += npairs, ++it) {
@@ -189,7 +203,13 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (g.bias != nullptr) {
         for (int e = et; e < BN; e += 256) {
           const int n = nb * BN + e;
-          sbias[b * BN + e] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
+          sbias[(b * 2) * BN + e] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
+        }
+      }
+      if (g.ln_c != nullptr) {
+        for (int e = et; e < BN; e += 256) {
+          const int n = nb * BN + e;
+          sbias[(b * 2 + 1) * BN + e] = (n < g.N) ? __ldg(g.ln_c + n) : 0.f;
         }
       }
       const int row = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32 + lane;
@@ -209,6 +229,20 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
         res_row = g.residual + size_t(rr) * g.ldr;
       }
+      float ln_rstd = 1.f, ln_nmr = 0.f;      // consumer of a folded LayerNorm: rstd and -mu*rstd of this thread's row
+      if (g.ln_stats != nullptr && row < g.M) {
+        const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + size_t(row) * 2 * g.ln_slots);
+        float sm = 0.f, sq = 0.f;
+        for (int i = 0; i < g.ln_slots / 2; ++i) {
+          const float4 v4 = __ldg(sp + i);
+          sm += v4.x + v4.z;
+          sq += v4.y + v4.w;
+        }
+        const float mu = sm * g.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(sq * g.ln_inv_k - mu * mu, 0.f) + g.ln_eps);
+        ln_nmr = -mu * ln_rstd;
+      }
+      float st_sum = 0.f, st_sq = 0.f;        // producer: row statistics of the fp32 output
       float4 rbuf[2][8];
       auto load_res = [&](int c, float4 (&dst)[8]) {
 #pragma unroll
@@ -218,7 +252,20 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      load_res(0, rbuf[0]);
+      if (tma_res) {
+        if (lane == 0) {
+          bulk_wait_read<0>();                          // the previous tile's stores have drained both staging tiles
+          const int trow0 = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            mbar_expect_tx(&resbar[ew * 2 + c], 4096);
+            tma_load_2d(&tmR, &resbar[ew * 2 + c], stg + c * 4096, ncol0 + c * 32, trow0);
+          }
+        }
+        __syncwarp();
+      } else {
+        load_res(0, rbuf[0]);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // bias staged (epilogue warps only)
       mbar_wait(&tfull[b], bph);
       tc_fence_after();
@@ -231,7 +278,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();                                            // chunk c is in v[c & 1]
         if (c + 1 < NCH) {
           tmem_ld32(t_addr + uint32_t((c + 1) * 32), v[(c + 1) & 1]);   // next chunk in flight while this one is stored
-          load_res(c + 1, rbuf[(c + 1) & 1]);
+          if (!tma_res) load_res(c + 1, rbuf[(c + 1) & 1]);
         } else {
           // all accumulator columns of this warp are in registers: hand the TMEM buffer back to the leader's MMA warp
           tc_fence_before();
@@ -244,18 +291,30 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[c & 1][j]);
-          if (g.bias != nullptr) {
+          if (g.ln_stats != nullptr) {
+            // y = rstd * (acc - mu * c_n) + d_n
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j4 * 4]);
+              const float4 dd = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j4 * 4]);
+              const float4 cc = *reinterpret_cast<const float4*>(&sbias[(b * 2 + 1) * BN + half * CW + c * 32 + j4 * 4]);
+              f[4 * j4] = fmaf(ln_rstd, f[4 * j4], fmaf(ln_nmr, cc.x, dd.x));
+              f[4 * j4 + 1] = fmaf(ln_rstd, f[4 * j4 + 1], fmaf(ln_nmr, cc.y, dd.y));
+              f[4 * j4 + 2] = fmaf(ln_rstd, f[4 * j4 + 2], fmaf(ln_nmr, cc.z, dd.z));
+              f[4 * j4 + 3] = fmaf(ln_rstd, f[4 * j4 + 3], fmaf(ln_nmr, cc.w, dd.w));
+            }
+          } else if (g.bias != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j4 * 4]);
               f[4 * j4] += bb.x; f[4 * j4 + 1] += bb.y; f[4 * j4 + 2] += bb.z; f[4 * j4 + 3] += bb.w;
             }
           }
-          if (g.relu) {
+          const bool relu_in_cvt = g.relu && g.out32 == nullptr && g.residual == nullptr;   // f16-only output: fused
+          if (g.relu && !relu_in_cvt) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (g.residual != nullptr) {
+          if (g.residual != nullptr && !tma_res) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 r = rbuf[c & 1][j4];
@@ -263,7 +322,58 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           const int trow = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32;
-          if (g.out32 != nullptr) {
+          if (tma_res) {
+            mbar_wait(&resbar[ew * 2 + c], uint32_t(it & 1));
+            uint8_t* dst = stg + c * 4096 + lane * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4* sp = reinterpret_cast<float4*>(dst + ((uint32_t(j4) ^ sw) << 4));
+              const float4 r = *sp;
+              f[4 * j4] += r.x; f[4 * j4 + 1] += r.y; f[4 * j4 + 2] += r.z; f[4 * j4 + 3] += r.w;
+              *sp = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC32, stg + c * 4096, n0, trow);
+              bulk_commit();
+            }
+            if (g.stats_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                st_sum += f[j];
+                st_sq = fmaf(f[j], f[j], st_sq);
+              }
+              if (c == NCH - 1 && row < g.M)
+                *reinterpret_cast<float2*>(g.stats_out + (size_t(row) * (g.N / 64) + size_t(ncol0 / 64)) * 2) =
+                    make_float2(st_sum, st_sq);
+            }
+            if (g.out16 != nullptr) {
+              // f16 copy of the fp32 result (the A operand of the GEMM that consumes the folded LayerNorm): third tile
+              if constexpr (S::STG_TILES == 3) {
+                uint4 pk[4];
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  pk[j8].x = pack_half2(f[8 * j8], f[8 * j8 + 1]);
+                  pk[j8].y = pack_half2(f[8 * j8 + 2], f[8 * j8 + 3]);
+                  pk[j8].z = pack_half2(f[8 * j8 + 4], f[8 * j8 + 5]);
+                  pk[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
+                }
+                uint8_t* hd = stg + 2 * 4096 + lane * 128;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                  *reinterpret_cast<uint4*>(hd + ((uint32_t((c & 1) * 4 + j8) ^ sw) << 4)) = pk[j8];
+                if (c & 1) {
+                  fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_2d(&tmC16, stg + 2 * 4096, n0 - 32, trow);
+                    bulk_commit();
+                  }
+                }
+              }
+            }
+          } else if (g.out32 != nullptr) {
             if (lane == 0) bulk_wait_read<1>();          // the store that last read this staging tile has drained
             __syncwarp();
             uint8_t* dst = stg + sbuf * 4096 + lane * 128;
@@ -279,15 +389,25 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             sbuf ^= 1;
           }
-          if (g.out16 != nullptr) {
+          if (g.out16 != nullptr && !tma_res) {
             // two 32-column chunks make one 64-column (128 B) staging row: the even chunk waits in registers
             uint4 p[4];
+            if (relu_in_cvt) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              p[j8].x = pack_half2(f[8 * j8], f[8 * j8 + 1]);
-              p[j8].y = pack_half2(f[8 * j8 + 2], f[8 * j8 + 3]);
-              p[j8].z = pack_half2(f[8 * j8 + 4], f[8 * j8 + 5]);
-              p[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
+              for (int j8 = 0; j8 < 4; ++j8) {
+                p[j8].x = pack_half2_relu(f[8 * j8], f[8 * j8 + 1]);
+                p[j8].y = pack_half2_relu(f[8 * j8 + 2], f[8 * j8 + 3]);
+                p[j8].z = pack_half2_relu(f[8 * j8 + 4], f[8 * j8 + 5]);
+                p[j8].w = pack_half2_relu(f[8 * j8 + 6], f[8 * j8 + 7]);
+              }
+            } else {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                p[j8].x = pack_half2(f[8 * j8], f[8 * j8 + 1]);
+                p[j8].y = pack_half2(f[8 * j8 + 2], f[8 * j8 + 3]);
+                p[j8].z = pack_half2(f[8 * j8 + 4], f[8 * j8 + 5]);
+                p[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
+              }
             }
             if ((c & 1) == 0) {
 #pragma unroll
@@ -319,8 +439,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c & 1][j8 * 8 + j]);
               if (g.bias != nullptr) {
-                const float4 b0 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&sbias[b * BN + half * CW + c * 32 + j8 * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j8 * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j8 * 8 + 4]);
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
@@ -367,7 +487,14 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN, bool CONV>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
   // output maps for the TMA-store epilogue: 32-row x 128-byte boxes (64 f16 / 32 fp32 columns), 128B swizzle
-  CUtensorMap tmC16 = tmA, tmC32 = tmA;     // placeholders when an output is absent (never dereferenced)
+  CUtensorMap tmC16 = tmA, tmC32 = tmA, tmR = tmA;     // placeholders when absent (never dereferenced)
+  if (!CONV && g.residual != nullptr && g.res_mod == 0) {
+    TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0);
+    const uint64_t dims[2] = {uint64_t(g.N), uint64_t(g.M)};
+    const uint64_t str[1] = {uint64_t(g.ldr) * 4};
+    const uint32_t box[2] = {32, 32};
+    TOCVP_TRY(encode_tmap(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.residual, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
   if (!CONV && g.out16 != nullptr) {
     const uint64_t dims[2] = {uint64_t(g.N), uint64_t(g.M)};
     const uint64_t str[1] = {uint64_t(g.ld16) * 2};
@@ -389,7 +516,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int tiles = ((g.M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((g.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_f16_kernel<BN, CONV><<<grid, G2_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, g);
+  gemm2_f16_kernel<BN, CONV><<<grid, G2_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -399,22 +526,28 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
 // (measured r1: N = 512 -> 128-wide tiles (5 waves beat 3 of twice the width), N = 1536 / 2048 -> 256-wide).
 int gemm2_pick_bn(int M, int N, int force) {
   if (force == 128 || force == 256) return force;
-  if (M < 1024 || N < 128 || N % 128 != 0) return 0;
+  if (M < 1024 || N < 128) return 0;   // ragged N is fine: TMA zero-fills W rows >= N and clips the stores
   const int pairs = num_sms() / 2;
   const int tm = (M + 255) / 256;
   auto waves = [&](int bn) { return (tm * ((N + bn - 1) / bn) + pairs - 1) / pairs; };
-  const double c256 = (N % 256 == 0) ? waves(256) * 256.0 : 1e30;
+  const double c256 = waves(256) * 256.0;
   const double c128 = waves(128) * 128.0 * 1.1;
   return c256 <= c128 ? 256 : 128;
 }
 
 int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
               const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16, int ld16,
-              cudaStream_t stream) {
+              cudaStream_t stream, const GemmLn* ln) {
+  // the fused f16 copy + row statistics live on the TMA-residual path: 128-wide tiles, plain residual rows, fp32 output
+  if (ln != nullptr && ln->stats_out != nullptr)
+    TOCVP_CHECK_ARG(bn == 128 && residual != nullptr && res_mod == 0 && out32 != nullptr && N % 128 == 0);
+  if (ln != nullptr && ln->stats != nullptr) TOCVP_CHECK_ARG(ln->slots >= 2 && ln->slots % 2 == 0);
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn / 2, G2_BK));
-  Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{}};
+  Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{},
+              ln ? ln->stats : nullptr, ln ? ln->slots : 0, ln ? ln->c : nullptr, ln ? ln->inv_k : 0.f, ln ? ln->eps : 0.f,
+              ln ? ln->stats_out : nullptr};
   if (bn == 256) return launch_gemm2<256, false>(tmA, tmB, g, stream);
   return launch_gemm2<128, false>(tmA, tmB, g, stream);
 }
@@ -424,7 +557,7 @@ int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, K, bn / 2, G2_BK));
-  Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm};
+  Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm, nullptr, 0, nullptr, 0.f, 0.f, nullptr};
   if (bn == 256) return launch_gemm2<256, true>(tmA, tmB, g, stream);
   return launch_gemm2<128, true>(tmA, tmB, g, stream);
 }

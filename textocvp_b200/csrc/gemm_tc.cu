@@ -305,7 +305,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 int gemm2_pick_bn(int M, int N, int force);
 int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
               const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16, int ld16,
-              cudaStream_t stream);
+              cudaStream_t stream, const GemmLn* ln);
 int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
                    int relu, float* out32, __half* out16, int ldo, cudaStream_t stream);
 
@@ -327,11 +327,11 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (g_gemm_mode != 1) {
     // CTA-pair kernel (256-row tiles, half the L2 operand traffic) for everything large enough to fill the chip
-    const int bn2 = (g_gemm_mode >= 128 && N % g_gemm_mode == 0 && N >= g_gemm_mode) ? g_gemm_mode
+    const int bn2 = (g_gemm_mode >= 128 && N >= g_gemm_mode) ? g_gemm_mode
                                                                                        : gemm2_pick_bn(M, N, 0);
     if (bn2 != 0)
       return gemm2_f16(bn2, A, lda, W, ldw, M, N, K, bias, relu, residual, ldr, res_div, res_mod, out32, ld32, out16, ld16,
-                       stream);
+                       stream, nullptr);
   }
   // Tile width: wide tiles for wide outputs; 64 keeps enough tiles in flight for narrow / short problems.
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
@@ -344,6 +344,18 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   GemmArgs g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{}};
   if (bn == 64) return launch_gemm<64, false>(tmA, tmB, g, stream);
   return launch_gemm<128, false>(tmA, tmB, g, stream);
+}
+
+bool gemm_ln_supported(int M, int N) { return g_gemm_mode != 1 && gemm2_pick_bn(M, N, 0) != 0 && N % 64 == 0; }
+
+int gemm_f16_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
+                const float* residual, int ldr, float* out32, int ld32, __half* out16, int ld16, const GemmLn& ln,
+                cudaStream_t stream) {
+  TOCVP_CHECK_ARG(A && W && gemm_ln_supported(M, N));
+  TOCVP_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && (out32 || out16));
+  // producers need the 128-wide tile (3 staging tiles per warp); consumers take the usual choice
+  const int bn = ln.stats_out != nullptr ? 128 : gemm2_pick_bn(M, N, g_gemm_mode >= 128 ? g_gemm_mode : 0);
+  return gemm2_f16(bn, A, lda, W, ldw, M, N, K, bias, relu, residual, ldr, 1, 0, out32, ld32, out16, ld16, stream, &ln);
 }
 
 int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const ConvMap& cm, const float* bias, int relu,

@@ -6,14 +6,12 @@
 //   * the residual stream stays fp32; only GEMM operands are f16
 //   * the text K|V projections are rollout-constant and hoisted out of the step loop (the reference recomputes them)
 //   * self-attention is unmasked and the temporal PE is re-flipped every step -> full window recompute (no KV cache)
+#include "gemm.h"
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace tocvp {
 
-int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
-             const float* residual, int ldr, int res_div, int res_mod, float* out32, int ld32, __half* out16,
-             int ld16, cudaStream_t stream);
 int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_rows, const float* gamma,
               const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
               cudaStream_t stream);
@@ -82,7 +80,7 @@ static inline int ew_grid(size_t n, int threads = 256) {
 }
 
 struct PredBuffers {
-  float *frames, *x32, *y32, *z32, *pred32;
+  float *frames, *x32, *y32, *z32, *pred32, *stats;
   __half *tok16, *h16, *qkv16, *att16, *q16, *mid16, *last16, *text16, *kv16;
 };
 
@@ -105,6 +103,7 @@ static size_t carve(const tocvp_pred_weights& w, int B, int L, int nctx, int npr
   t.y32 = reinterpret_cast<float*>(take(Mmax * T * 4));
   t.z32 = reinterpret_cast<float*>(take(Mmax * T * 4));
   t.pred32 = reinterpret_cast<float*>(take(size_t(B) * S * D * 4));
+  t.stats = reinterpret_cast<float*>(take(Mmax * size_t(T / 64) * 2 * 4));
   t.tok16 = reinterpret_cast<__half*>(take(Mmax * D * 2));
   t.h16 = reinterpret_cast<__half*>(take(Mmax * T * 2));
   t.qkv16 = reinterpret_cast<__half*>(take(Mmax * 3 * T * 2));
@@ -135,35 +134,79 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   const float* pe_n = w.pe_flipped + size_t(n - 1) * w.buffer_size * T;
   TOCVP_TRY(gemm_f16(pb.tok16, D, static_cast<const __half*>(w.mlp_in_w), D, M, T, D, w.mlp_in_b, 0, pe_n, T, S, n,
                      pb.x32, T, nullptr, 0, st));
+  // LayerNorm folding (M >= 1024 rows): the GEMM that writes a residual-stream tensor also emits its f16 copy (h16) and
+  // per-row [sum, sumsq] (stats); the projection that would consume LN(.) reads the raw copy with gamma-folded weights and
+  // finishes the normalisation in its epilogue.  4 LayerNorm launches per layer and their fp32 re-reads disappear.
+  const bool fold = gemm_ln_supported(M, T);
+  const float inv_t = 1.f / float(T);
+  const int slots = T / 64;
   for (int l = 0; l < w.num_layers; ++l) {
     const tocvp_pred_layer& ly = w.layers[l];
+    const bool last_layer = (l == w.num_layers - 1);
     // ---- y = x + MHSA(LN(x))                                       (attention.py:512-514)
-    TOCVP_TRY(layernorm(pb.x32, 0, T, nullptr, 0, ly.ln_q_g, ly.ln_q_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-    TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_qkv), T, M, 3 * T, T, nullptr, 0, nullptr, 0, 1, 0,
-                       nullptr, 0, pb.qkv16, 3 * T, st));
+    if (fold && l > 0) {
+      const GemmLn c{pb.stats, slots, ly.c_qkv, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_qkv_f), T, M, 3 * T, T, ly.d_qkv, 0, nullptr, 0,
+                            nullptr, 0, pb.qkv16, 3 * T, c, st));
+    } else {
+      TOCVP_TRY(layernorm(pb.x32, 0, T, nullptr, 0, ly.ln_q_g, ly.ln_q_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_qkv), T, M, 3 * T, T, nullptr, 0, nullptr, 0, 1, 0,
+                         nullptr, 0, pb.qkv16, 3 * T, st));
+    }
     TOCVP_TRY(mha_f16(pb.qkv16, 3 * T, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, n * S, n * S, w.num_heads, pb.att16, T,
                       st));
-    TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.w_o), T, M, T, T, nullptr, 0, pb.x32, T, 1, 0, pb.y32,
-                       T, nullptr, 0, st));
-    // ---- z = y + CrossAttn(LN(text), LN(y)) ; z = z + MLP_c(LN(z))  (attention.py:445-463)
-    TOCVP_TRY(layernorm(pb.y32, 0, T, nullptr, 0, ly.ln_cq_g, ly.ln_cq_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-    TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_q), T, M, T, T, nullptr, 0, nullptr, 0, 1, 0, nullptr,
-                       0, pb.q16, T, st));
+    if (fold) {
+      const GemmLn p{nullptr, 0, nullptr, 0.f, 0.f, pb.stats};
+      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.w_o), T, M, T, T, nullptr, 0, pb.x32, T, pb.y32, T,
+                            pb.h16, T, p, st));
+      // ---- z = y + CrossAttn(LN(text), LN(y))                      (attention.py:445-463)
+      const GemmLn c{pb.stats, slots, ly.c_cq, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_q_f), T, M, T, T, ly.d_cq, 0, nullptr, 0, nullptr,
+                            0, pb.q16, T, c, st));
+    } else {
+      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.w_o), T, M, T, T, nullptr, 0, pb.x32, T, 1, 0, pb.y32,
+                         T, nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.y32, 0, T, nullptr, 0, ly.ln_cq_g, ly.ln_cq_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_q), T, M, T, T, nullptr, 0, nullptr, 0, 1, 0, nullptr,
+                         0, pb.q16, T, st));
+    }
     const __half* kv = pb.kv16 + size_t(l) * B * L * 2 * T;
     TOCVP_TRY(mha_f16(pb.q16, T, kv, kv + T, 2 * T, B, n * S, L, w.cross_heads, pb.att16, T, st));
-    TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, M, T, T, ly.bc_o, 0, pb.y32, T, 1, 0, pb.z32,
-                       T, nullptr, 0, st));
-    TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_cm_g, ly.ln_cm_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-    TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_1), T, M, w.cross_hidden, T, ly.bc_1, 1, nullptr, 0, 1,
-                       0, nullptr, 0, pb.mid16, w.cross_hidden, st));
-    TOCVP_TRY(gemm_f16(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, M, T,
-                       w.cross_hidden, ly.bc_2, 0, pb.z32, T, 1, 0, pb.z32, T, nullptr, 0, st));
-    // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
-    TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_m_g, ly.ln_m_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-    TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_1), T, M, w.hidden_dim, T, ly.b_1, 1, nullptr, 0, 1, 0,
-                       nullptr, 0, pb.mid16, w.hidden_dim, st));
-    TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
-                       ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+    if (fold) {
+      const GemmLn p{nullptr, 0, nullptr, 0.f, 0.f, pb.stats};
+      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, M, T, T, ly.bc_o, 0, pb.y32, T, pb.z32, T,
+                            pb.h16, T, p, st));
+      // ---- z = z + MLP_c(LN(z))
+      const GemmLn c{pb.stats, slots, ly.c_c1, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_1_f), T, M, w.cross_hidden, T, ly.d_c1, 1, nullptr,
+                            0, nullptr, 0, pb.mid16, w.cross_hidden, c, st));
+      TOCVP_TRY(gemm_f16_ln(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, M, T,
+                            w.cross_hidden, ly.bc_2, 0, pb.z32, T, pb.z32, T, pb.h16, T, p, st));
+      // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
+      const GemmLn c2{pb.stats, slots, ly.c_1, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_1_f), T, M, w.hidden_dim, T, ly.d_1, 1, nullptr, 0,
+                            nullptr, 0, pb.mid16, w.hidden_dim, c2, st));
+      if (last_layer) {
+        TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
+                           ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+      } else {
+          TOCVP_TRY(gemm_f16_ln(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
+                              ly.b_2, 0, pb.y32, T, pb.x32, T, pb.h16, T, p, st));
+      }
+    } else {
+      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, M, T, T, ly.bc_o, 0, pb.y32, T, 1, 0, pb.z32,
+                         T, nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_cm_g, ly.ln_cm_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_1), T, M, w.cross_hidden, T, ly.bc_1, 1, nullptr, 0, 1,
+                         0, nullptr, 0, pb.mid16, w.cross_hidden, st));
+      TOCVP_TRY(gemm_f16(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, M, T,
+                         w.cross_hidden, ly.bc_2, 0, pb.z32, T, 1, 0, pb.z32, T, nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_m_g, ly.ln_m_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_1), T, M, w.hidden_dim, T, ly.b_1, 1, nullptr, 0, 1, 0,
+                         nullptr, 0, pb.mid16, w.hidden_dim, st));
+      TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
+                         ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+    }
   }
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
   last_frame_to_f16_kernel<<<ew_grid(size_t(B) * S * T / 4), 256, 0, st>>>(pb.x32, n, S, T, B, pb.last16);

@@ -49,7 +49,8 @@ SaW = _struct("SaW", [
 
 PredLayer = _struct("PredLayer", [
     "ln_q_g", "ln_q_b", "w_qkv", "w_o", "ln_cq_g", "ln_cq_b", "ln_ckv_g", "ln_ckv_b", "wc_q", "wc_kv", "wc_o", "bc_o",
-    "ln_cm_g", "ln_cm_b", "wc_1", "wc_2", "bc_1", "bc_2", "ln_m_g", "ln_m_b", "w_1", "w_2", "b_1", "b_2"], [])
+    "ln_cm_g", "ln_cm_b", "wc_1", "wc_2", "bc_1", "bc_2", "ln_m_g", "ln_m_b", "w_1", "w_2", "b_1", "b_2",
+    "w_qkv_f", "wc_q_f", "wc_1_f", "w_1_f", "c_qkv", "d_qkv", "c_cq", "d_cq", "c_c1", "d_c1", "c_1", "d_1"], [])
 
 PredW = type("PredW", (ctypes.Structure,), {"_fields_": [
     ("layers", ctypes.POINTER(PredLayer)),
@@ -958,6 +959,18 @@ class BaseTextOCVP(_Packed):
                 wc_1=_f16(c.mlp[0].weight), wc_2=_f16(c.mlp[2].weight), bc_1=_f32(c.mlp[0].bias), bc_2=_f32(c.mlp[2].bias),
                 ln_m_g=_f32(blk.layernorm_mlp.weight), ln_m_b=_f32(blk.layernorm_mlp.bias),
                 w_1=_f16(blk.mlp[0].weight), w_2=_f16(blk.mlp[2].weight), b_1=_f32(blk.mlp[0].bias), b_2=_f32(blk.mlp[2].bias))
+            # LayerNorm folded into the consuming projection (include/tocvp.h, tocvp_pred_layer)
+            def fold(w, ln, bias, names):
+                wf = _f16(w.detach().float() * ln.weight.detach().float()[None, :])
+                t[names[0]] = wf
+                t[names[1]] = wf.float().sum(1).contiguous()
+                d = w.detach().float() @ ln.bias.detach().float()
+                t[names[2]] = (d + bias.detach().float() if bias is not None else d).contiguous()
+            fold(torch.cat([blk.attn.q.weight, blk.attn.k.weight, blk.attn.v.weight], 0), blk.layernorm_query, None,
+                 ("w_qkv_f", "c_qkv", "d_qkv"))
+            fold(c.cross_attn.q.weight, c.ln_cross_att_q, None, ("wc_q_f", "c_cq", "d_cq"))
+            fold(c.mlp[0].weight, c.ln_mlp, c.mlp[0].bias, ("wc_1_f", "c_c1", "d_c1"))
+            fold(blk.mlp[0].weight, blk.layernorm_mlp, blk.mlp[0].bias, ("w_1_f", "c_1", "d_1"))
             keep.append(t)
             for n, v in t.items():
                 setattr(layers[i], n, v.data_ptr())
