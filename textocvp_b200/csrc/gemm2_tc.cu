@@ -25,7 +25,9 @@ namespace tocvp {
 
 constexpr int G2_BM = 128;          // rows per CTA (256 per pair)
 constexpr int G2_BK = 64;
-constexpr int G2_THREADS = 320;
+// TMA warp, MMA warp, ew epilogue warps.  8 is the measured optimum: 16 warps (4 per TMEM lane quarter, one staging
+// tile each, 96 registers) ran 25% SLOWER on every predictor shape in the same process (r1 A/B), so it is not built.
+constexpr int g2_threads(int ew) { return 64 + 32 * ew; }
 
 struct Gemm2Args {
   int M, N, K;
@@ -48,14 +50,15 @@ struct Gemm2Args {
   float* stats_out;       // producer: writes its [sum, sumsq] of 64 output columns to slot n/64 of the row (no atomics)
 };
 
-template <int BN>
+template <int BN, int EWN>
 struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;       // 16 KB (BN = 256) / 8 KB (BN = 128)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 5;
-  static constexpr int STG_TILES = (BN == 128) ? 3 : 2;     // staging tiles (32 rows x 128 B) per epilogue warp
-  static constexpr int STG_BYTES = 8 * STG_TILES * 4096;
+  static constexpr int EW = EWN;
+  static constexpr int STG_TILES = (BN == 128) ? 3 : (EWN == 16 ? 1 : 2);     // staging tiles (32 rows x 128 B) per epilogue warp
+  static constexpr int STG_BYTES = EW * STG_TILES * 4096;
   static constexpr int BAR_BYTES = 512 + 4 * BN * 4;        // barriers, then [2 buffers][bias | ln_c][BN] floats
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
 };
@@ -73,12 +76,12 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, bool CONV>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+template <int BN, bool CONV, int EWN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EWN), 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ Gemm2Args g) {
-  using S = G2Smem<BN>;
+  using S = G2Smem<BN, EWN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + S::STAGES * S::STAGE_BYTES;                              // 1024B aligned
@@ -110,7 +113,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 16);   // 8 epilogue warps x 2 CTAs
+      mbar_init(&tempty[b], 2 * S::EW);   // epilogue warps x 2 CTAs
     }
     for (int i = 0; i < 16; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
@@ -184,16 +187,17 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ epilogue (warps 2..9) on this CTA's 128 rows
     const int ew = warp - 2;
     const int q = warp & 3;               // TMEM lane quarter
-    const int half = ew >> 2;             // column half of the tile
-    const int et = threadIdx.x - 64;      // 0..255
-    constexpr int CW = BN / 2;            // columns per warp
+    const int half = ew >> 2;             // which column slice of the tile (BN / (EW/4) columns each)
+    const int et = threadIdx.x - 64;      // 0 .. 32*EW-1
+    constexpr int ETH = 32 * S::EW;
+    constexpr int CW = BN / (S::EW / 4);  // columns per warp: 64 (two 32-column chunks)
     constexpr int NCH = CW / 32;
     uint8_t* stg = stg_base + ew * (S::STG_TILES * 4096);  // this warp's staging tiles
     int sbuf = 0;
     // fp32 residual + fp32 output with two chunks per warp (the N = 512 projections of the predictor): the residual
     // tiles are TMA-LOADED into the staging tiles while the main loop of the tile runs, the accumulator is added in
     // place and the same tile is TMA-stored -- both directions in full 128-byte lines instead of 16 bytes per row
-    const bool tma_res = !CONV && NCH == 2 && g.residual != nullptr && g.res_mod == 0 && g.out32 != nullptr;
+    const bool tma_res = !CONV && S::STG_TILES == 3 && g.residual != nullptr && g.res_mod == 0 && g.out32 != nullptr;
     const uint32_t sw = uint32_t(lane & 7);
     int it = 0;
     for (int t = pair; t < num_tiles; t += npairs, ++it) {
@@ -201,13 +205,13 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int b = it & 1;
       const uint32_t bph = (it >> 1) & 1;
       if (g.bias != nullptr) {
-        for (int e = et; e < BN; e += 256) {
+        for (int e = et; e < BN; e += ETH) {
           const int n = nb * BN + e;
           sbias[(b * 2) * BN + e] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
         }
       }
       if (g.ln_c != nullptr) {
-        for (int e = et; e < BN; e += 256) {
+        for (int e = et; e < BN; e += ETH) {
           const int n = nb * BN + e;
           sbias[(b * 2 + 1) * BN + e] = (n < g.N) ? __ldg(g.ln_c + n) : 0.f;
         }
@@ -266,7 +270,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         load_res(0, rbuf[0]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // bias staged (epilogue warps only)
+      asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");   // bias staged (epilogue warps only)
       mbar_wait(&tfull[b], bph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + half * CW);
@@ -374,7 +378,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           } else if (g.out32 != nullptr) {
-            if (lane == 0) bulk_wait_read<1>();          // the store that last read this staging tile has drained
+            if (lane == 0) {                             // the store that last read this staging tile has drained
+              if (S::STG_TILES >= 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             __syncwarp();
             uint8_t* dst = stg + sbuf * 4096 + lane * 128;
 #pragma unroll
@@ -387,7 +393,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_store_2d(&tmC32, stg + sbuf * 4096, n0, trow);
               bulk_commit();
             }
-            sbuf ^= 1;
+            if (S::STG_TILES >= 2) sbuf ^= 1;
           }
           if (g.out16 != nullptr && !tma_res) {
             // two 32-column chunks make one 64-column (128 B) staging row: the even chunk waits in registers
@@ -413,7 +419,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) hold[j8] = p[j8];
             } else {
-              if (lane == 0) bulk_wait_read<1>();
+              if (lane == 0) {
+                if (S::STG_TILES >= 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+              }
               __syncwarp();
               uint8_t* dst = stg + sbuf * 4096 + lane * 128;
 #pragma unroll
@@ -427,7 +435,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_store_2d(&tmC16, stg + sbuf * 4096, n0 - 32, trow);
                 bulk_commit();
               }
-              sbuf ^= 1;
+              if (S::STG_TILES >= 2) sbuf ^= 1;
             }
           }
         } else if (row_ok && n0 < g.N) {
@@ -484,7 +492,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, bool CONV>
+template <int BN, bool CONV, int EWN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
   // output maps for the TMA-store epilogue: 32-row x 128-byte boxes (64 f16 / 32 fp32 columns), 128B swizzle
   CUtensorMap tmC16 = tmA, tmC32 = tmA, tmR = tmA;     // placeholders when absent (never dereferenced)
@@ -507,16 +515,16 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     const uint32_t box[2] = {32, 32};
     TOCVP_TRY(encode_tmap(&tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.out32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  using S = G2Smem<BN>;
+  using S = G2Smem<BN, EWN>;
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV, EWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles = ((g.M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((g.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_f16_kernel<BN, CONV><<<grid, G2_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
+  gemm2_f16_kernel<BN, CONV, EWN><<<grid, g2_threads(EWN), S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -548,8 +556,8 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
   Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{},
               ln ? ln->stats : nullptr, ln ? ln->slots : 0, ln ? ln->c : nullptr, ln ? ln->inv_k : 0.f, ln ? ln->eps : 0.f,
               ln ? ln->stats_out : nullptr};
-  if (bn == 256) return launch_gemm2<256, false>(tmA, tmB, g, stream);
-  return launch_gemm2<128, false>(tmA, tmB, g, stream);
+  if (bn == 256) return launch_gemm2<256, false, 8>(tmA, tmB, g, stream);
+  return launch_gemm2<128, false, 8>(tmA, tmB, g, stream);
 }
 
 int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
@@ -558,8 +566,8 @@ int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, K, bn / 2, G2_BK));
   Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm, nullptr, 0, nullptr, 0.f, 0.f, nullptr};
-  if (bn == 256) return launch_gemm2<256, true>(tmA, tmB, g, stream);
-  return launch_gemm2<128, true>(tmA, tmB, g, stream);
+  if (bn == 256) return launch_gemm2<256, true, 8>(tmA, tmB, g, stream);
+  return launch_gemm2<128, true, 8>(tmA, tmB, g, stream);
 }
 
 }  // namespace tocvp

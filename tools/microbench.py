@@ -29,8 +29,8 @@ def timeit(fn, iters=20, warm=3):
 
 def bench_gemm():
     """single-CTA (mode 1) vs CTA-pair kernel with 128 / 256-wide tiles vs the automatic choice (mode 0)"""
-    for M, N, K in [(20480, 1536, 512), (20480, 512, 512), (20480, 2048, 512), (20480, 512, 2048), (2048, 1536, 512),
-                    (6144, 512, 512), (10240, 2048, 512), (207360, 1024, 1024), (8192, 8192, 8192)]:
+    for M, N, K in [(20480, 1536, 512), (20480, 512, 512), (20480, 2048, 512), (20480, 512, 2048),
+                    (207360, 1024, 1024), (8192, 8192, 8192)]:
         a = torch.randn(M, K, device="cuda").half()
         w = torch.randn(N, K, device="cuda").half()
         res = []
