@@ -241,9 +241,13 @@ def run_ours(args):
                 per_launch += [nf * 8 * CONV_FLOP_PER_SLOTIMG] * 3
         conv_avg_ms = sum(conv_ms) / len(conv_ms)
         achieved = sum(per_launch) / (sum(conv_ms) / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<64,64,4,5,0> = conv5x5 64->64 (decoder layers 2-4)",
+        roofline = {"bound": "tensor", "kernel": "conv_tc2_kernel<64,64,4,5> = CTA-pair conv5x5 64->64 (decoder layers 2-4)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": conv_avg_ms,
+                    "traffic": 2.096e9 if B * NUM_PREDS >= 256 else None,
+                    "traffic_note": "bytes per launch of 2048 slot-images: dram__bytes_read.sum + dram__bytes_write.sum "
+                                    "from the ncu --set full capture in profiles/conv64_pair_r1_summary.md "
+                                    "(algorithmic: 2.147e9)",
+                    "peak_source": peak_src, "avg_launch_ms": conv_avg_ms,
                     "share_of_step": sum(conv_ms) / ms_total,
                     "flops_note": "FLOPs executed (layer 1 is computed algebraically, not as a convolution); "
                                   "operands f16 (kind::f16, same tensor rate as bf16), fp32 accumulate"}
