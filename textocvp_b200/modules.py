@@ -148,6 +148,70 @@ def _tr(t):  # [out,in] -> [in,out] fp32
     return t.detach().float().t().contiguous()
 
 
+
+# =====================================================================================================
+# weight-packing algebra (pure tensor functions: exercised on the CPU by tests/test_packing_cpu.py)
+# =====================================================================================================
+def fold_batchnorm(conv_w, conv_b, bn_w, bn_b, bn_mean, bn_var, eps):
+    """Eval-mode BatchNorm2d folded into the preceding conv: w' = w * gamma/sqrt(var+eps), b' = (b-mean)*scale + beta."""
+    scale = bn_w.float() / torch.sqrt(bn_var.float() + eps)
+    return conv_w.float() * scale[:, None, None, None], (conv_b.float() - bn_mean.float()) * scale + bn_b.float()
+
+
+def _phase_taps(p, d):
+    """3x3 taps (ky) of an Upsample(2)->conv3x3 pair that land on low-res offset d + p - 1 for output phase p."""
+    return ([0], [1, 2])[d] if p == 0 else ([0, 1], [2])[d]
+
+
+def pack_conv3x3_plain(w):
+    """[co,ci,3,3] -> [co, 9*ci], K index = (ky*3+kx)*ci + c (tap offsets (ky-1, kx-1))."""
+    co, ci = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci)
+
+
+def pack_conv3x3_phase(w):
+    """conv3x3 applied to a nearest-x2 upsampled input = four 2x2 phase convolutions on the low-res input:
+    [co,ci,3,3] -> [4*co, 4*ci], row = (py*2+px)*co + o, K index = (dy*2+dx)*ci + c, low-res offset (dy+py-1, dx+px-1)."""
+    co, ci = w.shape[:2]
+    packed = w.new_zeros(4, co, 4, ci)
+    for py in range(2):
+        for px in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    acc = 0
+                    for ky in _phase_taps(py, dy):
+                        for kx in _phase_taps(px, dx):
+                            acc = acc + w[:, :, ky, kx]
+                    packed[py * 2 + px, :, dy * 2 + dx] = acc
+    return packed.reshape(4 * co, 4 * ci)
+
+
+def pack_final_conv_phase(w, b, rows=64):
+    """Final conv3x3 -> 3 channels behind an Upsample(2): [16 used of `rows`, 9*ci] over the low-res 3x3 neighbourhood,
+    row = phase*4 + c (channel 3 = zero pad), zeros where a phase does not see a tap; bias [16]."""
+    ci = w.shape[1]
+    packed, bias = w.new_zeros(rows, 9, ci), w.new_zeros(16)
+    for py in range(2):
+        for px in range(2):
+            ph = py * 2 + px
+            bias[ph * 4:ph * 4 + 3] = b
+            for dy in range(2):
+                for dx in range(2):
+                    tap = (dy + py) * 3 + (dx + px)
+                    for ky in _phase_taps(py, dy):
+                        for kx in _phase_taps(px, dx):
+                            packed[ph * 4:ph * 4 + 3, tap] += w[:, :, ky, kx]
+    return packed.reshape(rows, 9 * ci), bias
+
+
+def fold_layernorm(w, ln_w, ln_b, bias=None):
+    """LN(x) @ w.T (+bias) = rstd * (x @ wf.T - mu * c) + d with wf = f16(w * gamma), c = rowsum(wf), d = w @ beta (+bias)."""
+    wf = (w.detach().float() * ln_w.detach().float()[None, :]).half()
+    c = wf.float().sum(1)
+    d = w.detach().float() @ ln_b.detach().float()
+    return wf.contiguous(), c.contiguous(), (d + bias.detach().float() if bias is not None else d).contiguous()
+
+
 # =====================================================================================================
 # building blocks (parameter containers with the reference's names)
 # =====================================================================================================
@@ -648,11 +712,6 @@ class MLPPatchDecoder(_Packed):
     def _sig(self):   # BatchNorm running statistics are buffers: include them
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in list(self.parameters()) + list(self.buffers()))
 
-    @staticmethod
-    def _phase_rows(p, d):
-        """3x3 taps (ky) of an Upsample(2)->conv3x3 pair that land on low-res offset d + p - 1 for output phase p."""
-        return ([0], [1, 2])[d] if p == 0 else ([0, 1], [2])[d]
-
     def _pack(self, dev):
         if not self.initial_layer_norm:
             raise L.TocvpError("MLPPatchDecoder kernels expect initial_layer_norm = true (ExtendedDINOSAUR.json)")
@@ -681,24 +740,13 @@ class MLPPatchDecoder(_Packed):
                     continue
                 if isinstance(m, ConvBlock):
                     conv, bn = m.block[0], m.block[1]
-                    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
-                    wt = conv.weight.detach().float() * scale[:, None, None, None]             # fold eval-mode BN
-                    b = (conv.bias.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+                    wt, b = fold_batchnorm(conv.weight.detach(), conv.bias.detach(), bn.weight.detach(), bn.bias.detach(),
+                                           bn.running_mean.detach(), bn.running_var.detach(), bn.eps)
                     co, cin = wt.shape[:2]
                     if not up_before:
-                        packed = wt.permute(0, 2, 3, 1).reshape(co, 9 * cin)
+                        packed = pack_conv3x3_plain(wt)
                     else:
-                        packed = wt.new_zeros(4, co, 4, cin)
-                        for py in range(2):
-                            for px in range(2):
-                                for dy in range(2):
-                                    for dx in range(2):
-                                        acc = 0
-                                        for ky in self._phase_rows(py, dy):
-                                            for kx in self._phase_rows(px, dx):
-                                                acc = acc + wt[:, :, ky, kx]
-                                        packed[py * 2 + px, :, dy * 2 + dx] = acc
-                        packed = packed.reshape(4 * co, 4 * cin)
+                        packed = pack_conv3x3_phase(wt)
                         b = b.repeat(4)
                     k[f"cnn_w{ci}"], k[f"cnn_b{ci}"] = _f16(packed), _f32(b)
                     w.cnn_w[ci], w.cnn_b[ci] = k[f"cnn_w{ci}"].data_ptr(), k[f"cnn_b{ci}"].data_ptr()
@@ -708,23 +756,13 @@ class MLPPatchDecoder(_Packed):
                 else:                                                    # final nn.Conv2d -> 3 channels
                     wt, b = m.weight.detach().float(), m.bias.detach().float()
                     cin = wt.shape[1]
-                    packed = wt.new_zeros(64, 9, cin)                    # >= one N-tile of rows allocated
-                    bias = wt.new_zeros(16)
                     if up_before:
-                        for py in range(2):
-                            for px in range(2):
-                                ph = py * 2 + px
-                                bias[ph * 4:ph * 4 + 3] = b
-                                for dy in range(2):
-                                    for dx in range(2):
-                                        tap = (dy + py) * 3 + (dx + px)     # low-res offset (dy+py-1, dx+px-1) + 1
-                                        for ky in self._phase_rows(py, dy):
-                                            for kx in self._phase_rows(px, dx):
-                                                packed[ph * 4:ph * 4 + 3, tap] += wt[:, :, ky, kx]
+                        packed, bias = pack_final_conv_phase(wt, b)
                     else:
-                        packed[:3] = wt.permute(0, 2, 3, 1).reshape(3, 9, cin)
+                        packed, bias = wt.new_zeros(64, 9 * cin), wt.new_zeros(16)
+                        packed[:3] = pack_conv3x3_plain(wt)
                         bias[:3] = b
-                    k["out_w"], k["out_b"] = _f16(packed.reshape(64, 9 * cin)), _f32(bias)
+                    k["out_w"], k["out_b"] = _f16(packed), _f32(bias)
                     w.out_w, w.out_b, w.out_cin, w.out_up = k["out_w"].data_ptr(), k["out_b"].data_ptr(), cin, int(up_before)
             w.n_cnn = ci
         for n in ("pos_embed", "ln_g", "ln_b"):
@@ -961,11 +999,7 @@ class BaseTextOCVP(_Packed):
                 w_1=_f16(blk.mlp[0].weight), w_2=_f16(blk.mlp[2].weight), b_1=_f32(blk.mlp[0].bias), b_2=_f32(blk.mlp[2].bias))
             # LayerNorm folded into the consuming projection (include/tocvp.h, tocvp_pred_layer)
             def fold(w, ln, bias, names):
-                wf = _f16(w.detach().float() * ln.weight.detach().float()[None, :])
-                t[names[0]] = wf
-                t[names[1]] = wf.float().sum(1).contiguous()
-                d = w.detach().float() @ ln.bias.detach().float()
-                t[names[2]] = (d + bias.detach().float() if bias is not None else d).contiguous()
+                t[names[0]], t[names[1]], t[names[2]] = fold_layernorm(w, ln.weight, ln.bias, bias)
             fold(torch.cat([blk.attn.q.weight, blk.attn.k.weight, blk.attn.v.weight], 0), blk.layernorm_query, None,
                  ("w_qkv_f", "c_qkv", "d_qkv"))
             fold(c.cross_attn.q.weight, c.ln_cross_att_q, None, ("wc_q_f", "c_cq", "d_cq"))
