@@ -159,13 +159,35 @@ def run_ours(args):
         return rollout.forward_eval(savi, pred, videos_d, text_d, NUM_CONTEXT, NUM_PREDS, init_slots=init,
                                     conv_events=events)
 
-    vbuf = torch.empty_like(videos_d)
-    tbuf = torch.empty_like(text_d)
+    # e2e: every step's inputs come from pinned host memory; double-buffered so that the H2D copy of step k+1 (copy
+    # stream) overlaps the compute of step k -- each step still pays for its own 268 MB inside the timed region
+    vbufs = [torch.empty_like(videos_d) for _ in range(2)]
+    tbufs = [torch.empty_like(text_d) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "primed": False}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])                 # the step that last read this slot has finished
+            vbufs[slot].copy_(videos_h, non_blocking=True)
+            tbufs[slot].copy_(text_h, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def step_e2e():
-        vbuf.copy_(videos_h, non_blocking=True)
-        tbuf.copy_(text_h, non_blocking=True)
-        out = rollout.forward_eval(savi, pred, vbuf, tbuf, NUM_CONTEXT, NUM_PREDS, init_slots=init)
+        k = state["k"]
+        slot = k & 1
+        if not state["primed"]:
+            for s_ in range(2):
+                consumed[s_].record()
+            issue_copy(slot)
+            state["primed"] = True
+        issue_copy(slot ^ 1)                                        # prefetch the next step's inputs
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out = rollout.forward_eval(savi, pred, vbufs[slot], tbufs[slot], NUM_CONTEXT, NUM_PREDS, init_slots=init)
+        consumed[slot].record()
+        state["k"] = k + 1
         return torch.stack([out["psnr"], out["mse"], out["ssim"]]).cpu()      # D2H of the step's metrics (synchronises)
 
     def barrier():

@@ -302,6 +302,10 @@ int tocvp_frame_metrics(const float* pred, const float* target, size_t target_se
                         int target_frame0, int n_img, int C, int H, int W, int clamp, float* mse, float* psnr, float* ssim,
                         void* stream);
 
+/* Tuning / test knob (process-wide): 1 = decoder layer 1 is generated inside the layer-2 convolution kernel and never
+ * stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation. */
+int tocvp_set_decode_mode(int fuse_layer1);
+
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
 int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,

@@ -76,10 +76,18 @@ def test_predictor_step(models, golden, golden_weights):
     assert O.rel_err(out1, golden["pred_step_n1"]) < STAGE_TOL
 
 
-def test_decode(models, golden, golden_weights):
+@pytest.mark.parametrize("fuse_layer1", [1, 0])
+def test_decode(models, golden, golden_weights, fuse_layer1):
+    """fuse_layer1 = 1: decoder layer 1 generated inside the layer-2 conv kernel; 0: separate kernel (default)."""
+    from textocvp_b200 import _lib as L
     savi, _ = models
     slots = golden["pred_slots"][:1, -1].cuda()
-    out = savi(mode="decode", slots=slots)
+    L.call("tocvp_set_decode_mode", L.c_int(fuse_layer1))
+    try:
+        out = savi(mode="decode", slots=slots)
+        torch.cuda.synchronize()
+    finally:
+        L.call("tocvp_set_decode_mode", L.c_int(0))
     assert O.rel_err(out["recons"], golden["dec_recons"]) < STAGE_TOL
     assert O.rel_err(out["masks"], golden["dec_masks"]) < STAGE_TOL
     assert O.rel_err(out["recons_imgs"], golden["dec_img"]) < STAGE_TOL

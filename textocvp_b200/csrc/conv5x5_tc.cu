@@ -240,18 +240,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // to 4 KB + 1 KB per SM -- the smem read port is what bounds the single-CTA kernel at N = 64 (ncu, profiles/) -- and
 // the per-SM L2 traffic for weights halves as well.
 // ------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int G, int KS>
+template <int CIN, int COUT, int G, int KS, bool GEN = false>
 struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
   using Base = ConvCfg<CIN, COUT, G, KS>;
   static constexpr int W_HALF = (COUT / 2) * Base::KB;
-  static constexpr int WSTAGES = (W_HALF >= 4096) ? 6 : 12;
-  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + 512 + 1024;
+  static constexpr int WSTAGES = GEN ? 4 : ((W_HALF >= 4096) ? 6 : 12);
+  static constexpr int GEN_BYTES = GEN ? 25 * CIN * 4 : 0;   // this tile's 5x5 border-pattern sums, fp32
+  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + 512 + 1024;
 };
 
-template <int CIN, int COUT, int G, int KS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
-  using C = ConvCfg2<CIN, COUT, G, KS>;
+// Generated input (decoder layer 2 only): instead of TMA-loading layer 1's activation, four extra warps COMPUTE the halo
+// tile in place -- layer 1 of the spatial-broadcast decoder is relu(P[y,x,:] + S[pattern(y,x),:]) with P batch
+// independent and S the 25 border-pattern tap sums of the slot (decoder.cu) -- so that activation (1 GiB written and
+// read back per 256-frame chunk) never exists in HBM.
+struct ConvGen {
+  const float* P;     // [H*W, CIN] fp32
+  const float* S;     // [n_img, 25, CIN] fp32
+};
+__device__ __forceinline__ int border_pat(int v, int n) { return v < 2 ? v : (v >= n - 2 ? v - (n - 5) : 2); }
+
+template <int CIN, int COUT, int G, int KS, bool GEN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a, ConvGen gen) {
+  using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -263,6 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* t_full = a_empty + 2;                                                 // per CTA
   uint64_t* t_empty = t_full + 2;                                                 // leader: 4 warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* sS = reinterpret_cast<float*>(sW + C::WSTAGES * C::W_HALF + 512);        // GEN: [25][CIN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -279,7 +291,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_init(&w_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_full[b], 1);
+      mbar_init(&a_full[b], GEN ? 8 : 1);     // GEN: one arrival per generator warp of both CTAs
       mbar_init(&a_empty[b], 1);
       mbar_init(&t_full[b], 1);
       mbar_init(&t_empty[b], 8);
@@ -309,9 +321,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int s = 0;
       uint32_t wph = 0;
       int it = 0;
-      if (pair < num_ptiles) load_halo(pair, 0);
+      if (!GEN && pair < num_ptiles) load_halo(pair, 0);
       for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
-        if (pt + npairs < num_ptiles) load_halo(pt + npairs, it + 1);
+        if (!GEN && pt + npairs < num_ptiles) load_halo(pt + npairs, it + 1);
         for (int tap = 0; tap < C::TAPS; ++tap) {
           mbar_wait(&w_empty[s], wph ^ 1);
           if (rank == 0) mbar_expect_tx(&w_full[s], 2 * C::W_HALF);
@@ -335,7 +347,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int buf = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&t_empty[buf], ph ^ 1);
-        mbar_wait(&a_full[buf], ph);
+        if (GEN) mbar_wait_cluster(&a_full[buf], ph);     // tiles written by generator warps of BOTH CTAs
+        else mbar_wait(&a_full[buf], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + buf * C::A_STRIDE);
         const uint32_t d_base = tmem_u + uint32_t(buf * C::ACC_COLS);
@@ -359,6 +372,68 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         umma_commit_pair(&a_empty[buf], leader);
         umma_commit_pair(&t_full[buf], leader);
+      }
+    }
+  } else if (GEN && warp >= 6) {
+    // ---------------------------------------------------------------- generator warps (GEN): compute the halo tile
+    if constexpr (GEN) {
+      static_assert(CIN == 64, "generator is written for 64-channel rows (128 B, SWIZZLE_128B)");
+      const int gt = threadIdx.x - 192;                       // 0..127
+      int it = 0;
+      for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int t = 2 * pt + int(rank);
+        const int img = t / tiles_per_img, r = t % tiles_per_img;
+        const int y0 = (r / tiles_x) * C::TILE_H - KS / 2, x0 = (r % tiles_x) * C::TILE_W - KS / 2;
+        asm volatile("bar.sync 2, 128;" ::: "memory");       // everyone is done reading the previous tile's patterns
+        const float* Sg = gen.S + size_t(img) * 25 * CIN;
+        for (int e = gt; e < 25 * CIN / 4; e += 128)
+          reinterpret_cast<float4*>(sS)[e] = __ldg(reinterpret_cast<const float4*>(Sg) + e);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        mbar_wait(&a_empty[buf], ph ^ 1);                      // the MMAs that read this buffer have completed
+        uint8_t* dstA = sA + buf * C::A_STRIDE;
+        // 16 halo pixels per pass (8 threads x 16 B per pixel row); GB passes are issued together so that their P loads
+        // (L2 hits, ~300+ cycles each) are in flight at once instead of serialising the generator behind the MMAs
+        constexpr int PASSES = C::HROWS * C::WBUF / 16;
+        constexpr int GB = 10;
+        static_assert(PASSES % GB == 0, "halo passes must split into equal batches");
+        const int j = gt & 7;
+        for (int p0 = 0; p0 < PASSES; p0 += GB) {
+          float4 pv[GB][2];
+          int pat[GB];
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            const int prow = (p0 + u) * 16 + (gt >> 3);
+            const int hy = prow / C::WBUF, hx = prow - hy * C::WBUF;
+            const int y = y0 + hy, x = x0 + hx;
+            pat[u] = -1;
+            if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+              const float* pp = gen.P + (size_t(y) * a.W + x) * CIN + j * 8;
+              pv[u][0] = __ldg(reinterpret_cast<const float4*>(pp));
+              pv[u][1] = __ldg(reinterpret_cast<const float4*>(pp + 4));
+              pat[u] = border_pat(y, a.H) * 5 + border_pat(x, a.W);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < GB; ++u) {
+            const int prow = (p0 + u) * 16 + (gt >> 3);
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);             // outside the image: the convolution's zero padding
+            if (pat[u] >= 0) {
+              const float* ss = sS + pat[u] * CIN + j * 8;
+              const float4 s0 = *reinterpret_cast<const float4*>(ss);
+              const float4 s1 = *reinterpret_cast<const float4*>(ss + 4);
+              pk.x = pack_half2_relu(pv[u][0].x + s0.x, pv[u][0].y + s0.y);
+              pk.y = pack_half2_relu(pv[u][0].z + s0.z, pv[u][0].w + s0.w);
+              pk.z = pack_half2_relu(pv[u][1].x + s1.x, pv[u][1].y + s1.y);
+              pk.w = pack_half2_relu(pv[u][1].z + s1.z, pv[u][1].w + s1.w);
+            }
+            *reinterpret_cast<uint4*>(dstA + prow * 128 + ((j ^ (prow & 7)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&a_full[buf]), 0));
       }
     }
   } else {
@@ -421,14 +496,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-template <int CIN, int COUT, int G, int KS>
+template <int CIN, int COUT, int G, int KS, bool GEN = false>
 static int launch_conv2(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
-                        int relu, cudaStream_t stream) {
-  using C = ConvCfg2<CIN, COUT, G, KS>;
+                        int relu, cudaStream_t stream, ConvGen gen = ConvGen{nullptr, nullptr}) {
+  using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM));
     attr_set = true;
   }
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -449,7 +525,7 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
   const int pairs = num_sms() / 2;
   const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
   ConvArgs a{n_img, H, W, bias, out, nullptr, relu};
-  conv_tc2_kernel<CIN, COUT, G, KS><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
+  conv_tc2_kernel<CIN, COUT, G, KS, GEN><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -505,6 +581,15 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
   }
   set_last_error(__FILE__, __LINE__, "conv5x5_f16: only 64->64 and 32->32 channels are instantiated");
   return TOCVP_ERR_BAD_ARG;
+}
+
+// Decoder layer 2 with layer 1 generated in the kernel (see ConvGen): P fp32 [H*W,64], S fp32 [n_img,25,64].
+// `x_dummy` only anchors the (unused) input tensor map: any valid device pointer.
+int conv5x5_gen_f16(const float* P, const float* S, const __half* x_dummy, const __half* wpacked, const float* bias,
+                    __half* out, int n_img, int H, int W, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(P && S && x_dummy && wpacked && bias && out && n_img > 0);
+  TOCVP_CHECK_ARG(H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0));
+  return launch_conv2<64, 64, 4, 5, true>(x_dummy, wpacked, bias, out, n_img, H, W, 1, stream, ConvGen{P, S});
 }
 
 // Decoder head: conv3x3 64 -> 4 (weights zero-padded to 16 output channels: the narrowest UMMA N for M = 128), no

@@ -24,6 +24,8 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream);
 int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, float* out4, int n_img, int H, int W,
                      cudaStream_t stream);
+int conv5x5_gen_f16(const float* P, const float* S, const __half* x_dummy, const __half* wpacked, const float* bias,
+                    __half* out, int n_img, int H, int W, cudaStream_t stream);
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4) {
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n4; e += size_t(gridDim.x) * blockDim.x) {
@@ -79,6 +81,29 @@ dec_l1_kernel(const float* __restrict__ taps, const float* __restrict__ P, __hal
   }
 }
 
+// Pattern sums only (fused path): S[img][pattern][c] = sum of the taps valid for that 5x5 border pattern; layer 1's
+// activation is then generated inside the layer-2 convolution kernel (conv5x5_tc.cu, ConvGen) and never stored.
+__global__ void __launch_bounds__(256)
+dec_l1_patterns_kernel(const float* __restrict__ taps, float* __restrict__ S, int n_img) {
+  constexpr int C = 64;
+  __shared__ float sT[4][25 * C];
+  const int sub = threadIdx.x >> 6, c = threadIdx.x & 63;       // 4 slot-images per CTA, one thread per channel
+  const int img = blockIdx.x * 4 + sub;
+  if (img >= n_img) return;
+  const float* t = taps + size_t(img) * 25 * C;
+  for (int k = 0; k < 25; ++k) sT[sub][k * C + c] = t[k * C + c];
+  float* o = S + size_t(img) * 25 * C;
+  for (int pat = 0; pat < 25; ++pat) {
+    const int py = pat / 5, px = pat % 5;
+    const int ky0 = py == 0 ? 2 : (py == 1 ? 1 : 0), ky1 = py == 4 ? 2 : (py == 3 ? 3 : 4);
+    const int kx0 = px == 0 ? 2 : (px == 1 ? 1 : 0), kx1 = px == 4 ? 2 : (px == 3 ? 3 : 4);
+    float s = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) s += sT[sub][(ky * 5 + kx) * C + c];
+    o[pat * C + c] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ compositing
 // maps: fp32 [n_frames*S, H*W, 4] (RGB + mask logit, SAVi.py:251-252) from the tcgen05 conv3x3 head.
 // imgs fp32 [n_frames,3,H,W]; recons (opt) [n_frames,S,3,H,W]; masks (opt) [n_frames,S,1,H,W].
@@ -113,9 +138,16 @@ composite_kernel(const float4* __restrict__ maps, float* __restrict__ imgs, floa
 
 constexpr int DEC_CHUNK_FRAMES = 256;
 
+// tocvp_set_decode_mode: 1 = generate layer 1 inside the layer-2 conv, 0 = separate bandwidth kernel (default).
+// Measured r1 (tools/ab_decode.py, same process): the fused layer-2 conv takes 1.86 ms instead of 1.44 ms per chunk -- the
+// generator warps share the shared-memory port and the issue slots the implicit GEMM is bound by -- which is more than the
+// 0.36 ms of dec_l1_kernel it removes, so the fused path is kept (tested, parity-green) but not the default.
+static int g_dec_fuse_l1 = 0;
+
 struct DecBuffers {
   __half* slots16;
   float* taps32;
+  float* pat32;
   __half *actA, *actB;
   float* maps4;
 };
@@ -134,6 +166,7 @@ static size_t dec_carve(const tocvp_dec_weights& w, int n_frames, DecBuffers* db
   DecBuffers t;
   t.slots16 = reinterpret_cast<__half*>(take(nsi * w.slot_dim * 2));
   t.taps32 = reinterpret_cast<float*>(take(nsi * 25 * w.hidden * 4));
+  t.pat32 = reinterpret_cast<float*>(take(nsi * 25 * w.hidden * 4));
   t.actA = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
   t.actB = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
   t.maps4 = reinterpret_cast<float*>(take(nsi * w.H * w.W * 4 * 4));
@@ -146,6 +179,11 @@ static size_t dec_carve(const tocvp_dec_weights& w, int n_frames, DecBuffers* db
 using namespace tocvp;
 
 extern "C" size_t tocvp_sizeof_dec_weights(void) { return sizeof(tocvp_dec_weights); }
+
+extern "C" int tocvp_set_decode_mode(int fuse_layer1) {
+  tocvp::g_dec_fuse_l1 = fuse_layer1 ? 1 : 0;
+  return TOCVP_OK;
+}
 
 extern "C" size_t tocvp_savi_decode_workspace_bytes(const tocvp_dec_weights* w, int n_frames) {
   if (!w || n_frames <= 0) return 0;
@@ -175,7 +213,13 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
     TOCVP_LAUNCHED();
     TOCVP_TRY(gemm_f16(db.slots16, D, static_cast<const __half*>(w->w1_taps), D, nsi, 25 * C, D, nullptr, 0, nullptr, 0,
                        1, 0, db.taps32, 25 * C, nullptr, 0, st));
-    dec_l1_kernel<<<nsi, 256, 0, st>>>(db.taps32, w->p1, db.actA, H, W);
+    // layer 1 is generated inside the layer-2 convolution whenever the pair kernel applies (even tile count)
+    const bool fused_l1 = ((nsi * (H / 16) * (W / 32)) % 2 == 0) && g_dec_fuse_l1;
+    if (fused_l1) {
+      dec_l1_patterns_kernel<<<(nsi + 3) / 4, 256, 0, st>>>(db.taps32, db.pat32, nsi);
+    } else {
+      dec_l1_kernel<<<nsi, 256, 0, st>>>(db.taps32, w->p1, db.actA, H, W);
+    }
     TOCVP_LAUNCHED();
     __half* bufs[2] = {db.actA, db.actB};
     for (int l = 0; l < 3; ++l) {
@@ -183,8 +227,13 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
       const int ev = 2 * ((f0 / DEC_CHUNK_FRAMES) * 3 + l);
       const bool prof = conv_events != nullptr && ev + 1 < n_conv_events;
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev]), st));
-      TOCVP_TRY(conv5x5_f16(bufs[l & 1], static_cast<const __half*>(w->w_conv[l]), w->b_conv[l], bufs[(l + 1) & 1], nsi, H,
-                            W, C, C, 1, st));
+      if (l == 0 && fused_l1) {
+        TOCVP_TRY(conv5x5_gen_f16(w->p1, db.pat32, db.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], db.actB,
+                                  nsi, H, W, st));
+      } else {
+        TOCVP_TRY(conv5x5_f16(bufs[l & 1], static_cast<const __half*>(w->w_conv[l]), w->b_conv[l], bufs[(l + 1) & 1], nsi,
+                              H, W, C, C, 1, st));
+      }
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev + 1]), st));
     }
     // conv3x3 64 -> 4 head on the tensor cores (N padded to 16), then softmax-over-slots compositing
