@@ -484,7 +484,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&t_empty[buf]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&t_empty[buf]), 0));
     }
   }
 

@@ -287,7 +287,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // all accumulator columns of this warp are in registers: hand the TMEM buffer back to the leader's MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[b]), 0));
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tempty[b]), 0));
         }
         const int n0 = ncol0 + c * 32;
         if constexpr (!CONV) {
@@ -415,7 +415,28 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 p[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
               }
             }
-            if ((c & 1) == 0) {
+            if (NCH == 4 && S::STG_TILES == 2 && g.out32 == nullptr) {
+              // f16-only output of a 256-wide tile: the warp's 128 columns fill exactly its two staging tiles, so ONE
+              // proxy fence and one bulk group per tile cover both TMA stores (the fence, not the math, is what an
+              // epilogue warp waits on: r1 A/B in profiles/gemm2_r1_summary.md)
+              if (c == 0) {
+                if (lane == 0) bulk_wait_read<0>();       // last tile's stores (issued a whole main loop ago) have drained
+                __syncwarp();
+              }
+              uint8_t* dst = stg + (c >> 1) * 4096 + lane * 128;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8)
+                *reinterpret_cast<uint4*>(dst + ((uint32_t((c & 1) * 4 + j8) ^ sw) << 4)) = p[j8];
+              if (c == NCH - 1) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmC16, stg, ncol0, trow);
+                  tma_store_2d(&tmC16, stg + 4096, ncol0 + 64, trow);
+                  bulk_commit();
+                }
+              }
+            } else if ((c & 1) == 0) {
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) hold[j8] = p[j8];
             } else {

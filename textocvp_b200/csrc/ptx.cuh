@@ -214,6 +214,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed variant for hand-backs that publish no memory (e.g. "this TMEM buffer has been read", ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync): a release here compiles to an ERRBAR that drains every
+// outstanding store of the thread before the arrive -- the top stall of the pair GEMM's epilogue in the r1 ncu capture.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
                                                  int c1) {
   asm volatile(
