@@ -34,11 +34,14 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// NT = compile-time bound on the number of 8-key tiles (score registers s[NT][4]): fewer registers for short key
+// sequences -> more resident CTAs per SM for a kernel that is pure latency.
+template <int NT>
 __global__ void __launch_bounds__(ATT_MAX_WARPS * 32)
 mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, const __half* __restrict__ v, int ldkv,
            int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out, int ldo) {
-  __shared__ __align__(16) __half sK[ATT_MAXK * ATT_KS];
-  __shared__ __align__(16) __half sV[ATT_MAXK * ATT_KS];
+  __shared__ __align__(16) __half sK[NT * 8 * ATT_KS];
+  __shared__ __align__(16) __half sV[NT * 8 * ATT_KS];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -71,9 +74,9 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
       qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c + 8) : 0u;
       qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c + 8) : 0u;
     }
-    float s[ATT_MAXK / 8][4];
+    float s[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       if (nt < n_tiles) {
         const __half* kr = sK + (nt * 8 + g) * ATT_KS + 2 * t;
@@ -88,7 +91,7 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
     // softmax over keys (rows g and g+8 of this tile; a row lives in the 4 lanes of a quad)
     float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
-    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       if (nt < n_tiles) {
         const int c = nt * 8 + 2 * t;
         if (c >= Tk) s[nt][0] = s[nt][2] = -1e30f;
@@ -103,7 +106,7 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < ATT_MAXK / 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       if (nt < n_tiles) {
         s[nt][0] = exp2f((s[nt][0] - mx0) * scale_log2e);
         s[nt][1] = exp2f((s[nt][1] - mx0) * scale_log2e);
@@ -122,7 +125,7 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
 #pragma unroll
     for (int nd = 0; nd < ATT_DH / 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < ATT_MAXK / 16; ++kk) {
+    for (int kk = 0; kk < NT / 2; ++kk) {
       if (kk * 2 < n_tiles) {
         uint32_t pa[4];
         pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
@@ -158,7 +161,14 @@ int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv
   const float scale_log2e = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (attention.py:187) * log2(e)
   int warps = (Tq + 15) / 16;
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
-  mha_kernel<<<B * heads, warps * 32, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo);
+  const int nt = ((Tk + 15) & ~15) / 8;
+#define MHA_LAUNCH(NTV) \
+  mha_kernel<NTV><<<B * heads, warps * 32, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo)
+  if (nt <= 4) MHA_LAUNCH(4);
+  else if (nt <= 10) MHA_LAUNCH(10);
+  else if (nt <= 14) MHA_LAUNCH(14);
+  else MHA_LAUNCH(16);
+#undef MHA_LAUNCH
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
