@@ -302,6 +302,35 @@ int tocvp_frame_metrics(const float* pred, const float* target, size_t target_se
                         int target_frame0, int n_img, int C, int H, int W, int clamp, float* mse, float* psnr, float* ssim,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TransformerTextEncoder.forward (src/models/EncodersDecoders/text_encoders.py:84-124), the text encoder of
+ * TextOCVP_CustomTF (src/models/Predictors/predictor_wrapper.py:106-110): embeddings -> LayerNorm(1e-8) -> padding mask ->
+ * num_layers x nn.TransformerEncoderLayer (post-norm, exact GELU, key-padding mask j >= length) -> LayerNorm -> Linear.
+ * All weights fp32; "_t" = transposed to [in][out].  One CTA per caption, fp32 end to end.
+ * ------------------------------------------------------------------------------------------ */
+#define TOCVP_TEXT_MAX_LAYERS 4
+typedef struct tocvp_text_layer {
+  const float *in_w_t, *in_b;   /* self_attn.in_proj_{weight,bias}: [D][3D], [3D] (q | k | v)  */
+  const float *out_w_t, *out_b; /* self_attn.out_proj                                          */
+  const float *ln1_g, *ln1_b;   /* norm1                                                       */
+  const float *ff1_w_t, *ff1_b; /* linear1 [D][F]                                              */
+  const float *ff2_w_t, *ff2_b; /* linear2 [F][D]                                              */
+  const float *ln2_g, *ln2_b;   /* norm2                                                       */
+} tocvp_text_layer;
+typedef struct tocvp_text_weights {
+  const float *tok_emb, *pos_emb; /* [vocab][D], [context_length][D]     */
+  const float *ln0_g, *ln0_b;     /* layer_norm (eps 1e-8)               */
+  tocvp_text_layer layers[TOCVP_TEXT_MAX_LAYERS];
+  const float *lnf_g, *lnf_b;     /* text_out_projection.0               */
+  const float *proj_w_t, *proj_b; /* text_out_projection.1: [D][out_dim] */
+  int num_layers, input_dim, ffn_dim, num_heads, output_dim, vocab_size, context_length;
+} tocvp_text_weights;
+
+size_t tocvp_sizeof_text_weights(void);
+/* tokens int64 [B, L], lengths int64 [B] (device) -> text embeddings fp32 [B, L, output_dim].  L <= 64. */
+int tocvp_text_encode(const tocvp_text_weights* w, const long long* tokens, const long long* lengths, int B, int L,
+                      float* out, void* stream);
+
 /* Tuning / test knob (process-wide): 1 = decoder layer 1 is generated inside the layer-2 convolution kernel and never
  * stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation. */
 int tocvp_set_decode_mode(int fuse_layer1);

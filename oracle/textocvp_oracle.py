@@ -397,6 +397,40 @@ def dino_rollout(dino_sd: SD, pred_sd: SD, feats: Tensor, text: Tensor, init_slo
 
 
 # --------------------------------------------------------------------------------------
+# TransformerTextEncoder.forward (src/models/EncodersDecoders/text_encoders.py:84-124); the encoder layers are
+# torch.nn.TransformerEncoderLayer(d_model, nhead, 4*d_model, activation="gelu"), post-norm (built at :42-50), eval mode.
+# --------------------------------------------------------------------------------------
+def text_encoder(sd: SD, text: Tensor, text_length: Tensor, num_heads: int = 4) -> Tensor:
+    """text [B,L] int64 token ids (0 = padding), text_length [B] -> [B,L,output_dim].  ``sd`` keys relative to the
+    TransformerTextEncoder module."""
+    B, L = text.shape
+    pos = torch.arange(L)[None].expand(B, L)
+    x = F.embedding(text, sd["token_embedding.weight"]) + F.embedding(pos, sd["position_embedding.weight"])
+    x = _ln(x, sd, "layer_norm", 1e-8)
+    x = x * (text != 0).unsqueeze(-1).to(x.dtype)                          # :107-108
+    pad = text_length.unsqueeze(1) < torch.ones_like(text).cumsum(dim=1)   # :110  True = masked key
+    D = x.shape[-1]
+    dh = D // num_heads
+    i = 0
+    while f"transformer.layers.{i}.self_attn.in_proj_weight" in sd:
+        p = f"transformer.layers.{i}"
+        qkv = F.linear(x, sd[p + ".self_attn.in_proj_weight"], sd[p + ".self_attn.in_proj_bias"])
+        q, k, v = qkv.split(D, dim=-1)
+        qh, kh, vh = (t.view(B, L, num_heads, dh).transpose(1, 2) for t in (q, k, v))
+        att = (qh @ kh.transpose(-1, -2)) * dh ** -0.5
+        att = att.masked_fill(pad[:, None, None, :], float("-inf")).softmax(dim=-1)
+        a = (att @ vh).transpose(1, 2).reshape(B, L, D)
+        a = F.linear(a, sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"])
+        x = _ln(x + a, sd, p + ".norm1", 1e-5)
+        h = F.linear(F.gelu(F.linear(x, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
+                     sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+        x = _ln(x + h, sd, p + ".norm2", 1e-5)
+        i += 1
+    x = _ln(x, sd, "text_out_projection.0", 1e-5)
+    return F.linear(x, sd["text_out_projection.1.weight"], sd["text_out_projection.1.bias"])
+
+
+# --------------------------------------------------------------------------------------
 # Evaluator.forward_eval composition (05_evaluate_predictor.py:82-96) and PSNR
 # --------------------------------------------------------------------------------------
 def rollout(savi_sd: SD, pred_sd: SD, videos: Tensor, text: Tensor, init_slots: Tensor,

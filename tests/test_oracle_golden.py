@@ -76,3 +76,13 @@ def test_dino_rollout(golden_dino, golden_dino_weights):
     assert O.rel_err(out["pred_slots"], g["pred_slots"]) < 1e-4
     p = O.psnr(out["pred_imgs"], g["pred_imgs"].view_as(out["pred_imgs"]).clamp(0, 1))
     assert p.min() > 70.0, p.min()
+
+
+def test_text_encoder_oracle_vs_reference():
+    import os
+    from textocvp_b200 import weights
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "text_encoder_b5.pt"), weights_only=False)
+    m = g["meta"]
+    sd = weights.text_encoder_state_dict(m["seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
+    tokens, lengths = weights.synthetic_captions(m["B"], m["L"], seed=m["cap_seed"])
+    assert O.rel_err(O.text_encoder(sd, tokens, lengths), g["out"]) < TOL

@@ -132,3 +132,25 @@ def test_predictor_step_folded_layernorm(models, golden, golden_weights):
     assert O.rel_err(out_unfolded, ref) < STAGE_TOL
     print(f"folded-LN predictor step: rel err {O.rel_err(out, ref):.2e} (delta {O.rel_err(d_out, d_ref):.2e}); "
           f"unfolded {O.rel_err(out_unfolded, ref):.2e}")
+
+
+def test_text_encoder(models):
+    """TransformerTextEncoder on the CUDA path (one fused fp32 kernel per caption) vs the real reference's output
+    (golden) and the oracle; fp32 end to end -> 1e-4."""
+    import os
+    from textocvp_b200 import weights
+    _, pred = models
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "text_encoder_b5.pt"), weights_only=False)
+    m = g["meta"]
+    sd = weights.text_encoder_state_dict(m["seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
+    enc = pred.predictor.text_encoder
+    enc.load_state_dict(sd, strict=True)
+    tokens, lengths = weights.synthetic_captions(m["B"], m["L"], seed=m["cap_seed"])
+    out = enc(tokens.cuda(), lengths.cuda())
+    assert O.rel_err(out, g["out"]) < 1e-4
+    # through the wrapper's caption path (predictor_wrapper.py:90-127)
+    emb = pred.encode_text_caption(caption_tokens=tokens, caption_lengths=lengths)
+    assert O.rel_err(emb, g["out"]) < 1e-4
+    # ragged: a longer batch with lengths down to 3 tokens
+    tok2, len2 = weights.synthetic_captions(9, 50, seed=11)
+    assert O.rel_err(enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)) < 1e-4

@@ -93,7 +93,8 @@ PatchW = type("PatchW", (ctypes.Structure,), {"_fields_": [
 def check_struct_sizes():
     lib = L.load()
     for name, st in (("sa_weights", SaW), ("pred_weights", PredW), ("pred_layer", PredLayer),
-                     ("enc_weights", EncW), ("dec_weights", DecW), ("proj_weights", ProjW), ("patch_weights", PatchW)):
+                     ("enc_weights", EncW), ("dec_weights", DecW), ("proj_weights", ProjW), ("patch_weights", PatchW),
+                     ("text_weights", TextW)):
         fn = getattr(lib, f"tocvp_sizeof_{name}")
         fn.restype = ctypes.c_size_t
         if fn() != ctypes.sizeof(st):
@@ -929,14 +930,26 @@ class ExtendedDINOSAUR(_Packed):
 # =====================================================================================================
 # Predictor
 # =====================================================================================================
-class TransformerTextEncoder(nn.Module):
-    """text_encoders.py:14-138.  NOT on the accelerated path: it runs once per rollout and the benchmark replaces
-    its output by synthetic embeddings (BASELINE.json north_star).  Kept as a plain torch module (the reference's own
-    composition of torch layers) so that checkpoints load strictly and captions can be encoded."""
+TEXT_MAX_LAYERS = 4
+TextLayer = _struct("TextLayer", ["in_w_t", "in_b", "out_w_t", "out_b", "ln1_g", "ln1_b", "ff1_w_t", "ff1_b", "ff2_w_t",
+                                  "ff2_b", "ln2_g", "ln2_b"], [])
+TextW = type("TextW", (ctypes.Structure,), {"_fields_": [
+    ("tok_emb", _f), ("pos_emb", _f), ("ln0_g", _f), ("ln0_b", _f), ("layers", TextLayer * TEXT_MAX_LAYERS),
+    ("lnf_g", _f), ("lnf_b", _f), ("proj_w_t", _f), ("proj_b", _f),
+    ("num_layers", ctypes.c_int), ("input_dim", ctypes.c_int), ("ffn_dim", ctypes.c_int), ("num_heads", ctypes.c_int),
+    ("output_dim", ctypes.c_int), ("vocab_size", ctypes.c_int), ("context_length", ctypes.c_int)]})
+
+
+class TransformerTextEncoder(_Packed):
+    """text_encoders.py:14-138.  forward(text [B,L] int64, text_length [B] int64) -> [B,L,output_dim].  The torch layers
+    (nn.TransformerEncoder, nn.Embedding, ...) are parameter containers with the reference's state_dict keys; the
+    arithmetic is one fused fp32 kernel per caption (csrc/text_encoder.cu).  Eval-mode semantics (dropout inactive)."""
 
     def __init__(self, input_dim, num_layers, num_heads, output_dim, vocab_size, context_length=50, dropout=0.1):
         super().__init__()
         self.vocab_size, self.padding_idx = vocab_size, 0
+        self.input_dim, self.num_layers, self.num_heads = input_dim, num_layers, num_heads
+        self.output_dim, self.context_length = output_dim, context_length
         layer = nn.TransformerEncoderLayer(d_model=input_dim, nhead=num_heads, dim_feedforward=input_dim * 4,
                                            dropout=dropout, activation="gelu")
         self.transformer = nn.TransformerEncoder(layer, num_layers, enable_nested_tensor=False)
@@ -945,14 +958,50 @@ class TransformerTextEncoder(nn.Module):
         self.layer_norm = nn.LayerNorm(input_dim, eps=1e-8)
         self.dropout = nn.Dropout(p=dropout)
         self.text_out_projection = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, output_dim))
+        with torch.no_grad():                                       # _init_weights (text_encoders.py:74-87)
+            for mod in self.modules():
+                if isinstance(mod, nn.Linear):
+                    mod.weight.normal_(0.0, 0.02)
+                elif isinstance(mod, nn.MultiheadAttention):
+                    mod.in_proj_weight.normal_(0.0, 0.02)
+                    mod.out_proj.weight.normal_(0.0, 0.02)
+                elif isinstance(mod, nn.Embedding):
+                    mod.weight.normal_(0.0, 0.02)
 
+    def _pack(self, dev):
+        if self.num_layers > TEXT_MAX_LAYERS:
+            raise L.TocvpError("text encoder kernels are built for <= 4 layers")
+        k = dict(tok_emb=_f32(self.token_embedding.weight), pos_emb=_f32(self.position_embedding.weight),
+                 ln0_g=_f32(self.layer_norm.weight), ln0_b=_f32(self.layer_norm.bias),
+                 lnf_g=_f32(self.text_out_projection[0].weight), lnf_b=_f32(self.text_out_projection[0].bias),
+                 proj_w_t=_tr(self.text_out_projection[1].weight), proj_b=_f32(self.text_out_projection[1].bias))
+        w = TextW()
+        for n, v in k.items():
+            setattr(w, n, v.data_ptr())
+        for i, lyr in enumerate(self.transformer.layers):
+            t = dict(in_w_t=_tr(lyr.self_attn.in_proj_weight), in_b=_f32(lyr.self_attn.in_proj_bias),
+                     out_w_t=_tr(lyr.self_attn.out_proj.weight), out_b=_f32(lyr.self_attn.out_proj.bias),
+                     ln1_g=_f32(lyr.norm1.weight), ln1_b=_f32(lyr.norm1.bias),
+                     ff1_w_t=_tr(lyr.linear1.weight), ff1_b=_f32(lyr.linear1.bias),
+                     ff2_w_t=_tr(lyr.linear2.weight), ff2_b=_f32(lyr.linear2.bias),
+                     ln2_g=_f32(lyr.norm2.weight), ln2_b=_f32(lyr.norm2.bias))
+            for n, v in t.items():
+                setattr(w.layers[i], n, v.data_ptr())
+            k[f"layer{i}"] = t
+        w.num_layers, w.input_dim, w.ffn_dim, w.num_heads = self.num_layers, self.input_dim, self.input_dim * 4, self.num_heads
+        w.output_dim, w.vocab_size, w.context_length = self.output_dim, self.vocab_size, self.context_length
+        self._keep, self._w = k, w
+
+    @torch.no_grad()
     def forward(self, text, text_length):
-        pos = torch.arange(text.shape[1], dtype=text.dtype, device=text.device)[None].repeat(text.shape[0], 1)
-        tok = self.layer_norm(self.token_embedding(text) + self.position_embedding(pos))
-        tok = self.dropout(tok) * (text != self.padding_idx).unsqueeze(-1).type(tok.dtype)
-        cap_mask = text_length.unsqueeze(1) < torch.ones_like(text).cumsum(dim=1)
-        emb = self.transformer(tok.permute(1, 0, 2), mask=None, src_key_padding_mask=cap_mask).permute(1, 0, 2)
-        return self.text_out_projection(emb)
+        self._ensure_packed()
+        B, Lt = text.shape
+        text = text.to(torch.int64).contiguous()
+        text_length = text_length.to(torch.int64).contiguous()
+        out = torch.empty(B, Lt, self.output_dim, device=text.device, dtype=torch.float32)
+        L.call("tocvp_text_encode", ctypes.byref(self._w), ptr(text), ptr(text_length), c_int(B), c_int(Lt), ptr(out),
+               stream())
+        return out
 
 
 class BaseTextOCVP(_Packed):

@@ -265,3 +265,48 @@ def synthetic_dino_inputs(B: int, T: int = 30, N: int = 81, feat_dim: int = 768,
     text = torch.randn(B, L, token_dim, generator=g)
     noise = torch.randn(B, num_slots, slot_dim, generator=g)
     return feats, text, noise
+
+
+def text_encoder_state_dict(seed: int = 18, input_dim: int = 128, num_layers: int = 2, output_dim: int = 512,
+                            vocab_size: int = 50, context_length: int = 50, bias_scale: float = 0.0,
+                            ln_jitter: float = 0.0) -> Dict[str, Tensor]:
+    """TransformerTextEncoder parameters (reference src/models/EncodersDecoders/text_encoders.py:36-87): N(0, 0.02)
+    matrices and embeddings, zero biases (perturbed by ``bias_scale`` for tests), unit LayerNorms (+ ``ln_jitter``)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    D = input_dim
+
+    def nrm(*shape):
+        return 0.02 * torch.randn(*shape, generator=g)
+
+    def bias(n):
+        return bias_scale * torch.randn(n, generator=g)
+
+    sd["token_embedding.weight"] = nrm(vocab_size, D)
+    sd["position_embedding.weight"] = nrm(context_length, D)
+    _ln(sd, "layer_norm", D, g, ln_jitter)
+    for i in range(num_layers):
+        p = f"transformer.layers.{i}"
+        sd[p + ".self_attn.in_proj_weight"] = nrm(3 * D, D)
+        sd[p + ".self_attn.in_proj_bias"] = bias(3 * D)
+        sd[p + ".self_attn.out_proj.weight"] = nrm(D, D)
+        sd[p + ".self_attn.out_proj.bias"] = bias(D)
+        sd[p + ".linear1.weight"] = nrm(4 * D, D)
+        sd[p + ".linear1.bias"] = bias(4 * D)
+        sd[p + ".linear2.weight"] = nrm(D, 4 * D)
+        sd[p + ".linear2.bias"] = bias(D)
+        _ln(sd, p + ".norm1", D, g, ln_jitter)
+        _ln(sd, p + ".norm2", D, g, ln_jitter)
+    _ln(sd, "text_out_projection.0", D, g, ln_jitter)
+    sd["text_out_projection.1.weight"] = nrm(output_dim, D)
+    sd["text_out_projection.1.bias"] = bias(output_dim)
+    return sd
+
+
+def synthetic_captions(B: int, L: int = 24, vocab_size: int = 50, seed: int = 0):
+    """Token ids [B,L] (0 = padding after the caption) and caption lengths [B] in 3..L."""
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(3, L + 1, (B,), generator=g)
+    tokens = torch.randint(1, vocab_size, (B, L), generator=g)
+    tokens = tokens * (torch.arange(L)[None] < lengths[:, None])
+    return tokens.long(), lengths.long()
