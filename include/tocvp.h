@@ -331,6 +331,28 @@ size_t tocvp_sizeof_text_weights(void);
 int tocvp_text_encode(const tocvp_text_weights* w, const long long* tokens, const long long* lengths, int B, int L,
                       float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Sibling predictors behind the same PredictorWrapper loop: VanillaTransformerPredictor (src/models/Predictors/OCVP.py:24-141)
+ * and OCVPSeq (OCVP.py:145-319).  `blocks` are pre-norm nn.TransformerEncoderLayer parameter sets (same fields as
+ * tocvp_text_layer); block_group[i] selects the keys a query attends to: 0 = all tokens of the window (Vanilla),
+ * 1 = tokens of the same frame (OCVPSeqLayer.object_encoder_block), 2 = the same slot over time (time_encoder_block).
+ * ------------------------------------------------------------------------------------------ */
+#define TOCVP_OCVP_MAX_BLOCKS 8
+typedef struct tocvp_ocvp_weights {
+  const float *mlp_in_w_t, *mlp_in_b;   /* [slot_dim][token_dim]                                  */
+  const float *mlp_out_w_t, *mlp_out_b; /* [token_dim][slot_dim]                                  */
+  const float* pe;                      /* sinusoidal table [max_len][token_dim] (model_blocks.py:261-266) */
+  tocvp_text_layer blocks[TOCVP_OCVP_MAX_BLOCKS];
+  int block_group[TOCVP_OCVP_MAX_BLOCKS];
+  int num_blocks, num_slots, slot_dim, token_dim, ffn_dim, num_heads, max_len, residual;
+} tocvp_ocvp_weights;
+
+size_t tocvp_sizeof_ocvp_weights(void);
+/* One prediction step (VanillaTransformerPredictor.forward / OCVPSeq.forward): sequence b's window [n, S, slot_dim] at
+ * slots + b*seq_stride (floats) -> out [B, S, slot_dim].  n * S <= 80 tokens, token_dim <= 128. */
+int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t seq_stride, int B, int n, float* out,
+                       void* stream);
+
 /* Tuning / test knob (process-wide): 1 = decoder layer 1 is generated inside the layer-2 convolution kernel and never
  * stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation. */
 int tocvp_set_decode_mode(int fuse_layer1);

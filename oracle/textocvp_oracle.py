@@ -431,6 +431,59 @@ def text_encoder(sd: SD, text: Tensor, text_length: Tensor, num_heads: int = 4) 
 
 
 # --------------------------------------------------------------------------------------
+# Sibling predictors: VanillaTransformerPredictor / OCVPSeq (src/models/Predictors/OCVP.py:24-319) over pre-norm
+# torch.nn.TransformerEncoderLayer blocks (ReLU, eps 1e-5, eval mode), SlotPositionalEncoding (model_blocks.py:230-290).
+# --------------------------------------------------------------------------------------
+def _encoder_layer_prenorm(sd: SD, p: str, x: Tensor, num_heads: int) -> Tensor:
+    """x [N, T, D]: x = x + SA(LN1(x)); x = x + FFN(LN2(x))."""
+    N, T, D = x.shape
+    dh = D // num_heads
+    h = _ln(x, sd, p + ".norm1", 1e-5)
+    q, k, v = F.linear(h, sd[p + ".self_attn.in_proj_weight"], sd[p + ".self_attn.in_proj_bias"]).split(D, dim=-1)
+    qh, kh, vh = (t.view(N, T, num_heads, dh).transpose(1, 2) for t in (q, k, v))
+    a = ((qh @ kh.transpose(-1, -2)) * dh ** -0.5).softmax(dim=-1) @ vh
+    a = a.transpose(1, 2).reshape(N, T, D)
+    x = x + F.linear(a, sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"])
+    h = _ln(x, sd, p + ".norm2", 1e-5)
+    return x + F.linear(F.relu(F.linear(h, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
+                        sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+
+
+def slot_positional_encoding(max_len: int, d_model: int) -> Tensor:
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def ocvp_step(sd: SD, slots: Tensor, kind: str, num_heads: int = 4, residual: bool = True, max_len: int = 10) -> Tensor:
+    """slots [B,n,S,Ds] -> [B,S,Ds].  kind = "VanillaTransformer" (OCVP.py:98-135) or "OCVPSeq" (OCVP.py:211-243)."""
+    B, n, S, _ = slots.shape
+    tok = _lin(slots, sd, "mlp_in")
+    D = tok.shape[-1]
+    tok = tok + slot_positional_encoding(max_len, D)[:n].view(1, n, 1, D)
+    i = 0
+    if kind == "VanillaTransformer":
+        x = tok.reshape(B, n * S, D)
+        while f"transformer_encoders.{i}.self_attn.in_proj_weight" in sd:
+            x = _encoder_layer_prenorm(sd, f"transformer_encoders.{i}", x, num_heads)
+            i += 1
+        tok = x.reshape(B, n, S, D)
+    else:
+        while f"transformer_encoders.{i}.object_encoder_block.self_attn.in_proj_weight" in sd:
+            p = f"transformer_encoders.{i}"
+            x = _encoder_layer_prenorm(sd, p + ".object_encoder_block", tok.reshape(B * n, S, D), num_heads)
+            x = x.reshape(B, n, S, D).transpose(1, 2).reshape(B * S, n, D)
+            x = _encoder_layer_prenorm(sd, p + ".time_encoder_block", x, num_heads)
+            tok = x.reshape(B, S, n, D).transpose(1, 2)
+            i += 1
+    out = _lin(tok[:, -1], sd, "mlp_out")
+    return out + slots[:, -1] if residual else out
+
+
+# --------------------------------------------------------------------------------------
 # Evaluator.forward_eval composition (05_evaluate_predictor.py:82-96) and PSNR
 # --------------------------------------------------------------------------------------
 def rollout(savi_sd: SD, pred_sd: SD, videos: Tensor, text: Tensor, init_slots: Tensor,

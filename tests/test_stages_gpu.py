@@ -154,3 +154,29 @@ def test_text_encoder(models):
     # ragged: a longer batch with lengths down to 3 tokens
     tok2, len2 = weights.synthetic_captions(9, 50, seed=11)
     assert O.rel_err(enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["VanillaTransformer", "OCVPSeq"])
+def test_sibling_predictors(kind):
+    """VanillaTransformerPredictor / OCVPSeq behind the same PredictorWrapper: one fused fp32 kernel
+    per prediction step vs the real reference's outputs (golden): single step and a 4-step autoregressive rollout."""
+    import os
+    from textocvp_b200 import modules as M, weights
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ocvp_b3.pt"), weights_only=False)
+    m = g["meta"]
+    ep = M.default_exp_params(num_context=m["num_context"], num_preds=m["num_preds"], input_buffer_size=m["input_buffer_size"])
+    ep["predictor"] = {"predictor_name": kind, "predictor_params": {"token_dim": 128, "hidden_dim": 256, "num_layers": 2,
+                                                                   "n_heads": 4, "residual": True}}
+    pred = M.setup_predictor(ep)
+    sd = weights.ocvp_state_dict(kind, m["seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
+    pred.predictor.load_state_dict(sd, strict=True)
+    pred = pred.cuda().eval()
+    out = pred.predictor(slots=g["slots"].cuda())
+    assert O.rel_err(out, g[kind + "_step"]) < 1e-4
+    roll = pred(g["hist"].cuda())
+    assert roll.shape == g[kind + "_rollout"].shape
+    assert O.rel_err(roll, g[kind + "_rollout"]) < 1e-4
+    # full 10-frame window of 8 slots (80 tokens, the kernel's maximum) against the oracle
+    slots = torch.randn(2, 10, 8, 128, generator=torch.Generator().manual_seed(3))
+    ref = O.ocvp_step(sd, slots, kind, max_len=m["input_buffer_size"])
+    assert O.rel_err(pred.predictor(slots=slots.cuda()), ref) < 1e-4

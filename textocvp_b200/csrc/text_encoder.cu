@@ -10,67 +10,15 @@
 // online softmax per (head, query) thread.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "small_tf.cuh"
 
 namespace tocvp {
-
-constexpr int TE_THREADS = 256;
-constexpr int TE_MAXL = 64;
-constexpr int TE_RB = 16;   // rows per accumulator block
-
-// y[r][n] = act(bias[n] + sum_k x[r][k] * Wt[k][n])   r < L;  x: smem [L][ldx], y: smem [L][ldy]
-__device__ void te_linear(const float* __restrict__ Wt, const float* __restrict__ bias, int K, int N, const float* x,
-                          int ldx, float* y, int ldy, int L, int act /*0 none, 1 gelu*/, const float* res, int ldr) {
-  for (int n = threadIdx.x; n < N; n += TE_THREADS) {
-    const float bv = bias ? __ldg(bias + n) : 0.f;
-    for (int r0 = 0; r0 < L; r0 += TE_RB) {
-      float acc[TE_RB];
-#pragma unroll
-      for (int r = 0; r < TE_RB; ++r) acc[r] = bv;
-#pragma unroll 4
-      for (int k = 0; k < K; ++k) {
-        const float w = __ldg(Wt + size_t(k) * N + n);
-#pragma unroll
-        for (int r = 0; r < TE_RB; ++r) acc[r] = fmaf(w, x[(r0 + r) * ldx + k], acc[r]);   // smem broadcast reads
-      }
-#pragma unroll
-      for (int r = 0; r < TE_RB; ++r) {
-        if (r0 + r < L) {
-          float v = acc[r];
-          if (act == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));            // exact GELU (torch default)
-          if (res) v += res[(r0 + r) * ldr + n];
-          y[(r0 + r) * ldy + n] = v;
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// in-place LayerNorm of x[L][D] (one warp per row), optional row mask (rows with keep[r] == 0 are zeroed afterwards)
-__device__ void te_layernorm(float* x, int ld, int L, int D, const float* __restrict__ g, const float* __restrict__ b,
-                             float eps, const unsigned char* keep) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < L; r += TE_THREADS / 32) {
-    float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += x[r * ld + c];
-    const float mean = warp_sum(s) / D;
-    float q = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float d = x[r * ld + c] - mean;
-      q += d * d;
-    }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
-    const float m = (keep && !keep[r]) ? 0.f : 1.f;
-    for (int c = lane; c < D; c += 32) x[r * ld + c] = ((x[r * ld + c] - mean) * rstd * __ldg(g + c) + __ldg(b + c)) * m;
-  }
-  __syncthreads();
-}
 
 __global__ void __launch_bounds__(TE_THREADS, 1)
 text_encoder_kernel(tocvp_text_weights w, const long long* __restrict__ tokens, const long long* __restrict__ lengths,
                     int L, float* __restrict__ out) {
   extern __shared__ float sm[];
-  const int D = w.input_dim, F = w.ffn_dim, H = w.num_heads, dh = D / H;
+  const int D = w.input_dim, F = w.ffn_dim, H = w.num_heads;
   const int ldq = 3 * D + 1;                                   // +1: query rows land in different banks
   float* x = sm;                                               // [L][D] residual stream
   float* big = x + TE_MAXL * D;                                // [L][3D+1] qkv, later [L][F] FFN hidden
@@ -93,37 +41,8 @@ text_encoder_kernel(tocvp_text_weights w, const long long* __restrict__ tokens, 
   for (int l = 0; l < w.num_layers; ++l) {
     const tocvp_text_layer& ly = w.layers[l];
     te_linear(ly.in_w_t, ly.in_b, D, 3 * D, x, D, big, ldq, L, 0, nullptr, 0);
-    // attention: thread = (head, query row); keys j >= len are masked (src_key_padding_mask, text_encoders.py:110)
-    {
-      const float scale = rsqrtf(float(dh));
-      for (int e = threadIdx.x; e < H * L; e += TE_THREADS) {
-        const int h = e / L, i = e - h * L;
-        const float* q = big + i * ldq + h * dh;
-        float m = -1e30f, den = 0.f;
-        float o[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) o[c] = 0.f;
-        for (int j = 0; j < L && j < len; ++j) {
-          const float* kk = big + j * ldq + D + h * dh;
-          const float* vv = big + j * ldq + 2 * D + h * dh;
-          float s = 0.f;
-          for (int c = 0; c < dh; ++c) s = fmaf(q[c], kk[c], s);
-          s *= scale;
-          const float mn = fmaxf(m, s);
-          const float corr = __expf(m - mn), p = __expf(s - mn);
-          den = den * corr + p;
-#pragma unroll
-          for (int c = 0; c < 64; ++c)
-            if (c < dh) o[c] = o[c] * corr + p * vv[c];
-          m = mn;
-        }
-        const float inv = 1.f / den;
-#pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if (c < dh) att[i * D + h * dh + c] = o[c] * inv;
-      }
-      __syncthreads();
-    }
+    // attention over the keys j < len (src_key_padding_mask, text_encoders.py:110)
+    te_attention(big, ldq, att, D, L, len < L ? len : L, D, H, 0, 1);
     te_linear(ly.out_w_t, ly.out_b, D, D, att, D, x, D, L, 0, x, D);          // x += out_proj(att)   (residual in place)
     te_layernorm(x, D, L, D, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr);
     te_linear(ly.ff1_w_t, ly.ff1_b, D, F, x, D, big, F, L, 1, nullptr, 0);

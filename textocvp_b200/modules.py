@@ -94,7 +94,7 @@ def check_struct_sizes():
     lib = L.load()
     for name, st in (("sa_weights", SaW), ("pred_weights", PredW), ("pred_layer", PredLayer),
                      ("enc_weights", EncW), ("dec_weights", DecW), ("proj_weights", ProjW), ("patch_weights", PatchW),
-                     ("text_weights", TextW)):
+                     ("text_weights", TextW), ("ocvp_weights", OcvpW)):
         fn = getattr(lib, f"tocvp_sizeof_{name}")
         fn.restype = ctypes.c_size_t
         if fn() != ctypes.sizeof(st):
@@ -1004,6 +1004,121 @@ class TransformerTextEncoder(_Packed):
         return out
 
 
+OCVP_MAX_BLOCKS = 8
+OcvpW = type("OcvpW", (ctypes.Structure,), {"_fields_": [
+    ("mlp_in_w_t", _f), ("mlp_in_b", _f), ("mlp_out_w_t", _f), ("mlp_out_b", _f), ("pe", _f),
+    ("blocks", TextLayer * OCVP_MAX_BLOCKS), ("block_group", ctypes.c_int * OCVP_MAX_BLOCKS),
+    ("num_blocks", ctypes.c_int), ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int), ("token_dim", ctypes.c_int),
+    ("ffn_dim", ctypes.c_int), ("num_heads", ctypes.c_int), ("max_len", ctypes.c_int), ("residual", ctypes.c_int)]})
+
+
+def _encoder_layer_ptrs(lyr, keep, dst):
+    """nn.TransformerEncoderLayer parameters -> tocvp_text_layer (fp32, matrices transposed to [in][out])."""
+    t = dict(in_w_t=_tr(lyr.self_attn.in_proj_weight), in_b=_f32(lyr.self_attn.in_proj_bias),
+             out_w_t=_tr(lyr.self_attn.out_proj.weight), out_b=_f32(lyr.self_attn.out_proj.bias),
+             ln1_g=_f32(lyr.norm1.weight), ln1_b=_f32(lyr.norm1.bias),
+             ff1_w_t=_tr(lyr.linear1.weight), ff1_b=_f32(lyr.linear1.bias),
+             ff2_w_t=_tr(lyr.linear2.weight), ff2_b=_f32(lyr.linear2.bias),
+             ln2_g=_f32(lyr.norm2.weight), ln2_b=_f32(lyr.norm2.bias))
+    for n, v in t.items():
+        setattr(dst, n, v.data_ptr())
+    keep.append(t)
+
+
+class SlotPositionalEncoding(nn.Module):
+    """model_blocks.py:230-290: sinusoidal table [1, max_len, 1, d_model], a plain attribute (not a buffer)."""
+
+    def __init__(self, d_model, dropout=0.1, max_len=50):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, 1, d_model)
+        pe[:, 0, 0::2] = torch.sin(position * div_term)
+        pe[:, 0, 1::2] = torch.cos(position * div_term)
+        self.pe = pe.view(1, max_len, 1, d_model)
+
+
+class OCVPSeqLayer(nn.Module):
+    """OCVP.py:247-319 (parameter container): object- then time-attention encoder blocks."""
+
+    def __init__(self, token_dim=128, hidden_dim=256, n_heads=4):
+        super().__init__()
+        mk = lambda: nn.TransformerEncoderLayer(d_model=token_dim, nhead=n_heads, batch_first=True, norm_first=True,
+                                                dim_feedforward=hidden_dim)
+        self.object_encoder_block, self.time_encoder_block = mk(), mk()
+
+
+class _OCVPBase(_Packed):
+    """Shared body of VanillaTransformerPredictor / OCVPSeq: forward(slots [B,n,S,D]) -> [B,S,D]; one fused fp32 kernel per
+    prediction step (csrc/ocvp.cu)."""
+
+    def __init__(self, num_slots, slot_dim, token_dim=128, hidden_dim=256, num_layers=2, n_heads=4, residual=False,
+                 input_buffer_size=5):
+        super().__init__()
+        self.num_slots, self.slot_dim, self.token_dim, self.hidden_dim = num_slots, slot_dim, token_dim, hidden_dim
+        self.num_layers, self.nhead, self.residual, self.input_buffer_size = num_layers, n_heads, residual, input_buffer_size
+        self.mlp_in = nn.Linear(slot_dim, token_dim)
+        self.mlp_out = nn.Linear(token_dim, slot_dim)
+        self.transformer_encoders = self._build_encoders()
+        self.pe = SlotPositionalEncoding(d_model=token_dim, max_len=input_buffer_size)
+
+    def _blocks(self):
+        raise NotImplementedError
+
+    def _pack(self, dev):
+        blocks = self._blocks()                                   # [(encoder layer, key group)]
+        if len(blocks) > OCVP_MAX_BLOCKS:
+            raise L.TocvpError("OCVP predictor kernels are built for <= 8 encoder blocks")
+        keep = [dict(mlp_in_w_t=_tr(self.mlp_in.weight), mlp_in_b=_f32(self.mlp_in.bias),
+                     mlp_out_w_t=_tr(self.mlp_out.weight), mlp_out_b=_f32(self.mlp_out.bias),
+                     pe=self.pe.pe.reshape(-1, self.token_dim).float().contiguous().to(dev))]
+        w = OcvpW()
+        for n, v in keep[0].items():
+            setattr(w, n, v.data_ptr())
+        for i, (lyr, group) in enumerate(blocks):
+            _encoder_layer_ptrs(lyr, keep, w.blocks[i])
+            w.block_group[i] = group
+        w.num_blocks, w.num_slots, w.slot_dim, w.token_dim = len(blocks), self.num_slots, self.slot_dim, self.token_dim
+        w.ffn_dim, w.num_heads, w.max_len, w.residual = self.hidden_dim, self.nhead, self.input_buffer_size, int(bool(self.residual))
+        self._keep, self._w = keep, w
+
+    @torch.no_grad()
+    def forward(self, slots, **kwargs):
+        self._ensure_packed()
+        B, n, S, D = slots.shape
+        slots = slots.float().contiguous()
+        out = torch.empty(B, S, D, device=slots.device, dtype=torch.float32)
+        self._w.num_slots = S
+        L.call("tocvp_ocvp_forward", ctypes.byref(self._w), ptr(slots), c_size_t(n * S * D), c_int(B), c_int(n), ptr(out),
+               stream())
+        return out
+
+
+class VanillaTransformerPredictor(_OCVPBase):
+    """OCVP.py:24-141: attention over all n*S tokens."""
+
+    def _build_encoders(self):
+        return nn.Sequential(*[nn.TransformerEncoderLayer(d_model=self.token_dim, nhead=self.nhead, batch_first=True,
+                                                          norm_first=True, dim_feedforward=self.hidden_dim)
+                               for _ in range(self.num_layers)])
+
+    def _blocks(self):
+        return [(lyr, 0) for lyr in self.transformer_encoders]
+
+
+class OCVPSeq(_OCVPBase):
+    """OCVP.py:145-243: [object-attention, time-attention] per layer."""
+
+    def _build_encoders(self):
+        return nn.Sequential(*[OCVPSeqLayer(self.token_dim, self.hidden_dim, self.nhead) for _ in range(self.num_layers)])
+
+    def _blocks(self):
+        out = []
+        for lyr in self.transformer_encoders:
+            out += [(lyr.object_encoder_block, 1), (lyr.time_encoder_block, 2)]
+        return out
+
+
 class BaseTextOCVP(_Packed):
     """text_cond_OCVP.py:22-121.  forward(slots [B,n,S,D], text_embeddings [B,L,T]) -> [B,S,D]."""
 
@@ -1143,6 +1258,8 @@ class PredictorWrapper(nn.Module):
 
     def encode_text_caption(self, **kwargs):
         """predictor_wrapper.py:90-127; additionally accepts precomputed ``text_embeddings`` [B,L,T]."""
+        if "TextOCVP" not in self.predictor_name:                  # predictor_wrapper.py:98-99
+            return None
         if kwargs.get("text_embeddings") is not None:
             return kwargs["text_embeddings"]
         caption = kwargs.get("caption_tokens", None)
@@ -1161,7 +1278,8 @@ class PredictorWrapper(nn.Module):
         num_preds = num_preds if num_preds is not None else self.num_preds
         teacher_force = self.exp_params["prediction_params"]["teacher_force"]      # see Appendix A.12
         text = self.encode_text_caption(**kwargs)
-        if not teacher_force and self.predictor.input_buffer_size == self.input_buffer_size:
+        if not teacher_force and hasattr(self.predictor, "rollout") and \
+                self.predictor.input_buffer_size == self.input_buffer_size:
             return self.predictor.rollout(slot_history, text, self.num_context, num_preds)
         # generic loop (teacher forcing): same composition as the reference, one library call per step
         window = slot_history[:, :self.num_context].clone()
@@ -1190,11 +1308,20 @@ def setup_model(model_params: Dict):
 def setup_predictor(exp_params: Dict):
     import copy
     pp = copy.deepcopy(exp_params["predictor"]["predictor_params"])
-    pp["predictor_params"]["input_buffer_size"] = exp_params["prediction_params"]["input_buffer_size"]
     name = exp_params["predictor"]["predictor_name"]
-    if name != "TextOCVP_CustomTF":
-        raise NotImplementedError(f"predictor {name}: only TextOCVP_CustomTF is available offline")
-    body = TextOCVP_CustomTF(slot_dim=exp_params["model"]["model_params"]["slot_dim"], **pp)
+    if "TextOCVP" in name:                                             # setup_model.py:103-104
+        pp["predictor_params"]["input_buffer_size"] = exp_params["prediction_params"]["input_buffer_size"]
+    mp = exp_params["model"]["model_params"]
+    if name == "TextOCVP_CustomTF":
+        body = TextOCVP_CustomTF(slot_dim=mp["slot_dim"], **pp)
+    elif name in ("VanillaTransformer", "OCVPSeq"):                    # setup_model.py:83-99
+        cls = VanillaTransformerPredictor if name == "VanillaTransformer" else OCVPSeq
+        body = cls(num_slots=mp["num_slots"], slot_dim=mp["slot_dim"],
+                   input_buffer_size=exp_params["prediction_params"]["input_buffer_size"],
+                   **exp_params["predictor"]["predictor_params"])
+    else:
+        raise NotImplementedError(f"predictor {name}: TextOCVP_T5 needs the T5 weights (network); available: "
+                                  "TextOCVP_CustomTF, VanillaTransformer, OCVPSeq")
     return PredictorWrapper(exp_params=exp_params, predictor=body)
 
 

@@ -310,3 +310,36 @@ def synthetic_captions(B: int, L: int = 24, vocab_size: int = 50, seed: int = 0)
     tokens = torch.randint(1, vocab_size, (B, L), generator=g)
     tokens = tokens * (torch.arange(L)[None] < lengths[:, None])
     return tokens.long(), lengths.long()
+
+
+def ocvp_state_dict(kind: str, seed: int = 19, slot_dim: int = 128, token_dim: int = 128, hidden_dim: int = 256,
+                    num_layers: int = 2, mlp_out_scale: float = 1.0, bias_scale: float = 0.0,
+                    ln_jitter: float = 0.0) -> Dict[str, Tensor]:
+    """VanillaTransformerPredictor / OCVPSeq parameters (reference src/models/Predictors/OCVP.py): PyTorch-default
+    initialisations of nn.Linear / nn.TransformerEncoderLayer (xavier in_proj, zero attention biases)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    T = token_dim
+    sd["mlp_in.weight"], sd["mlp_in.bias"] = _default_linear(g, T, slot_dim)
+    wo, bo = _default_linear(g, slot_dim, T)
+    sd["mlp_out.weight"], sd["mlp_out.bias"] = wo * mlp_out_scale, bo * mlp_out_scale
+
+    def enc(p):
+        sd[p + ".self_attn.in_proj_weight"] = _xavier(g, 3 * T, T)
+        sd[p + ".self_attn.in_proj_bias"] = bias_scale * torch.randn(3 * T, generator=g)
+        sd[p + ".self_attn.out_proj.weight"], _ = _default_linear(g, T, T, bias=False)
+        sd[p + ".self_attn.out_proj.bias"] = bias_scale * torch.randn(T, generator=g)
+        sd[p + ".linear1.weight"], sd[p + ".linear1.bias"] = _default_linear(g, hidden_dim, T)
+        sd[p + ".linear2.weight"], sd[p + ".linear2.bias"] = _default_linear(g, T, hidden_dim)
+        _ln(sd, p + ".norm1", T, g, ln_jitter)
+        _ln(sd, p + ".norm2", T, g, ln_jitter)
+
+    for i in range(num_layers):
+        if kind == "VanillaTransformer":
+            enc(f"transformer_encoders.{i}")
+        elif kind == "OCVPSeq":
+            enc(f"transformer_encoders.{i}.object_encoder_block")
+            enc(f"transformer_encoders.{i}.time_encoder_block")
+        else:
+            raise ValueError(kind)
+    return sd
