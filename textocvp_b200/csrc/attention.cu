@@ -38,8 +38,9 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 // sequences -> more resident CTAs per SM for a kernel that is pure latency.
 template <int NT>
 __global__ void __launch_bounds__(ATT_MAX_WARPS * 32)
-mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, const __half* __restrict__ v, int ldkv,
-           int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out, int ldo) {
+mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* __restrict__ k,
+           const __half* __restrict__ v, int ldkv, int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out,
+           int ldo) {
   __shared__ __align__(16) __half sK[NT * 8 * ATT_KS];
   __shared__ __align__(16) __half sV[NT * 8 * ATT_KS];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -60,7 +61,7 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
   }
   __syncthreads();
   const int n_tiles = TkP / 8;    // key tiles of 8
-  const __half* qb = q + size_t(b) * Tq * ldq + h * ATT_DH;
+  const __half* qb = q + size_t(b) * q_seq_rows * ldq + h * ATT_DH;   // q_seq_rows > Tq: a row subset per sequence
   __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
   for (int m0 = warp * 16; m0 < Tq; m0 += (blockDim.x >> 5) * 16) {
     const int r0 = m0 + g, r1 = m0 + g + 8;
@@ -153,9 +154,20 @@ mha_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, 
   }
 }
 
+int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk,
+                int heads, __half* out, int ldo, cudaStream_t stream);
+
 // q [B*Tq, ldq], k/v [B*Tk, ldkv] (all f16, head h at column h*64), out [B*Tq, ldo] f16.
 int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk, int heads,
             __half* out, int ldo, cudaStream_t stream) {
+  return mha_f16_sub(q, ldq, Tq, k, v, ldkv, B, Tq, Tk, heads, out, ldo, stream);
+}
+
+// Same with the Tq queries of sequence b starting at row b*q_seq_rows of q (q_seq_rows >= Tq): attention for a subset of
+// a sequence's rows (the newest frame's tokens in the predictor's last layer); out stays compact [B*Tq, ldo].
+int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk,
+                int heads, __half* out, int ldo, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(q_seq_rows >= Tq);
   TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && Tk > 0 && Tk <= ATT_MAXK && heads > 0);
   TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0);
   const float scale_log2e = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (attention.py:187) * log2(e)
@@ -163,7 +175,7 @@ int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
   const int nt = ((Tk + 15) & ~15) / 8;
 #define MHA_LAUNCH(NTV) \
-  mha_kernel<NTV><<<B * heads, warps * 32, 0, stream>>>(q, ldq, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo)
+  mha_kernel<NTV><<<B * heads, warps * 32, 0, stream>>>(q, ldq, q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo)
   if (nt <= 4) MHA_LAUNCH(4);
   else if (nt <= 10) MHA_LAUNCH(10);
   else if (nt <= 14) MHA_LAUNCH(14);

@@ -17,6 +17,20 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
               cudaStream_t stream);
 int mha_f16(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk, int heads,
             __half* out, int ldo, cudaStream_t stream);
+int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk,
+                int heads, __half* out, int ldo, cudaStream_t stream);
+
+// rows of the newest frame, fp32: tokens [B, n*S, T] -> [B*S, T]
+__global__ void last_frame_f32_kernel(const float* __restrict__ tokens, int n, int S, int T, int B, float* __restrict__ out) {
+  const size_t total4 = size_t(B) * S * T / 4;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total4; e += size_t(gridDim.x) * blockDim.x) {
+    const size_t el = e * 4;
+    const int row = int(el / T), c = int(el % T);
+    const int b = row / S, s = row % S;
+    *reinterpret_cast<float4*>(out + el) =
+        *reinterpret_cast<const float4*>(tokens + (size_t(b) * n * S + size_t(n - 1) * S + s) * T + c);
+  }
+}
 
 // frames [B, F_total, S*D] fp32 -> window tokens f16 [B, n, S*D] starting at frame f0
 __global__ void window_to_f16_kernel(const float* __restrict__ frames, size_t seq_stride, int f0, int n, int SD, int B,
@@ -80,7 +94,7 @@ static inline int ew_grid(size_t n, int threads = 256) {
 }
 
 struct PredBuffers {
-  float *frames, *x32, *y32, *z32, *pred32, *stats;
+  float *frames, *x32, *y32, *z32, *pred32, *stats, *xl32;
   __half *tok16, *h16, *qkv16, *att16, *q16, *mid16, *last16, *text16, *kv16;
 };
 
@@ -104,6 +118,7 @@ static size_t carve(const tocvp_pred_weights& w, int B, int L, int nctx, int npr
   t.z32 = reinterpret_cast<float*>(take(Mmax * T * 4));
   t.pred32 = reinterpret_cast<float*>(take(size_t(B) * S * D * 4));
   t.stats = reinterpret_cast<float*>(take(Mmax * size_t(T / 64) * 2 * 4));
+  t.xl32 = reinterpret_cast<float*>(take(size_t(B) * S * T * 4));
   t.tok16 = reinterpret_cast<__half*>(take(Mmax * D * 2));
   t.h16 = reinterpret_cast<__half*>(take(Mmax * T * 2));
   t.qkv16 = reinterpret_cast<__half*>(take(Mmax * 3 * T * 2));
@@ -134,17 +149,78 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   const float* pe_n = w.pe_flipped + size_t(n - 1) * w.buffer_size * T;
   TOCVP_TRY(gemm_f16(pb.tok16, D, static_cast<const __half*>(w.mlp_in_w), D, M, T, D, w.mlp_in_b, 0, pe_n, T, S, n,
                      pb.x32, T, nullptr, 0, st));
-  // LayerNorm folding (M >= 1024 rows): the GEMM that writes a residual-stream tensor also emits its f16 copy (h16) and
-  // per-row [sum, sumsq] (stats); the projection that would consume LN(.) reads the raw copy with gamma-folded weights and
-  // finishes the normalisation in its epilogue.  4 LayerNorm launches per layer and their fp32 re-reads disappear.
-  const bool fold = gemm_ln_supported(M, T);
+  // LayerNorm folding (>= 1024 rows): the GEMM that writes a residual-stream tensor also emits its f16 copy (h16) and
+  // per-row partial [sum, sumsq] (stats); the projection that would consume LN(.) reads the raw copy with gamma-folded
+  // weights and finishes the normalisation in its epilogue.  4 LayerNorm launches per layer and their fp32 re-reads
+  // disappear.
   const float inv_t = 1.f / float(T);
   const int slots = T / 64;
+  const GemmLn prod{nullptr, 0, nullptr, 0.f, 0.f, pb.stats};
+
+  // Everything of a layer behind the self-attention, on Mr rows = B sequences x tq rows each (att16 holds their attention
+  // output, xres their residual-stream rows): out-proj, cross-attention block, MLP.  Result in x32[0:Mr].
+  auto layer_tail = [&](const tocvp_pred_layer& ly, int l, int Mr, int tq, const float* xres, bool emit_next) -> int {
+    const bool fold = gemm_ln_supported(Mr, T);
+    if (fold) {
+      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.w_o), T, Mr, T, T, nullptr, 0, xres, T, pb.y32, T,
+                            pb.h16, T, prod, st));
+      // ---- z = y + CrossAttn(LN(text), LN(y))                      (attention.py:445-463)
+      const GemmLn c{pb.stats, slots, ly.c_cq, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_q_f), T, Mr, T, T, ly.d_cq, 0, nullptr, 0, nullptr,
+                            0, pb.q16, T, c, st));
+    } else {
+      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.w_o), T, Mr, T, T, nullptr, 0, xres, T, 1, 0, pb.y32, T,
+                         nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.y32, 0, T, nullptr, 0, ly.ln_cq_g, ly.ln_cq_b, w.ln_eps, Mr, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_q), T, Mr, T, T, nullptr, 0, nullptr, 0, 1, 0, nullptr,
+                         0, pb.q16, T, st));
+    }
+    const __half* kv = pb.kv16 + size_t(l) * B * L * 2 * T;
+    TOCVP_TRY(mha_f16(pb.q16, T, kv, kv + T, 2 * T, B, tq, L, w.cross_heads, pb.att16, T, st));
+    if (fold) {
+      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, Mr, T, T, ly.bc_o, 0, pb.y32, T, pb.z32, T,
+                            pb.h16, T, prod, st));
+      // ---- z = z + MLP_c(LN(z))
+      const GemmLn c{pb.stats, slots, ly.c_c1, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_1_f), T, Mr, w.cross_hidden, T, ly.d_c1, 1, nullptr,
+                            0, nullptr, 0, pb.mid16, w.cross_hidden, c, st));
+      TOCVP_TRY(gemm_f16_ln(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, Mr, T,
+                            w.cross_hidden, ly.bc_2, 0, pb.z32, T, pb.z32, T, pb.h16, T, prod, st));
+      // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
+      const GemmLn c2{pb.stats, slots, ly.c_1, inv_t, w.ln_eps, nullptr};
+      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_1_f), T, Mr, w.hidden_dim, T, ly.d_1, 1, nullptr, 0,
+                            nullptr, 0, pb.mid16, w.hidden_dim, c2, st));
+      if (!emit_next) {
+        TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, Mr, T, w.hidden_dim,
+                           ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+      } else {   // the next layer's QKV projection consumes the f16 copy + statistics of x
+        TOCVP_TRY(gemm_f16_ln(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, Mr, T, w.hidden_dim,
+                              ly.b_2, 0, pb.y32, T, pb.x32, T, pb.h16, T, prod, st));
+      }
+    } else {
+      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, Mr, T, T, ly.bc_o, 0, pb.y32, T, 1, 0, pb.z32,
+                         T, nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_cm_g, ly.ln_cm_b, w.ln_eps, Mr, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_1), T, Mr, w.cross_hidden, T, ly.bc_1, 1, nullptr, 0, 1,
+                         0, nullptr, 0, pb.mid16, w.cross_hidden, st));
+      TOCVP_TRY(gemm_f16(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, Mr, T,
+                         w.cross_hidden, ly.bc_2, 0, pb.z32, T, 1, 0, pb.z32, T, nullptr, 0, st));
+      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_m_g, ly.ln_m_b, w.ln_eps, Mr, T, pb.h16, T, nullptr, 0, st));
+      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_1), T, Mr, w.hidden_dim, T, ly.b_1, 1, nullptr, 0, 1, 0,
+                         nullptr, 0, pb.mid16, w.hidden_dim, st));
+      TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, Mr, T, w.hidden_dim,
+                         ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+    }
+    return TOCVP_OK;
+  };
+
+  const bool fold_all = gemm_ln_supported(M, T);
+  int n_out = n;                            // frames held by x32 after the last layer (1 when it was pruned)
   for (int l = 0; l < w.num_layers; ++l) {
     const tocvp_pred_layer& ly = w.layers[l];
     const bool last_layer = (l == w.num_layers - 1);
     // ---- y = x + MHSA(LN(x))                                       (attention.py:512-514)
-    if (fold && l > 0) {
+    if (fold_all && l > 0) {
       const GemmLn c{pb.stats, slots, ly.c_qkv, inv_t, w.ln_eps, nullptr};
       TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_qkv_f), T, M, 3 * T, T, ly.d_qkv, 0, nullptr, 0,
                             nullptr, 0, pb.qkv16, 3 * T, c, st));
@@ -153,63 +229,25 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
       TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_qkv), T, M, 3 * T, T, nullptr, 0, nullptr, 0, 1, 0,
                          nullptr, 0, pb.qkv16, 3 * T, st));
     }
-    TOCVP_TRY(mha_f16(pb.qkv16, 3 * T, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, n * S, n * S, w.num_heads, pb.att16, T,
-                      st));
-    if (fold) {
-      const GemmLn p{nullptr, 0, nullptr, 0.f, 0.f, pb.stats};
-      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.w_o), T, M, T, T, nullptr, 0, pb.x32, T, pb.y32, T,
-                            pb.h16, T, p, st));
-      // ---- z = y + CrossAttn(LN(text), LN(y))                      (attention.py:445-463)
-      const GemmLn c{pb.stats, slots, ly.c_cq, inv_t, w.ln_eps, nullptr};
-      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_q_f), T, M, T, T, ly.d_cq, 0, nullptr, 0, nullptr,
-                            0, pb.q16, T, c, st));
+    if (last_layer && n > 1) {
+      // mlp_out reads only the newest frame's tokens (text_cond_OCVP.py:103) and nothing else consumes this layer's
+      // output: behind the K/V projection only the S newest rows of every sequence are computed (exact, not an
+      // approximation) -- queries, out-proj, cross-attention and both MLPs on B*S rows instead of B*n*S.
+      const int Mc = B * S;
+      last_frame_f32_kernel<<<ew_grid(size_t(Mc) * T / 4), 256, 0, st>>>(pb.x32, n, S, T, B, pb.xl32);
+      TOCVP_LAUNCHED();
+      TOCVP_TRY(mha_f16_sub(pb.qkv16 + size_t(n - 1) * S * 3 * T, 3 * T, n * S, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, S,
+                            n * S, w.num_heads, pb.att16, T, st));
+      TOCVP_TRY(layer_tail(ly, l, Mc, S, pb.xl32, false));
+      n_out = 1;
     } else {
-      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.w_o), T, M, T, T, nullptr, 0, pb.x32, T, 1, 0, pb.y32,
-                         T, nullptr, 0, st));
-      TOCVP_TRY(layernorm(pb.y32, 0, T, nullptr, 0, ly.ln_cq_g, ly.ln_cq_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_q), T, M, T, T, nullptr, 0, nullptr, 0, 1, 0, nullptr,
-                         0, pb.q16, T, st));
-    }
-    const __half* kv = pb.kv16 + size_t(l) * B * L * 2 * T;
-    TOCVP_TRY(mha_f16(pb.q16, T, kv, kv + T, 2 * T, B, n * S, L, w.cross_heads, pb.att16, T, st));
-    if (fold) {
-      const GemmLn p{nullptr, 0, nullptr, 0.f, 0.f, pb.stats};
-      TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, M, T, T, ly.bc_o, 0, pb.y32, T, pb.z32, T,
-                            pb.h16, T, p, st));
-      // ---- z = z + MLP_c(LN(z))
-      const GemmLn c{pb.stats, slots, ly.c_c1, inv_t, w.ln_eps, nullptr};
-      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_1_f), T, M, w.cross_hidden, T, ly.d_c1, 1, nullptr,
-                            0, nullptr, 0, pb.mid16, w.cross_hidden, c, st));
-      TOCVP_TRY(gemm_f16_ln(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, M, T,
-                            w.cross_hidden, ly.bc_2, 0, pb.z32, T, pb.z32, T, pb.h16, T, p, st));
-      // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
-      const GemmLn c2{pb.stats, slots, ly.c_1, inv_t, w.ln_eps, nullptr};
-      TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_1_f), T, M, w.hidden_dim, T, ly.d_1, 1, nullptr, 0,
-                            nullptr, 0, pb.mid16, w.hidden_dim, c2, st));
-      if (last_layer) {
-        TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
-                           ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
-      } else {
-          TOCVP_TRY(gemm_f16_ln(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
-                              ly.b_2, 0, pb.y32, T, pb.x32, T, pb.h16, T, p, st));
-      }
-    } else {
-      TOCVP_TRY(gemm_f16(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, M, T, T, ly.bc_o, 0, pb.y32, T, 1, 0, pb.z32,
-                         T, nullptr, 0, st));
-      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_cm_g, ly.ln_cm_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.wc_1), T, M, w.cross_hidden, T, ly.bc_1, 1, nullptr, 0, 1,
-                         0, nullptr, 0, pb.mid16, w.cross_hidden, st));
-      TOCVP_TRY(gemm_f16(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, M, T,
-                         w.cross_hidden, ly.bc_2, 0, pb.z32, T, 1, 0, pb.z32, T, nullptr, 0, st));
-      TOCVP_TRY(layernorm(pb.z32, 0, T, nullptr, 0, ly.ln_m_g, ly.ln_m_b, w.ln_eps, M, T, pb.h16, T, nullptr, 0, st));
-      TOCVP_TRY(gemm_f16(pb.h16, T, static_cast<const __half*>(ly.w_1), T, M, w.hidden_dim, T, ly.b_1, 1, nullptr, 0, 1, 0,
-                         nullptr, 0, pb.mid16, w.hidden_dim, st));
-      TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, M, T, w.hidden_dim,
-                         ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
+      TOCVP_TRY(mha_f16(pb.qkv16, 3 * T, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, n * S, n * S, w.num_heads, pb.att16, T,
+                        st));
+      TOCVP_TRY(layer_tail(ly, l, M, n * S, pb.x32, fold_all && !last_layer));
     }
   }
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
-  last_frame_to_f16_kernel<<<ew_grid(size_t(B) * S * T / 4), 256, 0, st>>>(pb.x32, n, S, T, B, pb.last16);
+  last_frame_to_f16_kernel<<<ew_grid(size_t(B) * S * T / 4), 256, 0, st>>>(pb.x32, n_out, S, T, B, pb.last16);
   TOCVP_LAUNCHED();
   TOCVP_TRY(gemm_f16(pb.last16, T, static_cast<const __half*>(w.mlp_out_w), T, B * S, D, T, w.mlp_out_b, 0, nullptr, 0,
                      1, 0, pb.pred32, D, nullptr, 0, st));
