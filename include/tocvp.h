@@ -216,6 +216,7 @@ typedef struct tocvp_dec_weights {
   const void* w_out;         /* f16 [9][16][64]: (ky*3+kx, co zero-padded 4 -> 16, ci)  decoder.decoder.4 */
   const float* b_out;        /* [4] */
   int H, W, slot_dim, num_slots, hidden;
+  const void* w_out_taps;    /* f16 [48][64]: row (ky*3+kx)*4 + co (rows 36..47 zero), col ci: the 9 taps in the GEMM N dim */
 } tocvp_dec_weights;
 
 size_t tocvp_sizeof_dec_weights(void);
@@ -353,9 +354,10 @@ size_t tocvp_sizeof_ocvp_weights(void);
 int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t seq_stride, int B, int n, float* out,
                        void* stream);
 
-/* Tuning / test knob (process-wide): 1 = decoder layer 1 is generated inside the layer-2 convolution kernel and never
- * stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation. */
-int tocvp_set_decode_mode(int fuse_layer1);
+/* Tuning / test knob (process-wide), bit mask.  Bit 0: 1 = decoder layer 1 is generated inside the layer-2 convolution
+ * kernel and never stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation.
+ * Bit 1: 1 = first-version head conv3x3 (shifted windows, N = 16); 0 (default) = nine taps in the GEMM's N dimension. */
+int tocvp_set_decode_mode(int mode);
 
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */

@@ -24,6 +24,8 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream);
 int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, float* out4, int n_img, int H, int W,
                      cudaStream_t stream);
+int conv3x3_head_taps_f16(const __half* x, const __half* w_taps, const float* bias, float* out4, int n_img, int H, int W,
+                          cudaStream_t stream);
 int conv5x5_gen_f16(const float* P, const float* S, const __half* x_dummy, const __half* wpacked, const float* bias,
                     __half* out, int n_img, int H, int W, cudaStream_t stream);
 
@@ -143,6 +145,9 @@ constexpr int DEC_CHUNK_FRAMES = 256;
 // generator warps share the shared-memory port and the issue slots the implicit GEMM is bound by -- which is more than the
 // 0.36 ms of dec_l1_kernel it removes, so the fused path is kept (tested, parity-green) but not the default.
 static int g_dec_fuse_l1 = 0;
+// bit 1 of tocvp_set_decode_mode: 0 = head conv3x3 with the 9 taps in the GEMM's N dimension (default), 1 = shifted-window
+// kernel with N = 16 (first version, kept for A/B)
+static int g_dec_head_taps = 1;
 
 struct DecBuffers {
   __half* slots16;
@@ -180,8 +185,9 @@ using namespace tocvp;
 
 extern "C" size_t tocvp_sizeof_dec_weights(void) { return sizeof(tocvp_dec_weights); }
 
-extern "C" int tocvp_set_decode_mode(int fuse_layer1) {
-  tocvp::g_dec_fuse_l1 = fuse_layer1 ? 1 : 0;
+extern "C" int tocvp_set_decode_mode(int mode) {
+  tocvp::g_dec_fuse_l1 = (mode & 1) ? 1 : 0;
+  tocvp::g_dec_head_taps = (mode & 2) ? 0 : 1;
   return TOCVP_OK;
 }
 
@@ -237,7 +243,11 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev + 1]), st));
     }
     // conv3x3 64 -> 4 head on the tensor cores (N padded to 16), then softmax-over-slots compositing
-    TOCVP_TRY(conv3x3_head_f16(db.actB, static_cast<const __half*>(w->w_out), w->b_out, db.maps4, nsi, H, W, st));
+    if (g_dec_head_taps && w->w_out_taps != nullptr) {
+      TOCVP_TRY(conv3x3_head_taps_f16(db.actB, static_cast<const __half*>(w->w_out_taps), w->b_out, db.maps4, nsi, H, W, st));
+    } else {
+      TOCVP_TRY(conv3x3_head_f16(db.actB, static_cast<const __half*>(w->w_out), w->b_out, db.maps4, nsi, H, W, st));
+    }
     const size_t npix = size_t(nf) * plane;
     composite_kernel<<<int((npix + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const float4*>(db.maps4), recons_imgs + size_t(f0) * 3 * plane,

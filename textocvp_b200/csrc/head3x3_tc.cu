@@ -1,0 +1,189 @@
+// Decoder head: conv3x3 64 -> 4 (RGB + mask logit, reference src/models/EncodersDecoders/decoders.py:110-116) with the
+// nine filter taps in the N dimension of ONE tcgen05 GEMM per halo tile.
+//
+// The shifted-window implicit GEMM of conv5x5_tc.cu re-reads the 4 KB A operand from shared memory once per tap and
+// k-step; with only N = 16 output columns that operand read (not the tensor pipe, not HBM) sets the pace: 0.52 ms per
+// 2048 slot-images where the 1 GiB input takes 0.17 ms to stream (r1 ncu).  Here the UNSHIFTED halo tile is multiplied
+// by all nine taps at once,
+//     D[r][tap*4 + co] = sum_c X[r][c] * W[co][c][tap]        r = halo pixel (row-major 18 x 40), N = 36 (padded to 48),
+// 24 MMAs per tile instead of 144, and the shift moves to the epilogue: D goes TMEM -> registers -> shared memory and
+//     out[y][x][co] = b[co] + sum_tap D[(y+ty)*40 + (x+tx)][tap*4 + co]
+// is gathered from there (36 shared loads per pixel, bank-conflict free with an odd row stride).
+// One halo buffer: the TMA load of tile i+1 is issued as soon as tile i's MMAs have completed and overlaps its epilogue.
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-5: epilogue
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace tocvp {
+
+constexpr int HD_TH = 16, HD_TW = 32;            // output tile
+constexpr int HD_HR = HD_TH + 2, HD_WB = 40;     // halo rows, halo row pitch (pixels, multiple of 8 >= HD_TW + 2)
+constexpr int HD_ROWS = HD_HR * HD_WB;           // 720 halo pixels
+constexpr int HD_MT = (HD_ROWS + 127) / 128;     // 6 M-tiles
+constexpr int HD_N = 48;                         // 9 taps x 4 channels = 36, padded to a multiple of 16
+constexpr int HD_A_BYTES = HD_ROWS * 128;        // 92160 (multiple of 1024)
+constexpr int HD_W_BYTES = HD_N * 128;           // 6144
+constexpr int HD_DS = 37;                        // D staging row stride (floats), odd -> conflict free
+constexpr int HD_D_BYTES = HD_MT * 128 * HD_DS * 4;
+constexpr int HD_SMEM = HD_A_BYTES + HD_W_BYTES + HD_D_BYTES + 256 + 1024;
+constexpr int HD_TMEM_COLS = 512;                // 6 x 48 = 288 columns used
+
+__device__ __forceinline__ uint64_t hd_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, dense 128-byte rows
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+__global__ void __launch_bounds__(192, 1)
+head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int n_img, int H, int W,
+               const float* __restrict__ bias, float* __restrict__ out4) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + HD_A_BYTES;
+  float* sD = reinterpret_cast<float*>(sW + HD_W_BYTES);
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sD) + HD_D_BYTES);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* t_full = a_empty + 1;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = W / HD_TW, tiles_y = H / HD_TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int num_tiles = n_img * tiles_per_img;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, HD_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, HD_W_BYTES);
+      tma_load_2d(&tmW, w_full, sW, 0, 0);
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int img = t / tiles_per_img, r = t % tiles_per_img;
+        const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
+        mbar_wait(a_empty, ph ^ 1);                          // the MMAs that read the halo buffer have completed
+        mbar_expect_tx(a_full, HD_A_BYTES);
+        tma_load_4d(&tmX, a_full, sA, 0, x0 - 1, y0 - 1, img);   // out-of-image rows / columns are zero-filled
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_f16(128, HD_N, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t leader = elect_one_sync();
+    mbar_wait(w_full, 0);
+    const uint64_t db = hd_desc(smem_u32(sW));
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(t_empty, ph ^ 1);                            // the epilogue has copied the previous accumulators out
+      mbar_wait(a_full, ph);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA);
+#pragma unroll
+      for (int mt = 0; mt < HD_MT; ++mt) {
+        const uint64_t da = hd_desc(a_base + uint32_t(mt * 128 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_u + uint32_t(mt * HD_N), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, k != 0, leader);
+      }
+      umma_commit(a_empty, leader);
+      umma_commit(t_full, leader);
+      ph ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;                         // 0..127
+    const float4 b4 = *reinterpret_cast<const float4*>(bias);
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int img = t / tiles_per_img, r = t % tiles_per_img;
+      const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
+      mbar_wait(t_full, ph);
+      tc_fence_after();
+      // ---- phase 1: accumulators -> shared memory, D[halo pixel][tap*4 + co]
+#pragma unroll 1
+      for (int mt = 0; mt < HD_MT; ++mt) {
+        uint32_t v[32], v4[4];
+        const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mt * HD_N);
+        tmem_ld32(ta, v);
+        tmem_ld4(ta + 32, v4);
+        tmem_ld_wait();
+        float* d = sD + (mt * 128 + q * 32 + lane) * HD_DS;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[32 + j] = __uint_as_float(v4[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);                   // TMEM is free for the next tile's MMAs
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // D complete
+      // ---- phase 2: shift-and-add over the 9 taps; thread -> column x, rows y = (et >> 5) + 4 i
+      const int px = et & 31;
+#pragma unroll 1
+      for (int i = 0; i < HD_TH / 4; ++i) {
+        const int py = (et >> 5) + 4 * i;
+        float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const float* d = sD + ((py + tap / 3) * HD_WB + px + tap % 3) * HD_DS + tap * 4;
+          a0 += d[0]; a1 += d[1]; a2 += d[2]; a3 += d[3];
+        }
+        *reinterpret_cast<float4*>(out4 + ((size_t(img) * H + (y0 + py)) * W + (x0 + px)) * 4) = make_float4(a0, a1, a2, a3);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // everyone is done reading D
+      ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, HD_TMEM_COLS);
+  }
+}
+
+// x: f16 NHWC [n_img, H, W, 64]; w_taps: f16 [48, 64] (row tap*4 + co, rows 36..47 zero); bias fp32 [4];
+// out4: fp32 NHWC [n_img, H, W, 4].
+int conv3x3_head_taps_f16(const __half* x, const __half* w_taps, const float* bias, float* out4, int n_img, int H, int W,
+                          cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && w_taps && bias && out4 && n_img > 0 && H % HD_TH == 0 && W % HD_TW == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out4) & 15) == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOCVP_CUDA(cudaFuncSetAttribute(head3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tmX, tmW;
+  {
+    const uint64_t dims[4] = {64, uint64_t(W), uint64_t(H), uint64_t(n_img)};
+    const uint64_t str[3] = {128, uint64_t(W) * 128, uint64_t(H) * W * 128};
+    const uint32_t box[4] = {64, uint32_t(HD_WB), uint32_t(HD_HR), 1};
+    TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  TOCVP_TRY(encode_tmap_2d_f16(&tmW, w_taps, HD_N, 64, 64, HD_N, 64));
+  const int num_tiles = n_img * (H / HD_TH) * (W / HD_TW);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  head3x3_kernel<<<grid, 192, HD_SMEM, stream>>>(tmX, tmW, n_img, H, W, bias, out4);
+  TOCVP_LAUNCHED();
+  return TOCVP_OK;
+}
+
+}  // namespace tocvp

@@ -69,7 +69,7 @@ EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
 DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("slot_dim", ctypes.c_int), ("num_slots", ctypes.c_int),
-    ("hidden", ctypes.c_int)]})
+    ("hidden", ctypes.c_int), ("w_out_taps", _f)]})
 
 
 ProjW = type("ProjW", (ctypes.Structure,), {"_fields_": [
@@ -569,8 +569,12 @@ class SAVi(_Packed):
         wo[:, :4] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
         d["w_out"] = _f16(wo)
         d["b_out"] = _f32(last.bias)
+        wt = torch.zeros(48, 64, device=dev)                                     # row (ky*3+kx)*4 + co: the 9 taps in N
+        wt[:36] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(36, 64)
+        d["w_out_taps"] = _f16(wt)
         dw = DecW()
         dw.w1_taps, dw.p1, dw.w_out, dw.b_out = (d[n].data_ptr() for n in ("w1_taps", "p1", "w_out", "b_out"))
+        dw.w_out_taps = d["w_out_taps"].data_ptr()
         for i in range(3):
             dw.w_conv[i], dw.b_conv[i] = d[f"wc{i}"].data_ptr(), d[f"bc{i}"].data_ptr()
         dw.H, dw.W, dw.slot_dim, dw.num_slots, dw.hidden = dH, dW, self.slot_dim, self.num_slots, 64
