@@ -76,10 +76,11 @@ def test_predictor_step(models, golden, golden_weights):
     assert O.rel_err(out1, golden["pred_step_n1"]) < STAGE_TOL
 
 
-@pytest.mark.parametrize("fuse_layer1", [0, 1, 2])
+@pytest.mark.parametrize("fuse_layer1", [0, 1, 2, 4])
 def test_decode(models, golden, golden_weights, fuse_layer1):
     """tocvp_set_decode_mode bit mask.  0 (default): separate layer-1 kernel, head conv with the 9 taps in N;
-    1: decoder layer 1 generated inside the layer-2 conv kernel; 2: first-version head conv (shifted windows, N = 16)."""
+    1: decoder layer 1 generated inside the layer-2 conv kernel; 2: first-version head conv (shifted windows, N = 16);
+    4: first-version (image-stationary) layer-1 kernel."""
     from textocvp_b200 import _lib as L
     savi, _ = models
     slots = golden["pred_slots"][:1, -1].cuda()

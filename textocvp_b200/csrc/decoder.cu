@@ -106,6 +106,51 @@ dec_l1_patterns_kernel(const float* __restrict__ taps, float* __restrict__ S, in
   }
 }
 
+// Layer 1, second version (default): pixel-stationary.  A CTA owns 8 consecutive pixels of the image plane for ALL
+// slot-images: its 8 x 64 P values stay in registers, and per slot-image it reads only the pattern sums those 8 pixels
+// need (mostly the one interior pattern: 256 B instead of 8 x 256 B of P per image in dec_l1_kernel), so the kernel is
+// bound by its 1 GiB of output writes rather than by 2 GiB of L2 reads.  thread = (slot-image lane 0..31, 8-channel chunk).
+// S: fp32 [n_img, 25, 64] from dec_l1_patterns_kernel.  Requires W % 8 == 0.
+__global__ void __launch_bounds__(256)
+dec_l1_pixel_kernel(const float* __restrict__ S, const float* __restrict__ P, __half* __restrict__ out, int n_img, int H,
+                    int W) {
+  constexpr int C = 64;
+  const int pix0 = blockIdx.x * 8;
+  const int chunk = threadIdx.x & 7, il = threadIdx.x >> 3;         // 8-channel chunk, slot-image lane
+  const int y = pix0 / W, x0 = pix0 % W;
+  float p[8][8];
+  int pat[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8 + 4));
+    p[k][0] = a.x; p[k][1] = a.y; p[k][2] = a.z; p[k][3] = a.w;
+    p[k][4] = b.x; p[k][5] = b.y; p[k][6] = b.z; p[k][7] = b.w;
+    pat[k] = border_pattern(y, H) * 5 + border_pattern(x0 + k, W);
+  }
+  const size_t plane = size_t(H) * W;
+  for (int img = il; img < n_img; img += 32) {
+    const float* s = S + size_t(img) * 25 * C + chunk * 8;
+    __half* o = out + (size_t(img) * plane + pix0) * C + chunk * 8;
+    int cur = -1;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (pat[k] != cur) {                                           // at most 3 distinct patterns in 8 pixels of a row
+        cur = pat[k];
+        s0 = __ldg(reinterpret_cast<const float4*>(s + cur * C));
+        s1 = __ldg(reinterpret_cast<const float4*>(s + cur * C + 4));
+      }
+      uint4 r;
+      r.x = pack_half2_relu(p[k][0] + s0.x, p[k][1] + s0.y);
+      r.y = pack_half2_relu(p[k][2] + s0.z, p[k][3] + s0.w);
+      r.z = pack_half2_relu(p[k][4] + s1.x, p[k][5] + s1.y);
+      r.w = pack_half2_relu(p[k][6] + s1.z, p[k][7] + s1.w);
+      *reinterpret_cast<uint4*>(o + size_t(k) * C) = r;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ compositing
 // maps: fp32 [n_frames*S, H*W, 4] (RGB + mask logit, SAVi.py:251-252) from the tcgen05 conv3x3 head.
 // imgs fp32 [n_frames,3,H,W]; recons (opt) [n_frames,S,3,H,W]; masks (opt) [n_frames,S,1,H,W].
@@ -148,6 +193,8 @@ static int g_dec_fuse_l1 = 0;
 // bit 1 of tocvp_set_decode_mode: 0 = head conv3x3 with the 9 taps in the GEMM's N dimension (default), 1 = shifted-window
 // kernel with N = 16 (first version, kept for A/B)
 static int g_dec_head_taps = 1;
+// bit 2: 0 = pixel-stationary layer-1 kernel (default), 1 = image-stationary first version
+static int g_dec_l1_pixel = 1;
 
 struct DecBuffers {
   __half* slots16;
@@ -188,6 +235,7 @@ extern "C" size_t tocvp_sizeof_dec_weights(void) { return sizeof(tocvp_dec_weigh
 extern "C" int tocvp_set_decode_mode(int mode) {
   tocvp::g_dec_fuse_l1 = (mode & 1) ? 1 : 0;
   tocvp::g_dec_head_taps = (mode & 2) ? 0 : 1;
+  tocvp::g_dec_l1_pixel = (mode & 4) ? 0 : 1;
   return TOCVP_OK;
 }
 
@@ -221,12 +269,18 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
                        1, 0, db.taps32, 25 * C, nullptr, 0, st));
     // layer 1 is generated inside the layer-2 convolution whenever the pair kernel applies (even tile count)
     const bool fused_l1 = ((nsi * (H / 16) * (W / 32)) % 2 == 0) && g_dec_fuse_l1;
-    if (fused_l1) {
+    const bool pixel_l1 = !fused_l1 && (W % 8 == 0) && g_dec_l1_pixel;
+    if (fused_l1 || pixel_l1) {
       dec_l1_patterns_kernel<<<(nsi + 3) / 4, 256, 0, st>>>(db.taps32, db.pat32, nsi);
+      TOCVP_LAUNCHED();
+      if (pixel_l1) {
+        dec_l1_pixel_kernel<<<(H * W) / 8, 256, 0, st>>>(db.pat32, w->p1, db.actA, nsi, H, W);
+        TOCVP_LAUNCHED();
+      }
     } else {
       dec_l1_kernel<<<nsi, 256, 0, st>>>(db.taps32, w->p1, db.actA, H, W);
+      TOCVP_LAUNCHED();
     }
-    TOCVP_LAUNCHED();
     __half* bufs[2] = {db.actA, db.actB};
     for (int l = 0; l < 3; ++l) {
       // optional CUDA-event pair around each conv launch (bench.py measures the dominant kernel live, in the step)

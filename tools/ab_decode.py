@@ -21,7 +21,7 @@ def t(n=3):
     lay = [sum(per[l::3]) / n_chunks for l in range(3)]
     return e0.elapsed_time(e1) / n, lay
 for rep in range(2):
-    for mode in (0, 1, 2):
+    for mode in (0, 4, 2):
         L.call("tocvp_set_decode_mode", L.c_int(mode))
         ms, lay = t()
         print(f"decode mode {mode}: {ms:.1f} ms; conv layers 2/3/4: {lay[0]:.3f} {lay[1]:.3f} {lay[2]:.3f} ms", flush=True)
