@@ -195,9 +195,13 @@ typedef struct tocvp_enc_weights {
   const void* w_mlp2;        /* f16 [F, F]    encoder_mlp.3 */
   const float* b_mlp2;
   int H, W, in_channels, hidden, feat_dim;
+  const void* w_conv1_tc;    /* f16 [25,32,32] tap-major, input channels zero-padded 3 -> 32: conv 1 on the tensor cores */
 } tocvp_enc_weights;
 
 size_t tocvp_sizeof_enc_weights(void);
+/* Tuning / test knob (process-wide), bit mask: bit 0 = first-version fp32 SIMT conv 1 (default: tensor-core conv with
+ * zero-padded input channels), bit 1 = separate posemb + LayerNorm pass (default: fused into conv 4's epilogue). */
+int tocvp_set_encode_mode(int mode);
 size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img);
 /* frames fp32: image i = 3 planes of H x W at frames + i*img_stride (floats), so x[:, t] of a [B,T,3,H,W] video is
  * addressed in place; feats [n_img, H*W, F] written as f16 and/or fp32 (either may be NULL, not both). */

@@ -24,10 +24,19 @@ def models(golden_weights):
     return savi.cuda().eval(), pred.cuda().eval()
 
 
-def test_encode(models, golden, golden_weights):
+@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3])
+def test_encode(models, golden, golden_weights, enc_mode):
+    """tocvp_set_encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
+    into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass."""
+    from textocvp_b200 import _lib as L
     savi, _ = models
     x = golden_weights["videos"][:, 0].cuda()
-    feats = savi.encode(x)
+    L.call("tocvp_set_encode_mode", L.c_int(enc_mode))
+    try:
+        feats = savi.encode(x)
+        torch.cuda.synchronize()
+    finally:
+        L.call("tocvp_set_encode_mode", L.c_int(0))
     ref = O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())
     assert O.rel_err(feats, ref) < STAGE_TOL
     st = golden["meta"]["feat_stride"]

@@ -49,6 +49,12 @@ struct ConvArgs {
   __half* out;        // EPI 0: f16 NHWC [n_img, H, W, COUT]
   float* out4;        // EPI 1: fp32 NHWC [n_img, H, W, 4] (first 4 output channels, no activation)
   int relu;
+  // optional fused tail of the SAVi encoder (pair kernel, COUT = 32): y = LayerNorm(relu(conv + b) + posemb[pixel]) in
+  // fp32 straight from the accumulators (SoftPositionEmbed + encoder_mlp.0, reference src/models/SAVi.py:232-237, 116)
+  const float* ln_posemb;   // [H*W, COUT] or null
+  const float* ln_g;
+  const float* ln_b;
+  float ln_eps;
 };
 
 template <int CIN, int COUT, int G, int KS, int EPI>
@@ -454,6 +460,49 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll 1
       for (int j = 0; j < G; ++j) {
         __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
+        if constexpr (COUT == 32) {
+          if (a.ln_g != nullptr) {
+            // ---- relu(conv + b) + posemb -> LayerNorm over the pixel's 32 channels, all in this thread's registers
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT), v);
+            tmem_ld_wait();
+            const float* pe = a.ln_posemb + (size_t(y) * a.W + (x0 + 8 * j)) * COUT;
+            float f[32];
+            float sum = 0.f;
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias) + e4);
+              const float4 pp = __ldg(reinterpret_cast<const float4*>(pe) + e4);
+              f[4 * e4 + 0] = fmaxf(__uint_as_float(v[4 * e4 + 0]) + bb.x, 0.f) + pp.x;
+              f[4 * e4 + 1] = fmaxf(__uint_as_float(v[4 * e4 + 1]) + bb.y, 0.f) + pp.y;
+              f[4 * e4 + 2] = fmaxf(__uint_as_float(v[4 * e4 + 2]) + bb.z, 0.f) + pp.z;
+              f[4 * e4 + 3] = fmaxf(__uint_as_float(v[4 * e4 + 3]) + bb.w, 0.f) + pp.w;
+              sum += (f[4 * e4] + f[4 * e4 + 1]) + (f[4 * e4 + 2] + f[4 * e4 + 3]);
+            }
+            const float mean = sum * (1.f / 32.f);
+            float var = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              f[e] -= mean;
+              var = fmaf(f[e], f[e], var);
+            }
+            const float rstd = rsqrtf(var * (1.f / 32.f) + a.ln_eps);
+#pragma unroll
+            for (int e8 = 0; e8 < 4; ++e8) {
+              float g[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                g[e] = f[8 * e8 + e] * rstd * __ldg(a.ln_g + 8 * e8 + e) + __ldg(a.ln_b + 8 * e8 + e);
+              uint4 p;
+              p.x = pack_half2(g[0], g[1]);
+              p.y = pack_half2(g[2], g[3]);
+              p.z = pack_half2(g[4], g[5]);
+              p.w = pack_half2(g[6], g[7]);
+              *reinterpret_cast<uint4*>(o + 8 * e8) = p;
+            }
+            continue;
+          }
+        }
 #pragma unroll
         for (int c = 0; c < COUT / 32; ++c) {
           uint32_t v[32];
@@ -498,7 +547,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 template <int CIN, int COUT, int G, int KS, bool GEN = false>
 static int launch_conv2(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
-                        int relu, cudaStream_t stream, ConvGen gen = ConvGen{nullptr, nullptr}) {
+                        int relu, cudaStream_t stream, ConvGen gen = ConvGen{nullptr, nullptr},
+                        const float* ln_posemb = nullptr, const float* ln_g = nullptr, const float* ln_b = nullptr,
+                        float ln_eps = 0.f) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
   static bool attr_set = false;
@@ -524,7 +575,7 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
   const int num_ptiles = n_img * (H / C::TILE_H) * (W / C::TILE_W) / 2;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
-  ConvArgs a{n_img, H, W, bias, out, nullptr, relu};
+  ConvArgs a{n_img, H, W, bias, out, nullptr, relu, ln_posemb, ln_g, ln_b, ln_eps};
   conv_tc2_kernel<CIN, COUT, G, KS, GEN><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
@@ -559,7 +610,7 @@ static int launch_conv(const __half* x, const __half* wpacked, const float* bias
   }
   const int num_tiles = n_img * (H / C::TILE_H) * (W / C::TILE_W);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  ConvArgs a{n_img, H, W, bias, out, out4, relu};
+  ConvArgs a{n_img, H, W, bias, out, out4, relu, nullptr, nullptr, nullptr, 0.f};
   conv_tc_kernel<CIN, COUT, G, KS, EPI><<<grid, 192, C::SMEM, stream>>>(tmX, tmW, a);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
@@ -581,6 +632,15 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
   }
   set_last_error(__FILE__, __LINE__, "conv5x5_f16: only 64->64 and 32->32 channels are instantiated");
   return TOCVP_ERR_BAD_ARG;
+}
+
+// Encoder conv 4 with the positional-embedding add and LayerNorm(32) fused into the epilogue (pair kernel only).
+int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
+                   const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && wpacked && bias && posemb && ln_g && ln_b && out && n_img > 0);
+  TOCVP_CHECK_ARG(H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0));
+  return launch_conv2<32, 32, 4, 5>(x, wpacked, bias, out, n_img, H, W, 1, stream, ConvGen{nullptr, nullptr}, posemb, ln_g,
+                                    ln_b, ln_eps);
 }
 
 // Decoder layer 2 with layer 1 generated in the kernel (see ConvGen): P fp32 [H*W,64], S fp32 [n_img,25,64].

@@ -18,6 +18,27 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
               const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
               cudaStream_t stream);
 
+int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
+                   const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
+
+// tocvp_set_encode_mode: bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version)
+static int g_enc_mode = 0;
+
+// Frame -> tensor-core input of conv 1: NCHW fp32 [n,3,H,W] -> NHWC f16 [n,H,W,32] with channels 3..31 zero, so that conv 1
+// (3 -> 32, K = 75) runs on the same tcgen05 implicit-GEMM kernel as conv 2-4 with zero-padded input channels (ten times
+// the useful FLOPs, still 1.7x faster than the fp32 SIMT convolution it replaces: 3.5 -> 2.0 ms per 5120 frames).
+__global__ void __launch_bounds__(256)
+enc_pack_input_kernel(const float* __restrict__ x, size_t img_stride, __half* __restrict__ out, int plane, int n_img) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(n_img) * plane) return;
+  const int img = int(idx / plane), pix = int(idx % plane);
+  const float* xi = x + size_t(img) * img_stride + pix;
+  uint4 p0 = make_uint4(pack_half2(xi[0], xi[plane]), pack_half2(xi[2 * size_t(plane)], 0.f), 0u, 0u);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  uint4* o = reinterpret_cast<uint4*>(out + idx * 32);
+  o[0] = p0; o[1] = z; o[2] = z; o[3] = z;
+}
+
 constexpr int E1_TH = 8, E1_TW = 32, E1_CO = 32;
 
 // x: fp32 [n, 3, H, W] with image i at x + i*img_stride; w: fp32 [75][32] ((ky*5+kx)*3+ci major); out: f16 NHWC [n,H,W,32]
@@ -96,6 +117,11 @@ using namespace tocvp;
 
 extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
 
+extern "C" int tocvp_set_encode_mode(int mode) {
+  tocvp::g_enc_mode = mode & 3;
+  return TOCVP_OK;
+}
+
 extern "C" size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img) {
   if (!w || n_img <= 0) return 0;
   return enc_carve(*w, n_img, nullptr, nullptr);
@@ -117,14 +143,28 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
   const int H = w->H, W = w->W, C = w->hidden, F = w->feat_dim;
   const int M = n_img * H * W;
-  const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
-  enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
-  TOCVP_LAUNCHED();
+  if ((g_enc_mode & 1) || w->w_conv1_tc == nullptr) {
+    const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
+    enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
+    TOCVP_LAUNCHED();
+  } else {
+    const size_t npx = size_t(n_img) * H * W;
+    enc_pack_input_kernel<<<int((npx + 255) / 256), 256, 0, st>>>(frames, img_stride, eb.actB, H * W, n_img);
+    TOCVP_LAUNCHED();
+    TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv1_tc), w->b_conv1, eb.actA, n_img, H, W, C, C, 1, st));
+  }
   TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], eb.actB, n_img, H, W, C, C, 1, st));
   TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv[1]), w->b_conv[1], eb.actA, n_img, H, W, C, C, 1, st));
-  TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], eb.actB, n_img, H, W, C, C, 1, st));
-  // + positional embedding, LayerNorm(32) (eps 1e-5, SAVi.py:116)
-  TOCVP_TRY(layernorm(eb.actB, 1, C, w->posemb, H * W, w->ln_g, w->ln_b, 1e-5f, M, C, eb.h16, C, nullptr, 0, st));
+  const bool fuse_ln = !(g_enc_mode & 2) && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
+  if (fuse_ln) {
+    // conv 4 + positional embedding + LayerNorm(32) (eps 1e-5, SAVi.py:116) in one kernel: the LN input never leaves fp32
+    TOCVP_TRY(conv5x5_ln_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], w->posemb, w->ln_g, w->ln_b,
+                             1e-5f, eb.actB, n_img, H, W, st));
+    eb.h16 = eb.actB;
+  } else {
+    TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], eb.actB, n_img, H, W, C, C, 1, st));
+    TOCVP_TRY(layernorm(eb.actB, 1, C, w->posemb, H * W, w->ln_g, w->ln_b, 1e-5f, M, C, eb.h16, C, nullptr, 0, st));
+  }
   TOCVP_TRY(gemm_f16(eb.h16, C, static_cast<const __half*>(w->w_mlp1), C, M, F, C, w->b_mlp1, 1, nullptr, 0, 1, 0, nullptr,
                      0, eb.mid16, F, st));
   TOCVP_TRY(gemm_f16(eb.mid16, F, static_cast<const __half*>(w->w_mlp2), F, M, F, F, w->b_mlp2, 0, nullptr, 0, 1, 0,

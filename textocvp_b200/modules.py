@@ -64,7 +64,7 @@ EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
     ("w_conv1", _f), ("b_conv1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("posemb", _f),
     ("ln_g", _f), ("ln_b", _f), ("w_mlp1", _f), ("b_mlp1", _f), ("w_mlp2", _f), ("b_mlp2", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("in_channels", ctypes.c_int), ("hidden", ctypes.c_int),
-    ("feat_dim", ctypes.c_int)]})
+    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f)]})
 
 DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
@@ -529,6 +529,9 @@ class SAVi(_Packed):
         k = {}
         k["w_conv1"] = _f32(enc[0].weight.permute(2, 3, 1, 0).reshape(75, 32))
         k["b_conv1"] = _f32(enc[0].bias)
+        w1p = torch.zeros(25, 32, 32, device=dev)                                # conv 1 for the tensor cores: cin 3 -> 32
+        w1p[:, :, :3] = enc[0].weight.detach().float().permute(2, 3, 0, 1).reshape(25, 32, 3)
+        k["w_conv1_tc"] = _f16(w1p)
         for i in range(3):
             k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
             k[f"bc{i}"] = _f32(enc[i + 1].bias)
@@ -543,6 +546,7 @@ class SAVi(_Packed):
         for n in ("ln_g", "ln_b", "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2"):
             setattr(ew, n, k[n].data_ptr())
         ew.H, ew.W, ew.in_channels, ew.hidden, ew.feat_dim = H, W, self.in_channels, 32, self.mlp_encoder_dim
+        ew.w_conv1_tc = k["w_conv1_tc"].data_ptr()
         self._enc_keep, self._enc_w = k, ew
 
         # ---- decoder
