@@ -43,6 +43,8 @@ int tocvp_init(int device);
 const char* tocvp_last_error(void);
 /* Statistics: number of kernels this library has launched so far in this process (monotonic). */
 unsigned long long tocvp_kernel_launches(void);
+/* For callers that replay captured library calls from a CUDA graph: adds the graph's kernel count to the statistic. */
+void tocvp_note_graph_replay(unsigned long long n_kernels);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projection: C[M,N] = A[M,K] . W[N,K]^T (+bias) (ReLU) (+residual), tcgen05 / TMEM / TMA.

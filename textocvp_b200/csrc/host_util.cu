@@ -109,3 +109,9 @@ extern "C" int tocvp_abi_version(void) { return TOCVP_ABI_VERSION; }
 
 // Statistics only (monotonic counter of kernels this library has launched in this process).
 extern "C" unsigned long long tocvp_kernel_launches(void) { return tocvp::launch_count(); }
+
+// A caller that captured library calls into a CUDA graph reports each replay here (n = kernels in the graph), so that the
+// statistic keeps counting kernels that actually ran on the device.
+extern "C" void tocvp_note_graph_replay(unsigned long long n_kernels) {
+  for (unsigned long long i = 0; i < n_kernels; ++i) tocvp::count_launch();
+}

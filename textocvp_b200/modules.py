@@ -1219,23 +1219,55 @@ class BaseTextOCVP(_Packed):
         return out
 
     @torch.no_grad()
-    def rollout(self, slot_history, text_embeddings, num_context, num_preds):
-        """The whole autoregressive loop in one library call (all kernels enqueued from C++)."""
-        B, _, S, D = slot_history.shape
+    def _rollout_eager(self, sh, seq_stride, text, B, S, D, Lt, num_context, num_preds, out):
         w = self._weights(S)
         lib = L.load()
+        lib.tocvp_predictor_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_predictor_workspace_bytes(ctypes.byref(w), c_int(B), c_int(Lt), c_int(num_context),
+                                                                   c_int(num_preds)), sh.device)
+        L.call("tocvp_predictor_rollout", ctypes.byref(w), ptr(sh), c_size_t(seq_stride), ptr(text), c_int(B), c_int(Lt),
+               c_int(num_context), c_int(num_preds), ptr(out), ws, wsb, stream())
+
+    @torch.no_grad()
+    def rollout(self, slot_history, text_embeddings, num_context, num_preds):
+        """The whole autoregressive loop in one library call (all ~1300 kernels enqueued from C++).  With
+        ``self.use_cuda_graph`` (default) the enqueued kernel sequence is captured once per shape into a CUDA graph and
+        replayed: the first steps of a rollout run kernels of a few microseconds each, shorter than the host can enqueue
+        them (tensor-map encoding + launch), and the graph removes those gaps."""
+        B, _, S, D = slot_history.shape
+        self._weights(S)
         sh = slot_history.float()
         if sh.stride(-1) != 1 or sh.stride(2) != D or sh.stride(1) != S * D:
             sh = sh.contiguous()
         text = text_embeddings.float().contiguous()
         Lt = text.shape[1]
-        out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
-        lib.tocvp_predictor_workspace_bytes.restype = ctypes.c_size_t
-        ws, wsb = self._ws.get(lib.tocvp_predictor_workspace_bytes(ctypes.byref(w), c_int(B), c_int(Lt), c_int(num_context),
-                                                                   c_int(num_preds)), sh.device)
-        L.call("tocvp_predictor_rollout", ctypes.byref(w), ptr(sh), c_size_t(sh.stride(0)), ptr(text), c_int(B), c_int(Lt),
-               c_int(num_context), c_int(num_preds), ptr(out), ws, wsb, stream())
-        return out
+        if not getattr(self, "use_cuda_graph", True):
+            out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
+            self._rollout_eager(sh, sh.stride(0), text, B, S, D, Lt, num_context, num_preds, out)
+            return out
+        key = (B, S, D, Lt, num_context, num_preds, str(sh.device), self._pack_sig)
+        g = getattr(self, "_graph", None)
+        if g is None or g["key"] != key:
+            ctx = torch.empty(B, num_context, S, D, device=sh.device, dtype=torch.float32)
+            txt = torch.empty_like(text)
+            out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
+            ctx.copy_(sh[:, :num_context]); txt.copy_(text)
+            self._rollout_eager(ctx, ctx.stride(0), txt, B, S, D, Lt, num_context, num_preds, out)   # warm-up: attributes,
+            torch.cuda.synchronize(sh.device)                                                        # workspace growth
+            lib = L.load()
+            lib.tocvp_kernel_launches.restype = ctypes.c_ulonglong
+            n0 = lib.tocvp_kernel_launches()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._rollout_eager(ctx, ctx.stride(0), txt, B, S, D, Lt, num_context, num_preds, out)
+            g = {"key": key, "graph": graph, "ctx": ctx, "txt": txt, "out": out,
+                 "n_kernels": lib.tocvp_kernel_launches() - n0}
+            object.__setattr__(self, "_graph", g)
+        g["ctx"].copy_(sh[:, :num_context])
+        g["txt"].copy_(text)
+        g["graph"].replay()
+        L.load().tocvp_note_graph_replay(ctypes.c_ulonglong(g["n_kernels"]))
+        return g["out"].clone()
 
 
 class TextOCVP_CustomTF(BaseTextOCVP):
