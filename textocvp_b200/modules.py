@@ -1258,7 +1258,7 @@ class BaseTextOCVP(_Packed):
             lib.tocvp_kernel_launches.restype = ctypes.c_ulonglong
             n0 = lib.tocvp_kernel_launches()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                 self._rollout_eager(ctx, ctx.stride(0), txt, B, S, D, Lt, num_context, num_preds, out)
             g = {"key": key, "graph": graph, "ctx": ctx, "txt": txt, "out": out,
                  "n_kernels": lib.tocvp_kernel_launches() - n0}
