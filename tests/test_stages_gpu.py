@@ -191,3 +191,44 @@ def test_sibling_predictors(kind):
     slots = torch.randn(2, 10, 8, 128, generator=torch.Generator().manual_seed(3))
     ref = O.ocvp_step(sd, slots, kind, max_len=m["input_buffer_size"])
     assert O.rel_err(pred.predictor(slots=slots.cuda()), ref) < 1e-4
+
+
+def test_teacher_forcing_and_window(models, golden, golden_weights):
+    """PredictorWrapper's generic loop (predictor_wrapper.py:50-87, 143-153): teacher forcing feeds the encoded slots of
+    the next frame instead of the prediction, and the window keeps the last input_buffer_size frames.  Checked against
+    the oracle's predictor_step driven the same way (one library call per step instead of the fused rollout)."""
+    _, pred = models
+    sh = golden["slot_history"]
+    text = golden_weights["text"]
+    pcfg = O.PredCfg()
+    old = pred.exp_params["prediction_params"]["teacher_force"]
+    pred.exp_params["prediction_params"]["teacher_force"] = True
+    try:
+        out = pred(sh.cuda(), num_preds=12, text_embeddings=text.cuda())
+    finally:
+        pred.exp_params["prediction_params"]["teacher_force"] = old
+    window = sh[:, :1].clone()
+    ref = []
+    for t in range(12):
+        cur = O.predictor_step(golden_weights["pred_sd"], window, text, pcfg)
+        window = torch.cat([window, sh[:, 1 + t].unsqueeze(1)], dim=1)[:, -pcfg.input_buffer_size:]
+        ref.append(cur)
+    ref = torch.stack(ref, dim=1)
+    assert out.shape == ref.shape == (2, 12, 8, 128)
+    assert O.rel_err(out, ref) < STAGE_TOL
+
+
+def test_rollout_graph_matches_eager(models, golden, golden_weights):
+    """The CUDA-graph replay of the fused rollout is bit-identical to the eagerly enqueued kernel sequence, also when
+    called again with different inputs of the same shape."""
+    _, pred = models
+    text = golden_weights["text"].cuda()
+    body = pred.predictor
+    for scale in (1.0, 0.5):
+        sh = (golden["slot_history"] * scale).cuda()
+        body.use_cuda_graph = True
+        a = pred(sh, text_embeddings=text)
+        body.use_cuda_graph = False
+        b = pred(sh, text_embeddings=text)
+        body.use_cuda_graph = True
+        assert torch.equal(a, b)
