@@ -109,6 +109,9 @@ typedef struct tocvp_sa_weights {
 
 size_t tocvp_sizeof_sa_weights(void);
 size_t tocvp_slot_attention_workspace_bytes(int B);
+/* Tuning / test knob (per device, current device): 0 (default) = the per-slot update kernel (V projection, GRU, MLPs,
+ * transition) runs its 16-row matrix products as 3xTF32 mma.sync; 1 = first-version fp32 SIMT loops. */
+int tocvp_set_corrector_mode(int simt_update);
 /* feats fp32 or f16: sequence b's [N,128] block starts at feats + b*feats_seq_stride (elements), so the features of
  * frame t inside a [B,T,N,128] encode batch are used in place; slots_in [B,S,128]; slots_out row b at
  * slots_out + b*out_stride (floats), so results land straight in slot_history[:, t]; pred_out (optional) =

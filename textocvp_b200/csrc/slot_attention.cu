@@ -262,15 +262,99 @@ sa_stream_generic_kernel(const T* __restrict__ feats, size_t seq_stride, int N, 
 // transposed as [feature][row] so that a thread computing one output column reads the rows as float4.
 // ------------------------------------------------------------------------------------------------
 constexpr int UP_R = 16;
-constexpr int UP_THREADS = 256;
+constexpr int UP_THREADS = 512;   // 16 warps: the update kernel is latency-bound (weight fragments from L2), not issue-bound
+constexpr int UP_WARPS = UP_THREADS / 32;
 
 using SaWeights = tocvp_sa_weights;  // include/tocvp.h
 
-// ys[o][r] = act(bias[o] + sum_k Wt[k][o] * xs[k][r])  for r < UP_R
-__device__ void linear_T(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
-                         const float* xs, float* ys, bool relu) {
+// 3xTF32 split: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); hi*hi + lo*hi + hi*lo keeps ~21 mantissa bits, i.e. fp32
+// accuracy for the recurrent slot state, on the (legacy-path) tensor cores.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ys[o][r] = act(bias[o] + sum_k Wt[k][o] * xs[k][r])  for r < UP_R = 16 = one mma M tile.
+// mma.sync m16n8k8 (3xTF32): warp w owns the 8-column tiles w, w+16, ...; the A fragment of a k-step (the 16 activation rows)
+// is split once and reused for all of the warp's column tiles.  ~5x fewer instructions than the SIMT loop it replaces
+// (kept below as linear_T_simt) at the same fp32-level accuracy.
+template <int NT>
+__device__ __forceinline__ void linear_T_mma(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+                                             const float* xs, float* ys, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll 4
+  for (int k0 = 0; k0 < IN; k0 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32(xs[(k0 + t) * UP_R + g], ah[0], al[0]);
+    split_tf32(xs[(k0 + t) * UP_R + g + 8], ah[1], al[1]);
+    split_tf32(xs[(k0 + t + 4) * UP_R + g], ah[2], al[2]);
+    split_tf32(xs[(k0 + t + 4) * UP_R + g + 8], ah[3], al[3]);
+    float bw[NT][2];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int n = (warp + UP_WARPS * i) * 8 + g;
+      bw[i][0] = __ldg(Wt + size_t(k0 + t) * OUT + n);
+      bw[i][1] = __ldg(Wt + size_t(k0 + t + 4) * OUT + n);
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(bw[i][0], bh0, bl0);
+      split_tf32(bw[i][1], bh1, bl1);
+      mma_tf32(acc[i], al, bh0, bh1);
+      mma_tf32(acc[i], ah, bl0, bl1);
+      mma_tf32(acc[i], ah, bh0, bh1);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int n = (warp + UP_WARPS * i) * 8 + 2 * t;
+    const float b0 = bias ? __ldg(bias + n) : 0.f, b1 = bias ? __ldg(bias + n + 1) : 0.f;
+    float v0 = acc[i][0] + b0, v1 = acc[i][1] + b1, v2 = acc[i][2] + b0, v3 = acc[i][3] + b1;
+    if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+    ys[n * UP_R + g] = v0;
+    ys[(n + 1) * UP_R + g] = v1;
+    ys[n * UP_R + g + 8] = v2;
+    ys[(n + 1) * UP_R + g + 8] = v3;
+  }
+  __syncthreads();
+}
+
+__device__ void linear_T_simt(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+                              const float* xs, float* ys, bool relu);
+
+__device__ int g_sa_update_simt = 0;   // tocvp_set_corrector_mode(1): first-version SIMT matvecs (A/B, tests)
+
+__device__ __forceinline__ void linear_T(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+                                         const float* xs, float* ys, bool relu) {
+  if (g_sa_update_simt || (OUT != 128 && OUT != 256 && OUT != 384 && OUT != 512) || IN % 8 != 0) {
+    linear_T_simt(Wt, bias, IN, OUT, xs, ys, relu);
+    return;
+  }
+  switch (OUT) {   // column tiles per warp = OUT / (8 * UP_WARPS)
+    case 128: linear_T_mma<128 / (8 * UP_WARPS)>(Wt, bias, IN, OUT, xs, ys, relu); break;
+    case 256: linear_T_mma<256 / (8 * UP_WARPS)>(Wt, bias, IN, OUT, xs, ys, relu); break;
+    case 384: linear_T_mma<384 / (8 * UP_WARPS)>(Wt, bias, IN, OUT, xs, ys, relu); break;
+    default: linear_T_mma<512 / (8 * UP_WARPS)>(Wt, bias, IN, OUT, xs, ys, relu); break;
+  }
+}
+
+// First version: ys[o][r] = act(bias[o] + sum_k Wt[k][o] * xs[k][r]) with one thread per output column.
+__device__ void linear_T_simt(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+                              const float* xs, float* ys, bool relu) {
   const int tid = threadIdx.x;
-  if (OUT >= UP_THREADS) {
+  if (OUT != 128 || UP_THREADS != 256) {
     for (int o = tid; o < OUT; o += UP_THREADS) {
       float acc[UP_R];
       const float bv = bias ? bias[o] : 0.f;
@@ -314,21 +398,31 @@ __device__ void linear_T(const float* __restrict__ Wt, const float* __restrict__
   __syncthreads();
 }
 
-// LayerNorm over the feature axis of xs[D][R] -> ys[D][R] (one thread per row; rows are consecutive banks)
+// LayerNorm over the feature axis of xs[D][R] -> ys[D][R]: one warp per row (2 rows per warp), lane l owns features
+// l, l+32, ... (two-pass variance).  The first version used one THREAD per row (16 of 256 threads busy, 3 serial passes
+// over 128 features) and was, with the other 16-thread sections, what the update kernel actually spent its time in once
+// the matrix products moved to the tensor cores.
 __device__ void layernorm_T(const float* xs, float* ys, const float* __restrict__ g, const float* __restrict__ b,
                             float eps, int D) {
-  const int r = threadIdx.x;
-  if (r < UP_R) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < UP_R; r += UP_THREADS / 32) {
+    float v[4];
     float s = 0.f;
-    for (int k = 0; k < D; ++k) s += xs[k * UP_R + r];
-    const float mean = s / D;
-    float q = 0.f;
-    for (int k = 0; k < D; ++k) {
-      const float d = xs[k * UP_R + r] - mean;
-      q += d * d;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = xs[(lane + 32 * j) * UP_R + r];
+      s += v[j];
     }
-    const float rstd = rsqrtf(q / D + eps);
-    for (int k = 0; k < D; ++k) ys[k * UP_R + r] = (xs[k * UP_R + r] - mean) * rstd * g[k] + b[k];
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] -= mean;
+      q += v[j] * v[j];
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ys[(lane + 32 * j) * UP_R + r] = v[j] * rstd * g[lane + 32 * j] + b[lane + 32 * j];
   }
   __syncthreads();
 }
@@ -417,26 +511,40 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
     linear_T(w.t_wk_t, nullptr, D, D, cur, t1, false);           // k -> t1
     linear_T(w.t_wv_t, nullptr, D, D, cur, big0, false);         // v -> big0[0..127]
     float* att = big1;                                           // attention output [128][R]
+    float* sc = big1 + D * UP_R;                                 // scores [R][H][16]
     const int H = w.t_heads, dh = D / H;
-    const float sc = rsqrtf(float(dh));
-    for (int e = tid; e < UP_R * H; e += UP_THREADS) {
-      const int r = e % UP_R, h = e / UP_R;                      // query row r (seq = r / S)
-      const int rs = (r / S) * S;
-      float sco[16];
-      float mx = -1e30f;
+    const float scl = rsqrtf(float(dh));
+    // phase 1: thread = (query row r, head h, key pair jp): two of the <= 16 scores each
+    for (int e = tid; e < UP_R * H * 8; e += UP_THREADS) {
+      const int r = e % UP_R, h = (e / UP_R) % H, jp = e / (UP_R * H);
       if (r >= RPC) continue;                                    // padding rows
-      for (int j = 0; j < S; ++j) {
-        float d = 0.f;
-        for (int c = 0; c < dh; ++c) d += t0[(h * dh + c) * UP_R + r] * t1[(h * dh + c) * UP_R + rs + j];
-        sco[j] = d * sc;
-        mx = fmaxf(mx, sco[j]);
+      const int rs = (r / S) * S;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * jp + jj;
+        if (j < S) {
+          float d = 0.f;
+          for (int c = 0; c < dh; ++c) d = fmaf(t0[(h * dh + c) * UP_R + r], t1[(h * dh + c) * UP_R + rs + j], d);
+          sc[(r * H + h) * 16 + j] = d * scl;
+        }
       }
+    }
+    __syncthreads();
+    // phase 2: thread = (row r, head h, 1/4 of the head's channels): softmax over the S keys, weighted sum of V
+    for (int e = tid; e < UP_R * H * 4; e += UP_THREADS) {
+      const int r = e % UP_R, h = (e / UP_R) % H, cg = e / (UP_R * H);
+      if (r >= RPC) continue;
+      const int rs = (r / S) * S;
+      float pj[16];
+      float mx = -1e30f;
+      for (int j = 0; j < S; ++j) { pj[j] = sc[(r * H + h) * 16 + j]; mx = fmaxf(mx, pj[j]); }
       float den = 0.f;
-      for (int j = 0; j < S; ++j) { sco[j] = __expf(sco[j] - mx); den += sco[j]; }
+      for (int j = 0; j < S; ++j) { pj[j] = __expf(pj[j] - mx); den += pj[j]; }
       const float inv = 1.f / den;
-      for (int c = 0; c < dh; ++c) {
+      const int cw = dh / 4;
+      for (int c = cg * cw; c < (cg + 1) * cw; ++c) {
         float o = 0.f;
-        for (int j = 0; j < S; ++j) o += sco[j] * big0[(h * dh + c) * UP_R + rs + j];
+        for (int j = 0; j < S; ++j) o = fmaf(pj[j], big0[(h * dh + c) * UP_R + rs + j], o);
         att[(h * dh + c) * UP_R + r] = o * inv;
       }
     }
@@ -470,17 +578,25 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
         gvec[size_t(b) * PART + i * D + f] = w.scale * t0[f * UP_R + r] * w.ln_in_g[f];
       }
     }
-    if (tid < UP_R && row0 + tid < n_rows) {
-      const int r = tid;
-      float sgv = 0.f, cbv = 0.f;
-      for (int f = 0; f < D; ++f) {
-        const float qt = t0[f * UP_R + r];
-        sgv += qt * w.ln_in_g[f];
-        cbv += qt * w.ln_in_b[f] + t1[f * UP_R + r] * w.bk[f];
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int r = warp; r < UP_R; r += UP_THREADS / 32) {          // warp per row: sg = sum qt*gamma, cb = qt.beta + q.bk
+        float sgv = 0.f, cbv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = lane + 32 * j;
+          const float qt = t0[f * UP_R + r];
+          sgv += qt * w.ln_in_g[f];
+          cbv += qt * w.ln_in_b[f] + t1[f * UP_R + r] * w.bk[f];
+        }
+        sgv = warp_sum(sgv);
+        cbv = warp_sum(cbv);
+        if (lane == 0 && row0 + r < n_rows) {
+          const int b = (row0 + r) / S, i = (row0 + r) % S;
+          gvec[size_t(b) * PART + S * D + i] = w.scale * sgv;
+          gvec[size_t(b) * PART + S * D + S + i] = w.scale * cbv;
+        }
       }
-      const int b = (row0 + r) / S, i = (row0 + r) % S;
-      gvec[size_t(b) * PART + S * D + i] = w.scale * sgv;
-      gvec[size_t(b) * PART + S * D + S + i] = w.scale * cbv;
     }
   }
 }
@@ -591,6 +707,12 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
 }  // namespace tocvp
 
 extern "C" size_t tocvp_slot_attention_workspace_bytes(int B) { return tocvp::slot_attention_workspace_bytes(B); }
+
+extern "C" int tocvp_set_corrector_mode(int simt_update) {
+  const int v = simt_update ? 1 : 0;
+  if (cudaMemcpyToSymbol(tocvp::g_sa_update_simt, &v, sizeof(int)) != cudaSuccess) return TOCVP_ERR_CUDA;
+  return TOCVP_OK;
+}
 
 extern "C" int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats_f16,
                                     size_t feats_seq_stride, int B, int N,
