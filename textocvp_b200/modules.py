@@ -1247,7 +1247,8 @@ class BaseTextOCVP(_Packed):
             return out
         key = (B, S, D, Lt, num_context, num_preds, str(sh.device), self._pack_sig)
         g = getattr(self, "_graph", None)
-        if g is None or g["key"] != key:
+        ws_ptr = self._ws.buf.data_ptr() if self._ws.buf is not None else 0
+        if g is None or g["key"] != key or g["ws_ptr"] != ws_ptr:   # the graph bakes in the workspace address
             ctx = torch.empty(B, num_context, S, D, device=sh.device, dtype=torch.float32)
             txt = torch.empty_like(text)
             out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
@@ -1260,7 +1261,7 @@ class BaseTextOCVP(_Packed):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                 self._rollout_eager(ctx, ctx.stride(0), txt, B, S, D, Lt, num_context, num_preds, out)
-            g = {"key": key, "graph": graph, "ctx": ctx, "txt": txt, "out": out,
+            g = {"key": key, "graph": graph, "ctx": ctx, "txt": txt, "out": out, "ws_ptr": self._ws.buf.data_ptr(),
                  "n_kernels": lib.tocvp_kernel_launches() - n0}
             object.__setattr__(self, "_graph", g)
         g["ctx"].copy_(sh[:, :num_context])
