@@ -205,7 +205,9 @@ typedef struct tocvp_enc_weights {
 
 size_t tocvp_sizeof_enc_weights(void);
 /* Tuning / test knob (process-wide), bit mask: bit 0 = first-version fp32 SIMT conv 1 (default: tensor-core conv with
- * zero-padded input channels), bit 1 = separate posemb + LayerNorm pass (default: fused into conv 4's epilogue). */
+ * zero-padded input channels), bit 1 = separate posemb + LayerNorm pass (default: fused into conv 4's epilogue),
+ * bit 2 = the 32 -> 128 -> 128 MLP as two GEMMs (default: one kernel with two chained tcgen05 GEMMs when only f16
+ * features are requested). */
 int tocvp_set_encode_mode(int mode);
 size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img);
 /* frames fp32: image i = 3 planes of H x W at frames + i*img_stride (floats), so x[:, t] of a [B,T,3,H,W] video is

@@ -24,7 +24,7 @@ def models(golden_weights):
     return savi.cuda().eval(), pred.cuda().eval()
 
 
-@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4])
 def test_encode(models, golden, golden_weights, enc_mode):
     """tocvp_set_encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
     into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass."""
@@ -33,10 +33,12 @@ def test_encode(models, golden, golden_weights, enc_mode):
     x = golden_weights["videos"][:, 0].cuda()
     L.call("tocvp_set_encode_mode", L.c_int(enc_mode))
     try:
-        feats = savi.encode(x)
+        feats = savi.encode(x)                                   # fp32 features: the MLP runs as two GEMMs
+        f16, _ = savi._encode_raw(x, x.shape[0], x[0].numel(), want_f32=False)   # pipeline format: fused MLP unless bit 2
         torch.cuda.synchronize()
     finally:
         L.call("tocvp_set_encode_mode", L.c_int(0))
+    assert O.rel_err(f16.float(), O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())) < STAGE_TOL
     ref = O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())
     assert O.rel_err(feats, ref) < STAGE_TOL
     st = golden["meta"]["feat_stride"]

@@ -18,10 +18,13 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
               const float* beta, float eps, int rows, int D, __half* out16, int ld16, float* out32, int ld32,
               cudaStream_t stream);
 
+int enc_mlp_f16(const __half* x, const __half* w1, const float* b1, const __half* w2, const float* b2, __half* y, int M,
+                cudaStream_t stream);
 int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
                    const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
 
-// tocvp_set_encode_mode: bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version)
+// tocvp_set_encode_mode: bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version),
+// bit 2 = the MLP as two separate GEMMs (first version)
 static int g_enc_mode = 0;
 
 // Frame -> tensor-core input of conv 1: NCHW fp32 [n,3,H,W] -> NHWC f16 [n,H,W,32] with channels 3..31 zero, so that conv 1
@@ -118,7 +121,7 @@ using namespace tocvp;
 extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
 
 extern "C" int tocvp_set_encode_mode(int mode) {
-  tocvp::g_enc_mode = mode & 3;
+  tocvp::g_enc_mode = mode & 7;
   return TOCVP_OK;
 }
 
@@ -164,6 +167,11 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   } else {
     TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], eb.actB, n_img, H, W, C, C, 1, st));
     TOCVP_TRY(layernorm(eb.actB, 1, C, w->posemb, H * W, w->ln_g, w->ln_b, 1e-5f, M, C, eb.h16, C, nullptr, 0, st));
+  }
+  if (!(g_enc_mode & 4) && feats_f32 == nullptr && F == 128 && C == 32) {
+    // both MLP layers in one kernel: the 128-wide hidden activation never leaves the SM (enc_mlp_tc.cu)
+    return enc_mlp_f16(eb.h16, static_cast<const __half*>(w->w_mlp1), w->b_mlp1, static_cast<const __half*>(w->w_mlp2),
+                       w->b_mlp2, static_cast<__half*>(feats_f16), M, st);
   }
   TOCVP_TRY(gemm_f16(eb.h16, C, static_cast<const __half*>(w->w_mlp1), C, M, F, C, w->b_mlp1, 1, nullptr, 0, 1, 0, nullptr,
                      0, eb.mid16, F, st));
