@@ -36,8 +36,10 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 
 // NT = compile-time bound on the number of 8-key tiles (score registers s[NT][4]): fewer registers for short key
 // sequences -> more resident CTAs per SM for a kernel that is pure latency.
-template <int NT>
-__global__ void __launch_bounds__(ATT_MAX_WARPS * 32)
+// WARPS / MINB: launch bounds.  The kernel is a latency chain per CTA (load K/V -> sync -> compute -> store), so resident
+// CTAs per SM are what hide it: the 5-warp / 80-key shape of the named config is capped at 96 registers for 4 CTAs per SM.
+template <int NT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* __restrict__ k,
            const __half* __restrict__ v, int ldkv, int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out,
            int ldo) {
@@ -174,12 +176,18 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
   int warps = (Tq + 15) / 16;
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
   const int nt = ((Tk + 15) & ~15) / 8;
-#define MHA_LAUNCH(NTV) \
-  mha_kernel<NTV><<<B * heads, warps * 32, 0, stream>>>(q, ldq, q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo)
-  if (nt <= 4) MHA_LAUNCH(4);
-  else if (nt <= 10) MHA_LAUNCH(10);
-  else if (nt <= 14) MHA_LAUNCH(14);
-  else MHA_LAUNCH(16);
+#define MHA_LAUNCH(NTV, W, MB)                                                                                        \
+  mha_kernel<NTV, W, MB><<<B * heads, warps * 32, 0, stream>>>(q, ldq, q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, \
+                                                               out, ldo)
+  if (nt <= 4) {
+    if (warps <= 5) MHA_LAUNCH(4, 5, 6); else MHA_LAUNCH(4, 8, 3);
+  } else if (nt <= 10) {
+    if (warps <= 5) MHA_LAUNCH(10, 5, 4); else MHA_LAUNCH(10, 8, 2);
+  } else if (nt <= 14) {
+    MHA_LAUNCH(14, 8, 2);
+  } else {
+    MHA_LAUNCH(16, 8, 2);
+  }
 #undef MHA_LAUNCH
   TOCVP_LAUNCHED();
   return TOCVP_OK;
