@@ -317,7 +317,7 @@ def run_ours(args):
                     "flops_note": "FLOPs executed (layer 1 is computed algebraically, not as a convolution); "
                                   "operands f16 (kind::f16, same tensor rate as bf16), fp32 accumulate"}
         cpu_baseline = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed at N = 1 only
             times, cores = cpu_rollout_time(args.cpu_batch, 4)
             tt = times[1:]
             cpu_fps = args.cpu_batch * NUM_PREDS * len(tt) / sum(tt)
