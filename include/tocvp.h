@@ -59,7 +59,8 @@ int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
                    void* stream);
 
 /* Tuning / test knob (process-wide): 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) GEMM
- * kernels (default), 1 = single-CTA kernel only, 128 / 256 = pair kernel with that tile width wherever applicable. */
+ * kernels (default), 1 = single-CTA kernel only, 128 / 256 = pair kernel with that tile width wherever applicable;
+ * 258 / 259 = W-resident variant of the 256-wide pair kernel (K <= 512) off / on (default on). */
 int tocvp_set_gemm_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------

@@ -50,17 +50,26 @@ struct Gemm2Args {
   float* stats_out;       // producer: writes its [sum, sumsq] of 64 output columns to slot n/64 of the row (no atomics)
 };
 
-template <int BN, int EWN>
+// WRES ("W resident", K <= 512, 256-wide tiles): a pair keeps ITS half of the W tile for the whole K extent in shared memory
+// (8 k-blocks x 16 KB) and owns one column block nb for its entire life, so only A streams through the ring: the per-SM
+// operand traffic drops from 64 to 32 B/clk.  At K = 512 the kernel is bound by the L2 -> SM fabric (operand re-reads plus the
+// output stores, ~10 TB/s in total; profiles/gemm2_r1_summary.md), not by the tensor pipe, so halving the re-reads is time.
+template <int BN, int EWN, bool WRES>
 struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;       // 16 KB (BN = 256) / 8 KB (BN = 128)
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 5;
+  static constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STAGES = WRES ? 3 : ((BN == 256) ? 4 : 5);
+  static constexpr int W_KB = 8;                             // k-blocks held by the resident W half (K <= 512)
+  static constexpr int W_BYTES = WRES ? W_KB * B_BYTES : 0;
   static constexpr int EW = EWN;
-  static constexpr int STG_TILES = (BN == 128) ? 3 : (EWN == 16 ? 1 : 2);     // staging tiles (32 rows x 128 B) per epilogue warp
+  static constexpr int STG_TILES = WRES ? 1 : ((BN == 128) ? 3 : (EWN == 16 ? 1 : 2));   // staging tiles per epilogue warp
   static constexpr int STG_BYTES = EW * STG_TILES * 4096;
   static constexpr int BAR_BYTES = 512 + 4 * BN * 4;        // barriers, then [2 buffers][bias | ln_c][BN] floats
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr int OFF_W = STAGES * STAGE_BYTES;
+  static constexpr int OFF_STG = OFF_W + W_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr int TOTAL = OFF_BAR + BAR_BYTES + 1024;
 };
 
 // TMA store of one staging tile (32 rows x 128 B, 128B-swizzled) to global; clipped at the tensor bounds by the TMA unit
@@ -76,24 +85,24 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, bool CONV, int EWN>
+template <int BN, bool CONV, int EWN, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EWN), 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ Gemm2Args g) {
-  using S = G2Smem<BN, EWN>;
+  using S = G2Smem<BN, EWN, WRES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg_base = smem + S::STAGES * S::STAGE_BYTES;                              // 1024B aligned
-  smem += S::STG_BYTES;   // barrier block follows the staging tiles (the stage ring is addressed from stage_base)
-  uint8_t* stage_base = smem - S::STG_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);   // used in the leader only
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_base = stage_base + S::OFF_W;                                            // WRES: resident W half, [kb][BN/2 x 64]
+  uint8_t* stg_base = stage_base + S::OFF_STG;                                        // 1024B aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + S::OFF_BAR);              // used in the leader only
   uint64_t* empty = full + S::STAGES;                                                 // per CTA (multicast commit)
   uint64_t* tfull = empty + S::STAGES;                                                // per CTA (multicast commit)
-  uint64_t* tempty = tfull + 2;                                                       // leader only, 16 arrivals
+  uint64_t* tempty = tfull + 2;                                                       // leader only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint64_t* resbar = tempty + 4;                                                      // [8 warps][2]: residual tiles landed
-  float* sbias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 512);   // [2][2][BN]: bias, ln_c
+  uint64_t* wfull = resbar + 16;                                                      // WRES, leader: resident W landed
+  float* sbias = reinterpret_cast<float*>(stage_base + S::OFF_BAR + 512);             // [2][2][BN]: bias, ln_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -103,6 +112,21 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (g.K + G2_BK - 1) / G2_BK;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  // i-th tile of this pair.  Default: round-robin over (mb, nb).  WRES: the pair keeps column block nb = pair / ppn and
+  // walks the row blocks slot, slot + ppn, ... (ppn = pairs per column block).
+  const int ppn = WRES ? npairs / tiles_n : 1;
+  auto tile_at = [&](int i, int& mb, int& nb) -> bool {
+    if constexpr (WRES) {
+      nb = pair / ppn;
+      mb = pair % ppn + i * ppn;
+      return nb < tiles_n && mb < tiles_m;
+    } else {
+      const int t = pair + i * npairs;
+      mb = t / tiles_n;
+      nb = t % tiles_n;
+      return t < num_tiles;
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -116,6 +140,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tempty[b], 2 * S::EW);   // epilogue warps x 2 CTAs
     }
     for (int i = 0; i < 16; ++i) mbar_init(&resbar[i], 1);
+    mbar_init(wfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
@@ -129,8 +154,16 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = pair; t < num_tiles; t += npairs) {
-        const int mb = t / tiles_n, nb = t % tiles_n;
+      int mb, nb;
+      if constexpr (WRES) {
+        if (tile_at(0, mb, nb)) {                          // this pair's W half for every k-block, once
+          const uint32_t wfull_leader = mapa_rank(smem_u32(wfull), 0);
+          if (rank == 0) mbar_expect_tx(wfull, 2 * num_kb * S::B_BYTES);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_2d_pair(&tmB, wfull_leader, w_base + kb * S::B_BYTES, kb * G2_BK, nb * BN + int(rank) * (BN / 2));
+        }
+      }
+      for (int i = 0; tile_at(i, mb, nb); ++i) {
         const int m0 = mb * 2 * G2_BM + int(rank) * G2_BM;
         const int n0 = nb * BN + int(rank) * (BN / 2);
         const int phase = (CONV && g.cm.tiles_per_phase > 0) ? nb / g.cm.tiles_per_phase : 0;
@@ -147,7 +180,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
           uint8_t* st = stage_base + s * S::STAGE_BYTES;
           tma_load_2d_pair(&tmA, full_leader, st, acol, arow);
-          tma_load_2d_pair(&tmB, full_leader, st + S::A_BYTES, kb * G2_BK, n0);
+          if constexpr (!WRES) tma_load_2d_pair(&tmB, full_leader, st + S::A_BYTES, kb * G2_BK, n0);
           if (++s == S::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -160,8 +193,11 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t leader = elect_one_sync();
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      int mb, nb;
+      if constexpr (WRES) {
+        if (tile_at(0, mb, nb)) mbar_wait(wfull, 0);
+      }
+      for (int it = 0; tile_at(it, mb, nb); ++it) {
         const int b = it & 1;
         const uint32_t bph = (it >> 1) & 1;
         mbar_wait(&tempty[b], bph ^ 1);
@@ -173,7 +209,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t a0 = smem_u32(stage_base + s * S::STAGE_BYTES);
           const uint64_t da = make_desc_sw128(a0, 1024);
-          const uint64_t db = make_desc_sw128(a0 + S::A_BYTES, 1024);
+          const uint64_t db = make_desc_sw128(WRES ? smem_u32(w_base + kb * S::B_BYTES) : a0 + S::A_BYTES, 1024);
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k)
             umma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0, leader);
@@ -199,9 +235,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // place and the same tile is TMA-stored -- both directions in full 128-byte lines instead of 16 bytes per row
     const bool tma_res = !CONV && S::STG_TILES == 3 && g.residual != nullptr && g.res_mod == 0 && g.out32 != nullptr;
     const uint32_t sw = uint32_t(lane & 7);
-    int it = 0;
-    for (int t = pair; t < num_tiles; t += npairs, ++it) {
-      const int mb = t / tiles_n, nb = t % tiles_n;
+    int mb, nb;
+    for (int it = 0; tile_at(it, mb, nb); ++it) {
       const int b = it & 1;
       const uint32_t bph = (it >> 1) & 1;
       if (g.bias != nullptr) {
@@ -513,7 +548,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, bool CONV, int EWN>
+template <int BN, bool CONV, int EWN, bool WRES = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
   // output maps for the TMA-store epilogue: 32-row x 128-byte boxes (64 f16 / 32 fp32 columns), 128B swizzle
   CUtensorMap tmC16 = tmA, tmC32 = tmA, tmR = tmA;     // placeholders when absent (never dereferenced)
@@ -536,19 +571,27 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     const uint32_t box[2] = {32, 32};
     TOCVP_TRY(encode_tmap(&tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.out32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  using S = G2Smem<BN, EWN>;
+  using S = G2Smem<BN, EWN, WRES>;
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV, EWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV, EWN, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  const int tiles = ((g.M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((g.N + BN - 1) / BN);
+  const int tiles_m = (g.M + 2 * G2_BM - 1) / (2 * G2_BM), tiles_n = (g.N + BN - 1) / BN;
+  const int tiles = tiles_m * tiles_n;
   const int pairs = num_sms() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_f16_kernel<BN, CONV, EWN><<<grid, g2_threads(EWN), S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
+  int grid = 2 * (tiles < pairs ? tiles : pairs);
+  if (WRES) {                                          // tiles_n column blocks x ppn pairs each
+    int ppn = pairs / tiles_n;
+    ppn = ppn < tiles_m ? ppn : tiles_m;
+    grid = 2 * tiles_n * ppn;
+  }
+  gemm2_f16_kernel<BN, CONV, EWN, WRES><<<grid, g2_threads(EWN), S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
+
+int g_gemm2_wres = 1;   // tocvp_set_gemm_mode(258): W-resident variant off (A/B)
 
 // Tile width for the pair kernel, or 0 if the problem should stay on the single-CTA kernel.
 // cost model: waves of pair-tiles x tile width, with the narrower tile paying ~10% for its higher L2 traffic per FLOP
@@ -577,7 +620,18 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
   Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{},
               ln ? ln->stats : nullptr, ln ? ln->slots : 0, ln ? ln->c : nullptr, ln ? ln->inv_k : 0.f, ln ? ln->eps : 0.f,
               ln ? ln->stats_out : nullptr};
-  if (bn == 256) return launch_gemm2<256, false, 8>(tmA, tmB, g, stream);
+  if (bn == 256) {
+    // W-resident variant: K <= 512 and a column-block-stationary schedule that needs no more rounds than round-robin
+    const int pairs = num_sms() / 2;
+    const int tiles_m = (M + 255) / 256, tiles_n = (N + 255) / 256;
+    if (g_gemm2_wres && K <= 512 && K % G2_BK == 0 && tiles_n <= pairs) {
+      int ppn = pairs / tiles_n;
+      ppn = ppn < tiles_m ? ppn : tiles_m;
+      const int rounds_w = (tiles_m + ppn - 1) / ppn, rounds_rr = (tiles_m * tiles_n + pairs - 1) / pairs;
+      if (rounds_w <= rounds_rr) return launch_gemm2<256, false, 8, true>(tmA, tmB, g, stream);
+    }
+    return launch_gemm2<256, false, 8>(tmA, tmB, g, stream);
+  }
   return launch_gemm2<128, false, 8>(tmA, tmB, g, stream);
 }
 

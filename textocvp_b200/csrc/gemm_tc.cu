@@ -392,7 +392,13 @@ int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const Conv
 
 }  // namespace tocvp
 
+namespace tocvp { extern int g_gemm2_wres; }
+
 extern "C" int tocvp_set_gemm_mode(int mode) {
+  if (mode == 258 || mode == 259) {          // 258 / 259: W-resident variant of the 256-wide pair kernel off / on
+    tocvp::g_gemm2_wres = (mode == 259);
+    return TOCVP_OK;
+  }
   if (mode != 0 && mode != 1 && mode != 128 && mode != 256) return TOCVP_ERR_BAD_ARG;
   tocvp::g_gemm_mode = mode;
   return TOCVP_OK;

@@ -29,8 +29,8 @@ def timeit(fn, iters=20, warm=3):
 
 def bench_gemm():
     """single-CTA (mode 1) vs CTA-pair kernel with 128 / 256-wide tiles vs the automatic choice (mode 0)"""
-    for M, N, K in [(20480, 1536, 512), (20480, 512, 512), (20480, 2048, 512), (20480, 512, 2048),
-                    (207360, 1024, 1024), (8192, 8192, 8192)]:
+    for M, N, K in [(20480, 1536, 512), (20480, 512, 512), (20480, 2048, 512), (20480, 512, 2048), (10240, 2048, 512),
+                    (4096, 1536, 512), (207360, 1024, 1024), (8192, 8192, 8192)]:
         a = torch.randn(M, K, device="cuda").half()
         w = torch.randn(N, K, device="cuda").half()
         res = []
@@ -38,6 +38,11 @@ def bench_gemm():
             ops.set_gemm_mode(mode)
             ms = timeit(lambda: ops.gemm_f16(a, w, out_f32=False, out_f16=True))
             res.append(f"mode{mode}: {ms*1e3:7.1f} us {2*M*N*K/ms/1e9:7.1f} TF")
+        ops.set_gemm_mode(258)                                   # 256-wide tiles without the W-resident variant
+        ops.set_gemm_mode(256)
+        ms = timeit(lambda: ops.gemm_f16(a, w, out_f32=False, out_f16=True))
+        res.append(f"256/noWres: {ms*1e3:7.1f} us {2*M*N*K/ms/1e9:7.1f} TF")
+        ops.set_gemm_mode(259)
         ops.set_gemm_mode(0)
         ms_t = timeit(lambda: a @ w.t())
         print(f"gemm {M}x{N}x{K}: " + " | ".join(res) + f" | cuBLAS {2*M*N*K/ms_t/1e9:.1f}", flush=True)
