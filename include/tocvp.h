@@ -369,7 +369,9 @@ int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t s
 /* Tuning / test knob (process-wide), bit mask.  Bit 0: 1 = decoder layer 1 is generated inside the layer-2 convolution
  * kernel and never stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation.
  * Bit 1: 1 = first-version head conv3x3 (shifted windows, N = 16); 0 (default) = nine taps in the GEMM's N dimension.
- * Bit 2: 1 = first-version (image-stationary) layer-1 kernel; 0 (default) = pixel-stationary kernel. */
+ * Bit 2: 1 = first-version (image-stationary) layer-1 kernel; 0 (default) = pixel-stationary kernel.
+ * Bit 3: 1 = serial chunks; 0 (default) = chunk-pipelined: layer 1 of chunk i+1 is written on an internal side stream
+ * (forked from and joined back into the caller's stream by events) under the convolutions of chunk i. */
 int tocvp_set_decode_mode(int mode);
 
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the

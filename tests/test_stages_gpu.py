@@ -106,6 +106,36 @@ def test_decode(models, golden, golden_weights, fuse_layer1):
     assert O.rel_err(out["recons_imgs"], golden["dec_img"]) < STAGE_TOL
 
 
+def test_decode_chunk_pipeline_matches_serial(models, golden):
+    """Multi-chunk decode (256-frame chunks + a ragged tail): the chunk-pipelined driver (layer 1 of chunk i+1 on a side
+    stream under the convolutions of chunk i, three activation buffers) must be bit-identical to the serial one, and chunk
+    k must equal a stand-alone decode of the same slots (no cross-chunk aliasing)."""
+    from textocvp_b200 import _lib as L
+    savi, _ = models
+    g = torch.Generator().manual_seed(5)
+    base = golden["pred_slots"][:1, -1]
+    slots = (base + 0.3 * torch.randn(256 * 2 + 37, 8, 128, generator=g)).cuda()
+    outs = {}
+    for mode in (0, 8):
+        L.call("tocvp_set_decode_mode", L.c_int(mode))
+        try:
+            for _ in range(2):   # second call re-uses the side stream / events
+                o = savi(mode="decode", slots=slots)
+            torch.cuda.synchronize()
+            outs[mode] = {k: v.clone() for k, v in o.items()}
+        finally:
+            L.call("tocvp_set_decode_mode", L.c_int(0))
+    for k in ("recons_imgs", "recons", "masks"):
+        assert torch.equal(outs[0][k], outs[8][k]), k
+    tail = savi(mode="decode", slots=slots[512:].contiguous())
+    mid = savi(mode="decode", slots=slots[256:300].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(tail["recons_imgs"], outs[0]["recons_imgs"][512:])
+    assert torch.equal(mid["masks"], outs[0]["masks"][256:300])
+    ref = O.rel_err(outs[0]["recons_imgs"][:1], savi(mode="decode", slots=slots[:1].contiguous())["recons_imgs"])
+    assert ref == 0.0
+
+
 def test_full_rollout_psnr(models, golden, golden_weights):
     """Evaluator composition (05_evaluate_predictor.py:82-96) end to end vs the real reference's frames."""
     savi, pred = models

@@ -12,6 +12,8 @@
 //  final conv3x3 64->4 (decoders.py:110-116): the same tcgen05 implicit-GEMM kernel with a 3x3 tap set and the output
 //      channels zero-padded to N = 16; it writes one float4 (RGB + mask logit) per pixel and slot.
 //  compositing (SAVi.py:251-255): `composite_kernel`, softmax over the slot axis + weighted sum, one thread per pixel.
+#include <mutex>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -196,13 +198,45 @@ static int g_dec_head_taps = 1;
 // bit 2: 0 = pixel-stationary layer-1 kernel (default), 1 = image-stationary first version
 static int g_dec_l1_pixel = 1;
 
+// bit 3: 0 = chunk-pipelined decode (default): layer 1 of chunk i+1 is written on a side stream while the convolutions of
+// chunk i run (the pixel-stationary kernel needs no shared memory / TMEM and 1 CTA per SM of registers, so it is
+// co-resident with the persistent conv CTAs and its 1 GiB write stream hides under tensor-bound time); 1 = serial.
+static int g_dec_overlap = 1;
+
 struct DecBuffers {
-  __half* slots16;
-  float* taps32;
-  float* pat32;
-  __half *actA, *actB;
+  __half* slots16;    // [n_frames*S, D]   (all chunks: the layer-1 front end runs once for the whole call)
+  float* taps32;      // [n_frames*S, 25*C]
+  float* pat32;       // [n_frames*S, 25*C]
+  __half *actA, *actB, *actC;
   float* maps4;
 };
+
+// Side stream + events of the pipelined decode, one set per device, created on first use.  The side stream only ever runs
+// work that is forked from / joined back into the caller's stream by events inside one call, so calls stay ordered on
+// the caller's stream (and capturable).  The set is guarded by a mutex held for the enqueue phase of a call.
+struct DecSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, l1_done[2] = {nullptr, nullptr}, conv_done[2] = {nullptr, nullptr};
+};
+static std::mutex g_side_mutex;
+static DecSide g_side[16];
+
+static int dec_side(DecSide** out) {
+  int dev = 0;
+  TOCVP_CUDA(cudaGetDevice(&dev));
+  TOCVP_CHECK_ARG(dev >= 0 && dev < 16);
+  DecSide& sd = g_side[dev];
+  if (!sd.stream) {
+    TOCVP_CUDA(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
+    TOCVP_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      TOCVP_CUDA(cudaEventCreateWithFlags(&sd.l1_done[i], cudaEventDisableTiming));
+      TOCVP_CUDA(cudaEventCreateWithFlags(&sd.conv_done[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &sd;
+  return TOCVP_OK;
+}
 
 static size_t align256d(size_t n) { return (n + 255) & ~size_t(255); }
 
@@ -215,12 +249,14 @@ static size_t dec_carve(const tocvp_dec_weights& w, int n_frames, DecBuffers* db
     off += align256d(bytes);
     return p;
   };
+  const size_t nsi_all = size_t(n_frames) * w.num_slots;
   DecBuffers t;
-  t.slots16 = reinterpret_cast<__half*>(take(nsi * w.slot_dim * 2));
-  t.taps32 = reinterpret_cast<float*>(take(nsi * 25 * w.hidden * 4));
-  t.pat32 = reinterpret_cast<float*>(take(nsi * 25 * w.hidden * 4));
+  t.slots16 = reinterpret_cast<__half*>(take(nsi_all * w.slot_dim * 2));
+  t.taps32 = reinterpret_cast<float*>(take(nsi_all * 25 * w.hidden * 4));
+  t.pat32 = reinterpret_cast<float*>(take(nsi_all * 25 * w.hidden * 4));
   t.actA = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
   t.actB = reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2));
+  t.actC = n_frames > chunk ? reinterpret_cast<__half*>(take(nsi * w.H * w.W * w.hidden * 2)) : nullptr;
   t.maps4 = reinterpret_cast<float*>(take(nsi * w.H * w.W * 4 * 4));
   if (db) *db = t;
   return off;
@@ -236,6 +272,7 @@ extern "C" int tocvp_set_decode_mode(int mode) {
   tocvp::g_dec_fuse_l1 = (mode & 1) ? 1 : 0;
   tocvp::g_dec_head_taps = (mode & 2) ? 0 : 1;
   tocvp::g_dec_l1_pixel = (mode & 4) ? 0 : 1;
+  tocvp::g_dec_overlap = (mode & 8) ? 0 : 1;
   return TOCVP_OK;
 }
 
@@ -259,43 +296,87 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
   dec_carve(*w, n_frames, &db, static_cast<uint8_t*>(workspace));
   const int S = w->num_slots, D = w->slot_dim, H = w->H, W = w->W, C = w->hidden;
   const size_t plane = size_t(H) * W;
-  for (int f0 = 0; f0 < n_frames; f0 += DEC_CHUNK_FRAMES) {
-    const int nf = (n_frames - f0) < DEC_CHUNK_FRAMES ? (n_frames - f0) : DEC_CHUNK_FRAMES;
-    const int nsi = nf * S;
-    const size_t n4 = size_t(nsi) * D / 4;
-    f32_to_f16_kernel<<<int((n4 + 255) / 256), 256, 0, st>>>(slots + size_t(f0) * S * D, db.slots16, n4);
+  const int nsi_all = n_frames * S;
+  // ---- layer-1 front end for the whole call: f16 slots, per-tap vectors (one GEMM), 5x5 border-pattern sums
+  {
+    const size_t n4 = size_t(nsi_all) * D / 4;
+    f32_to_f16_kernel<<<int((n4 + 255) / 256), 256, 0, st>>>(slots, db.slots16, n4);
     TOCVP_LAUNCHED();
-    TOCVP_TRY(gemm_f16(db.slots16, D, static_cast<const __half*>(w->w1_taps), D, nsi, 25 * C, D, nullptr, 0, nullptr, 0,
-                       1, 0, db.taps32, 25 * C, nullptr, 0, st));
-    // layer 1 is generated inside the layer-2 convolution whenever the pair kernel applies (even tile count)
-    const bool fused_l1 = ((nsi * (H / 16) * (W / 32)) % 2 == 0) && g_dec_fuse_l1;
-    const bool pixel_l1 = !fused_l1 && (W % 8 == 0) && g_dec_l1_pixel;
-    if (fused_l1 || pixel_l1) {
-      dec_l1_patterns_kernel<<<(nsi + 3) / 4, 256, 0, st>>>(db.taps32, db.pat32, nsi);
+    TOCVP_TRY(gemm_f16(db.slots16, D, static_cast<const __half*>(w->w1_taps), D, nsi_all, 25 * C, D, nullptr, 0, nullptr,
+                       0, 1, 0, db.taps32, 25 * C, nullptr, 0, st));
+  }
+  const int chunk0 = n_frames < DEC_CHUNK_FRAMES ? n_frames : DEC_CHUNK_FRAMES;
+  // layer 1 is generated inside the layer-2 convolution only on request (tocvp_set_decode_mode bit 0) and when the pair
+  // kernel applies to every chunk (even tile count)
+  const bool even_tiles = ((chunk0 * S * (H / 16) * (W / 32)) % 2 == 0) && (((n_frames % chunk0) * S * (H / 16) * (W / 32)) % 2 == 0);
+  const bool fused_l1 = even_tiles && g_dec_fuse_l1;
+  const bool pixel_l1 = !fused_l1 && (W % 8 == 0) && g_dec_l1_pixel;
+  if (fused_l1 || pixel_l1) {
+    dec_l1_patterns_kernel<<<(nsi_all + 3) / 4, 256, 0, st>>>(db.taps32, db.pat32, nsi_all);
+    TOCVP_LAUNCHED();
+  }
+  const int n_chunks = (n_frames + DEC_CHUNK_FRAMES - 1) / DEC_CHUNK_FRAMES;
+  const bool overlap = g_dec_overlap && pixel_l1 && n_chunks > 1;
+  std::unique_lock<std::mutex> side_lock(g_side_mutex, std::defer_lock);
+  DecSide* sd = nullptr;
+  if (overlap) {
+    side_lock.lock();
+    TOCVP_TRY(dec_side(&sd));
+    TOCVP_CUDA(cudaEventRecord(sd->fork, st));
+    TOCVP_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+  }
+  // chunk i: layer 1 -> X[i&1];  L2: X -> actB;  L3: actB -> X;  L4: X -> actB;  head reads actB.  (serial mode: X = actA)
+  __half* xbuf[2] = {db.actA, overlap ? db.actC : db.actA};
+  auto layer1 = [&](int ci, cudaStream_t s_l1) -> int {
+    const int f0 = ci * DEC_CHUNK_FRAMES;
+    const int nsi = ((n_frames - f0) < DEC_CHUNK_FRAMES ? (n_frames - f0) : DEC_CHUNK_FRAMES) * S;
+    const size_t so = size_t(f0) * S * 25 * C;
+    if (pixel_l1) {
+      dec_l1_pixel_kernel<<<(H * W) / 8, 256, 0, s_l1>>>(db.pat32 + so, w->p1, xbuf[ci & 1], nsi, H, W);
       TOCVP_LAUNCHED();
-      if (pixel_l1) {
-        dec_l1_pixel_kernel<<<(H * W) / 8, 256, 0, st>>>(db.pat32, w->p1, db.actA, nsi, H, W);
-        TOCVP_LAUNCHED();
-      }
-    } else {
-      dec_l1_kernel<<<nsi, 256, 0, st>>>(db.taps32, w->p1, db.actA, H, W);
+    } else if (!fused_l1) {
+      dec_l1_kernel<<<nsi, 256, 0, s_l1>>>(db.taps32 + so, w->p1, xbuf[ci & 1], H, W);
       TOCVP_LAUNCHED();
     }
-    __half* bufs[2] = {db.actA, db.actB};
+    return TOCVP_OK;
+  };
+  if (overlap) {
+    TOCVP_TRY(layer1(0, sd->stream));
+    TOCVP_CUDA(cudaEventRecord(sd->l1_done[0], sd->stream));
+  }
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int f0 = ci * DEC_CHUNK_FRAMES;
+    const int nf = (n_frames - f0) < DEC_CHUNK_FRAMES ? (n_frames - f0) : DEC_CHUNK_FRAMES;
+    const int nsi = nf * S;
+    if (overlap) {
+      if (ci + 1 < n_chunks) {
+        // X[(ci+1)&1] was last read by layer 4 of chunk ci-1
+        if (ci >= 1) TOCVP_CUDA(cudaStreamWaitEvent(sd->stream, sd->conv_done[(ci - 1) & 1], 0));
+        TOCVP_TRY(layer1(ci + 1, sd->stream));
+        TOCVP_CUDA(cudaEventRecord(sd->l1_done[(ci + 1) & 1], sd->stream));
+      }
+      TOCVP_CUDA(cudaStreamWaitEvent(st, sd->l1_done[ci & 1], 0));
+    } else {
+      TOCVP_TRY(layer1(ci, st));
+    }
+    __half* X = xbuf[ci & 1];
+    const __half* src[3] = {X, db.actB, X};
+    __half* dst[3] = {db.actB, X, db.actB};
     for (int l = 0; l < 3; ++l) {
       // optional CUDA-event pair around each conv launch (bench.py measures the dominant kernel live, in the step)
-      const int ev = 2 * ((f0 / DEC_CHUNK_FRAMES) * 3 + l);
+      const int ev = 2 * (ci * 3 + l);
       const bool prof = conv_events != nullptr && ev + 1 < n_conv_events;
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev]), st));
       if (l == 0 && fused_l1) {
-        TOCVP_TRY(conv5x5_gen_f16(w->p1, db.pat32, db.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], db.actB,
-                                  nsi, H, W, st));
+        TOCVP_TRY(conv5x5_gen_f16(w->p1, db.pat32 + size_t(f0) * S * 25 * C, X, static_cast<const __half*>(w->w_conv[0]),
+                                  w->b_conv[0], db.actB, nsi, H, W, st));
       } else {
-        TOCVP_TRY(conv5x5_f16(bufs[l & 1], static_cast<const __half*>(w->w_conv[l]), w->b_conv[l], bufs[(l + 1) & 1], nsi,
-                              H, W, C, C, 1, st));
+        TOCVP_TRY(conv5x5_f16(src[l], static_cast<const __half*>(w->w_conv[l]), w->b_conv[l], dst[l], nsi, H, W, C, C, 1,
+                              st));
       }
       if (prof) TOCVP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(conv_events[ev + 1]), st));
     }
+    if (overlap) TOCVP_CUDA(cudaEventRecord(sd->conv_done[ci & 1], st));
     // conv3x3 64 -> 4 head on the tensor cores (N padded to 16), then softmax-over-slots compositing
     if (g_dec_head_taps && w->w_out_taps != nullptr) {
       TOCVP_TRY(conv3x3_head_taps_f16(db.actB, static_cast<const __half*>(w->w_out_taps), w->b_out, db.maps4, nsi, H, W, st));
