@@ -122,6 +122,18 @@ int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats
                          const float* slots_in, int iters, float* slots_out, int out_stride, float* pred_out,
                          void* workspace, size_t ws_bytes, void* stream);
 
+/* The corrector chain of SAVi.forward_decomp (reference src/models/SAVi.py:178-204) over n_frames consecutive frames in
+ * one call: slots_t = SlotAttention(feats_t, cur, t == 0 ? iters_first : iters) -> slot_history + t*hist_frame_stride
+ * (row b at + b*hist_seq_stride, floats); cur = transition(slots_t) (requires the TransformerBlock transition weights).
+ * Frame t's features start at feats + t*feats_frame_stride (elements), sequence b's at + b*feats_seq_stride.
+ * carry_out [B,S,128] receives transition(slots of the last frame) = the slots_in of a following call.  Pass
+ * iters_first = iters when the first frame of this call is not step 0 of the video. */
+size_t tocvp_slot_attention_seq_workspace_bytes(int B);
+int tocvp_slot_attention_seq(const tocvp_sa_weights* w, const void* feats, int feats_f16, size_t feats_seq_stride,
+                             size_t feats_frame_stride, int B, int N, int n_frames, int iters_first, int iters,
+                             const float* slots_in, float* slot_history, size_t hist_seq_stride,
+                             size_t hist_frame_stride, float* carry_out, void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Short-sequence multi-head attention (head dim 64, <= 128 keys, fp32 softmax, no mask).
  * q [B*Tq, ldq], k / v [B*Tk, ldkv] f16 with head h at column offset h*64; out [B*Tq, ldo] f16.
@@ -373,6 +385,11 @@ int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t s
  * Bit 3: 1 = serial chunks; 0 (default) = chunk-pipelined: layer 1 of chunk i+1 is written on an internal side stream
  * (forked from and joined back into the caller's stream by events) under the convolutions of chunk i. */
 int tocvp_set_decode_mode(int mode);
+
+/* Tuning / test knob (process-wide): 1 = the predictor-path kernels (GEMMs, attention, LayerNorm, window /
+ * commit kernels) are launched with programmatic stream serialization, so a kernel's prologue overlaps the previous
+ * kernel's tail; 0 (default: measured no gain under graph replay in round 1) = plain stream order.  Bit-identical. */
+int tocvp_set_pdl(int on);
 
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */

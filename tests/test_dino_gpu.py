@@ -64,6 +64,13 @@ def test_decomp(dmodels, golden_dino, golden_dino_weights):
     assert sh.shape == (m["B"], m["T"], 10, 128)
     assert O.rel_err(sh[:, 0], golden_dino["slot_history"][:, 0]) < STAGE_TOL
     assert O.rel_err(sh, golden_dino["slot_history"]) < 3 * STAGE_TOL
+    dino.chain_corrector = False                       # one library call per frame (first version): bit-identical
+    try:
+        ref = dino(mode="decomp", x=golden_dino_weights["feats"].cuda(), num_imgs=m["T"], decode=False,
+                   init_slots=golden_dino_weights["init"].cuda())["slot_history"]
+    finally:
+        dino.chain_corrector = True
+    assert torch.equal(sh, ref)
 
 
 def test_patch_decode(dmodels, golden_dino):

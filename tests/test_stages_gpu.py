@@ -73,6 +73,34 @@ def test_decomp_and_transition(models, golden, golden_weights):
     assert O.rel_err(sh, golden["slot_history"]) < 3 * STAGE_TOL
 
 
+def test_decomp_chained_matches_per_frame(models, golden_weights):
+    """tocvp_slot_attention_seq (whole corrector + transition chain in one call, the frame-finishing update launch also
+    emits the next frame's query vectors) must be bit-identical to one tocvp_slot_attention call per frame -- also when
+    the frames are encoded in several chunks (the carry crosses library calls) and with decode=True."""
+    savi, _ = models
+    v = golden_weights["videos"].cuda()
+    init = golden_weights["init"].cuda()
+    res = {}
+    old_max = savi.max_encode_images
+    try:
+        for chain in (False, True):
+            for max_imgs in (8192, 2 * 3):                  # 2 sequences x 3 frames per encode chunk -> 7 chunks
+                savi.chain_corrector, savi.max_encode_images = chain, max_imgs
+                res[(chain, max_imgs)] = savi(mode="decomp", x=v, num_imgs=20, decode=False, init_slots=init)["slot_history"]
+        savi.chain_corrector, savi.max_encode_images = True, old_max
+        dec = savi(mode="decomp", x=v[:, :3], num_imgs=3, decode=True, init_slots=init)
+        savi.chain_corrector = False
+        dec_ref = savi(mode="decomp", x=v[:, :3], num_imgs=3, decode=True, init_slots=init)
+        torch.cuda.synchronize()
+    finally:
+        savi.chain_corrector, savi.max_encode_images = True, old_max
+    ref = res[(False, 8192)]
+    for k, val in res.items():
+        assert torch.equal(val, ref), k
+    for k in ("slot_history", "recons_imgs", "recons_objs", "masks"):
+        assert torch.equal(dec[k], dec_ref[k]), k
+
+
 def test_predictor_step(models, golden, golden_weights):
     _, pred = models
     sh = golden["slot_history"].cuda()

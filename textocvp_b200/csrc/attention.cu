@@ -27,6 +27,19 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(smem_row)));
 }
 
+// four 8x8 b16 tiles, not transposed: B fragments (k = head-dim, n = key) of two adjacent k-steps of one 8-key tile
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -51,6 +64,25 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   const int TkP = (Tk + 15) & ~15;
   const __half* kb = k + size_t(b) * Tk * ldkv + h * ATT_DH;
   const __half* vb = v + size_t(b) * Tk * ldkv + h * ATT_DH;
+  const __half* qb = q + size_t(b) * q_seq_rows * ldq + h * ATT_DH;   // q_seq_rows > Tq: a row subset per sequence
+  __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
+  pdl_wait();
+  pdl_trigger();
+  uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
+  auto load_q = [&](int m0) {
+    const int r0 = m0 + g, r1 = m0 + g + 8;
+    const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa[ks][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c)) : 0u;
+      qa[ks][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c)) : 0u;
+      qa[ks][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c + 8)) : 0u;
+      qa[ks][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c + 8)) : 0u;
+    }
+  };
+  // the first query tile's fragments are requested together with K / V: one global-latency phase per CTA instead of two
+  if (warp * 16 < Tq) load_q(warp * 16);
   for (int e = threadIdx.x; e < TkP * 8; e += blockDim.x) {
     const int r = e >> 3, c = e & 7;
     uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -63,31 +95,23 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   }
   __syncthreads();
   const int n_tiles = TkP / 8;    // key tiles of 8
-  const __half* qb = q + size_t(b) * q_seq_rows * ldq + h * ATT_DH;   // q_seq_rows > Tq: a row subset per sequence
-  __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
   for (int m0 = warp * 16; m0 < Tq; m0 += (blockDim.x >> 5) * 16) {
     const int r0 = m0 + g, r1 = m0 + g + 8;
     const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
-    uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int c = ks * 16 + 2 * t;
-      qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c) : 0u;
-      qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c) : 0u;
-      qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c + 8) : 0u;
-      qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c + 8) : 0u;
-    }
+    if (m0 != warp * 16) load_q(m0);
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       if (nt < n_tiles) {
-        const __half* kr = sK + (nt * 8 + g) * ATT_KS + 2 * t;
+        // lane l supplies the row address of key nt*8 + (l & 7), head-dim block p*32 + 8*(l >> 3)
+        const __half* kr = sK + (nt * 8 + (lane & 7)) * ATT_KS + ((lane >> 3) << 3);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-          mma_16816(s[nt], qa[ks], b0, b1);
+        for (int p = 0; p < 2; ++p) {
+          uint32_t kb4[4];
+          ldmatrix_x4(kb4, kr + p * 32);
+          mma_16816(s[nt], qa[2 * p], kb4[0], kb4[1]);
+          mma_16816(s[nt], qa[2 * p + 1], kb4[2], kb4[3]);
         }
       }
     }
@@ -111,10 +135,10 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       if (nt < n_tiles) {
-        s[nt][0] = exp2f((s[nt][0] - mx0) * scale_log2e);
-        s[nt][1] = exp2f((s[nt][1] - mx0) * scale_log2e);
-        s[nt][2] = exp2f((s[nt][2] - mx1) * scale_log2e);
-        s[nt][3] = exp2f((s[nt][3] - mx1) * scale_log2e);
+        s[nt][0] = ex2_ftz((s[nt][0] - mx0) * scale_log2e);
+        s[nt][1] = ex2_ftz((s[nt][1] - mx0) * scale_log2e);
+        s[nt][2] = ex2_ftz((s[nt][2] - mx1) * scale_log2e);
+        s[nt][3] = ex2_ftz((s[nt][3] - mx1) * scale_log2e);
         sum0 += s[nt][0] + s[nt][1];
         sum1 += s[nt][2] + s[nt][3];
       }
@@ -177,10 +201,10 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
   const int nt = ((Tk + 15) & ~15) / 8;
 #define MHA_LAUNCH(NTV, W, MB)                                                                                        \
-  mha_kernel<NTV, W, MB><<<B * heads, warps * 32, 0, stream>>>(q, ldq, q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, \
-                                                               out, ldo)
+  TOCVP_CUDA(launch_pdl(mha_kernel<NTV, W, MB>, dim3(B * heads), dim3(warps * 32), 0, stream, q, ldq, q_seq_rows, k, v, \
+                        ldkv, Tq, Tk, heads, scale_log2e, out, ldo))
   if (nt <= 4) {
-    if (warps <= 5) MHA_LAUNCH(4, 5, 6); else MHA_LAUNCH(4, 8, 3);
+    if (warps <= 5) MHA_LAUNCH(4, 5, 5); else MHA_LAUNCH(4, 8, 3);
   } else if (nt <= 10) {
     if (warps <= 5) MHA_LAUNCH(10, 5, 4); else MHA_LAUNCH(10, 8, 2);
   } else if (nt <= 14) {
@@ -189,7 +213,7 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
     MHA_LAUNCH(16, 8, 2);
   }
 #undef MHA_LAUNCH
-  TOCVP_LAUNCHED();
+  count_launch();
   return TOCVP_OK;
 }
 

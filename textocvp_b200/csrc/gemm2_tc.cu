@@ -148,6 +148,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();              // barrier inits + TMEM allocation visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The W-resident producer lane
+  // additionally issues its (constant) weight loads before it waits for the previous grid's activations.
+  if (!(WRES && threadIdx.x == 0)) pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (each CTA loads its halves)
@@ -162,6 +166,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < num_kb; ++kb)
             tma_load_2d_pair(&tmB, wfull_leader, w_base + kb * S::B_BYTES, kb * G2_BK, nb * BN + int(rank) * (BN / 2));
         }
+        pdl_wait();
       }
       for (int i = 0; tile_at(i, mb, nb); ++i) {
         const int m0 = mb * 2 * G2_BM + int(rank) * G2_BM;
@@ -586,8 +591,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     ppn = ppn < tiles_m ? ppn : tiles_m;
     grid = 2 * tiles_n * ppn;
   }
-  gemm2_f16_kernel<BN, CONV, EWN, WRES><<<grid, g2_threads(EWN), S::TOTAL, stream>>>(tmA, tmB, tmC16, tmC32, tmR, g);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(gemm2_f16_kernel<BN, CONV, EWN, WRES>, dim3(grid), dim3(g2_threads(EWN)), S::TOTAL, stream, tmA,
+                        tmB, tmC16, tmC32, tmR, g));
+  count_launch();
   return TOCVP_OK;
 }
 

@@ -81,6 +81,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the previous kernel's tail (launch_pdl)
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -297,8 +299,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_f16_kernel<BN, CONV><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, g);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(gemm_f16_kernel<BN, CONV>, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, tmA, tmB, g));
+  count_launch();
   return TOCVP_OK;
 }
 

@@ -74,6 +74,10 @@ int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static std::atomic<int> g_pdl{0};   // measured r1 (tools/ab_pdl.py): no gain under graph replay -> opt-in
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -102,6 +106,11 @@ extern "C" int tocvp_init(int device) {
     return TOCVP_ERR_ARCH;
   }
   if (cudaSetDevice(device) != cudaSuccess) return TOCVP_ERR_CUDA;
+  return TOCVP_OK;
+}
+
+extern "C" int tocvp_set_pdl(int on) {
+  tocvp::set_pdl(on);
   return TOCVP_OK;
 }
 

@@ -55,4 +55,26 @@ int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64
 
 int num_sms();
 
+// Programmatic dependent launch (tocvp_set_pdl, default on): the kernel may become resident while the previous kernel of
+// the stream drains; it runs its prologue (barrier init, TMEM allocation, descriptor prefetch, constant-weight loads) and
+// blocks in griddepcontrol.wait (pdl_wait(), ptx.cuh) until the previous grid has completed and flushed.  ONLY for kernels
+// that execute pdl_wait() before their first access to memory another kernel produces or consumes.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace tocvp

@@ -31,6 +31,8 @@ layernorm_kernel(const TIN* __restrict__ x, int ldx, int x_div, const float* __r
                  __half* __restrict__ out16, int ld16, float* __restrict__ out32, int ld32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (warp >= rows) return;
   const TIN* xr = x + size_t(warp / x_div) * ldx;   // x_div > 1: each input row is broadcast to x_div output rows
   const float* ar = add ? add + size_t(warp % add_rows) * D : nullptr;
@@ -160,12 +162,12 @@ int layernorm_bcast(const void* x, int x_is_f16, int ldx, int x_div, const float
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   if (x_is_f16)
-    layernorm_kernel<__half><<<grid, wpb * 32, 0, stream>>>(static_cast<const __half*>(x), ldx, x_div, add, add_rows, gamma,
-                                                            beta, eps, rows, D, out16, ld16, out32, ld32);
+    TOCVP_CUDA(launch_pdl(layernorm_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, stream, static_cast<const __half*>(x),
+                          ldx, x_div, add, add_rows, gamma, beta, eps, rows, D, out16, ld16, out32, ld32));
   else
-    layernorm_kernel<float><<<grid, wpb * 32, 0, stream>>>(static_cast<const float*>(x), ldx, x_div, add, add_rows, gamma,
-                                                           beta, eps, rows, D, out16, ld16, out32, ld32);
-  TOCVP_LAUNCHED();
+    TOCVP_CUDA(launch_pdl(layernorm_kernel<float>, dim3(grid), dim3(wpb * 32), 0, stream, static_cast<const float*>(x),
+                          ldx, x_div, add, add_rows, gamma, beta, eps, rows, D, out16, ld16, out32, ld32));
+  count_launch();
   return TOCVP_OK;
 }
 

@@ -22,6 +22,8 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
 
 // rows of the newest frame, fp32: tokens [B, n*S, T] -> [B*S, T]
 __global__ void last_frame_f32_kernel(const float* __restrict__ tokens, int n, int S, int T, int B, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total4 = size_t(B) * S * T / 4;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total4; e += size_t(gridDim.x) * blockDim.x) {
     const size_t el = e * 4;
@@ -35,6 +37,8 @@ __global__ void last_frame_f32_kernel(const float* __restrict__ tokens, int n, i
 // frames [B, F_total, S*D] fp32 -> window tokens f16 [B, n, S*D] starting at frame f0
 __global__ void window_to_f16_kernel(const float* __restrict__ frames, size_t seq_stride, int f0, int n, int SD, int B,
                                      __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total4 = size_t(B) * n * SD / 4;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total4; e += size_t(gridDim.x) * blockDim.x) {
     const size_t el = e * 4;
@@ -51,6 +55,8 @@ __global__ void window_to_f16_kernel(const float* __restrict__ frames, size_t se
 // rows of the newest frame: tokens fp32 [B, n*S, T] -> f16 [B*S, T]
 __global__ void last_frame_to_f16_kernel(const float* __restrict__ tokens, int n, int S, int T, int B,
                                          __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total4 = size_t(B) * S * T / 4;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total4; e += size_t(gridDim.x) * blockDim.x) {
     const size_t el = e * 4;
@@ -68,6 +74,8 @@ __global__ void last_frame_to_f16_kernel(const float* __restrict__ tokens, int n
 __global__ void commit_prediction_kernel(const float* __restrict__ pred, float* __restrict__ frames, size_t seq_stride,
                                          int f_last, int f_new, int residual, float* __restrict__ pred_out,
                                          size_t pred_seq_stride, int t, int SD, int B) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = size_t(B) * SD;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += size_t(gridDim.x) * blockDim.x) {
     const int b = int(e / SD), r = int(e % SD);
@@ -80,6 +88,8 @@ __global__ void commit_prediction_kernel(const float* __restrict__ pred, float* 
 
 __global__ void copy_context_kernel(const float* __restrict__ src, size_t src_seq_stride, float* __restrict__ frames,
                                     size_t seq_stride, int nctx, int SD, int B) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = size_t(B) * nctx * SD;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += size_t(gridDim.x) * blockDim.x) {
     const int b = int(e / (size_t(nctx) * SD));
@@ -142,8 +152,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   const int S = w.num_slots, D = w.slot_dim, T = w.token_dim;
   const int M = B * n * S;
   const size_t seq_stride = size_t(ftot) * S * D;
-  window_to_f16_kernel<<<ew_grid(size_t(M) * D / 4), 256, 0, st>>>(pb.frames, seq_stride, f0, n, S * D, B, pb.tok16);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(window_to_f16_kernel, dim3(ew_grid(size_t(M) * D / 4)), dim3(256), 0, st, pb.frames, seq_stride, f0, n, S * D, B, pb.tok16));
+  count_launch();
   // tokens = mlp_in(slots) + flip(pe[:n])   (text_cond_OCVP.py:86-91, model_blocks.py:375-377): the pre-flipped
   // table for window length n is added in the GEMM epilogue, row -> frame index (row / S) % n.
   const float* pe_n = w.pe_flipped + size_t(n - 1) * w.buffer_size * T;
@@ -234,8 +244,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
       // output: behind the K/V projection only the S newest rows of every sequence are computed (exact, not an
       // approximation) -- queries, out-proj, cross-attention and both MLPs on B*S rows instead of B*n*S.
       const int Mc = B * S;
-      last_frame_f32_kernel<<<ew_grid(size_t(Mc) * T / 4), 256, 0, st>>>(pb.x32, n, S, T, B, pb.xl32);
-      TOCVP_LAUNCHED();
+      TOCVP_CUDA(launch_pdl(last_frame_f32_kernel, dim3(ew_grid(size_t(Mc) * T / 4)), dim3(256), 0, st, pb.x32, n, S, T, B, pb.xl32));
+      count_launch();
       TOCVP_TRY(mha_f16_sub(pb.qkv16 + size_t(n - 1) * S * 3 * T, 3 * T, n * S, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, S,
                             n * S, w.num_heads, pb.att16, T, st));
       TOCVP_TRY(layer_tail(ly, l, Mc, S, pb.xl32, false));
@@ -247,8 +257,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
     }
   }
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
-  last_frame_to_f16_kernel<<<ew_grid(size_t(B) * S * T / 4), 256, 0, st>>>(pb.x32, n_out, S, T, B, pb.last16);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(last_frame_to_f16_kernel, dim3(ew_grid(size_t(B) * S * T / 4)), dim3(256), 0, st, pb.x32, n_out, S, T, B, pb.last16));
+  count_launch();
   TOCVP_TRY(gemm_f16(pb.last16, T, static_cast<const __half*>(w.mlp_out_w), T, B * S, D, T, w.mlp_out_b, 0, nullptr, 0,
                      1, 0, pb.pred32, D, nullptr, 0, st));
   return TOCVP_OK;
@@ -306,19 +316,16 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
   const int S = w->num_slots, D = w->slot_dim, SD = S * D;
   const int ftot = num_context + num_preds;
   const size_t seq_stride = size_t(ftot) * SD;
-  copy_context_kernel<<<ew_grid(size_t(B) * num_context * SD), 256, 0, st>>>(slot_history, hist_seq_stride, pb.frames,
-                                                                            seq_stride, num_context, SD, B);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * num_context * SD)), dim3(256), 0, st, slot_history, hist_seq_stride, pb.frames, seq_stride, num_context, SD, B));
+  count_launch();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   for (int t = 0; t < num_preds; ++t) {
     const int have = num_context + t;                                   // frames available
     const int n = have < w->buffer_size ? have : w->buffer_size;        // predictor_wrapper.py:143-153
     const int f0 = have - n;
     TOCVP_TRY(predictor_step(*w, pb, B, L, f0, n, ftot, st));
-    commit_prediction_kernel<<<ew_grid(size_t(B) * SD), 256, 0, st>>>(pb.pred32, pb.frames, seq_stride, have - 1, have,
-                                                                     w->residual, pred_slots, size_t(num_preds) * SD, t,
-                                                                     SD, B);
-    TOCVP_LAUNCHED();
+    TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32, pb.frames, seq_stride, have - 1, have, w->residual, pred_slots, size_t(num_preds) * SD, t, SD, B));
+    count_launch();
   }
   return TOCVP_OK;
 }
@@ -339,12 +346,11 @@ extern "C" int tocvp_predictor_forward(const tocvp_pred_weights* w, const float*
   carve(*w, B, L, n, 1, &pb, static_cast<uint8_t*>(workspace));
   const int SD = w->num_slots * w->slot_dim;
   const size_t seq_stride = size_t(n + 1) * SD;
-  copy_context_kernel<<<ew_grid(size_t(B) * n * SD), 256, 0, st>>>(slots, size_t(n) * SD, pb.frames, seq_stride, n, SD, B);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * n * SD)), dim3(256), 0, st, slots, size_t(n) * SD, pb.frames, seq_stride, n, SD, B));
+  count_launch();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   TOCVP_TRY(predictor_step(*w, pb, B, L, 0, n, n + 1, st));
-  commit_prediction_kernel<<<ew_grid(size_t(B) * SD), 256, 0, st>>>(pb.pred32, pb.frames, seq_stride, n - 1, n,
-                                                                   w->residual, out, size_t(SD), 0, SD, B);
-  TOCVP_LAUNCHED();
+  TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32, pb.frames, seq_stride, n - 1, n, w->residual, out, size_t(SD), 0, SD, B));
+  count_launch();
   return TOCVP_OK;
 }

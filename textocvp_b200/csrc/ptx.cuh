@@ -13,6 +13,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------- mbarrier
+// Programmatic dependent launch (host side: launch_pdl in host_util.h).  pdl_wait(): block until every grid this one
+// depends on has completed and its memory operations are visible (no-op for a normally launched grid).
+// pdl_trigger(): the next grid of the stream may start becoming resident once every CTA of this grid has issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -639,6 +639,40 @@ static int launch_generic(const void* feats, int feats_f16, size_t seq_stride, i
   return TOCVP_OK;
 }
 
+// One streaming pass of the corrector over the features of one frame (g / sg / cb in gvec -> partial sums).
+static int sa_stream_pass(const SaWeights& w, const void* feats, int feats_f16, size_t feats_seq_stride, int B, int N,
+                          bool fast, int chunks, const float* gvec, float* partial, cudaStream_t stream) {
+  const int S = w.num_slots;
+  if (fast && feats_f16) {
+    // pipeline format: tcgen05 streaming kernel (slot_attention_tc.cu)
+    TOCVP_TRY(sa_stream_tc(static_cast<const __half*>(feats), feats_seq_stride, B, N, gvec, partial, w.ln_eps_sa,
+                           w.attn_eps, stream));
+  } else if (fast) {
+    // fp32 features (the reference dtype at the module boundary): all-fp32 SIMT kernel
+    const dim3 grid(SA_CHUNKS, B);
+    sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec,
+                                                      partial, w.ln_eps_sa, w.attn_eps);
+    TOCVP_LAUNCHED();
+  } else {
+    int r = TOCVP_ERR_BAD_ARG;
+    switch (S) {
+#define SA_GENERIC_CASE(SS)                                                                                        \
+  case SS:                                                                                                         \
+  r = launch_generic<SS>(feats, feats_f16, feats_seq_stride, B, N, chunks, gvec, partial, w.ln_eps_sa, w.attn_eps, \
+                         stream);                                                                                \
+  break;
+      SA_GENERIC_CASE(4) SA_GENERIC_CASE(5) SA_GENERIC_CASE(6) SA_GENERIC_CASE(7) SA_GENERIC_CASE(8)
+      SA_GENERIC_CASE(9) SA_GENERIC_CASE(10) SA_GENERIC_CASE(11)
+#undef SA_GENERIC_CASE
+      default:
+        set_last_error(__FILE__, __LINE__, "slot_attention: num_slots must be in 4..11");
+        return TOCVP_ERR_BAD_ARG;
+    }
+    TOCVP_TRY(r);
+  }
+  return TOCVP_OK;
+}
+
 // feats [B,N,128] (fp32 or f16), slots_in [B,S,128] fp32 -> slots_out (row b at slots_out + b*out_stride), and,
 // if pred_out != null, pred_out = transition(slots_out) [B,S,128].
 int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t feats_seq_stride, int B, int N, const float* slots_in, int iters,
@@ -665,33 +699,7 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
   TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_A, slots_in, nullptr, nullptr, 0, nullptr, gvec, stream));
   const float* cur = slots_in;
   for (int it = 0; it < iters; ++it) {
-    if (fast && feats_f16) {
-      // pipeline format: tcgen05 streaming kernel (slot_attention_tc.cu)
-      TOCVP_TRY(sa_stream_tc(static_cast<const __half*>(feats), feats_seq_stride, B, N, gvec, partial, w.ln_eps_sa,
-                             w.attn_eps, stream));
-    } else if (fast) {
-      // fp32 features (the reference dtype at the module boundary): all-fp32 SIMT kernel
-      const dim3 grid(SA_CHUNKS, B);
-      sa_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), feats_seq_stride, N, gvec,
-                                                        partial, w.ln_eps_sa, w.attn_eps);
-      TOCVP_LAUNCHED();
-    } else {
-      int r = TOCVP_ERR_BAD_ARG;
-      switch (S) {
-#define SA_GENERIC_CASE(SS)                                                                                        \
-  case SS:                                                                                                         \
-    r = launch_generic<SS>(feats, feats_f16, feats_seq_stride, B, N, chunks, gvec, partial, w.ln_eps_sa, w.attn_eps, \
-                           stream);                                                                                \
-    break;
-        SA_GENERIC_CASE(4) SA_GENERIC_CASE(5) SA_GENERIC_CASE(6) SA_GENERIC_CASE(7) SA_GENERIC_CASE(8)
-        SA_GENERIC_CASE(9) SA_GENERIC_CASE(10) SA_GENERIC_CASE(11)
-#undef SA_GENERIC_CASE
-        default:
-          set_last_error(__FILE__, __LINE__, "slot_attention: num_slots must be in 4..11");
-          return TOCVP_ERR_BAD_ARG;
-      }
-      TOCVP_TRY(r);
-    }
+    TOCVP_TRY(sa_stream_pass(w, feats, feats_f16, feats_seq_stride, B, N, fast, chunks, gvec, partial, stream));
     const bool last = (it == iters - 1);
     if (!last) {
       TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_C | UP_DO_A, cur, partial, tmp_slots, S * SA_D, nullptr, gvec, stream));
@@ -700,6 +708,61 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
       TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_C | (pred_out ? UP_DO_T : 0), cur, partial, slots_out, out_stride,
                               pred_out, gvec, stream));
     }
+  }
+  return TOCVP_OK;
+}
+
+size_t slot_attention_seq_workspace_bytes(int B) {
+  return slot_attention_workspace_bytes(B) + size_t(B) * SA_MAX_S * SA_D * sizeof(float);
+}
+
+// The corrector chain of SAVi.forward_decomp (SAVi.py:178-204) over n_frames consecutive frames in ONE call:
+//   for t: slots_t = SlotAttention(feats_t, cur, iters_t) -> slot_history[:, t];  cur = transition(slots_t)
+// The update launch that finishes frame t also applies the transition and emits the query vectors of frame t+1's
+// streaming pass (UP_DO_C | UP_DO_T | UP_DO_A), so a frame costs two kernels (one streaming pass + one per-slot update)
+// instead of three, and the host enqueues the whole chain without returning to Python.
+int slot_attention_seq(const SaWeights& w, const void* feats, int feats_f16, size_t feats_seq_stride,
+                       size_t feats_frame_stride, int B, int N, int n_frames, int iters_first, int iters,
+                       const float* slots_in, float* slot_history, size_t hist_seq_stride, size_t hist_frame_stride,
+                       float* carry_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const int S = w.num_slots;
+  TOCVP_CHECK_ARG(feats && slots_in && slot_history && carry_out && workspace && B > 0 && N >= 1 && n_frames >= 1);
+  TOCVP_CHECK_ARG(iters_first >= 1 && iters >= 1 && S >= 1 && S <= SA_MAX_S);
+  TOCVP_CHECK_ARG(feats_seq_stride >= size_t(N) * SA_D && feats_seq_stride % 8 == 0 && feats_frame_stride % 8 == 0);
+  TOCVP_CHECK_ARG(w.mlp_hidden <= 512 && w.t_hidden <= 512 && w.mlp_hidden % 256 == 0);
+  TOCVP_CHECK_ARG(w.t_heads > 0 && SA_D % w.t_heads == 0 && w.t_hidden % 256 == 0);   // the chain needs the transition
+  TOCVP_CHECK_ARG(hist_seq_stride <= size_t(INT32_MAX));
+  if (ws_bytes < slot_attention_seq_workspace_bytes(B)) {
+    set_last_error(__FILE__, __LINE__, "slot_attention_seq: workspace too small");
+    return TOCVP_ERR_WORKSPACE;
+  }
+  const bool fast = (S == SA_S) && (N % (SA_CHUNKS * 128) == 0);
+  const int chunks = fast ? SA_CHUNKS : (N >= 1024 ? 4 : (N >= 256 ? 2 : 1));
+  const int part = S * SA_D + 2 * S;
+  float* gvec = static_cast<float*>(workspace);
+  float* partial = gvec + size_t(B) * part;
+  float* tmp_slots = partial + size_t(B) * chunks * part;
+  float* pp = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + slot_attention_workspace_bytes(B));
+  const size_t esz = feats_f16 ? 2 : 4;
+  TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_A, slots_in, nullptr, nullptr, 0, nullptr, gvec, stream));
+  const float* cur = slots_in;
+  for (int t = 0; t < n_frames; ++t) {
+    const void* ft = static_cast<const uint8_t*>(feats) + size_t(t) * feats_frame_stride * esz;
+    float* out_t = slot_history + size_t(t) * hist_frame_stride;
+    float* nxt = ((n_frames - 1 - t) & 1) ? pp : carry_out;      // the last frame's transition output lands in carry_out
+    const int its = (t == 0) ? iters_first : iters;
+    const float* c = cur;
+    for (int it = 0; it < its; ++it) {
+      TOCVP_TRY(sa_stream_pass(w, ft, feats_f16, feats_seq_stride, B, N, fast, chunks, gvec, partial, stream));
+      if (it < its - 1) {
+        TOCVP_TRY(launch_update(w, S, chunks, B, UP_DO_C | UP_DO_A, c, partial, tmp_slots, S * SA_D, nullptr, gvec, stream));
+        c = tmp_slots;
+      } else {
+        const int flags = UP_DO_C | UP_DO_T | ((t + 1 < n_frames) ? UP_DO_A : 0);
+        TOCVP_TRY(launch_update(w, S, chunks, B, flags, c, partial, out_t, int(hist_seq_stride), nxt, gvec, stream));
+      }
+    }
+    cur = nxt;
   }
   return TOCVP_OK;
 }
@@ -724,6 +787,22 @@ extern "C" int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats
   }
   return tocvp::slot_attention(*w, feats, feats_f16, feats_seq_stride, B, N, slots_in, iters, slots_out, out_stride, pred_out, workspace,
                                ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t tocvp_slot_attention_seq_workspace_bytes(int B) { return tocvp::slot_attention_seq_workspace_bytes(B); }
+
+extern "C" int tocvp_slot_attention_seq(const tocvp_sa_weights* w, const void* feats, int feats_f16,
+                                        size_t feats_seq_stride, size_t feats_frame_stride, int B, int N, int n_frames,
+                                        int iters_first, int iters, const float* slots_in, float* slot_history,
+                                        size_t hist_seq_stride, size_t hist_frame_stride, float* carry_out,
+                                        void* workspace, size_t ws_bytes, void* stream) {
+  if (w == nullptr) {
+    tocvp::set_last_error(__FILE__, __LINE__, "null weights");
+    return TOCVP_ERR_BAD_ARG;
+  }
+  return tocvp::slot_attention_seq(*w, feats, feats_f16, feats_seq_stride, feats_frame_stride, B, N, n_frames,
+                                   iters_first, iters, slots_in, slot_history, hist_seq_stride, hist_frame_stride,
+                                   carry_out, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t tocvp_sizeof_sa_weights(void) { return sizeof(tocvp_sa_weights); }

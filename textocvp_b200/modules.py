@@ -449,6 +449,21 @@ class SlotAttention(_Packed):
                c_size_t(feats_seq_stride), c_int(B), c_int(N), ptr(slots), c_int(iters), ptr(slots_out),
                c_int(out_stride), ptr(pred_out), ws, wsb, stream())
 
+    def run_seq(self, feats, feats_seq_stride, feats_frame_stride, B, N, n_frames, first_step, slots, slot_history,
+                hist_seq_stride, hist_frame_stride, carry_out):
+        """Raw call: the corrector + transition chain of forward_decomp (SAVi.py:178-204) over ``n_frames`` consecutive
+        frames in one library call (two kernels per frame).  ``slot_history`` points at the first frame's [S,D] block of
+        sequence 0; ``carry_out`` [B,S,D] receives transition(slots of the last frame)."""
+        self._ensure_packed()
+        lib = L.load()
+        lib.tocvp_slot_attention_seq_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_slot_attention_seq_workspace_bytes(c_int(B)), slots.device)
+        it_first = self.num_iters_first if first_step == 0 else self.num_iters
+        L.call("tocvp_slot_attention_seq", ctypes.byref(self._w), ptr(feats), c_int(int(feats.dtype == torch.float16)),
+               c_size_t(feats_seq_stride), c_size_t(feats_frame_stride), c_int(B), c_int(N), c_int(n_frames),
+               c_int(it_first), c_int(self.num_iters), ptr(slots), ptr(slot_history), c_size_t(hist_seq_stride),
+               c_size_t(hist_frame_stride), ptr(carry_out), ws, wsb, stream())
+
     @torch.no_grad()
     def forward(self, inputs, slots, step=0, **kwargs):
         B, N, _ = inputs.shape
@@ -507,6 +522,7 @@ class SAVi(_Packed):
         self._init_model()
         self._ws_enc, self._ws_dec = _Workspace(), _Workspace()
         self.max_encode_images = 8192     # images encoded per library call (bounds the activation workspace)
+        self.chain_corrector = True       # False: one library call per frame (first version, kept for A/B and tests)
 
     @torch.no_grad()
     def _init_model(self):
@@ -636,6 +652,17 @@ class SAVi(_Packed):
             nt = t1 - t0
             xs = x[:, t0:t1].contiguous()                                        # [B,nt,3,H,W]
             feats, _ = self._encode_raw(xs, B * nt, xs[0, 0].numel(), want_f32=False)   # image index b*nt + (t-t0)
+            if has_t and self.chain_corrector:
+                # whole chunk in one library call: two kernels per frame, no return to Python between frames
+                FD = N * self.mlp_encoder_dim
+                self.slot_attention.run_seq(feats, nt * FD, FD, B, N, nt, t0, cur, slot_history[:, t0], num_imgs * S * D,
+                                            S * D, nxt)
+                cur, nxt = nxt, cur
+                if decode:
+                    for t in range(t0, t1):
+                        o = self.decode(slot_history[:, t].contiguous())
+                        recs.append(o["recons_imgs"]); objs.append(o["recons"]); msks.append(o["masks"])
+                continue
             for t in range(t0, t1):
                 ft = feats[(t - t0):]                                            # sequence stride nt*N*F
                 iters = self.slot_attention.num_iters_first if t == 0 else self.slot_attention.num_iters
@@ -842,6 +869,7 @@ class ExtendedDINOSAUR(_Packed):
         if isinstance(self.transition_module, TransformerBlock):
             object.__setattr__(self.slot_attention, "_transition", self.transition_module)
         self._init_model()
+        self.chain_corrector = True
         self._ws = _Workspace()
 
     @torch.no_grad()
@@ -914,7 +942,13 @@ class ExtendedDINOSAUR(_Packed):
         has_t = isinstance(self.transition_module, TransformerBlock)
         nxt = torch.empty_like(cur) if has_t else None
         outs = []
-        for t in range(num_imgs):
+        chain = has_t and self.chain_corrector
+        if chain:
+            self.slot_attention.run_seq(proj, num_imgs * N * D, N * D, B, N, num_imgs, 0, cur, slot_history,
+                                        num_imgs * S * D, S * D, nxt)
+            if decode:
+                outs = [self.decode(slot_history[:, t].contiguous()) for t in range(num_imgs)]
+        for t in range(0 if not chain else num_imgs, num_imgs):
             iters = self.slot_attention.num_iters_first if t == 0 else self.slot_attention.num_iters
             out_t = slot_history[:, t]
             self.slot_attention.run(proj[:, t:], num_imgs * N * D, B, N, cur, iters, out_t, num_imgs * S * D, nxt)
