@@ -50,9 +50,9 @@ mse_psnr_kernel(MetricArgs a, float* __restrict__ mse, float* __restrict__ psnr)
   }
 }
 
-// SSIM with an 11-tap separable Gaussian window, valid convolution.  grid = (tiles_x * tiles_y, C, n_img); a CTA owns a
-// 32 x 32 tile of the (H-10) x (W-10) output map: loads the 42 x 42 inputs, filters x, y, x^2, y^2, xy horizontally
-// into shared memory, then vertically per output pixel, and adds its share of the mean to ssim[img].
+// SSIM with an 11-tap separable Gaussian window, valid convolution.  grid = n_img; a CTA walks the (channel, 32 x 32 tile)
+// items of its image's (H-10) x (W-10) output map: loads the 42 x 42 inputs, filters x, y, x^2, y^2, xy horizontally
+// into shared memory, then vertically per output pixel, and accumulates the mean in a fixed order.
 constexpr int SS_T = 32, SS_K = 11, SS_IN = SS_T + SS_K - 1;
 
 __global__ void __launch_bounds__(256)
@@ -62,9 +62,8 @@ ssim_kernel(MetricArgs a, float sigma, float c1, float c2, float* __restrict__ s
   __shared__ float sg[SS_K];
   __shared__ float s_red[8];
   const int Ho = a.H - SS_K + 1, Wo = a.W - SS_K + 1;
-  const int tiles_x = (Wo + SS_T - 1) / SS_T;
-  const int ty0 = (blockIdx.x / tiles_x) * SS_T, tx0 = (blockIdx.x % tiles_x) * SS_T;
-  const int ch = blockIdx.y, img = blockIdx.z;
+  const int tiles_x = (Wo + SS_T - 1) / SS_T, tiles_y = (Ho + SS_T - 1) / SS_T;
+  const int img = blockIdx.x;
   if (threadIdx.x < SS_K) {
     float g[SS_K], s = 0.f;
     for (int k = 0; k < SS_K; ++k) {
@@ -74,51 +73,59 @@ ssim_kernel(MetricArgs a, float sigma, float c1, float c2, float* __restrict__ s
     }
     sg[threadIdx.x] = g[threadIdx.x] / s;
   }
-  const float* p = a.pred + (size_t(img) * a.C + ch) * a.H * a.W;
-  const float* t = target_img(a, img) + size_t(ch) * a.H * a.W;
-  for (int e = threadIdx.x; e < SS_IN * SS_IN; e += 256) {
-    const int r = e / SS_IN, c = e % SS_IN;
-    const int y = ty0 + r, x = tx0 + c;
-    const bool ok = y < a.H && x < a.W;
-    sx[r][c] = ok ? clamp01(__ldg(p + size_t(y) * a.W + x), a.clamp) : 0.f;
-    sy[r][c] = ok ? clamp01(__ldg(t + size_t(y) * a.W + x), a.clamp) : 0.f;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < SS_IN * SS_T; e += 256) {
-    const int r = e / SS_T, c = e % SS_T;
-    float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
-#pragma unroll
-    for (int k = 0; k < SS_K; ++k) {
-      const float g = sg[k], vx = sx[r][c + k], vy = sy[r][c + k];
-      mx += g * vx; my += g * vy; xx += g * vx * vx; yy += g * vy * vy; xy += g * vx * vy;
+  // One CTA per image walks its (channel, tile) work items in a fixed order and thread 0 carries the running sum: the
+  // result does not depend on scheduling (no atomics), so a frame's SSIM is bit-identical wherever it sits in a batch.
+  float total = 0.f;
+  for (int work = 0; work < a.C * tiles_y * tiles_x; ++work) {
+    const int ch = work / (tiles_y * tiles_x), tile = work % (tiles_y * tiles_x);
+    const int ty0 = (tile / tiles_x) * SS_T, tx0 = (tile % tiles_x) * SS_T;
+    const float* p = a.pred + (size_t(img) * a.C + ch) * a.H * a.W;
+    const float* t = target_img(a, img) + size_t(ch) * a.H * a.W;
+    for (int e = threadIdx.x; e < SS_IN * SS_IN; e += 256) {
+      const int r = e / SS_IN, c = e % SS_IN;
+      const int y = ty0 + r, x = tx0 + c;
+      const bool ok = y < a.H && x < a.W;
+      sx[r][c] = ok ? clamp01(__ldg(p + size_t(y) * a.W + x), a.clamp) : 0.f;
+      sy[r][c] = ok ? clamp01(__ldg(t + size_t(y) * a.W + x), a.clamp) : 0.f;
     }
-    sh[0][r][c] = mx; sh[1][r][c] = my; sh[2][r][c] = xx; sh[3][r][c] = yy; sh[4][r][c] = xy;
-  }
-  __syncthreads();
-  float acc = 0.f;
-  for (int e = threadIdx.x; e < SS_T * SS_T; e += 256) {
-    const int r = e / SS_T, c = e % SS_T;
-    if (ty0 + r < Ho && tx0 + c < Wo) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < SS_IN * SS_T; e += 256) {
+      const int r = e / SS_T, c = e % SS_T;
       float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
 #pragma unroll
       for (int k = 0; k < SS_K; ++k) {
-        const float g = sg[k];
-        mx += g * sh[0][r + k][c]; my += g * sh[1][r + k][c]; xx += g * sh[2][r + k][c];
-        yy += g * sh[3][r + k][c]; xy += g * sh[4][r + k][c];
+        const float g = sg[k], vx = sx[r][c + k], vy = sy[r][c + k];
+        mx += g * vx; my += g * vy; xx += g * vx * vx; yy += g * vy * vy; xy += g * vx * vy;
       }
-      const float mxx = mx * mx, myy = my * my, mxy = mx * my;
-      const float cs = (2.f * (xy - mxy) + c2) / ((xx - mxx) + (yy - myy) + c2);
-      acc += (2.f * mxy + c1) / (mxx + myy + c1) * cs;
+      sh[0][r][c] = mx; sh[1][r][c] = my; sh[2][r][c] = xx; sh[3][r][c] = yy; sh[4][r][c] = xy;
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < SS_T * SS_T; e += 256) {
+      const int r = e / SS_T, c = e % SS_T;
+      if (ty0 + r < Ho && tx0 + c < Wo) {
+        float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS_K; ++k) {
+          const float g = sg[k];
+          mx += g * sh[0][r + k][c]; my += g * sh[1][r + k][c]; xx += g * sh[2][r + k][c];
+          yy += g * sh[3][r + k][c]; xy += g * sh[4][r + k][c];
+        }
+        const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+        const float cs = (2.f * (xy - mxy) + c2) / ((xx - mxx) + (yy - myy) + c2);
+        acc += (2.f * mxy + c1) / (mxx + myy + c1) * cs;
+      }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();                    // also: everyone is done with sx / sy / sh before the next item overwrites them
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += s_red[w];
+      total += s;
     }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += s_red[w];
-    atomicAdd(ssim + img, s / (float(a.C) * float(Ho) * float(Wo)));
-  }
+  if (threadIdx.x == 0) ssim[img] = total / (float(a.C) * float(Ho) * float(Wo));
 }
 
 }  // namespace tocvp
@@ -138,11 +145,8 @@ extern "C" int tocvp_frame_metrics(const float* pred, const float* target, size_
     TOCVP_LAUNCHED();
   }
   if (ssim) {
-    TOCVP_CHECK_ARG(H >= SS_K && W >= SS_K && C <= 65535 && n_img <= 65535);
-    TOCVP_CUDA(cudaMemsetAsync(ssim, 0, size_t(n_img) * sizeof(float), st));
-    const int Ho = H - SS_K + 1, Wo = W - SS_K + 1;
-    const dim3 grid(((Ho + SS_T - 1) / SS_T) * ((Wo + SS_T - 1) / SS_T), C, n_img);
-    ssim_kernel<<<grid, 256, 0, st>>>(a, 1.5f, 0.01f * 0.01f, 0.03f * 0.03f, ssim);
+    TOCVP_CHECK_ARG(H >= SS_K && W >= SS_K);
+    ssim_kernel<<<n_img, 256, 0, st>>>(a, 1.5f, 0.01f * 0.01f, 0.03f * 0.03f, ssim);
     TOCVP_LAUNCHED();
   }
   return TOCVP_OK;
