@@ -56,8 +56,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* __restrict__ k,
            const __half* __restrict__ v, int ldkv, int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out,
            int ldo) {
-  __shared__ __align__(16) __half sK[NT * 8 * ATT_KS];
-  __shared__ __align__(16) __half sV[NT * 8 * ATT_KS];
+  extern __shared__ __align__(16) __half att_smem[];
+  __half* sK = att_smem;                       // [NT * 8][ATT_KS]
+  __half* sV = sK + NT * 8 * ATT_KS;           // [NT * 8][ATT_KS]
+  __half* sQ = sV + NT * 8 * ATT_KS;           // [WARPS * 16][ATT_KS]: per-warp query / output tiles
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -68,20 +70,19 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
   pdl_wait();
   pdl_trigger();
-  uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
+  // The warp's 16 query rows go through a warp-private shared tile: 16-byte coalesced global loads (8 lanes per 128-byte
+  // row) + ldmatrix, instead of 4-byte fragment loads that touch 8 half-used sectors per instruction; the same tile is
+  // reused to write the output rows back in full 16-byte pieces (the LSU wavefront count was the busiest unit, ncu r1).
+  __half* sQw = sQ + warp * 16 * ATT_KS;
+  uint4 qv[4];
   auto load_q = [&](int m0) {
-    const int r0 = m0 + g, r1 = m0 + g + 8;
-    const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int c = ks * 16 + 2 * t;
-      qa[ks][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c)) : 0u;
-      qa[ks][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c)) : 0u;
-      qa[ks][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r0) * ldq + c + 8)) : 0u;
-      qa[ks][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t*>(qb + size_t(r1) * ldq + c + 8)) : 0u;
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 3) + 4 * i, c = lane & 7;
+      qv[i] = (m0 + r < Tq) ? __ldg(reinterpret_cast<const uint4*>(qb + size_t(m0 + r) * ldq + c * 8)) : make_uint4(0, 0, 0, 0);
     }
   };
-  // the first query tile's fragments are requested together with K / V: one global-latency phase per CTA instead of two
+  // the first query tile is requested together with K / V: one global-latency phase per CTA instead of two
   if (warp * 16 < Tq) load_q(warp * 16);
   for (int e = threadIdx.x; e < TkP * 8; e += blockDim.x) {
     const int r = e >> 3, c = e & 7;
@@ -96,9 +97,16 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   __syncthreads();
   const int n_tiles = TkP / 8;    // key tiles of 8
   for (int m0 = warp * 16; m0 < Tq; m0 += (blockDim.x >> 5) * 16) {
-    const int r0 = m0 + g, r1 = m0 + g + 8;
-    const bool ok0 = r0 < Tq, ok1 = r1 < Tq;
     if (m0 != warp * 16) load_q(m0);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(sQw + ((lane >> 3) + 4 * i) * ATT_KS + (lane & 7) * 8) = qv[i];
+    __syncwarp();
+    uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldmatrix_x4(qa[ks], sQw + ((lane & 7) + ((lane >> 3) & 1) * 8) * ATT_KS + ks * 16 + (lane >> 4) * 8);
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -171,11 +179,19 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
       }
     }
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    __syncwarp();                                   // every lane has consumed its Q fragments
 #pragma unroll
     for (int nd = 0; nd < ATT_DH / 8; ++nd) {
       const int c = nd * 8 + 2 * t;
-      if (ok0) *reinterpret_cast<__half2*>(ob + size_t(r0) * ldo + c) = __floats2half2_rn(o[nd][0] * inv0, o[nd][1] * inv0);
-      if (ok1) *reinterpret_cast<__half2*>(ob + size_t(r1) * ldo + c) = __floats2half2_rn(o[nd][2] * inv1, o[nd][3] * inv1);
+      *reinterpret_cast<__half2*>(sQw + g * ATT_KS + c) = __floats2half2_rn(o[nd][0] * inv0, o[nd][1] * inv0);
+      *reinterpret_cast<__half2*>(sQw + (g + 8) * ATT_KS + c) = __floats2half2_rn(o[nd][2] * inv1, o[nd][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 3) + 4 * i, c = lane & 7;
+      if (m0 + r < Tq)
+        *reinterpret_cast<uint4*>(ob + size_t(m0 + r) * ldo + c * 8) = *reinterpret_cast<const uint4*>(sQw + r * ATT_KS + c * 8);
     }
   }
 }
@@ -195,14 +211,22 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
                 int heads, __half* out, int ldo, cudaStream_t stream) {
   TOCVP_CHECK_ARG(q_seq_rows >= Tq);
   TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && Tk > 0 && Tk <= ATT_MAXK && heads > 0);
-  TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0);
+  TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0);
   const float scale_log2e = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (attention.py:187) * log2(e)
   int warps = (Tq + 15) / 16;
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
   const int nt = ((Tk + 15) & ~15) / 8;
 #define MHA_LAUNCH(NTV, W, MB)                                                                                        \
-  TOCVP_CUDA(launch_pdl(mha_kernel<NTV, W, MB>, dim3(B * heads), dim3(warps * 32), 0, stream, q, ldq, q_seq_rows, k, v, \
-                        ldkv, Tq, Tk, heads, scale_log2e, out, ldo))
+  do {                                                                                                                \
+    constexpr int smem_bytes = (2 * NTV * 8 + W * 16) * ATT_KS * 2;                                                   \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set && smem_bytes > 48 * 1024) {                                                                        \
+      TOCVP_CUDA(cudaFuncSetAttribute(mha_kernel<NTV, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    TOCVP_CUDA(launch_pdl(mha_kernel<NTV, W, MB>, dim3(B * heads), dim3(warps * 32), smem_bytes, stream, q, ldq,      \
+                          q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo));                             \
+  } while (0)
   if (nt <= 4) {
     if (warps <= 5) MHA_LAUNCH(4, 5, 5); else MHA_LAUNCH(4, 8, 3);
   } else if (nt <= 10) {

@@ -74,7 +74,7 @@ int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static std::atomic<int> g_pdl{0};   // measured r1 (tools/ab_pdl.py): no gain under graph replay -> opt-in
+static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 

@@ -12,5 +12,7 @@ dino, dpred, _ = rollout.build_dino_models(dev, num_preds=2)
 dpred.predictor.use_cuda_graph = False
 feats, dtext, _ = weights.synthetic_dino_inputs(2, 3, 81, L=16, seed=0)
 o2 = rollout.forward_eval_dino(dino, dpred, feats.to(dev), dtext.to(dev), 1, 2)
+# multi-chunk decode: the chunk-pipelined driver (side stream, three activation buffers) with a ragged tail
+d2 = savi.decode(torch.randn(256 + 8, 8, 128, device=dev), only_imgs=True)
 torch.cuda.synchronize()
 print("ok", float(out["psnr"].mean()), tuple(o2["pred_imgs"].shape))
