@@ -152,7 +152,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   const int S = w.num_slots, D = w.slot_dim, T = w.token_dim;
   const int M = B * n * S;
   const size_t seq_stride = size_t(ftot) * S * D;
-  TOCVP_CUDA(launch_pdl(window_to_f16_kernel, dim3(ew_grid(size_t(M) * D / 4)), dim3(256), 0, st, pb.frames, seq_stride, f0, n, S * D, B, pb.tok16));
+  TOCVP_CUDA(launch_pdl(window_to_f16_kernel, dim3(ew_grid(size_t(M) * D / 4)), dim3(256), 0, st, pb.frames, seq_stride,
+                        f0, n, S * D, B, pb.tok16));
   count_launch();
   // tokens = mlp_in(slots) + flip(pe[:n])   (text_cond_OCVP.py:86-91, model_blocks.py:375-377): the pre-flipped
   // table for window length n is added in the GEMM epilogue, row -> frame index (row / S) % n.
@@ -244,7 +245,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
       // output: behind the K/V projection only the S newest rows of every sequence are computed (exact, not an
       // approximation) -- queries, out-proj, cross-attention and both MLPs on B*S rows instead of B*n*S.
       const int Mc = B * S;
-      TOCVP_CUDA(launch_pdl(last_frame_f32_kernel, dim3(ew_grid(size_t(Mc) * T / 4)), dim3(256), 0, st, pb.x32, n, S, T, B, pb.xl32));
+      TOCVP_CUDA(launch_pdl(last_frame_f32_kernel, dim3(ew_grid(size_t(Mc) * T / 4)), dim3(256), 0, st, pb.x32, n, S, T,
+                            B, pb.xl32));
       count_launch();
       TOCVP_TRY(mha_f16_sub(pb.qkv16 + size_t(n - 1) * S * 3 * T, 3 * T, n * S, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, S,
                             n * S, w.num_heads, pb.att16, T, st));
@@ -257,7 +259,8 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
     }
   }
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
-  TOCVP_CUDA(launch_pdl(last_frame_to_f16_kernel, dim3(ew_grid(size_t(B) * S * T / 4)), dim3(256), 0, st, pb.x32, n_out, S, T, B, pb.last16));
+  TOCVP_CUDA(launch_pdl(last_frame_to_f16_kernel, dim3(ew_grid(size_t(B) * S * T / 4)), dim3(256), 0, st, pb.x32, n_out,
+                        S, T, B, pb.last16));
   count_launch();
   TOCVP_TRY(gemm_f16(pb.last16, T, static_cast<const __half*>(w.mlp_out_w), T, B * S, D, T, w.mlp_out_b, 0, nullptr, 0,
                      1, 0, pb.pred32, D, nullptr, 0, st));
@@ -316,7 +319,8 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
   const int S = w->num_slots, D = w->slot_dim, SD = S * D;
   const int ftot = num_context + num_preds;
   const size_t seq_stride = size_t(ftot) * SD;
-  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * num_context * SD)), dim3(256), 0, st, slot_history, hist_seq_stride, pb.frames, seq_stride, num_context, SD, B));
+  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * num_context * SD)), dim3(256), 0, st,
+                        slot_history, hist_seq_stride, pb.frames, seq_stride, num_context, SD, B));
   count_launch();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   for (int t = 0; t < num_preds; ++t) {
@@ -324,7 +328,9 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
     const int n = have < w->buffer_size ? have : w->buffer_size;        // predictor_wrapper.py:143-153
     const int f0 = have - n;
     TOCVP_TRY(predictor_step(*w, pb, B, L, f0, n, ftot, st));
-    TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32, pb.frames, seq_stride, have - 1, have, w->residual, pred_slots, size_t(num_preds) * SD, t, SD, B));
+    TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32,
+                          pb.frames, seq_stride, have - 1, have, w->residual, pred_slots, size_t(num_preds) * SD, t, SD,
+                          B));
     count_launch();
   }
   return TOCVP_OK;
@@ -346,11 +352,13 @@ extern "C" int tocvp_predictor_forward(const tocvp_pred_weights* w, const float*
   carve(*w, B, L, n, 1, &pb, static_cast<uint8_t*>(workspace));
   const int SD = w->num_slots * w->slot_dim;
   const size_t seq_stride = size_t(n + 1) * SD;
-  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * n * SD)), dim3(256), 0, st, slots, size_t(n) * SD, pb.frames, seq_stride, n, SD, B));
+  TOCVP_CUDA(launch_pdl(copy_context_kernel, dim3(ew_grid(size_t(B) * n * SD)), dim3(256), 0, st, slots, size_t(n) * SD,
+                        pb.frames, seq_stride, n, SD, B));
   count_launch();
   TOCVP_TRY(hoist_text_kv(*w, pb, text, B, L, st));
   TOCVP_TRY(predictor_step(*w, pb, B, L, 0, n, n + 1, st));
-  TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32, pb.frames, seq_stride, n - 1, n, w->residual, out, size_t(SD), 0, SD, B));
+  TOCVP_CUDA(launch_pdl(commit_prediction_kernel, dim3(ew_grid(size_t(B) * SD)), dim3(256), 0, st, pb.pred32, pb.frames,
+                        seq_stride, n - 1, n, w->residual, out, size_t(SD), 0, SD, B));
   count_launch();
   return TOCVP_OK;
 }
