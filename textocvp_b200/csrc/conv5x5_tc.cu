@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
   using C = ConvCfg<CIN, COUT, G, KS>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;                       // 2 halo buffers
   uint8_t* sW = smem + 2 * C::A_STRIDE;     // weight ring
   uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_BYTES);
@@ -270,7 +270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a, ConvGen gen) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sW = smem + 2 * C::A_STRIDE;
   uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_HALF);   // leader: bytes of both halves

@@ -45,7 +45,7 @@ enc_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY, int M,
                const float* __restrict__ b1, const float* __restrict__ b2) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EM_OFF_BAR);
   uint64_t* a1_full = bars;                 // [4]
   uint64_t* a1_empty = a1_full + EM_STAGES; // [4]

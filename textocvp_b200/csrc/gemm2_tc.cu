@@ -92,7 +92,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ Gemm2Args g) {
   using S = G2Smem<BN, EWN, WRES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem_align1024(smem_raw);
   uint8_t* w_base = stage_base + S::OFF_W;                                            // WRES: resident W half, [kb][BN/2 x 64]
   uint8_t* stg_base = stage_base + S::OFF_STG;                                        // 1024B aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + S::OFF_BAR);              // used in the leader only

@@ -5,48 +5,53 @@
 // k-step; with only N = 16 output columns that operand read (not the tensor pipe, not HBM) sets the pace: 0.52 ms per
 // 2048 slot-images where the 1 GiB input takes 0.17 ms to stream (r1 ncu).  Here the UNSHIFTED halo tile is multiplied
 // by all nine taps at once,
-//     D[r][tap*4 + co] = sum_c X[r][c] * W[co][c][tap]        r = halo pixel (row-major 18 x 40), N = 36 (padded to 48),
-// 24 MMAs per tile instead of 144, and the shift moves to the epilogue: D goes TMEM -> registers -> shared memory and
-//     out[y][x][co] = b[co] + sum_tap D[(y+ty)*40 + (x+tx)][tap*4 + co]
+//     D[r][tap*4 + co] = sum_c X[r][c] * W[co][c][tap]        r = halo pixel (row-major 10 x 34), N = 36 (padded to 48),
+// 12 MMAs per 8 x 32 tile instead of 72, and the shift moves to the epilogue: D goes TMEM -> registers -> shared memory and
+//     out[y][x][co] = b[co] + sum_tap D[(y+ty)*34 + (x+tx)][tap*4 + co]
 // is gathered from there (36 shared loads per pixel, bank-conflict free with an odd row stride).
-// One halo buffer: the TMA load of tile i+1 is issued as soon as tile i's MMAs have completed and overlaps its epilogue.
+// Two halo buffers and two accumulator sets: load of tile i+1, MMAs of tile i and epilogue of tile i-1 overlap.
 //   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-5: epilogue
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace tocvp {
 
-constexpr int HD_TH = 16, HD_TW = 32;            // output tile
-constexpr int HD_HR = HD_TH + 2, HD_WB = 40;     // halo rows, halo row pitch (pixels, multiple of 8 >= HD_TW + 2)
-constexpr int HD_ROWS = HD_HR * HD_WB;           // 720 halo pixels
-constexpr int HD_MT = (HD_ROWS + 127) / 128;     // 6 M-tiles
+constexpr int HD_TH = 8, HD_TW = 32;             // output tile
+constexpr int HD_HR = HD_TH + 2, HD_WB = HD_TW + 2;   // halo rows, halo row pitch (pixels)
+constexpr int HD_ROWS = HD_HR * HD_WB;           // 340 halo pixels
+constexpr int HD_MT = (HD_ROWS + 127) / 128;     // 3 M-tiles (the last one reads 44 rows past the tile: never used)
 constexpr int HD_N = 48;                         // 9 taps x 4 channels = 36, padded to a multiple of 16
-constexpr int HD_A_BYTES = HD_ROWS * 128;        // 92160 (multiple of 1024)
+constexpr int HD_A_BYTES = HD_ROWS * 128;        // 43520 bytes landed by the TMA
+constexpr int HD_A_STRIDE = HD_MT * 128 * 128;   // 49152: buffer pitch, covers the over-read, 1024-aligned
 constexpr int HD_W_BYTES = HD_N * 128;           // 6144
 constexpr int HD_DS = 37;                        // D staging row stride (floats), odd -> conflict free
 constexpr int HD_D_BYTES = HD_MT * 128 * HD_DS * 4;
-constexpr int HD_SMEM = HD_A_BYTES + HD_W_BYTES + HD_D_BYTES + 256 + 1024;
-constexpr int HD_TMEM_COLS = 512;                // 6 x 48 = 288 columns used
+constexpr int HD_SMEM = 2 * HD_A_STRIDE + HD_W_BYTES + HD_D_BYTES + 256 + 1024;
+constexpr int HD_TMEM_COLS = 512;                // 2 x 3 x 48 = 288 columns used (two accumulator sets)
 
 __device__ __forceinline__ uint64_t hd_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, dense 128-byte rows
   return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
 
+// Pipeline (r1, second version): TWO halo buffers and TWO accumulator sets, so the TMA load of tile i+1, the MMAs of
+// tile i and the shift-and-add epilogue of tile i-1 all overlap and the kernel runs at the rate its input streams in.
+// (First version: one 18 x 40 halo buffer of a 16 x 32 tile; load and MMAs of consecutive tiles serialised, 303 us per
+// 2048 slot-images.)  The 8 x 32 tile with a 34-pixel pitch re-reads 1.33x its pixels (L2 hits) instead of 1.41x.
 __global__ void __launch_bounds__(192, 1)
 head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int n_img, int H, int W,
                const float* __restrict__ bias, float* __restrict__ out4) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + HD_A_BYTES;
+  uint8_t* sW = smem + 2 * HD_A_STRIDE;
   float* sD = reinterpret_cast<float*>(sW + HD_W_BYTES);
   uint64_t* w_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sD) + HD_D_BYTES);
-  uint64_t* a_full = w_full + 1;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* t_full = a_empty + 1;
-  uint64_t* t_empty = t_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+  uint64_t* a_full = w_full + 1;     // [2]
+  uint64_t* a_empty = a_full + 2;    // [2]
+  uint64_t* t_full = a_empty + 2;    // [2]
+  uint64_t* t_empty = t_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = W / HD_TW, tiles_y = H / HD_TH;
@@ -57,10 +62,12 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     mbar_init(w_full, 1);
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    mbar_init(t_full, 1);
-    mbar_init(t_empty, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], 1);
+      mbar_init(&a_empty[b], 1);
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, HD_TMEM_COLS);
@@ -73,14 +80,15 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       mbar_expect_tx(w_full, HD_W_BYTES);
       tma_load_2d(&tmW, w_full, sW, 0, 0);
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
         const int img = t / tiles_per_img, r = t % tiles_per_img;
         const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
-        mbar_wait(a_empty, ph ^ 1);                          // the MMAs that read the halo buffer have completed
-        mbar_expect_tx(a_full, HD_A_BYTES);
-        tma_load_4d(&tmX, a_full, sA, 0, x0 - 1, y0 - 1, img);   // out-of-image rows / columns are zero-filled
-        ph ^= 1;
+        mbar_wait(&a_empty[buf], ph ^ 1);                    // the MMAs that read this halo buffer have completed
+        mbar_expect_tx(&a_full[buf], HD_A_BYTES);
+        tma_load_4d(&tmX, &a_full[buf], sA + buf * HD_A_STRIDE, 0, x0 - 1, y0 - 1, img);   // out-of-image: zero-filled
       }
     }
   } else if (warp == 1) {
@@ -89,38 +97,42 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t leader = elect_one_sync();
     mbar_wait(w_full, 0);
     const uint64_t db = hd_desc(smem_u32(sW));
-    uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(t_empty, ph ^ 1);                            // the epilogue has copied the previous accumulators out
-      mbar_wait(a_full, ph);
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&t_empty[buf], ph ^ 1);                      // the epilogue has copied this accumulator set out
+      mbar_wait(&a_full[buf], ph);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(sA);
+      const uint32_t a_base = smem_u32(sA + buf * HD_A_STRIDE);
+      const uint32_t d_base = tmem_u + uint32_t(buf * HD_MT * HD_N);
 #pragma unroll
       for (int mt = 0; mt < HD_MT; ++mt) {
         const uint64_t da = hd_desc(a_base + uint32_t(mt * 128 * 128));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_u + uint32_t(mt * HD_N), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, k != 0, leader);
+          umma_f16(d_base + uint32_t(mt * HD_N), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, k != 0, leader);
       }
-      umma_commit(a_empty, leader);
-      umma_commit(t_full, leader);
-      ph ^= 1;
+      umma_commit(&a_empty[buf], leader);
+      umma_commit(&t_full[buf], leader);
     }
   } else {
     const int q = warp & 3;
     const int et = threadIdx.x - 64;                         // 0..127
     const float4 b4 = *reinterpret_cast<const float4*>(bias);
-    uint32_t ph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
       const int img = t / tiles_per_img, r = t % tiles_per_img;
       const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
-      mbar_wait(t_full, ph);
+      mbar_wait(&t_full[buf], ph);
       tc_fence_after();
       // ---- phase 1: accumulators -> shared memory, D[halo pixel][tap*4 + co]
 #pragma unroll 1
       for (int mt = 0; mt < HD_MT; ++mt) {
         uint32_t v[32], v4[4];
-        const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mt * HD_N);
+        const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * HD_MT * HD_N + mt * HD_N);
         tmem_ld32(ta, v);
         tmem_ld4(ta + 32, v4);
         tmem_ld_wait();
@@ -132,7 +144,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty);                   // TMEM is free for the next tile's MMAs
+      if (lane == 0) mbar_arrive(&t_empty[buf]);             // this accumulator set is free for the MMAs of tile it+2
       asm volatile("bar.sync 1, 128;" ::: "memory");         // D complete
       // ---- phase 2: shift-and-add over the 9 taps; thread -> column x, rows y = (et >> 5) + 4 i
       const int px = et & 31;
@@ -148,7 +160,6 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         *reinterpret_cast<float4*>(out4 + ((size_t(img) * H + (y0 + py)) * W + (x0 + px)) * 4) = make_float4(a0, a1, a2, a3);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");         // everyone is done reading D
-      ph ^= 1;
     }
   }
 

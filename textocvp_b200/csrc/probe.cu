@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128, 1)
 probe_shift_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, float* out,
                    int shift, int base_offset_mode) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sX = smem;               // 256 rows x 128 B
   uint8_t* sW = smem + 256 * 128;   // 64 rows x 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(sW + 64 * 128);

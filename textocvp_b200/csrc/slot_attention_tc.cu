@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
 sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ gvec, float* __restrict__ partial,
                     int tiles_per_chunk, float ln_eps, float attn_eps) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sG = smem + ST_OFF_G;
   uint8_t* sW = smem + ST_OFF_W;
   uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + ST_OFF_BAR);
