@@ -214,13 +214,15 @@ typedef struct tocvp_enc_weights {
   const float* b_mlp2;
   int H, W, in_channels, hidden, feat_dim;
   const void* w_conv1_tc;    /* f16 [25,32,32] tap-major, input channels zero-padded 3 -> 32: conv 1 on the tensor cores */
+  const void* w_conv1_vp;    /* f16 [3,32,32]: conv 1 with the 5 x-taps x 3 channels of two filter rows folded into K = 32
+                                (k = half*16 + kx*3 + c), three vertical taps two rows apart; null = use w_conv1_tc */
 } tocvp_enc_weights;
 
 size_t tocvp_sizeof_enc_weights(void);
 /* Tuning / test knob (process-wide), bit mask: bit 0 = first-version fp32 SIMT conv 1 (default: tensor-core conv with
  * zero-padded input channels), bit 1 = separate posemb + LayerNorm pass (default: fused into conv 4's epilogue),
  * bit 2 = the 32 -> 128 -> 128 MLP as two GEMMs (default: one kernel with two chained tcgen05 GEMMs when only f16
- * features are requested). */
+ * features are requested), bit 3 = conv 1 as 25 taps over zero-padded channels (default: x-taps folded into K, 3 taps). */
 int tocvp_set_encode_mode(int mode);
 size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img);
 /* frames fp32: image i = 3 planes of H x W at frames + i*img_stride (floats), so x[:, t] of a [B,T,3,H,W] video is

@@ -87,3 +87,24 @@ def test_layernorm_fold():
     assert float((out - ref).norm() / ref.norm()) < 1e-3        # only the f16 rounding of w*gamma separates them
     exact = rstd * (x @ (w * gamma).t() - mu * (w * gamma).sum(1)) + d
     assert torch.allclose(exact, ref, atol=1e-4)
+
+
+def test_conv1_vertical_pair_packing():
+    """Encoder conv 1 with the x-taps folded into K: sum over 3 vertical taps of Wp[j] . P[y + 2j - 2] on the x-im2col input
+    (modules.im2col_x_row_pairs = what enc_pack_vp_kernel writes) equals the 5x5 convolution with zero padding."""
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(32, 3, 5, 5, generator=g)
+    b = torch.randn(32, generator=g)
+    x = torch.rand(2, 3, 16, 32, generator=g)
+    ref = F.conv2d(x, w, b, padding=2)                                          # [n, 32, H, W]
+    wp = M.pack_conv1_vertical_pairs(w)                                          # [3, 32, 32]
+    P = M.im2col_x_row_pairs(x)                                                  # [n, H+1, W, 32], stored row r = image row r-1
+    assert wp.shape == (3, 32, 32) and P.shape == (2, 17, 32, 32)
+    assert (wp[:, :, 15] == 0).all() and (wp[:, :, 31] == 0).all() and (wp[2, :, 16:] == 0).all()
+    H = x.shape[2]
+    Pz = F.pad(P, (0, 0, 0, 0, 2, 2))                                            # stored rows -2 .. H+2 (TMA zero fill)
+    out = b.view(1, 1, 1, -1).expand(2, H, 32, 32).clone()
+    for j in range(3):
+        rows = Pz[:, 2 * j + 1:2 * j + 1 + H]                                    # stored row (y + 2j - 2) + 1, offset by the pad 2
+        out = out + torch.einsum("nyxk,ok->nyxo", rows, wp[j])
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-4, rtol=1e-4)

@@ -24,7 +24,7 @@ def models(golden_weights):
     return savi.cuda().eval(), pred.cuda().eval()
 
 
-@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4, 8])
 def test_encode(models, golden, golden_weights, enc_mode):
     """tocvp_set_encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
     into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass."""

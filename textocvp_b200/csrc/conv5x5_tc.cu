@@ -265,10 +265,14 @@ struct ConvGen {
 };
 __device__ __forceinline__ int border_pat(int v, int n) { return v < 2 ? v : (v >= n - 2 ? v - (n - 5) : 2); }
 
-template <int CIN, int COUT, int G, int KS, bool GEN>
+// VP ("vertical pairs", encoder conv 1): the input rows already hold an x-im2col of TWO image rows (encoder.cu,
+// enc_pack_vp_kernel), so the filter collapses to (KS+1)/2 vertical taps two rows apart, all at the centre column; the
+// packed tensor has one extra row on top (stored row r = image row r-1).
+template <int CIN, int COUT, int G, int KS, bool GEN, bool VP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a, ConvGen gen) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
+  constexpr int NTAPS = VP ? (KS + 1) / 2 : C::TAPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
@@ -321,8 +325,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int y0 = (r / tiles_x) * C::TILE_H, x0 = (r % tiles_x) * C::TILE_W;
         mbar_wait(&a_empty[buf], ph ^ 1);
         if (rank == 0) mbar_expect_tx(&a_full[buf], 2 * C::A_BYTES);
-        tma_load_4d_pair(&tmX, mapa_rank(smem_u32(&a_full[buf]), 0), sA + buf * C::A_STRIDE, 0, x0 - KS / 2, y0 - KS / 2,
-                         img);
+        tma_load_4d_pair(&tmX, mapa_rank(smem_u32(&a_full[buf]), 0), sA + buf * C::A_STRIDE, 0, x0 - KS / 2,
+                         y0 - KS / 2 + (VP ? 1 : 0), img);
       };
       int s = 0;
       uint32_t wph = 0;
@@ -330,7 +334,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (!GEN && pair < num_ptiles) load_halo(pair, 0);
       for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
         if (!GEN && pt + npairs < num_ptiles) load_halo(pt + npairs, it + 1);
-        for (int tap = 0; tap < C::TAPS; ++tap) {
+        for (int tap = 0; tap < NTAPS; ++tap) {
           mbar_wait(&w_empty[s], wph ^ 1);
           if (rank == 0) mbar_expect_tx(&w_full[s], 2 * C::W_HALF);
           tma_load_2d_pair(&tmW, mapa_rank(smem_u32(&w_full[s]), 0), sW + s * C::W_HALF, 0,
@@ -359,8 +363,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t a_base = smem_u32(sA + buf * C::A_STRIDE);
         const uint32_t d_base = tmem_u + uint32_t(buf * C::ACC_COLS);
 #pragma unroll 1
-        for (int tap = 0; tap < C::TAPS; ++tap) {
-          const int ty = tap / KS, tx = tap % KS;
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const int ty = VP ? 2 * tap : tap / KS, tx = VP ? KS / 2 : tap % KS;
           mbar_wait(&w_full[s], wph);
           tc_fence_after();
           const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_HALF), 8 * C::KB, C::LAYOUT);
@@ -545,7 +549,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-template <int CIN, int COUT, int G, int KS, bool GEN = false>
+template <int CIN, int COUT, int G, int KS, bool GEN = false, bool VP = false>
 static int launch_conv2(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
                         int relu, cudaStream_t stream, ConvGen gen = ConvGen{nullptr, nullptr},
                         const float* ln_posemb = nullptr, const float* ln_g = nullptr, const float* ln_b = nullptr,
@@ -554,20 +558,21 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
   static bool attr_set = false;
   if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM));
     attr_set = true;
   }
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmX, tmW;
   {
-    const uint64_t dims[4] = {uint64_t(CIN), uint64_t(W), uint64_t(H), uint64_t(n_img)};
-    const uint64_t str[3] = {uint64_t(CIN) * 2, uint64_t(W) * CIN * 2, uint64_t(H) * W * CIN * 2};
+    const uint64_t Hin = uint64_t(H) + (VP ? 1 : 0);    // VP: one extra packed row on top of every image
+    const uint64_t dims[4] = {uint64_t(CIN), uint64_t(W), Hin, uint64_t(n_img)};
+    const uint64_t str[3] = {uint64_t(CIN) * 2, uint64_t(W) * CIN * 2, Hin * W * CIN * 2};
     const uint32_t box[4] = {uint32_t(CIN), uint32_t(C::WBUF), uint32_t(C::HROWS), 1};
     TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, sw));
   }
   {
-    const uint64_t dims[2] = {uint64_t(CIN), uint64_t(C::TAPS * COUT)};
+    const uint64_t dims[2] = {uint64_t(CIN), uint64_t((VP ? (KS + 1) / 2 : C::TAPS) * COUT)};
     const uint64_t str[1] = {uint64_t(CIN) * 2};
     const uint32_t box[2] = {uint32_t(CIN), uint32_t(COUT / 2)};
     TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
@@ -576,7 +581,7 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
   const int pairs = num_sms() / 2;
   const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
   ConvArgs a{n_img, H, W, bias, out, nullptr, relu, ln_posemb, ln_g, ln_b, ln_eps};
-  conv_tc2_kernel<CIN, COUT, G, KS, GEN><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
+  conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -641,6 +646,14 @@ int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, co
   TOCVP_CHECK_ARG(H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0));
   return launch_conv2<32, 32, 4, 5>(x, wpacked, bias, out, n_img, H, W, 1, stream, ConvGen{nullptr, nullptr}, posemb, ln_g,
                                     ln_b, ln_eps);
+}
+
+// Encoder conv 1 on the x-im2col packed input (encoder.cu): xp f16 [n_img, H+1, W, 32], wpacked f16 [3, 32, 32].
+int conv5x5_vp_f16(const __half* xp, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
+                   cudaStream_t stream) {
+  TOCVP_CHECK_ARG(xp && wpacked && bias && out && n_img > 0);
+  TOCVP_CHECK_ARG(H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0));
+  return launch_conv2<32, 32, 4, 5, false, true>(xp, wpacked, bias, out, n_img, H, W, 1, stream);
 }
 
 // Decoder layer 2 with layer 1 generated in the kernel (see ConvGen): P fp32 [H*W,64], S fp32 [n_img,25,64].

@@ -20,11 +20,13 @@ int layernorm(const void* x, int x_is_f16, int ldx, const float* add, int add_ro
 
 int enc_mlp_f16(const __half* x, const __half* w1, const float* b1, const __half* w2, const float* b2, __half* y, int M,
                 cudaStream_t stream);
+int conv5x5_vp_f16(const __half* xp, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
+                   cudaStream_t stream);
 int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
                    const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
 
 // tocvp_set_encode_mode: bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version),
-// bit 2 = the MLP as two separate GEMMs (first version)
+// bit 2 = the MLP as two separate GEMMs (first version), bit 3 = conv 1 over zero-padded channels (25 taps, second version)
 static int g_enc_mode = 0;
 
 // Frame -> tensor-core input of conv 1: NCHW fp32 [n,3,H,W] -> NHWC f16 [n,H,W,32] with channels 3..31 zero, so that conv 1
@@ -40,6 +42,44 @@ enc_pack_input_kernel(const float* __restrict__ x, size_t img_stride, __half* __
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   uint4* o = reinterpret_cast<uint4*>(out + idx * 32);
   o[0] = p0; o[1] = z; o[2] = z; o[3] = z;
+}
+
+// Frame -> x-im2col input of conv 1 (third version): NCHW fp32 [n,3,H,W] -> f16 [n, H+1, W, 32].  Stored row r stands for
+// image row y' = r-1; a pixel's 32 values are the 5 x 3 x-neighbourhood of image row y' (k = kx*3 + c, k = 15 zero) and of
+// image row y'+1 (k = 16 + kx*3 + c, k = 31 zero), zeros outside the image.  Conv 1 then needs 3 vertical taps of K = 32
+// (6 MMAs per 128 pixels) instead of 25 taps over zero-padded channels (50): the 5 x 3 useful inputs of a filter row fill
+// half a k-block instead of 3 of its 32 lanes.  modules.im2col_x_row_pairs is the torch statement of this layout.
+__global__ void __launch_bounds__(256)
+enc_pack_vp_kernel(const float* __restrict__ x, size_t img_stride, __half* __restrict__ out, int H, int W, int n_img) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t per_img = size_t(H + 1) * W;
+  if (idx >= size_t(n_img) * per_img) return;
+  const int img = int(idx / per_img);
+  const int rem = int(idx % per_img);
+  const int r = rem / W, px = rem % W;
+  const float* xi = x + size_t(img) * img_stride;
+  const size_t plane = size_t(H) * W;
+  uint32_t w[16];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int y = r - 1 + half;
+    float v[16];
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const int xx = px + kx - 2;
+      const bool ok = y >= 0 && y < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[kx * 3 + c] = ok ? __ldg(xi + c * plane + size_t(y) * W + xx) : 0.f;
+    }
+    v[15] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[half * 8 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + idx * 32);
+  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+  o[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
 constexpr int E1_TH = 8, E1_TW = 32, E1_CO = 32;
@@ -106,8 +146,9 @@ static size_t enc_carve(const tocvp_enc_weights& w, int n, EncBuffers* eb, uint8
     return p;
   };
   EncBuffers t;
+  const size_t px1 = size_t(n) * (w.H + 1) * w.W;     // conv 1's packed input carries one extra row per image
   t.actA = reinterpret_cast<__half*>(take(px * w.hidden * 2));
-  t.actB = reinterpret_cast<__half*>(take(px * w.hidden * 2));
+  t.actB = reinterpret_cast<__half*>(take(px1 * w.hidden * 2));
   t.h16 = t.actA;   // LN output reuses actA (conv 4 lands in actB)
   t.mid16 = reinterpret_cast<__half*>(take(px * w.feat_dim * 2));
   if (eb) *eb = t;
@@ -121,7 +162,7 @@ using namespace tocvp;
 extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
 
 extern "C" int tocvp_set_encode_mode(int mode) {
-  tocvp::g_enc_mode = mode & 7;
+  tocvp::g_enc_mode = mode & 15;
   return TOCVP_OK;
 }
 
@@ -150,6 +191,11 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
     const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
     enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
     TOCVP_LAUNCHED();
+  } else if (!(g_enc_mode & 8) && w->w_conv1_vp != nullptr && ((n_img * (H / 16) * (W / 32)) % 2 == 0)) {
+    const size_t npx = size_t(n_img) * (H + 1) * W;
+    enc_pack_vp_kernel<<<int((npx + 255) / 256), 256, 0, st>>>(frames, img_stride, eb.actB, H, W, n_img);
+    TOCVP_LAUNCHED();
+    TOCVP_TRY(conv5x5_vp_f16(eb.actB, static_cast<const __half*>(w->w_conv1_vp), w->b_conv1, eb.actA, n_img, H, W, st));
   } else {
     const size_t npx = size_t(n_img) * H * W;
     enc_pack_input_kernel<<<int((npx + 255) / 256), 256, 0, st>>>(frames, img_stride, eb.actB, H * W, n_img);

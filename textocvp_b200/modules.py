@@ -26,6 +26,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib as L
 from ._lib import c_int, c_size_t, ptr, stream
@@ -64,7 +65,7 @@ EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
     ("w_conv1", _f), ("b_conv1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("posemb", _f),
     ("ln_g", _f), ("ln_b", _f), ("w_mlp1", _f), ("b_mlp1", _f), ("w_mlp2", _f), ("b_mlp2", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("in_channels", ctypes.c_int), ("hidden", ctypes.c_int),
-    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f)]})
+    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f), ("w_conv1_vp", _f)]})
 
 DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
@@ -216,6 +217,36 @@ def fold_layernorm(w, ln_w, ln_b, bias=None):
 # =====================================================================================================
 # building blocks (parameter containers with the reference's names)
 # =====================================================================================================
+def pack_conv1_vertical_pairs(w):
+    """Encoder conv 1 (3 -> 32, 5x5) for the x-im2col input of `im2col_x_row_pairs`: weight [32, 3, 5, 5] ->
+    [3 vertical taps, 32 out, 32 k] with k = half*16 + kx*3 + c (k = 15, 31 zero); tap j holds filter rows 2j (lower half)
+    and 2j+1 (upper half, zero for the non-existent row 5).  conv1(x)[y] = sum_j Wp[j] . P[y + 2j - 2]."""
+    co, ci, kh, kw = w.shape
+    assert (ci, kh, kw) == (3, 5, 5)
+    wp = torch.zeros(3, co, 32, dtype=torch.float32, device=w.device)
+    wf = w.detach().float()
+    for j in range(3):
+        for half in range(2):
+            ky = 2 * j + half
+            if ky < kh:
+                wp[j, :, half * 16:half * 16 + 15] = wf[:, :, ky, :].permute(0, 2, 1).reshape(co, 15)   # [co, kx, c]
+    return wp
+
+
+def im2col_x_row_pairs(x):
+    """Reference (torch) statement of what enc_pack_vp_kernel writes: frames [n, 3, H, W] -> [n, H+1, W, 32] where stored row
+    r stands for image row y' = r - 1 and holds, per pixel, the 5 x 3 x-neighbourhood of image row y' (k = kx*3 + c) and of
+    image row y'+1 (k = 16 + kx*3 + c), zeros outside the image."""
+    n, c, H, W = x.shape
+    xp = F.pad(x.float(), (2, 2, 1, 1))                                            # cols -2..W+1, rows -1..H
+    out = torch.zeros(n, H + 1, W, 32, dtype=torch.float32, device=x.device)
+    for half in range(2):
+        rows = xp[:, :, half:half + H + 1]                                          # image rows y' + half, y' = -1..H-1
+        for kx in range(5):
+            out[..., half * 16 + kx * 3:half * 16 + kx * 3 + 3] = rows[:, :, :, kx:kx + W].permute(0, 2, 3, 1)
+    return out
+
+
 def build_grid(resolution):
     """model_utils.py:12-34 -> [1,4,H,W] fp32 (y, x, 1-y, 1-x)."""
     ranges = [np.linspace(-1.0, 1.0, num=r) for r in resolution]
@@ -548,6 +579,7 @@ class SAVi(_Packed):
         w1p = torch.zeros(25, 32, 32, device=dev)                                # conv 1 for the tensor cores: cin 3 -> 32
         w1p[:, :, :3] = enc[0].weight.detach().float().permute(2, 3, 0, 1).reshape(25, 32, 3)
         k["w_conv1_tc"] = _f16(w1p)
+        k["w_conv1_vp"] = _f16(pack_conv1_vertical_pairs(enc[0].weight))           # conv 1 with the x-taps folded into K
         for i in range(3):
             k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
             k[f"bc{i}"] = _f32(enc[i + 1].bias)
@@ -563,6 +595,7 @@ class SAVi(_Packed):
             setattr(ew, n, k[n].data_ptr())
         ew.H, ew.W, ew.in_channels, ew.hidden, ew.feat_dim = H, W, self.in_channels, 32, self.mlp_encoder_dim
         ew.w_conv1_tc = k["w_conv1_tc"].data_ptr()
+        ew.w_conv1_vp = k["w_conv1_vp"].data_ptr()
         self._enc_keep, self._enc_w = k, ew
 
         # ---- decoder

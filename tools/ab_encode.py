@@ -15,7 +15,7 @@ def t(n=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 for rep in range(2):
-    for mode in (0, 4, 3, 7):
+    for mode in (0, 8, 4, 0, 8):
         L.call("tocvp_set_encode_mode", L.c_int(mode))
         print(f"encode mode {mode}: {t():.2f} ms", flush=True)
 L.call("tocvp_set_encode_mode", L.c_int(0))
