@@ -34,6 +34,13 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_r
                : "r"(smem_u32(smem_row)));
 }
 
+// 16-byte asynchronous global -> shared copy; `valid` false writes 16 zero bytes (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -74,35 +81,33 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   // row) + ldmatrix, instead of 4-byte fragment loads that touch 8 half-used sectors per instruction; the same tile is
   // reused to write the output rows back in full 16-byte pieces (the LSU wavefront count was the busiest unit, ncu r1).
   __half* sQw = sQ + warp * 16 * ATT_KS;
-  uint4 qv[4];
+  // All of the CTA's inputs are requested up front with cp.async (16 bytes per request, zero-filled past the ends): no
+  // staging registers, every load in flight at once, one global-latency phase per CTA.
   auto load_q = [&](int m0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = (lane >> 3) + 4 * i, c = lane & 7;
-      qv[i] = (m0 + r < Tq) ? __ldg(reinterpret_cast<const uint4*>(qb + size_t(m0 + r) * ldq + c * 8)) : make_uint4(0, 0, 0, 0);
+      const bool ok = m0 + r < Tq;
+      cp_async16(sQw + r * ATT_KS + c * 8, ok ? qb + size_t(m0 + r) * ldq + c * 8 : qb, ok);
     }
   };
-  // the first query tile is requested together with K / V: one global-latency phase per CTA instead of two
   if (warp * 16 < Tq) load_q(warp * 16);
   for (int e = threadIdx.x; e < TkP * 8; e += blockDim.x) {
     const int r = e >> 3, c = e & 7;
-    uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (r < Tk) {
-      kk = __ldg(reinterpret_cast<const uint4*>(kb + size_t(r) * ldkv + c * 8));
-      vv = __ldg(reinterpret_cast<const uint4*>(vb + size_t(r) * ldkv + c * 8));
-    }
-    *reinterpret_cast<uint4*>(sK + r * ATT_KS + c * 8) = kk;
-    *reinterpret_cast<uint4*>(sV + r * ATT_KS + c * 8) = vv;    // padded keys are zero rows (their P is exactly 0)
+    const bool ok = r < Tk;                                      // padded keys are zero rows (their P is exactly 0)
+    cp_async16(sK + r * ATT_KS + c * 8, ok ? kb + size_t(r) * ldkv + c * 8 : kb, ok);
+    cp_async16(sV + r * ATT_KS + c * 8, ok ? vb + size_t(r) * ldkv + c * 8 : vb, ok);
   }
+  cp_async_wait_all();
   __syncthreads();
   const int n_tiles = TkP / 8;    // key tiles of 8
   for (int m0 = warp * 16; m0 < Tq; m0 += (blockDim.x >> 5) * 16) {
-    if (m0 != warp * 16) load_q(m0);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<uint4*>(sQw + ((lane >> 3) + 4 * i) * ATT_KS + (lane & 7) * 8) = qv[i];
-    __syncwarp();
+    if (m0 != warp * 16) {
+      __syncwarp();
+      load_q(m0);
+      cp_async_wait_all();
+      __syncwarp();
+    }
     uint32_t qa[4][4];   // A fragments for the 4 k-steps of the head dim
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
