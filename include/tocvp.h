@@ -394,6 +394,11 @@ int tocvp_set_decode_mode(int mode);
  * Results are bit-identical either way (tools/ab_pdl.py: predictor rollout 45.7 -> 45.1 ms under graph replay). */
 int tocvp_set_pdl(int on);
 
+/* Tuning / test knob (process-wide): 1 (default) = the predictor alternates the row-block traversal direction of
+ * consecutive GEMM / attention kernels, so a consumer starts with the rows its producer wrote last (still in L2) instead
+ * of re-streaming tensors larger than the L2 in the same order; 0 = every kernel walks ascending.  Bit-identical. */
+int tocvp_set_tile_order(int alternate);
+
 /* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
  * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
 int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,

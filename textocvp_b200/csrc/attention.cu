@@ -62,12 +62,13 @@ template <int NT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* __restrict__ k,
            const __half* __restrict__ v, int ldkv, int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out,
-           int ldo) {
+           int ldo, int rev) {
   extern __shared__ __align__(16) __half att_smem[];
   __half* sK = att_smem;                       // [NT * 8][ATT_KS]
   __half* sV = sK + NT * 8 * ATT_KS;           // [NT * 8][ATT_KS]
   __half* sQ = sV + NT * 8 * ATT_KS;           // [WARPS * 16][ATT_KS]: per-warp query / output tiles
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int bid = rev ? int(gridDim.x) - 1 - int(blockIdx.x) : int(blockIdx.x);   // rev: last sequences first (L2 reuse)
+  const int b = bid / heads, h = bid % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int TkP = (Tk + 15) & ~15;
@@ -221,6 +222,7 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
   int warps = (Tq + 15) / 16;
   warps = warps > ATT_MAX_WARPS ? ATT_MAX_WARPS : warps;
   const int nt = ((Tk + 15) & ~15) / 8;
+  const int rev = tile_order_reversed();
 #define MHA_LAUNCH(NTV, W, MB)                                                                                        \
   do {                                                                                                                \
     constexpr int smem_bytes = (2 * NTV * 8 + W * 16) * ATT_KS * 2;                                                   \
@@ -230,7 +232,7 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     TOCVP_CUDA(launch_pdl(mha_kernel<NTV, W, MB>, dim3(B * heads), dim3(warps * 32), smem_bytes, stream, q, ldq,      \
-                          q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo));                             \
+                          q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo, rev));                        \
   } while (0)
   if (nt <= 4) {
     if (warps <= 5) MHA_LAUNCH(4, 5, 5); else MHA_LAUNCH(4, 8, 3);

@@ -48,6 +48,7 @@ struct Gemm2Args {
   const float* ln_c;      // consumer: per-column c_n = sum_k W'[n,k] (bias then holds d_n)
   float ln_inv_k, ln_eps; // 1 / (LayerNorm width), eps
   float* stats_out;       // producer: writes its [sum, sumsq] of 64 output columns to slot n/64 of the row (no atomics)
+  int rev;                // 1: walk the row blocks from the last to the first (see g_tile_rev, host_util.h)
 };
 
 // WRES ("W resident", K <= 512, 256-wide tiles): a pair keeps ITS half of the W tile for the whole K extent in shared memory
@@ -116,16 +117,19 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // walks the row blocks slot, slot + ppn, ... (ppn = pairs per column block).
   const int ppn = WRES ? npairs / tiles_n : 1;
   auto tile_at = [&](int i, int& mb, int& nb) -> bool {
+    bool ok;
     if constexpr (WRES) {
       nb = pair / ppn;
       mb = pair % ppn + i * ppn;
-      return nb < tiles_n && mb < tiles_m;
+      ok = nb < tiles_n && mb < tiles_m;
     } else {
       const int t = pair + i * npairs;
       mb = t / tiles_n;
       nb = t % tiles_n;
-      return t < num_tiles;
+      ok = t < num_tiles;
     }
+    if (g.rev) mb = tiles_m - 1 - mb;      // same tiles, opposite order: most recently produced rows first
+    return ok;
   };
 
   if (threadIdx.x == 0) {
@@ -623,9 +627,10 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn / 2, G2_BK));
+  const int rev = tile_order_reversed();
   Gemm2Args g{M, N, K, bias, residual, ldr, res_div, res_mod, relu, out32, ld32, out16, ld16, ConvMap{},
               ln ? ln->stats : nullptr, ln ? ln->slots : 0, ln ? ln->c : nullptr, ln ? ln->inv_k : 0.f, ln ? ln->eps : 0.f,
-              ln ? ln->stats_out : nullptr};
+              ln ? ln->stats_out : nullptr, rev};
   if (bn == 256) {
     // W-resident variant: K <= 512 and a column-block-stationary schedule that needs no more rounds than round-robin
     const int pairs = num_sms() / 2;
@@ -646,7 +651,7 @@ int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, K, bn / 2, G2_BK));
-  Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm, nullptr, 0, nullptr, 0.f, 0.f, nullptr};
+  Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm, nullptr, 0, nullptr, 0.f, 0.f, nullptr, 0};
   if (bn == 256) return launch_gemm2<256, true, 8>(tmA, tmB, g, stream);
   return launch_gemm2<128, true, 8>(tmA, tmB, g, stream);
 }

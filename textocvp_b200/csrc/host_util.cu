@@ -78,6 +78,17 @@ static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 
+static thread_local int g_next_rev = 0;
+static std::atomic<int> g_tile_alt{1};
+void set_next_tile_order(int reversed) { g_next_rev = (reversed && g_tile_alt.load(std::memory_order_relaxed)) ? 1 : 0; }
+int tile_order_reversed() {
+  const int r = g_next_rev;
+  g_next_rev = 0;
+  return r;
+}
+bool tile_order_alternation() { return g_tile_alt.load(std::memory_order_relaxed) != 0; }
+void set_tile_alternation(int on) { g_tile_alt.store(on ? 1 : 0); }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -106,6 +117,11 @@ extern "C" int tocvp_init(int device) {
     return TOCVP_ERR_ARCH;
   }
   if (cudaSetDevice(device) != cudaSuccess) return TOCVP_ERR_CUDA;
+  return TOCVP_OK;
+}
+
+extern "C" int tocvp_set_tile_order(int alternate) {
+  tocvp::set_tile_alternation(alternate);
   return TOCVP_OK;
 }
 

@@ -61,6 +61,14 @@ int num_sms();
 // that execute pdl_wait() before their first access to memory another kernel produces or consumes.
 bool pdl_enabled();
 
+// Tile traversal order of the NEXT pair-GEMM / attention launch of this thread (consumed by the launch, then reset to
+// ascending).  A driver that chains producer -> consumer kernels over tensors larger than the L2 (predictor.cu) alternates
+// the direction, so that a consumer starts with the rows its producer wrote LAST -- still L2 resident -- instead of
+// streaming in the same order and missing on everything (LRU).  Results do not depend on the order.
+void set_next_tile_order(int reversed);
+int tile_order_reversed();          // reads and resets
+bool tile_order_alternation();      // tocvp_set_tile_order knob (default on)
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {

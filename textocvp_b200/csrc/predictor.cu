@@ -173,10 +173,12 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
   auto layer_tail = [&](const tocvp_pred_layer& ly, int l, int Mr, int tq, const float* xres, bool emit_next) -> int {
     const bool fold = gemm_ln_supported(Mr, T);
     if (fold) {
+      set_next_tile_order(1);   // out-proj: the attention wrote its last rows last
       TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.w_o), T, Mr, T, T, nullptr, 0, xres, T, pb.y32, T,
                             pb.h16, T, prod, st));
       // ---- z = y + CrossAttn(LN(text), LN(y))                      (attention.py:445-463)
       const GemmLn c{pb.stats, slots, ly.c_cq, inv_t, w.ln_eps, nullptr};
+      set_next_tile_order(0);
       TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_q_f), T, Mr, T, T, ly.d_cq, 0, nullptr, 0, nullptr,
                             0, pb.q16, T, c, st));
     } else {
@@ -187,20 +189,26 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
                          0, pb.q16, T, st));
     }
     const __half* kv = pb.kv16 + size_t(l) * B * L * 2 * T;
+    set_next_tile_order(1);
     TOCVP_TRY(mha_f16(pb.q16, T, kv, kv + T, 2 * T, B, tq, L, w.cross_heads, pb.att16, T, st));
     if (fold) {
+      set_next_tile_order(0);
       TOCVP_TRY(gemm_f16_ln(pb.att16, T, static_cast<const __half*>(ly.wc_o), T, Mr, T, T, ly.bc_o, 0, pb.y32, T, pb.z32, T,
                             pb.h16, T, prod, st));
       // ---- z = z + MLP_c(LN(z))
       const GemmLn c{pb.stats, slots, ly.c_c1, inv_t, w.ln_eps, nullptr};
+      set_next_tile_order(1);
       TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.wc_1_f), T, Mr, w.cross_hidden, T, ly.d_c1, 1, nullptr,
                             0, nullptr, 0, pb.mid16, w.cross_hidden, c, st));
+      set_next_tile_order(0);
       TOCVP_TRY(gemm_f16_ln(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, Mr, T,
                             w.cross_hidden, ly.bc_2, 0, pb.z32, T, pb.z32, T, pb.h16, T, prod, st));
       // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
       const GemmLn c2{pb.stats, slots, ly.c_1, inv_t, w.ln_eps, nullptr};
+      set_next_tile_order(1);
       TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_1_f), T, Mr, w.hidden_dim, T, ly.d_1, 1, nullptr, 0,
                             nullptr, 0, pb.mid16, w.hidden_dim, c2, st));
+      set_next_tile_order(0);
       if (!emit_next) {
         TOCVP_TRY(gemm_f16(pb.mid16, w.hidden_dim, static_cast<const __half*>(ly.w_2), w.hidden_dim, Mr, T, w.hidden_dim,
                            ly.b_2, 0, pb.y32, T, 1, 0, pb.x32, T, nullptr, 0, st));
@@ -225,6 +233,9 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
     return TOCVP_OK;
   };
 
+  // Tile order: consecutive kernels of a layer walk the rows in opposite directions (set_next_tile_order, host_util.h) --
+  // QKV down, attention up, out-proj down, cross-q up, cross-attention down, cross-out up, MLP_c up-proj down, down-proj up,
+  // MLP up-proj down, down-proj up -- so each starts with what its producer wrote last.
   const bool fold_all = gemm_ln_supported(M, T);
   int n_out = n;                            // frames held by x32 after the last layer (1 when it was pruned)
   for (int l = 0; l < w.num_layers; ++l) {
@@ -233,6 +244,7 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
     // ---- y = x + MHSA(LN(x))                                       (attention.py:512-514)
     if (fold_all && l > 0) {
       const GemmLn c{pb.stats, slots, ly.c_qkv, inv_t, w.ln_eps, nullptr};
+      set_next_tile_order(1);   // the previous layer's last GEMM walked ascending
       TOCVP_TRY(gemm_f16_ln(pb.h16, T, static_cast<const __half*>(ly.w_qkv_f), T, M, 3 * T, T, ly.d_qkv, 0, nullptr, 0,
                             nullptr, 0, pb.qkv16, 3 * T, c, st));
     } else {
@@ -253,11 +265,13 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
       TOCVP_TRY(layer_tail(ly, l, Mc, S, pb.xl32, false));
       n_out = 1;
     } else {
+      set_next_tile_order(0);
       TOCVP_TRY(mha_f16(pb.qkv16, 3 * T, pb.qkv16 + T, pb.qkv16 + 2 * T, 3 * T, B, n * S, n * S, w.num_heads, pb.att16, T,
                         st));
       TOCVP_TRY(layer_tail(ly, l, M, n * S, pb.x32, fold_all && !last_layer));
     }
   }
+  set_next_tile_order(0);
   // ---- mlp_out on the newest frame's tokens (text_cond_OCVP.py:103)
   TOCVP_CUDA(launch_pdl(last_frame_to_f16_kernel, dim3(ew_grid(size_t(B) * S * T / 4)), dim3(256), 0, st, pb.x32, n_out,
                         S, T, B, pb.last16));
