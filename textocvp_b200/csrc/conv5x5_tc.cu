@@ -250,7 +250,10 @@ template <int CIN, int COUT, int G, int KS, bool GEN = false>
 struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
   using Base = ConvCfg<CIN, COUT, G, KS>;
   static constexpr int W_HALF = (COUT / 2) * Base::KB;
-  static constexpr int WSTAGES = GEN ? 4 : ((W_HALF >= 4096) ? 6 : 12);
+  // 5 (not 6) stages at 64 channels: 230912 + 1024 static + 1024 reserved bytes per CTA left no room for the 1 KB a second,
+  // shared-memory-free CTA needs on the SM, so the decoder's layer-1 kernel (chunk pipeline, decoder.cu) could never be
+  // co-resident with this kernel (r1 timeline: the convolution waited ~250 us per chunk for layer-1 CTAs to exit).
+  static constexpr int WSTAGES = GEN ? 4 : ((W_HALF >= 4096) ? 5 : 12);
   static constexpr int GEN_BYTES = GEN ? 25 * CIN * 4 : 0;   // this tile's 5x5 border-pattern sums, fp32
   static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + 512 + 1024;
 };

@@ -117,38 +117,43 @@ __global__ void __launch_bounds__(256)
 dec_l1_pixel_kernel(const float* __restrict__ S, const float* __restrict__ P, __half* __restrict__ out, int n_img, int H,
                     int W) {
   constexpr int C = 64;
-  const int pix0 = blockIdx.x * 8;
   const int chunk = threadIdx.x & 7, il = threadIdx.x >> 3;         // 8-channel chunk, slot-image lane
-  const int y = pix0 / W, x0 = pix0 % W;
-  float p[8][8];
-  int pat[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8 + 4));
-    p[k][0] = a.x; p[k][1] = a.y; p[k][2] = a.z; p[k][3] = a.w;
-    p[k][4] = b.x; p[k][5] = b.y; p[k][6] = b.z; p[k][7] = b.w;
-    pat[k] = border_pattern(y, H) * 5 + border_pattern(x0 + k, W);
-  }
-  const size_t plane = size_t(H) * W;
-  for (int img = il; img < n_img; img += 32) {
-    const float* s = S + size_t(img) * 25 * C + chunk * 8;
-    __half* o = out + (size_t(img) * plane + pix0) * C + chunk * 8;
-    int cur = -1;
-    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  // Persistent over the 8-pixel groups (grid <= number of SMs): every CTA is resident from the first dispatch, so a
+  // kernel submitted on another stream right behind this one (the decoder's convolutions, chunk pipeline) is not held
+  // back by a queue of pending CTAs.
+  for (int pg = blockIdx.x; pg < (H * W) / 8; pg += gridDim.x) {
+    const int pix0 = pg * 8;
+    const int y = pix0 / W, x0 = pix0 % W;
+    float p[8][8];
+    int pat[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (pat[k] != cur) {                                           // at most 3 distinct patterns in 8 pixels of a row
-        cur = pat[k];
-        s0 = __ldg(reinterpret_cast<const float4*>(s + cur * C));
-        s1 = __ldg(reinterpret_cast<const float4*>(s + cur * C + 4));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(P + size_t(pix0 + k) * C + chunk * 8 + 4));
+      p[k][0] = a.x; p[k][1] = a.y; p[k][2] = a.z; p[k][3] = a.w;
+      p[k][4] = b.x; p[k][5] = b.y; p[k][6] = b.z; p[k][7] = b.w;
+      pat[k] = border_pattern(y, H) * 5 + border_pattern(x0 + k, W);
+    }
+    const size_t plane = size_t(H) * W;
+    for (int img = il; img < n_img; img += 32) {
+      const float* s = S + size_t(img) * 25 * C + chunk * 8;
+      __half* o = out + (size_t(img) * plane + pix0) * C + chunk * 8;
+      int cur = -1;
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (pat[k] != cur) {                                           // at most 3 distinct patterns in 8 pixels of a row
+          cur = pat[k];
+          s0 = __ldg(reinterpret_cast<const float4*>(s + cur * C));
+          s1 = __ldg(reinterpret_cast<const float4*>(s + cur * C + 4));
+        }
+        uint4 r;
+        r.x = pack_half2_relu(p[k][0] + s0.x, p[k][1] + s0.y);
+        r.y = pack_half2_relu(p[k][2] + s0.z, p[k][3] + s0.w);
+        r.z = pack_half2_relu(p[k][4] + s1.x, p[k][5] + s1.y);
+        r.w = pack_half2_relu(p[k][6] + s1.z, p[k][7] + s1.w);
+        *reinterpret_cast<uint4*>(o + size_t(k) * C) = r;
       }
-      uint4 r;
-      r.x = pack_half2_relu(p[k][0] + s0.x, p[k][1] + s0.y);
-      r.y = pack_half2_relu(p[k][2] + s0.z, p[k][3] + s0.w);
-      r.z = pack_half2_relu(p[k][4] + s1.x, p[k][5] + s1.y);
-      r.w = pack_half2_relu(p[k][6] + s1.z, p[k][7] + s1.w);
-      *reinterpret_cast<uint4*>(o + size_t(k) * C) = r;
     }
   }
 }
@@ -332,7 +337,9 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
     const int nsi = ((n_frames - f0) < DEC_CHUNK_FRAMES ? (n_frames - f0) : DEC_CHUNK_FRAMES) * S;
     const size_t so = size_t(f0) * S * 25 * C;
     if (pixel_l1) {
-      dec_l1_pixel_kernel<<<(H * W) / 8, 256, 0, s_l1>>>(db.pat32 + so, w->p1, xbuf[ci & 1], nsi, H, W);
+      const int groups = (H * W) / 8;
+      dec_l1_pixel_kernel<<<groups < num_sms() ? groups : num_sms(), 256, 0, s_l1>>>(db.pat32 + so, w->p1, xbuf[ci & 1], nsi,
+                                                                                    H, W);
       TOCVP_LAUNCHED();
     } else if (!fused_l1) {
       dec_l1_kernel<<<nsi, 256, 0, s_l1>>>(db.taps32 + so, w->p1, xbuf[ci & 1], H, W);
@@ -350,7 +357,11 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
     const int nsi = nf * S;
     if (overlap) {
       if (ci + 1 < n_chunks) {
-        // X[(ci+1)&1] was last read by layer 4 of chunk ci-1
+        // Layer 1 of chunk ci+1 starts when layer 4 of chunk ci-1 has finished (the last reader of its buffer X[(ci+1)&1]):
+        // it shares the HBM with the bandwidth-bound head conv + compositing of chunk ci-1 (neither is power-hungry) and
+        // whatever is left of it runs co-resident with the first convolution of chunk ci.  Starting it under the
+        // convolutions only (r1 A/B) gains on a box with power headroom but nothing on a power-capped one: the conv slows
+        // down by exactly the layer-1 time.
         if (ci >= 1) TOCVP_CUDA(cudaStreamWaitEvent(sd->stream, sd->conv_done[(ci - 1) & 1], 0));
         TOCVP_TRY(layer1(ci + 1, sd->stream));
         TOCVP_CUDA(cudaEventRecord(sd->l1_done[(ci + 1) & 1], sd->stream));
