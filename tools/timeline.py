@@ -1,4 +1,4 @@
-"""Kernel timeline (CUPTI via torch.profiler) of one decode call: start / duration / gap per kernel for two chunks, and the
+"""Kernel timeline (CUPTI via torch.profiler) of one call of a stage (decode | predict | decomp | eval): start / duration / gap per kernel for a window, the
 totals of busy time vs wall time.  Dev tool."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +12,12 @@ savi, pred, _ = rollout.build_models(dev)
 ps = torch.randn(B * 19, 8, 128, device=dev)
 sh = torch.randn(B, 20, 8, 128, device=dev)
 text = torch.randn(B, 32, 512, device=dev)
-fn = (lambda: savi.decode(ps, only_imgs=True)) if stage == "decode" else (lambda: pred(sh, text_embeddings=text))
+videos = torch.rand(B, 20, 3, 64, 64, device=dev)
+init = torch.randn(B, 8, 128, device=dev)
+fn = {"decode": lambda: savi.decode(ps, only_imgs=True),
+      "predict": lambda: pred(sh, text_embeddings=text),
+      "decomp": lambda: savi(mode="decomp", x=videos, num_imgs=20, decode=False, init_slots=init),
+      "eval": lambda: rollout.forward_eval(savi, pred, videos, text, 1, 19, init_slots=init)}[stage]
 for _ in range(3): fn()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -23,7 +28,8 @@ t0 = evs[0].time_range.start
 busy = sum(e.time_range.end - e.time_range.start for e in evs)
 wall = max(e.time_range.end for e in evs) - t0
 print(f"{stage}: {len(evs)} kernels, wall {wall/1e3:.2f} ms, sum of kernel durations {busy/1e3:.2f} ms")
-lo, hi = (len(evs) // 2, len(evs) // 2 + 16) if stage == "decode" else (len(evs) - 100, len(evs) - 70)
+lo, hi = {"decode": (len(evs) // 2, len(evs) // 2 + 16), "predict": (len(evs) - 100, len(evs) - 70),
+          "decomp": (0, 40), "eval": (0, 0)}[stage]
 prev_end = None
 for e in evs[lo:hi]:
     s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
@@ -36,3 +42,10 @@ for e in evs[1:]:
     if e.time_range.start > cur_end: idle += e.time_range.start - cur_end
     cur_end = max(cur_end, e.time_range.end)
 print(f"idle (no kernel resident) {idle/1e3:.3f} ms")
+# the largest idle gaps and what follows them
+gaps, cur_end = [], evs[0].time_range.end
+for e in evs[1:]:
+    if e.time_range.start > cur_end: gaps.append((e.time_range.start - cur_end, e.time_range.start - t0, e.name[:50]))
+    cur_end = max(cur_end, e.time_range.end)
+for g, at, name in sorted(gaps, reverse=True)[:8]:
+    print(f"  gap {g:8.1f} us at t={at/1e3:8.3f} ms before {name}")
