@@ -360,7 +360,9 @@ int tocvp_text_encode(const tocvp_text_weights* w, const long long* tokens, cons
 
 /* ------------------------------------------------------------------------------------------
  * Sibling predictors behind the same PredictorWrapper loop: VanillaTransformerPredictor (src/models/Predictors/OCVP.py:24-141)
- * and OCVPSeq (OCVP.py:145-319).  `blocks` are pre-norm nn.TransformerEncoderLayer parameter sets (same fields as
+ * OCVPSeq (OCVP.py:145-319) and OCVPPar (OCVP.py:324-548: object- and time-attention in PARALLEL on the same normed input,
+ * expressed as two blocks: [attention over the frame's slots, no feed-forward] + [attention along the slot's history on the
+ * SAME LayerNorm-1 output, then the layer's feed-forward]).  `blocks` are pre-norm nn.TransformerEncoderLayer parameter sets (same fields as
  * tocvp_text_layer); block_group[i] selects the keys a query attends to: 0 = all tokens of the window (Vanilla),
  * 1 = tokens of the same frame (OCVPSeqLayer.object_encoder_block), 2 = the same slot over time (time_encoder_block).
  * ------------------------------------------------------------------------------------------ */
@@ -371,6 +373,8 @@ typedef struct tocvp_ocvp_weights {
   const float* pe;                      /* sinusoidal table [max_len][token_dim] (model_blocks.py:261-266) */
   tocvp_text_layer blocks[TOCVP_OCVP_MAX_BLOCKS];
   int block_group[TOCVP_OCVP_MAX_BLOCKS];
+  int block_flags[TOCVP_OCVP_MAX_BLOCKS]; /* bit 0: no feed-forward half (first branch of an OCVP-Par layer); bit 1: reuse the
+                                             previous block's LayerNorm-1 output (second branch of an OCVP-Par layer) */
   int num_blocks, num_slots, slot_dim, token_dim, ffn_dim, num_heads, max_len, residual;
 } tocvp_ocvp_weights;
 

@@ -1,6 +1,7 @@
 """
-Golden vectors for the sibling predictors (VanillaTransformer, OCVPSeq) from the REAL reference modules
-(src/models/Predictors/OCVP.py through lib/setup_model.setup_predictor, imported read-only).
+Golden vectors for the sibling predictors (VanillaTransformer, OCVPSeq, OCVPPar) from the REAL reference modules
+(src/models/Predictors/OCVP.py through lib/setup_model.setup_predictor, imported read-only; OCVPPar has no factory entry
+in the reference and is instantiated directly with OCVPSeq.json's parameters inside the reference's PredictorWrapper).
 TEST INFRASTRUCTURE -- build container only:    python -m oracle.make_golden_ocvp
 """
 from __future__ import annotations
@@ -38,13 +39,24 @@ def main():
         slots = torch.randn(m["B"], m["n"], m["S"], 128, generator=g)
         hist = torch.randn(m["B"], m["num_context"] + m["num_preds"], m["S"], 128, generator=g)
         out["slots"], out["hist"] = slots, hist
-        for kind in ("VanillaTransformer", "OCVPSeq"):
+        for kind in ("VanillaTransformer", "OCVPSeq", "OCVPPar"):
             with contextlib.redirect_stdout(io.StringIO()):
+                cfg = "OCVPSeq" if kind == "OCVPPar" else kind
                 exp = {"model": {"model_name": "SAVi", "model_params": json.load(open("src/configs/models/SAVi.json"))},
-                       "predictor": json.load(open(f"src/configs/predictors/{kind}.json")),
+                       "predictor": json.load(open(f"src/configs/predictors/{cfg}.json")),
                        "prediction_params": {**DEFAULTS["prediction_params"], "num_context": m["num_context"],
                                              "num_preds": m["num_preds"], "input_buffer_size": m["input_buffer_size"]}}
-                pred = sm.setup_predictor(copy.deepcopy(exp)).eval()
+                if kind == "OCVPPar":
+                    from models.Predictors.OCVP import OCVPPar
+                    from models.Predictors.predictor_wrapper import PredictorWrapper
+                    pp = exp["predictor"]["predictor_params"]
+                    body = OCVPPar(num_slots=exp["model"]["model_params"]["num_slots"],
+                                   slot_dim=exp["model"]["model_params"]["slot_dim"], token_dim=pp["token_dim"],
+                                   hidden_dim=pp["hidden_dim"], num_layers=pp["num_layers"], n_heads=pp["n_heads"],
+                                   residual=pp["residual"], input_buffer_size=m["input_buffer_size"])
+                    pred = PredictorWrapper(exp_params=copy.deepcopy(exp), predictor=body).eval()
+                else:
+                    pred = sm.setup_predictor(copy.deepcopy(exp)).eval()
             sd = weights.ocvp_state_dict(kind, m["seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
             pred.predictor.load_state_dict(sd, strict=True)
             pred.encode_text_caption = lambda **kw: None

@@ -434,6 +434,16 @@ def text_encoder(sd: SD, text: Tensor, text_length: Tensor, num_heads: int = 4) 
 # Sibling predictors: VanillaTransformerPredictor / OCVPSeq (src/models/Predictors/OCVP.py:24-319) over pre-norm
 # torch.nn.TransformerEncoderLayer blocks (ReLU, eps 1e-5, eval mode), SlotPositionalEncoding (model_blocks.py:230-290).
 # --------------------------------------------------------------------------------------
+def _torch_mha(sd: SD, p: str, h: Tensor, num_heads: int) -> Tensor:
+    """nn.MultiheadAttention(batch_first=True)(h, h, h) with the parameters under prefix p; h [N, T, D]."""
+    N, T, D = h.shape
+    dh = D // num_heads
+    q, k, v = F.linear(h, sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]).split(D, dim=-1)
+    qh, kh, vh = (t.reshape(N, T, num_heads, dh).transpose(1, 2) for t in (q, k, v))
+    a = ((qh @ kh.transpose(-1, -2)) * dh ** -0.5).softmax(dim=-1) @ vh
+    return F.linear(a.transpose(1, 2).reshape(N, T, D), sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
 def _encoder_layer_prenorm(sd: SD, p: str, x: Tensor, num_heads: int) -> Tensor:
     """x [N, T, D]: x = x + SA(LN1(x)); x = x + FFN(LN2(x))."""
     N, T, D = x.shape
@@ -459,7 +469,8 @@ def slot_positional_encoding(max_len: int, d_model: int) -> Tensor:
 
 
 def ocvp_step(sd: SD, slots: Tensor, kind: str, num_heads: int = 4, residual: bool = True, max_len: int = 10) -> Tensor:
-    """slots [B,n,S,Ds] -> [B,S,Ds].  kind = "VanillaTransformer" (OCVP.py:98-135) or "OCVPSeq" (OCVP.py:211-243)."""
+    """slots [B,n,S,Ds] -> [B,S,Ds].  kind = "VanillaTransformer" (OCVP.py:98-135), "OCVPSeq" (OCVP.py:211-243) or "OCVPPar"
+    (OCVP.py:397-432)."""
     B, n, S, _ = slots.shape
     tok = _lin(slots, sd, "mlp_in")
     D = tok.shape[-1]
@@ -471,6 +482,21 @@ def ocvp_step(sd: SD, slots: Tensor, kind: str, num_heads: int = 4, residual: bo
             x = _encoder_layer_prenorm(sd, f"transformer_encoders.{i}", x, num_heads)
             i += 1
         tok = x.reshape(B, n, S, D)
+    elif kind == "OCVPPar":
+        # OCVPParLayer.forward / _sa_block (OCVP.py:499-546), pre-norm: x = x + MHA_obj(LN1 x) + MHA_time(LN1 x);
+        # x = x + FFN(LN2 x).  Object attention runs inside each frame, time attention along each slot's history.
+        while f"transformer_encoders.{i}.self_attn_obj.in_proj_weight" in sd:
+            p = f"transformer_encoders.{i}"
+            h = _ln(tok, sd, p + ".norm1", 1e-5)
+            ho = h.reshape(B * n, S, D)
+            xo = _torch_mha(sd, p + ".self_attn_obj", ho, num_heads).reshape(B, n, S, D)
+            ht = h.transpose(1, 2).reshape(B * S, n, D)
+            xt = _torch_mha(sd, p + ".self_attn_time", ht, num_heads).reshape(B, S, n, D).transpose(1, 2)
+            tok = tok + xo + xt
+            h2 = _ln(tok, sd, p + ".norm2", 1e-5)
+            tok = tok + F.linear(F.relu(F.linear(h2, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
+                                 sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+            i += 1
     else:
         while f"transformer_encoders.{i}.object_encoder_block.self_attn.in_proj_weight" in sd:
             p = f"transformer_encoders.{i}"

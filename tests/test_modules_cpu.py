@@ -44,3 +44,23 @@ def test_no_cpu_fallback():
         savi(mode="nope")
     with pytest.raises(KeyError):
         pred(torch.zeros(1, 1, 8, 128))            # caption_tokens missing, as in the reference
+
+
+def test_ocvp_par_state_dict_matches_reference_class():
+    """OCVPPar has no factory entry in the reference (lib/setup_model.py:83-99) but the class exists (OCVP.py:324-548): our
+    parameter container must expose exactly its parameter names / shapes, including the inherited, unused ``self_attn``."""
+    import contextlib, io
+    from textocvp_b200 import modules as M, weights
+    ref_import._prepare()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.Predictors.OCVP import OCVPPar as RefPar
+        ref = RefPar(num_slots=8, slot_dim=128, token_dim=128, hidden_dim=256, num_layers=2, n_heads=4, residual=True,
+                     input_buffer_size=10)
+    ours = M.OCVPPar(num_slots=8, slot_dim=128, token_dim=128, hidden_dim=256, num_layers=2, n_heads=4, residual=True,
+                     input_buffer_size=10)
+    a, b = ours.state_dict(), ref.state_dict()
+    assert set(a) == set(b)
+    assert all(a[k].shape == b[k].shape for k in b)
+    sd = weights.ocvp_state_dict("OCVPPar", 19)
+    ref.load_state_dict(sd, strict=True)
+    ours.load_state_dict(sd, strict=True)

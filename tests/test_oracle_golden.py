@@ -89,12 +89,12 @@ def test_text_encoder_oracle_vs_reference():
 
 
 def test_ocvp_oracle_vs_reference():
-    """VanillaTransformerPredictor / OCVPSeq restatement against the real modules (one step on a 7-frame window)."""
+    """VanillaTransformerPredictor / OCVPSeq / OCVPPar restatement against the real modules (one step on a 7-frame window)."""
     import os
     from textocvp_b200 import weights
     g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ocvp_b3.pt"), weights_only=False)
     m = g["meta"]
-    for kind in ("VanillaTransformer", "OCVPSeq"):
+    for kind in ("VanillaTransformer", "OCVPSeq", "OCVPPar"):
         sd = weights.ocvp_state_dict(kind, m["seed"], bias_scale=m["bias_scale"], ln_jitter=m["ln_jitter"])
         out = O.ocvp_step(sd, g["slots"], kind, max_len=m["input_buffer_size"])
         assert O.rel_err(out, g[kind + "_step"]) < TOL, kind

@@ -227,9 +227,9 @@ def test_text_encoder(models):
     assert O.rel_err(enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)) < 1e-4
 
 
-@pytest.mark.parametrize("kind", ["VanillaTransformer", "OCVPSeq"])
+@pytest.mark.parametrize("kind", ["VanillaTransformer", "OCVPSeq", "OCVPPar"])
 def test_sibling_predictors(kind):
-    """VanillaTransformerPredictor / OCVPSeq behind the same PredictorWrapper: one fused fp32 kernel
+    """VanillaTransformerPredictor / OCVPSeq / OCVPPar behind the same PredictorWrapper: one fused fp32 kernel
     per prediction step vs the real reference's outputs (golden): single step and a 4-step autoregressive rollout."""
     import os
     from textocvp_b200 import modules as M, weights

@@ -3,7 +3,8 @@
 // time encoding shared by the slots of a frame (SlotPositionalEncoding, src/models/Blocks/model_blocks.py:230-290) ->
 // pre-norm torch.nn.TransformerEncoderLayer blocks (ReLU, eps 1e-5) -> mlp_out on the newest frame (+ residual).
 // Vanilla attends over all n*S tokens; an OCVP-Seq layer is an OBJECT block (attention inside each frame) followed by a
-// TIME block (attention along each slot's history): the same token array with two different key groups.
+// TIME block (attention along each slot's history): the same token array with two different key groups.  OCVP-Par
+// (OCVP.py:324-548) applies both attentions to the same normed input and adds them (block flags).
 //
 // One prediction step of one sequence runs in ONE CTA, fp32 end to end: <= 80 tokens x 128 features is a latency
 // problem.  Token t = frame * S + slot.
@@ -33,11 +34,15 @@ ocvp_step_kernel(tocvp_ocvp_weights w, const float* __restrict__ slots, size_t s
   __syncthreads();
   for (int l = 0; l < w.num_blocks; ++l) {
     const tocvp_text_layer& ly = w.blocks[l];
-    // pre-norm encoder layer: x = x + SA(LN1(x)); x = x + FFN(LN2(x))
-    te_layernorm_to(x, h, D, T, D, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr);
+    // pre-norm encoder layer: x = x + SA(LN1(x)); x = x + FFN(LN2(x)).  The attention output overwrites the q columns of the
+    // packed qkv rows (a thread rewrites only the q it has read), so h keeps LN1(x): an OCVP-Par layer (OCVP.py:499-546,
+    // x + SA_obj(LN1 x) + SA_time(LN1 x)) is two blocks -- the second reuses h (flag bit 1), the first skips the FFN (bit 0).
+    const int flags = w.block_flags[l];
+    if (!(flags & 2)) te_layernorm_to(x, h, D, T, D, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr);
     te_linear(ly.in_w_t, ly.in_b, D, 3 * D, h, D, big, ldq, T, 0, nullptr, 0);
-    te_attention(big, ldq, h, D, T, T, D, H, w.block_group[l], S);
-    te_linear(ly.out_w_t, ly.out_b, D, D, h, D, x, D, T, 0, x, D);
+    te_attention(big, ldq, big, ldq, T, T, D, H, w.block_group[l], S);
+    te_linear(ly.out_w_t, ly.out_b, D, D, big, ldq, x, D, T, 0, x, D);
+    if (flags & 1) continue;
     te_layernorm_to(x, h, D, T, D, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr);
     te_linear(ly.ff1_w_t, ly.ff1_b, D, F, h, D, big, F, T, 2, nullptr, 0);
     te_linear(ly.ff2_w_t, ly.ff2_b, F, D, big, F, x, D, T, 0, x, D);

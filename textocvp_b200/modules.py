@@ -1083,14 +1083,16 @@ OCVP_MAX_BLOCKS = 8
 OcvpW = type("OcvpW", (ctypes.Structure,), {"_fields_": [
     ("mlp_in_w_t", _f), ("mlp_in_b", _f), ("mlp_out_w_t", _f), ("mlp_out_b", _f), ("pe", _f),
     ("blocks", TextLayer * OCVP_MAX_BLOCKS), ("block_group", ctypes.c_int * OCVP_MAX_BLOCKS),
-    ("num_blocks", ctypes.c_int), ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int), ("token_dim", ctypes.c_int),
+    ("block_flags", ctypes.c_int * OCVP_MAX_BLOCKS), ("num_blocks", ctypes.c_int), ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int), ("token_dim", ctypes.c_int),
     ("ffn_dim", ctypes.c_int), ("num_heads", ctypes.c_int), ("max_len", ctypes.c_int), ("residual", ctypes.c_int)]})
 
 
-def _encoder_layer_ptrs(lyr, keep, dst):
-    """nn.TransformerEncoderLayer parameters -> tocvp_text_layer (fp32, matrices transposed to [in][out])."""
-    t = dict(in_w_t=_tr(lyr.self_attn.in_proj_weight), in_b=_f32(lyr.self_attn.in_proj_bias),
-             out_w_t=_tr(lyr.self_attn.out_proj.weight), out_b=_f32(lyr.self_attn.out_proj.bias),
+def _encoder_layer_ptrs(lyr, keep, dst, attn=None):
+    """nn.TransformerEncoderLayer parameters -> tocvp_text_layer (fp32, matrices transposed to [in][out]); ``attn`` selects
+    another nn.MultiheadAttention of the layer (OCVPParLayer.self_attn_obj / self_attn_time)."""
+    attn = lyr.self_attn if attn is None else attn
+    t = dict(in_w_t=_tr(attn.in_proj_weight), in_b=_f32(attn.in_proj_bias),
+             out_w_t=_tr(attn.out_proj.weight), out_b=_f32(attn.out_proj.bias),
              ln1_g=_f32(lyr.norm1.weight), ln1_b=_f32(lyr.norm1.bias),
              ff1_w_t=_tr(lyr.linear1.weight), ff1_b=_f32(lyr.linear1.bias),
              ff2_w_t=_tr(lyr.linear2.weight), ff2_b=_f32(lyr.linear2.bias),
@@ -1141,7 +1143,7 @@ class _OCVPBase(_Packed):
         raise NotImplementedError
 
     def _pack(self, dev):
-        blocks = self._blocks()                                   # [(encoder layer, key group)]
+        blocks = self._blocks()                                   # [(encoder layer, key group[, flags, attention module])]
         if len(blocks) > OCVP_MAX_BLOCKS:
             raise L.TocvpError("OCVP predictor kernels are built for <= 8 encoder blocks")
         keep = [dict(mlp_in_w_t=_tr(self.mlp_in.weight), mlp_in_b=_f32(self.mlp_in.bias),
@@ -1150,9 +1152,11 @@ class _OCVPBase(_Packed):
         w = OcvpW()
         for n, v in keep[0].items():
             setattr(w, n, v.data_ptr())
-        for i, (lyr, group) in enumerate(blocks):
-            _encoder_layer_ptrs(lyr, keep, w.blocks[i])
-            w.block_group[i] = group
+        for i, blk in enumerate(blocks):
+            lyr, group = blk[0], blk[1]
+            flags, attn = (blk[2], blk[3]) if len(blk) > 2 else (0, None)
+            _encoder_layer_ptrs(lyr, keep, w.blocks[i], attn)
+            w.block_group[i], w.block_flags[i] = group, flags
         w.num_blocks, w.num_slots, w.slot_dim, w.token_dim = len(blocks), self.num_slots, self.slot_dim, self.token_dim
         w.ffn_dim, w.num_heads, w.max_len, w.residual = self.hidden_dim, self.nhead, self.input_buffer_size, int(bool(self.residual))
         self._keep, self._w = keep, w
@@ -1191,6 +1195,31 @@ class OCVPSeq(_OCVPBase):
         out = []
         for lyr in self.transformer_encoders:
             out += [(lyr.object_encoder_block, 1), (lyr.time_encoder_block, 2)]
+        return out
+
+
+class OCVPParLayer(nn.TransformerEncoderLayer):
+    """OCVP.py:436-548 (parameter container): a pre-norm encoder layer with two extra attention modules applied in parallel
+    on the same normed input; the inherited ``self_attn`` exists in the state_dict but is never used (as in the reference)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1):
+        super().__init__(d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward, dropout=dropout, batch_first=True,
+                         norm_first=True)
+        self.self_attn_obj = nn.MultiheadAttention(embed_dim=d_model, num_heads=nhead, dropout=dropout, batch_first=True)
+        self.self_attn_time = nn.MultiheadAttention(embed_dim=d_model, num_heads=nhead, dropout=dropout, batch_first=True)
+
+
+class OCVPPar(_OCVPBase):
+    """OCVP.py:324-432: object- and time-attention in parallel, x + SA_obj(LN1 x) + SA_time(LN1 x), then the feed-forward."""
+
+    def _build_encoders(self):
+        return nn.Sequential(*[OCVPParLayer(self.token_dim, self.nhead, dim_feedforward=self.hidden_dim)
+                               for _ in range(self.num_layers)])
+
+    def _blocks(self):
+        out = []
+        for lyr in self.transformer_encoders:   # flags: 1 = no feed-forward half, 2 = reuse the previous LN1 output
+            out += [(lyr, 1, 1, lyr.self_attn_obj), (lyr, 2, 2, lyr.self_attn_time)]
         return out
 
 
@@ -1422,8 +1451,8 @@ def setup_predictor(exp_params: Dict):
     mp = exp_params["model"]["model_params"]
     if name == "TextOCVP_CustomTF":
         body = TextOCVP_CustomTF(slot_dim=mp["slot_dim"], **pp)
-    elif name in ("VanillaTransformer", "OCVPSeq"):                    # setup_model.py:83-99
-        cls = VanillaTransformerPredictor if name == "VanillaTransformer" else OCVPSeq
+    elif name in ("VanillaTransformer", "OCVPSeq", "OCVPPar"):         # setup_model.py:83-99 (OCVPPar: OCVP.py:324, no
+        cls = {"VanillaTransformer": VanillaTransformerPredictor, "OCVPSeq": OCVPSeq, "OCVPPar": OCVPPar}[name]   # factory entry in the reference)
         body = cls(num_slots=mp["num_slots"], slot_dim=mp["slot_dim"],
                    input_buffer_size=exp_params["prediction_params"]["input_buffer_size"],
                    **exp_params["predictor"]["predictor_params"])

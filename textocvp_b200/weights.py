@@ -315,7 +315,7 @@ def synthetic_captions(B: int, L: int = 24, vocab_size: int = 50, seed: int = 0)
 def ocvp_state_dict(kind: str, seed: int = 19, slot_dim: int = 128, token_dim: int = 128, hidden_dim: int = 256,
                     num_layers: int = 2, mlp_out_scale: float = 1.0, bias_scale: float = 0.0,
                     ln_jitter: float = 0.0) -> Dict[str, Tensor]:
-    """VanillaTransformerPredictor / OCVPSeq parameters (reference src/models/Predictors/OCVP.py): PyTorch-default
+    """VanillaTransformerPredictor / OCVPSeq / OCVPPar parameters (reference src/models/Predictors/OCVP.py): PyTorch-default
     initialisations of nn.Linear / nn.TransformerEncoderLayer (xavier in_proj, zero attention biases)."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
@@ -340,6 +340,14 @@ def ocvp_state_dict(kind: str, seed: int = 19, slot_dim: int = 128, token_dim: i
         elif kind == "OCVPSeq":
             enc(f"transformer_encoders.{i}.object_encoder_block")
             enc(f"transformer_encoders.{i}.time_encoder_block")
+        elif kind == "OCVPPar":        # OCVPParLayer: an encoder layer (its own self_attn is unused) + two attention modules
+            p = f"transformer_encoders.{i}"
+            enc(p)
+            for a in ("self_attn_obj", "self_attn_time"):
+                sd[f"{p}.{a}.in_proj_weight"] = _xavier(g, 3 * T, T)
+                sd[f"{p}.{a}.in_proj_bias"] = bias_scale * torch.randn(3 * T, generator=g)
+                sd[f"{p}.{a}.out_proj.weight"], _ = _default_linear(g, T, T, bias=False)
+                sd[f"{p}.{a}.out_proj.bias"] = bias_scale * torch.randn(T, generator=g)
         else:
             raise ValueError(kind)
     return sd
