@@ -84,7 +84,8 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int img = t / tiles_per_img, r = t % tiles_per_img;
+        const int tr = num_tiles - 1 - t;   // last tiles first: layer 4 wrote them last, ~100 MB of them are still in L2
+        const int img = tr / tiles_per_img, r = tr % tiles_per_img;
         const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
         mbar_wait(&a_empty[buf], ph ^ 1);                    // the MMAs that read this halo buffer have completed
         mbar_expect_tx(&a_full[buf], HD_A_BYTES);
@@ -124,7 +125,8 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const int img = t / tiles_per_img, r = t % tiles_per_img;
+      const int tr = num_tiles - 1 - t;
+      const int img = tr / tiles_per_img, r = tr % tiles_per_img;
       const int y0 = (r / tiles_x) * HD_TH, x0 = (r % tiles_x) * HD_TW;
       mbar_wait(&t_full[buf], ph);
       tc_fence_after();
