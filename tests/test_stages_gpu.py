@@ -178,6 +178,27 @@ def test_full_rollout_psnr(models, golden, golden_weights):
     assert p.min() >= 40.0, (p.min(), p.mean())
 
 
+@pytest.mark.parametrize("B", [1, 3])
+def test_rollout_small_and_odd_batches(models, golden_weights, B):
+    """Batch 1 and 3: odd tile counts take the single-CTA conv kernels instead of the CTA-pair ones, the GEMMs run below
+    the 1024-row threshold of the pair / folded-LayerNorm kernels for the first steps, the decoder has a single ragged chunk.
+    Whole evaluator composition against the CPU oracle."""
+    from textocvp_b200 import rollout, weights
+    savi, pred = models
+    videos, text, noise = weights.synthetic_inputs(B, 20, 32, seed=40 + B)
+    sd = golden_weights["savi_sd"]
+    init = sd["initializer.slots_mu"] + sd["initializer.slots_sigma"] * noise
+    out = rollout.forward_eval(savi, pred, videos.cuda(), text.cuda(), 1, 19, init_slots=init.cuda())
+    ref = O.rollout(sd, golden_weights["pred_sd"], videos, text, init, O.SAViCfg(), O.PredCfg(num_context=1, num_preds=19))
+    assert out["pred_imgs"].shape == (B, 19, 3, 64, 64)
+    assert O.rel_err(out["slot_history"], ref["slot_history"]) < 3e-3
+    assert O.rel_err(out["pred_slots"], ref["pred_slots"]) < 5e-3
+    p = O.psnr(out["pred_imgs"].cpu(), ref["pred_imgs"])
+    assert p.min() >= 40.0, (p.min(), p.mean())
+    tgt = videos[:, 1:20].clamp(0, 1)
+    assert (out["psnr"].cpu() - O.psnr(out["pred_imgs"].cpu(), tgt)).abs().max() < 1e-3
+
+
 def test_predictor_step_folded_layernorm(models, golden, golden_weights):
     """M = B*n*S >= 1024 rows takes the CTA-pair GEMMs with LayerNorm folded into the projections (row statistics from
     the producing GEMM, gamma-folded weights, rstd / mu applied in the epilogue).  Checked against the fp32 oracle on
