@@ -164,6 +164,23 @@ def test_decode_chunk_pipeline_matches_serial(models, golden):
     assert ref == 0.0
 
 
+def test_decode_is_graph_capturable(models, golden):
+    """The chunk-pipelined decode forks to / joins from its internal side stream with events only, so a caller may capture
+    it into a CUDA graph; the replay equals the eager call."""
+    savi, _ = models
+    g = torch.Generator().manual_seed(9)
+    slots = (golden["pred_slots"][:1, -1] + 0.3 * torch.randn(256 + 40, 8, 128, generator=g)).cuda()
+    eager = savi.decode(slots, only_imgs=True)["recons_imgs"].clone()      # also sizes the workspace before the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        out = savi.decode(slots, only_imgs=True)["recons_imgs"]
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+
+
 def test_full_rollout_psnr(models, golden, golden_weights):
     """Evaluator composition (05_evaluate_predictor.py:82-96) end to end vs the real reference's frames."""
     savi, pred = models
