@@ -15,7 +15,7 @@
 //
 // warp 0: TMA producer (3-stage ring)   warp 1: TMEM alloc + MMA issue (MMA1 of tile t+1 is issued before MMA2 of tile t)
 // warps 2-5 / 6-9: two softmax groups working on even / odd tiles (each owns one D1 and one Wt buffer), so the
-// per-tile register-level latency chain of one group overlaps the other's.  ~113 KB smem, 128 TMEM columns -> 2 CTAs / SM.
+// per-tile register-level latency chain of one group overlaps the other's.  113 KB smem, 128 TMEM columns -> 2 CTAs / SM.
 #include "host_util.h"
 #include "ptx.cuh"
 #include "slot_attention.h"
@@ -30,7 +30,11 @@ constexpr int ST_W_BYTES = 2 * 16 * 128;        // Wt: two location halves of [1
 constexpr int ST_OFF_G = ST_STAGES * ST_X_BYTES;
 constexpr int ST_OFF_W = ST_OFF_G + ST_G_BYTES;
 constexpr int ST_OFF_BAR = ST_OFF_W + 2 * ST_W_BYTES;
-constexpr int ST_SMEM = ST_OFF_BAR + 1024 + 1024;   // barriers + reduction scratch, alignment slack
+// barriers + reduction scratch; NO alignment slack: the dynamic shared array is declared __align__(1024) (checked at run
+// time), which brings the CTA to 115712 B -- with the 1 KB the hardware reserves per CTA exactly half of the SM's 233472 B,
+// so TWO CTAs are resident per SM.  (With the usual 1 KB of slack it was 116736 B and one CTA per SM: ncu r1 showed
+// occupancy limited to 1 by shared memory and 42 % DRAM throughput.)
+constexpr int ST_SMEM = ST_OFF_BAR + 1024;
 constexpr int ST_TMEM_COLS = 128;               // D1: 2 x 32 columns, U: 16 columns at column 64
 
 // byte offset of element (row r, k-element e) in a K-major 128B-swizzled operand stored as halves of 64 k-elements
@@ -44,8 +48,9 @@ constexpr int ST_THREADS = 320;   // TMA warp, MMA warp, 2 softmax groups of 4 w
 __global__ void __launch_bounds__(ST_THREADS, 2)
 sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ gvec, float* __restrict__ partial,
                     int tiles_per_chunk, float ln_eps, float attn_eps) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_align1024(smem_raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // the swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* sG = smem + ST_OFF_G;
   uint8_t* sW = smem + ST_OFF_W;
   uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + ST_OFF_BAR);
