@@ -61,7 +61,7 @@ template <int CIN, int COUT, int G, int KS, int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a) {
   using C = ConvCfg<CIN, COUT, G, KS>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;                       // 2 halo buffers
   uint8_t* sW = smem + 2 * C::A_STRIDE;     // weight ring
@@ -253,9 +253,12 @@ struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
   // 5 (not 6) stages at 64 channels: 230912 + 1024 static + 1024 reserved bytes per CTA left no room for the 1 KB a second,
   // shared-memory-free CTA needs on the SM, so the decoder's layer-1 kernel (chunk pipeline, decoder.cu) could never be
   // co-resident with this kernel (r1 timeline: the convolution waited ~250 us per chunk for layer-1 CTAs to exit).
-  static constexpr int WSTAGES = GEN ? 4 : ((W_HALF >= 4096) ? 5 : 12);
+  static constexpr int WSTAGES = GEN ? 4 : ((W_HALF >= 4096) ? 5 : 8);
   static constexpr int GEN_BYTES = GEN ? 25 * CIN * 4 : 0;   // this tile's 5x5 border-pattern sums, fp32
-  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + 512 + 1024;
+  // no alignment slack: the dynamic shared array is declared __align__(1024) and checked at run time.  The 32-channel
+  // configuration (111104 B, 161 registers x 192 threads, 256 TMEM columns) then fits TWO CTAs per SM.
+  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + 512;
+  static constexpr int CTAS_PER_SM = (2 * (SMEM + 2048) <= 233472 && 2 * Base::TMEM_COLS <= 512 && !GEN) ? 2 : 1;
 };
 
 // Generated input (decoder layer 2 only): instead of TMA-loading layer 1's activation, four extra warps COMPUTE the halo
@@ -272,12 +275,13 @@ __device__ __forceinline__ int border_pat(int v, int n) { return v < 2 ? v : (v 
 // enc_pack_vp_kernel), so the filter collapses to (KS+1)/2 vertical taps two rows apart, all at the centre column; the
 // packed tensor has one extra row on top (stored row r = image row r-1).
 template <int CIN, int COUT, int G, int KS, bool GEN, bool VP = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, ConvCfg2<CIN, COUT, G, KS, GEN>::CTAS_PER_SM)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a, ConvGen gen) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   constexpr int NTAPS = VP ? (KS + 1) / 2 : C::TAPS;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_align1024(smem_raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // swizzled TMA / UMMA tiles need 1024-byte alignment
   uint8_t* sA = smem;
   uint8_t* sW = smem + 2 * C::A_STRIDE;
   uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + C::WSTAGES * C::W_HALF);   // leader: bytes of both halves
@@ -581,7 +585,7 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
     TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
   }
   const int num_ptiles = n_img * (H / C::TILE_H) * (W / C::TILE_W) / 2;
-  const int pairs = num_sms() / 2;
+  const int pairs = (num_sms() / 2) * C::CTAS_PER_SM;
   const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
   ConvArgs a{n_img, H, W, bias, out, nullptr, relu, ln_posemb, ln_g, ln_b, ln_eps};
   conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
