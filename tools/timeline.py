@@ -18,6 +18,9 @@ fn = {"decode": lambda: savi.decode(ps, only_imgs=True),
       "predict": lambda: pred(sh, text_embeddings=text),
       "decomp": lambda: savi(mode="decomp", x=videos, num_imgs=20, decode=False, init_slots=init),
       "eval": lambda: rollout.forward_eval(savi, pred, videos, text, 1, 19, init_slots=init)}[stage]
+if len(sys.argv) > 2:                      # optional: tocvp_set_gemm_mode(<mode>) before the run (e.g. 260 / 261)
+    from textocvp_b200 import ops
+    ops.set_gemm_mode(int(sys.argv[2]))
 for _ in range(3): fn()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -42,6 +45,14 @@ for e in evs[1:]:
     if e.time_range.start > cur_end: idle += e.time_range.start - cur_end
     cur_end = max(cur_end, e.time_range.end)
 print(f"idle (no kernel resident) {idle/1e3:.3f} ms")
+# time per kernel name (durations include the griddepcontrol.wait overlap of programmatic dependent launches)
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in evs:
+    agg[e.name[:78]][0] += 1
+    agg[e.name[:78]][1] += e.time_range.end - e.time_range.start
+for name, (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:10]:
+    print(f"  {tot/1e3:8.2f} ms  x{cnt:5d}  avg {tot/cnt:7.1f} us  {name}")
 # the largest idle gaps and what follows them
 gaps, cur_end = [], evs[0].time_range.end
 for e in evs[1:]:
