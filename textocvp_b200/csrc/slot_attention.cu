@@ -267,12 +267,15 @@ constexpr int UP_WARPS = UP_THREADS / 32;
 
 using SaWeights = tocvp_sa_weights;  // include/tocvp.h
 
-// 3xTF32 split: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); hi*hi + lo*hi + hi*lo keeps ~21 mantissa bits, i.e. fp32
-// accuracy for the recurrent slot state, on the (legacy-path) tensor cores.
+// 3xTF32 split: x = hi + lo with hi = x truncated to tf32 (low 13 mantissa bits cleared) and lo = x - hi (exact in fp32;
+// the tensor core reads only the tf32 bits of it); hi*hi + lo*hi + hi*lo keeps ~20 mantissa bits, i.e. fp32-level accuracy
+// for the recurrent slot state, on the (legacy-path) tensor cores.  Two instructions.  The first version used
+// cvt.rna.tf32.f32 for both halves: sm_100 has no instruction for it, each expands to ~7 FSETP / SEL / LOP3 / IADD3, and they
+// were HALF of the update kernel's 42 M warp instructions (ncu opcode histogram: FSETP 18 %, IADD3 13 %, LOP3 10 %, SEL 9 %,
+// HMMA 6 %).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
