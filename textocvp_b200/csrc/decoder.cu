@@ -90,21 +90,28 @@ dec_l1_kernel(const float* __restrict__ taps, const float* __restrict__ P, __hal
 __global__ void __launch_bounds__(256)
 dec_l1_patterns_kernel(const float* __restrict__ taps, float* __restrict__ S, int n_img) {
   constexpr int C = 64;
-  __shared__ float sT[4][25 * C];
   const int sub = threadIdx.x >> 6, c = threadIdx.x & 63;       // 4 slot-images per CTA, one thread per channel
   const int img = blockIdx.x * 4 + sub;
   if (img >= n_img) return;
-  const float* t = taps + size_t(img) * 25 * C;
-  for (int k = 0; k < 25; ++k) sT[sub][k * C + c] = t[k * C + c];
-  float* o = S + size_t(img) * 25 * C;
+  const float* t = taps + size_t(img) * 25 * C + c;
+  float tv[25];                                                 // this channel's 25 tap values (coalesced over c)
+#pragma unroll
+  for (int k = 0; k < 25; ++k) tv[k] = __ldg(t + k * C);
+  float* o = S + size_t(img) * 25 * C + c;
+  // all bounds are compile-time constants after unrolling: no branches, same summation order (ky outer, kx inner) as the
+  // first version (which looped with run-time bounds over a shared-memory copy and was issue-bound: 91 % issue-active)
+#pragma unroll
   for (int pat = 0; pat < 25; ++pat) {
     const int py = pat / 5, px = pat % 5;
     const int ky0 = py == 0 ? 2 : (py == 1 ? 1 : 0), ky1 = py == 4 ? 2 : (py == 3 ? 3 : 4);
     const int kx0 = px == 0 ? 2 : (px == 1 ? 1 : 0), kx1 = px == 4 ? 2 : (px == 3 ? 3 : 4);
     float s = 0.f;
-    for (int ky = ky0; ky <= ky1; ++ky)
-      for (int kx = kx0; kx <= kx1; ++kx) s += sT[sub][(ky * 5 + kx) * C + c];
-    o[pat * C + c] = s;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+        if (ky >= ky0 && ky <= ky1 && kx >= kx0 && kx <= kx1) s += tv[ky * 5 + kx];
+    o[pat * C] = s;
   }
 }
 

@@ -58,18 +58,20 @@ enc_pack_vp_kernel(const float* __restrict__ x, size_t img_stride, __half* __res
   const int rem = int(idx % per_img);
   const int r = rem / W, px = rem % W;
   const float* xi = x + size_t(img) * img_stride;
-  const size_t plane = size_t(H) * W;
+  const int plane = H * W;
   uint32_t w[16];
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int y = r - 1 + half;
+    const bool yok = y >= 0 && y < H;
+    const float* row = xi + (yok ? y : 0) * W + px - 2;          // one pointer per row; taps / channels are constant offsets
     float v[16];
 #pragma unroll
     for (int kx = 0; kx < 5; ++kx) {
       const int xx = px + kx - 2;
-      const bool ok = y >= 0 && y < H && xx >= 0 && xx < W;
+      const bool ok = yok && xx >= 0 && xx < W;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[kx * 3 + c] = ok ? __ldg(xi + c * plane + size_t(y) * W + xx) : 0.f;
+      for (int c = 0; c < 3; ++c) v[kx * 3 + c] = ok ? __ldg(row + c * plane + kx) : 0.f;
     }
     v[15] = 0.f;
 #pragma unroll
