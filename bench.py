@@ -35,11 +35,62 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU (BASELINE config 3: 256)")
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU (BASELINE config 3: 256); weak scaling")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling (BASELINE configs[4]: 2048): the global batch is fixed and sharded evenly over the "
+                         "ranks (batch per GPU = global / N); overrides --batch")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational extras (stage times, CLIPort config)")
     ap.add_argument("--cpu-batch", type=int, default=4,
                     help="sequences per CPU-baseline step (4 keeps all host cores busy: measured faster per frame than 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+# provenance of roofline.traffic (an ncu --set full capture cannot run inside the timed bench; the number is per launch
+# of the dominant kernel over 2048 slot-images, like roofline.achieved)
+TRAFFIC = {"bytes_per_launch": 2.096e9, "algorithmic_bytes_per_launch": 2.147e9,
+           "metric": "dram__bytes_read.sum + dram__bytes_write.sum", "file": "profiles/conv64_pair_r1_summary.md",
+           "captured": "2026-10-18 (round 1, ncu --set full --clock-control none, gpurun_out/conv64_r1_final.ncu-rep); the "
+                       "kernel source has not changed since"}
+# The CPU arm times the ORACLE PORT (oracle/textocvp_oracle.py), because /root/reference cannot travel to the GPU box.  Port
+# and reference modules were timed side by side in the build container (8 threads, B = 1): reference 11.1 frames/s, port
+# 14.8 frames/s -- the port is 1.33x FASTER than the reference's own modules, so GPU / CPU ratios quoted against it are
+# conservative.  It runs at a small batch (the whole B = 256 step would take ~100 s per step on 16 cores); frames/s on the
+# CPU does not improve beyond B = 4 (measured 39-41 at B = 1, 48 at B = 4).
+CPU_NOTE = {"port_vs_reference_modules": "port is 1.33x faster than the reference's nn.Modules (14.8 vs 11.1 frames/s, 8 "
+                                         "threads, build container; judge-measured round 1)",
+            "batch_note": "CPU arm at B=4 per step (frames/s saturates: 39-41 at B=1, 48 at B=4); the GPU arm runs B=256"}
+
+
+def cliport_extras(dev, timed, tf_peak):
+    """BASELINE configs[3]: CLIPort shape (128x128 frames, 81 ViT patch tokens x 768, 10 slots, MLP patch decoder), 29-step
+    rollout, batch 128, features resident; one evaluator pass = decomp over 30 frames -> 29-step rollout -> decode."""
+    import torch
+    from textocvp_b200 import rollout, weights
+    Bc, NP = 128, 29
+    dino, predc, _ = rollout.build_dino_models(dev, num_preds=NP)
+    feats, text, noise = weights.synthetic_dino_inputs(Bc, NP + 1, 81, L=16, seed=0)
+    feats, text = feats.to(dev), text.to(dev)
+    dsd = weights.dino_state_dict(16)
+    init = (dsd["initializer.slots_mu"] + dsd["initializer.slots_sigma"] * noise).to(dev)
+    ms_dec, out = timed(lambda: dino(mode="decomp", x=feats, num_imgs=NP + 1, decode=False, init_slots=init))
+    sh = out["slot_history"]
+    ms_pred, ps = timed(lambda: predc(sh, text_embeddings=text))
+    ms_decode, _ = timed(lambda: dino.decode(ps.reshape(Bc * NP, 10, 128), only_imgs=True))
+    ms_all, _ = timed(lambda: rollout.forward_eval_dino(dino, predc, feats, text, 1, NP, init_slots=init))
+    fl_dec, fl_pred = Bc * NP * (4.89e9 + 10.46e9), Bc * 234.7e9
+    res = {"config": "configs[3]: ExtendedDINOSAUR + MLPPatchDecoder, 128x128, 81 patches x 768, 10 slots, B=128, 1 + 29 "
+                     "frames, L=16, synthetic patch features (frozen ViT not in the timed region)",
+           "value": Bc * NP / (ms_all / 1e3), "unit": "frames/s", "ms_per_step": ms_all,
+           "stage_ms": {"decomp_30_frames": ms_dec, "predict_29_steps": ms_pred, "decode": ms_decode},
+           "stage_frac_of_roofline": {"predictor": fl_pred / (ms_pred / 1e3) / 1e12 / tf_peak,
+                                      "decoder": fl_dec / (ms_decode / 1e3) / 1e12 / tf_peak,
+                                      "whole_step": (fl_dec + fl_pred) / (ms_all / 1e3) / 1e12 / tf_peak,
+                                      "definitions": "SURVEY 8(d) config 4 @128: predictor 234.7 GFLOP / sequence, MLP decoder "
+                                                     "4.89 + CNN 10.46 GFLOP / frame (dense formulation), tensor roofline"}}
+    del dino, predc, feats
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -122,7 +173,7 @@ def run_reference(args):
         "config": {"workload": f"CATER-shape TextOCVP rollout, 20-frame decomp + 19 preds + decode, L={L_TEXT}",
                    "batch_per_step": b, "note": "reference algorithm (oracle port, torch CPU fp32) on host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"B={b} sequences x 19 predicted frames per step, {len(t)} timed steps"},
+                         "sample": f"B={b} sequences x 19 predicted frames per step, {len(t)} timed steps", **CPU_NOTE},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -145,7 +196,12 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    strong = args.global_batch > 0
+    if strong:
+        lo, hi = rollout.shard_range(rank, world, args.global_batch)   # rank r <- sequences [r*G/N, (r+1)*G/N)
+        B = hi - lo
+    else:
+        B = args.batch
     savi, pred, _ = rollout.build_models(dev, num_context=NUM_CONTEXT, num_preds=NUM_PREDS)
     videos_h, text_h, noise = weights.synthetic_inputs(B, T_FRAMES, L_TEXT, seed=100 + rank)
     videos_h, text_h = videos_h.pin_memory(), text_h.pin_memory()
@@ -246,7 +302,7 @@ def run_ours(args):
     # ---- informational extras (rank 0, outside the headline regions): per-stage times, the seed-only decomp variant of
     #      SURVEY 8(d) config 3 and the corrector microbench of config 2
     extras = None
-    if rank == 0 and world == 1:      # single-GPU runs only: other ranks must not wait for rank 0's extra measurements
+    if rank == 0 and world == 1 and not args.no_extras:   # single-GPU runs only: other ranks must not wait for rank 0
         def timed(fn, n=3):
             fn(); torch.cuda.synchronize()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,6 +312,9 @@ def run_ours(args):
             b_.record(); torch.cuda.synchronize()
             return a.elapsed_time(b_) / n, r
         ms_dec, od = timed(lambda: savi(mode="decomp", x=videos_d, num_imgs=T_FRAMES, decode=False, init_slots=init))
+        xs = videos_d.reshape(B * T_FRAMES, 3, 64, 64)
+        ms_enc, (f16_all, _) = timed(lambda: savi._encode_raw(xs, B * T_FRAMES, 3 * 64 * 64, False))
+        del f16_all
         ms_pred, ps = timed(lambda: pred(od["slot_history"], text_embeddings=text_d))
         ms_decode, _ = timed(lambda: savi.decode(ps.reshape(B * NUM_PREDS, savi.num_slots, savi.slot_dim), only_imgs=True))
         ms_seed, _ = timed(lambda: rollout.forward_eval(savi, pred, videos_d, text_d, NUM_CONTEXT, NUM_PREDS,
@@ -270,13 +329,23 @@ def run_ours(args):
         except Exception:
             pass
         hbm = float(peaks_.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks_.get("bf16_tflops_sustained", 1400.0))
+        ms_corr = max(ms_dec - ms_enc, 1e-3)                       # corrector chain = decomp minus the encoder
+        corr_bytes = T_FRAMES * sa_bytes                           # features of every frame read once + slots in / out
         extras = {
-            "stage_ms": {"decomp_20_frames": ms_dec, "predict_19_steps": ms_pred, "decode_composite": ms_decode},
+            "stage_ms": {"decomp_20_frames": ms_dec, "encode_20_frames": ms_enc, "corrector_chain_20_frames": ms_corr,
+                         "predict_19_steps": ms_pred, "decode_composite": ms_decode},
             "stage_frac_of_roofline": {
-                "predictor_tensor (29.3 TFLOP dense formulation / measured sustained bf16 peak)":
-                    29.3e12 * (B / 256) / (ms_pred / 1e3) / 1e12 / float(peaks_.get("bf16_tflops_sustained", 1400.0)),
-                "decoder_tensor_executed (98.1 TFLOP executed; 163.9 dense)":
-                    98.1e12 * (B / 256) / (ms_decode / 1e3) / 1e12 / float(peaks_.get("bf16_tflops_sustained", 1400.0))},
+                "encoder": 0.817e9 * B * T_FRAMES / (ms_enc / 1e3) / 1e12 / tf_peak,
+                "corrector": corr_bytes / (ms_corr / 1e3) / 1e9 / hbm,
+                "predictor": 29.3e12 * (B / 256) / (ms_pred / 1e3) / 1e12 / tf_peak,
+                "decoder": 98.1e12 * (B / 256) / (ms_decode / 1e3) / 1e12 / tf_peak,
+                "decoder_dense_formulation": 163.9e12 * (B / 256) / (ms_decode / 1e3) / 1e12 / tf_peak,
+                "definitions": "SURVEY 8(d): encoder 0.817 GFLOP / frame (tensor); corrector 258 MiB of f16 features per frame "
+                               "of 256 sequences read once + slots (HBM; 22 passes are made: 3 on frame 0); predictor 29.3 "
+                               "TFLOP dense formulation per 256 sequences (tensor); decoder 98.1 TFLOP executed (layer 1 is "
+                               "computed algebraically) / 163.9 TFLOP dense formulation (tensor).  Tensor peak = measured "
+                               "sustained bf16, HBM peak = measured copy bandwidth (MEASURED_PEAKS.json)"},
             "seed_only_decomp": {"value": B * NUM_PREDS / (ms_seed / 1e3), "unit": "frames/s", "ms_per_step": ms_seed,
                                  "note": "num_imgs = num_context = 1: only the seed frame is encoded (SURVEY 8d config 3 variant)"},
             "corrector_microbench": {"config": "SlotAttention 3 iterations, 8 slots, 64x64 grid, batch %d, f16 features" % B,
@@ -285,7 +354,12 @@ def run_ours(args):
                                      "frac_read_once": sa_bytes / (ms_sa / 1e3) / 1e9 / hbm},
         }
 
-    frames_per_step = world * B * NUM_PREDS
+        try:
+            extras["cliport"] = cliport_extras(dev, timed, tf_peak)
+        except Exception as e:                                     # informational: never fail the headline for it
+            extras["cliport"] = {"error": repr(e)[:200]}
+
+    frames_per_step = (args.global_batch if strong else world * B) * NUM_PREDS
     value = frames_per_step * args.steps / (ms_total / 1e3)
     e2e_value = frames_per_step * args.steps / (e2e_ms / 1e3)
 
@@ -312,10 +386,8 @@ def run_ours(args):
         achieved_alone = sum(per_launch[i] for i in alone) / (sum(conv_ms[i] for i in alone) / 1e3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_tc2_kernel<64,64,4,5> = CTA-pair conv5x5 64->64 (decoder layers 2-4)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": 2.096e9 if B * NUM_PREDS >= 256 else None,
-                    "traffic_note": "bytes per launch of 2048 slot-images: dram__bytes_read.sum + dram__bytes_write.sum "
-                                    "from the ncu --set full capture in profiles/conv64_pair_r1_summary.md "
-                                    "(algorithmic: 2.147e9)",
+                    "traffic": TRAFFIC["bytes_per_launch"] if B * NUM_PREDS >= 256 else None,
+                    "traffic_source": TRAFFIC,
                     "peak_source": peak_src, "avg_launch_ms": conv_avg_ms,
                     "achieved_launches_running_alone": achieved_alone, "frac_launches_running_alone": achieved_alone / peak_tf,
                     "note": "achieved / frac average ALL launches inside the timed steps; one launch in three (decoder layer "
@@ -331,16 +403,19 @@ def run_ours(args):
             cpu_fps = args.cpu_batch * NUM_PREDS * len(tt) / sum(tt)
             cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                             "sample": f"B={args.cpu_batch} sequence(s), full 20-frame decomp + 19-step rollout + decode, "
-                                      f"{len(tt)} timed reps after 1 warm-up (oracle port, torch CPU fp32)"}
+                                      f"{len(tt)} timed reps after 1 warm-up (oracle port, torch CPU fp32)", **CPU_NOTE}
         line = {
             "metric": "predicted frames/sec (19-step rollout)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": "Full CATER-shape TextOCVP rollout (configs[2]): 64x64 RGB, 8 slots x 128-d, 1 seed + 19 "
                                    "predicted frames, 20-frame decomp (evaluator-faithful), L=32 synthetic text embeddings, "
                                    "random init (mlp_out x0.1)",
-                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch-sharded x{world}",
+                       "batch_per_gpu": B, "global_batch": args.global_batch if strong else world * B,
+                       "parallelism": (f"batch-sharded x{world}, STRONG scaling: global batch {args.global_batch} fixed "
+                                       f"(BASELINE configs[4])" if strong else
+                                       f"batch-sharded x{world}, WEAK scaling: {B} sequences per GPU (configs[2] per GPU)"),
                        "l2": "inputs (251 MB video / step) and activations exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": videos_h.numel() * 4 + text_h.numel() * 4,
                     "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_ms / args.steps},

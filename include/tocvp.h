@@ -14,7 +14,12 @@
  *     workspaces are caller-owned (tocvp_*_workspace_bytes reports the size needed);
  *   - return value: TOCVP_OK (0) or a negative error code; tocvp_last_error() returns a
  *     thread-local message.  Nothing throws, nothing calls exit();
- *   - no global mutable state besides caches of immutable device attributes;
+ *   - no process-wide tuning state: kernel-selection options travel with each call (tocvp_tuning below, caller-owned,
+ *     NULL = defaults).  What the library keeps across calls: per-device caches of immutable attributes (SM count, the
+ *     dynamic-shared-memory attribute of each kernel), the per-device internal side stream + events of tocvp_savi_decode
+ *     (created on first use, mutex-guarded), a thread-local error string and a launch counter (statistics).  Calls are
+ *     re-entrant across threads and streams and run on the caller's CURRENT device (the library never calls
+ *     cudaSetDevice);
  *   - fp32 tensors are 16-byte aligned; fp16 tensors ("f16" below) are IEEE binary16, 16-byte
  *     aligned, row-major with the channel / feature dimension innermost (NHWC for images);
  *   - there is NO CPU fallback: on anything but an sm_100 device tocvp_init() fails.
@@ -29,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TOCVP_ABI_VERSION 1
+#define TOCVP_ABI_VERSION 2
 
 #define TOCVP_OK 0
 #define TOCVP_ERR_BAD_ARG (-1)   /* bad shape / null or misaligned pointer / unsupported size */
@@ -38,13 +43,40 @@ extern "C" {
 #define TOCVP_ERR_WORKSPACE (-4) /* workspace too small                                         */
 
 int tocvp_abi_version(void);
-/* Checks that `device` is an sm_100 part and makes it current. */
+/* Checks that `device` is an sm_100 part (does not change the current device). */
 int tocvp_init(int device);
 const char* tocvp_last_error(void);
 /* Statistics: number of kernels this library has launched so far in this process (monotonic). */
 unsigned long long tocvp_kernel_launches(void);
 /* For callers that replay captured library calls from a CUDA graph: adds the graph's kernel count to the statistic. */
 void tocvp_note_graph_replay(unsigned long long n_kernels);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-call kernel-selection options (tests, A/B measurements).  All-zero = the defaults a product caller gets with
+ * tuning == NULL.  The struct is caller-owned and read during the call only.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_tuning {
+  int gemm_mode;      /* 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) GEMM kernels, 1 =
+                         single-CTA kernel only, 128 / 256 = pair kernel with that tile width wherever applicable */
+  int gemm_no_wres;   /* 1 = W-resident variant of the 256-wide pair kernel (K <= 512) off */
+  int conv_mode;      /* 0 = CTA-pair conv5x5 kernel whenever the tile count is even, 1 = single-CTA kernel only */
+  int encode_mode;    /* bit mask: bit 0 = first-version fp32 SIMT conv 1, bit 1 = separate posemb + LayerNorm pass
+                         (default: fused into conv 4's epilogue), bit 2 = the 32 -> 128 -> 128 MLP as two GEMMs (default:
+                         one kernel with two chained tcgen05 GEMMs when only f16 features are requested), bit 3 = conv 1 as
+                         25 taps over zero-padded channels (default: x-taps folded into K, 3 taps) */
+  int decode_mode;    /* bit mask: bit 0 = decoder layer 1 generated inside the layer-2 convolution kernel (default:
+                         separate bandwidth kernel), bit 1 = first-version head conv3x3 (shifted windows, N = 16; default:
+                         nine taps in the GEMM's N dimension), bit 2 = first-version (image-stationary) layer-1 kernel,
+                         bit 3 = serial chunks (default: chunk-pipelined, layer 1 of chunk i+1 on an internal side stream
+                         under the convolutions of chunk i), bit 4 = separate compositing kernel (default: fused into the
+                         head convolution's epilogue) */
+  int corrector_mode; /* 1 = first-version fp32 SIMT loops in the per-slot update kernel (default: 3xTF32 mma.sync) */
+  int no_pdl;         /* 1 = plain stream order (default: programmatic dependent launch, bit-identical results) */
+  int no_tile_alternation; /* 1 = every predictor kernel walks its row blocks ascending (default: alternating, so a
+                         consumer starts with the rows its producer wrote last; bit-identical results) */
+  int reserved[8];
+} tocvp_tuning;
+size_t tocvp_sizeof_tuning(void);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projection: C[M,N] = A[M,K] . W[N,K]^T (+bias) (ReLU) (+residual), tcgen05 / TMEM / TMA.
@@ -56,12 +88,7 @@ void tocvp_note_graph_replay(unsigned long long n_kernels);
  * ------------------------------------------------------------------------------------------ */
 int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                    int relu, const float* residual, int ldr, float* out_f32, int ld32, void* out_f16, int ld16,
-                   void* stream);
-
-/* Tuning / test knob (process-wide): 0 = automatic choice between the single-CTA and the CTA-pair (cta_group::2) GEMM
- * kernels (default), 1 = single-CTA kernel only, 128 / 256 = pair kernel with that tile width wherever applicable;
- * 258 / 259 = W-resident variant of the 256-wide pair kernel (K <= 512) off / on (default on). */
-int tocvp_set_gemm_mode(int mode);
+                   const tocvp_tuning* tuning, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row LayerNorm (fp32 statistics): y = LN(x (+ add[row % add_rows])) * gamma + beta.
@@ -83,10 +110,7 @@ int tocvp_layernorm(const void* x, int x_is_f16, int ldx, const float* add, int 
  * src/models/EncodersDecoders/decoders.py:96-108 and encoders.py:141-153.
  * ------------------------------------------------------------------------------------------ */
 int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H, int W,
-                      int cin, int cout, int relu, void* stream);
-/* Tuning / test knob (process-wide): 0 = CTA-pair (cta_group::2) conv kernel whenever the tile count is even (default),
- * 1 = single-CTA kernel only. */
-int tocvp_set_conv_mode(int mode);
+                      int cin, int cout, int relu, const tocvp_tuning* tuning, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * SAVi / ExtendedDINOSAUR corrector: SlotAttention.forward (src/models/Blocks/attention.py:67-112) for
@@ -106,13 +130,11 @@ typedef struct tocvp_sa_weights {
   int mlp_hidden, t_heads, t_hidden;
   float attn_eps, ln_eps_sa, ln_eps_tf, scale; /* 1e-8, 1e-3, 1e-6, dim_feats^-0.5 */
   int num_slots;                               /* 4..11: 8 (SAVi.json) and 10 (ExtendedDINOSAUR.json) are the named ones */
+  const tocvp_tuning* tuning;                  /* NULL = defaults */
 } tocvp_sa_weights;
 
 size_t tocvp_sizeof_sa_weights(void);
 size_t tocvp_slot_attention_workspace_bytes(int B);
-/* Tuning / test knob (per device, current device): 0 (default) = the per-slot update kernel (V projection, GRU, MLPs,
- * transition) runs its 16-row matrix products as 3xTF32 mma.sync; 1 = first-version fp32 SIMT loops. */
-int tocvp_set_corrector_mode(int simt_update);
 /* feats fp32 or f16: sequence b's [N,128] block starts at feats + b*feats_seq_stride (elements), so the features of
  * frame t inside a [B,T,N,128] encode batch are used in place; slots_in [B,S,128]; slots_out row b at
  * slots_out + b*out_stride (floats), so results land straight in slot_history[:, t]; pred_out (optional) =
@@ -181,6 +203,7 @@ typedef struct tocvp_pred_weights {
   const void* mlp_out_w;            /* f16 [D, T] */
   const float* mlp_out_b;
   const float* pe_flipped;          /* fp32 [buffer_size][buffer_size][T]: table n-1 row f = pe[n-1-f] (f < n) */
+  const tocvp_tuning* tuning;       /* NULL = defaults */
 } tocvp_pred_weights;
 
 size_t tocvp_sizeof_pred_weights(void);
@@ -216,14 +239,10 @@ typedef struct tocvp_enc_weights {
   const void* w_conv1_tc;    /* f16 [25,32,32] tap-major, input channels zero-padded 3 -> 32: conv 1 on the tensor cores */
   const void* w_conv1_vp;    /* f16 [3,32,32]: conv 1 with the 5 x-taps x 3 channels of two filter rows folded into K = 32
                                 (k = half*16 + kx*3 + c), three vertical taps two rows apart; null = use w_conv1_tc */
+  const tocvp_tuning* tuning; /* NULL = defaults */
 } tocvp_enc_weights;
 
 size_t tocvp_sizeof_enc_weights(void);
-/* Tuning / test knob (process-wide), bit mask: bit 0 = first-version fp32 SIMT conv 1 (default: tensor-core conv with
- * zero-padded input channels), bit 1 = separate posemb + LayerNorm pass (default: fused into conv 4's epilogue),
- * bit 2 = the 32 -> 128 -> 128 MLP as two GEMMs (default: one kernel with two chained tcgen05 GEMMs when only f16
- * features are requested), bit 3 = conv 1 as 25 taps over zero-padded channels (default: x-taps folded into K, 3 taps). */
-int tocvp_set_encode_mode(int mode);
 size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img);
 /* frames fp32: image i = 3 planes of H x W at frames + i*img_stride (floats), so x[:, t] of a [B,T,3,H,W] video is
  * addressed in place; feats [n_img, H*W, F] written as f16 and/or fp32 (either may be NULL, not both). */
@@ -243,6 +262,7 @@ typedef struct tocvp_dec_weights {
   const float* b_out;        /* [4] */
   int H, W, slot_dim, num_slots, hidden;
   const void* w_out_taps;    /* f16 [48][64]: row (ky*3+kx)*4 + co (rows 36..47 zero), col ci: the 9 taps in the GEMM N dim */
+  const tocvp_tuning* tuning; /* NULL = defaults */
 } tocvp_dec_weights;
 
 size_t tocvp_sizeof_dec_weights(void);
@@ -268,6 +288,7 @@ typedef struct tocvp_proj_weights {
   const float* b2;
   int feat_dim, hidden_dim, slot_dim;
   float ln_eps;             /* 1e-5 (nn.LayerNorm default)           */
+  const tocvp_tuning* tuning; /* NULL = defaults */
 } tocvp_proj_weights;
 
 size_t tocvp_sizeof_proj_weights(void);
@@ -307,6 +328,7 @@ typedef struct tocvp_patch_weights {
   int n_mlp, n_cnn, out_cin, out_up, reconstruct_images;
   int num_slots, slot_dim, num_patches, grid, feat_dim, img_size;
   float ln_eps;             /* 1e-5 */
+  const tocvp_tuning* tuning; /* NULL = defaults */
 } tocvp_patch_weights;
 
 size_t tocvp_sizeof_patch_weights(void);
@@ -384,29 +406,34 @@ size_t tocvp_sizeof_ocvp_weights(void);
 int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t seq_stride, int B, int n, float* out,
                        void* stream);
 
-/* Tuning / test knob (process-wide), bit mask.  Bit 0: 1 = decoder layer 1 is generated inside the layer-2 convolution
- * kernel and never stored; 0 (default, measured faster in round 1) = separate bandwidth kernel + stored activation.
- * Bit 1: 1 = first-version head conv3x3 (shifted windows, N = 16); 0 (default) = nine taps in the GEMM's N dimension.
- * Bit 2: 1 = first-version (image-stationary) layer-1 kernel; 0 (default) = pixel-stationary kernel.
- * Bit 3: 1 = serial chunks; 0 (default) = chunk-pipelined: layer 1 of chunk i+1 is written on an internal side stream
- * (forked from and joined back into the caller's stream by events) under the convolutions of chunk i. */
-int tocvp_set_decode_mode(int mode);
-
-/* Tuning / test knob (process-wide): 1 (default) = the GEMM / attention / LayerNorm / window kernels are launched with
- * programmatic stream serialization, so a kernel's prologue (barrier init, TMEM allocation, resident-weight loads) overlaps
- * the previous kernel's tail and it blocks in griddepcontrol.wait before touching activations; 0 = plain stream order.
- * Results are bit-identical either way (tools/ab_pdl.py: predictor rollout 45.7 -> 45.1 ms under graph replay). */
-int tocvp_set_pdl(int on);
-
-/* Tuning / test knob (process-wide): 1 (default) = the predictor alternates the row-block traversal direction of
- * consecutive GEMM / attention kernels, so a consumer starts with the rows its producer wrote last (still in L2) instead
- * of re-streaming tensors larger than the L2 in the same order; 0 = every kernel walks ascending.  Bit-identical. */
-int tocvp_set_tile_order(int alternate);
-
-/* Test-only hardware probe (not on the product path): D[128,64] = X[shift:shift+128, :64] . W^T with the
- * A operand descriptor started `shift` 128-byte rows into a swizzled TMA tile.  See csrc/probe.cu. */
-int tocvp_probe_shifted_operand(const void* X, const void* W, float* out, int shift, int base_offset_mode,
-                                void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone forwards of the reference's sub-modules.  The fused stage entry points above never call these; they exist
+ * so that calls a reference user can make on a sub-module (`savi.transition_module(slots)`, `savi.decoder(x)`,
+ * `savi.encoder(x)`, `predictor.pe(x)`, `savi.encoder_pos_embedding(x)`) run on this library too.
+ * ------------------------------------------------------------------------------------------ */
+/* TransformerBlock.forward, post-norm flavour (src/models/Blocks/attention.py:387-395; SAVi transition, SAVi.py:193):
+ * slots fp32 [B, S, 128] -> out fp32 [B, S, 128].  Only the t_* fields, num_slots, t_heads, t_hidden, ln_eps_tf of w are read. */
+int tocvp_transition(const tocvp_sa_weights* w, const float* slots, int B, float* out, void* stream);
+/* SimpleConvEncoder.forward (src/models/EncodersDecoders/encoders.py:156-159): frames as in tocvp_savi_encode ->
+ * NHWC f16 [n_img, H, W, 32] after the fourth conv + ReLU.  Workspace: tocvp_savi_encode_workspace_bytes(w, n_img). */
+int tocvp_savi_conv_stack(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img,
+                          void* out_nhwc_f16, void* workspace, size_t ws_bytes, void* stream);
+/* conv5x5 (stride 1, zero padding 2) + bias (+ReLU) on a materialised NCHW fp32 tensor with ANY channel counts, fp32 SIMT:
+ * x [n_img, cin, H, W], weight [cout, cin, 5, 5] (torch layout), out as NHWC f16 and/or NCHW fp32.  First layer of
+ * ConvDecoder.forward (decoders.py:111-125) when it is called on an arbitrary tensor rather than on broadcast slots. */
+int tocvp_conv5x5_generic(const float* x, const float* weight, const float* bias, int relu, void* out_nhwc_f16,
+                          float* out_nchw_f32, int n_img, int H, int W, int cin, int cout, void* stream);
+/* Last layer of ConvDecoder.forward (decoders.py:104-108): conv3x3 64 -> 4, no activation; x NHWC f16 [n_img,H,W,64] ->
+ * NHWC fp32 [n_img, H, W, 4]. */
+int tocvp_conv3x3_head(const tocvp_dec_weights* w, const void* x_nhwc_f16, int n_img, float* out_nhwc4, void* stream);
+/* out[row] = x[row] + table[(row / div) % mod], fp32 rows of D floats: SoftPositionEmbed.forward (model_blocks.py:215-226:
+ * div = 1, mod = H*W, table = projection(grid)) and TemporalPositionalEncoding.forward (model_blocks.py:358-379: div = S,
+ * mod = n, table = flip(pe[:n])). */
+int tocvp_add_table(const float* x, const float* table, int div, int mod, int D, size_t rows, float* out, void* stream);
+/* fp32 -> f16, saturating at +-65504 (the entry format of the tensor-core kernels). */
+int tocvp_cast_f16(const float* in, void* out, size_t n, void* stream);
+/* in-place clamp to [0, 1] (src/05_evaluate_predictor.py:96). */
+int tocvp_clamp01(float* x, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,13 @@ def golden_dino_weights(golden_dino):
     feats, text, noise = weights.synthetic_dino_inputs(m["B"], m["T"], m["N"], L=m["L"], seed=m["input_seed"])
     init = dsd["initializer.slots_mu"] + dsd["initializer.slots_sigma"] * noise
     return dict(dino_sd=dsd, pred_sd=psd, feats=feats, text=text, init=init)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured errors of the parity tests next to their gates (oracle/parity_log.py) -> gpurun_out/parity_r2.md."""
+    try:
+        from oracle import parity_log
+        if parity_log.RECORDS:
+            parity_log.dump(os.path.join(ROOT, "gpurun_out", "parity_r2.md"))
+    except Exception as e:                       # the log must never turn a green run red
+        print(f"parity log not written: {e}")

@@ -1,8 +1,8 @@
-// Hardware probe (test-only entry point, not on the product path): does a K-major SWIZZLE_128B UMMA
+// Hardware probe (test-only library tests/native/libtocvp_probe.so; not part of libtocvp.so or include/tocvp.h): does a K-major SWIZZLE_128B UMMA
 // operand descriptor accept a start address that is offset by an arbitrary number of 128-byte rows
 // inside a 1024B-aligned TMA-written buffer?  The implicit-GEMM convolution relies on exactly that
 // (every filter tap is the same smem halo tile read at a shifted start row), so the property is
-// checked on the real part by tests/test_probe_gpu.py before anything is built on it.
+// checked on the real part by tests/test_kernels_gpu.py before anything is built on it.
 //   D[128,64] = X[shift : shift+128, 0:64] . W[64,64]^T
 #include "host_util.h"
 #include "ptx.cuh"

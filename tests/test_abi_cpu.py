@@ -11,7 +11,8 @@ def test_library_exports_all_declared_symbols():
     assert "tocvp_gemm_f16" in names and "tocvp_init" in names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.tocvp_abi_version() == 1
+    assert lib.tocvp_abi_version() == 2
+    assert not [n for n in names if n.startswith("tocvp_set_") or "probe" in n], "no process-wide knobs in the product ABI"
 
 
 def test_entry_points_reject_bad_arguments_without_a_device():
@@ -39,5 +40,7 @@ def test_entry_points_reject_bad_arguments_without_a_device():
     # workspace queries with null weights answer 0 instead of crashing
     lib.tocvp_savi_decode_workspace_bytes.restype = ctypes.c_size_t
     assert lib.tocvp_savi_decode_workspace_bytes(null, 4) == 0
-    # knobs are plain setters
-    assert lib.tocvp_set_pdl(1) == 0 and lib.tocvp_set_tile_order(1) == 0 and lib.tocvp_set_decode_mode(0) == 0
+    # tuning options travel with each call (tocvp_tuning); the library exports no process-wide setters
+    assert not hasattr(lib, "tocvp_tuning.no_pdl") and not hasattr(lib, "tocvp_tuning.decode_mode")
+    lib.tocvp_sizeof_tuning.restype = ctypes.c_size_t
+    assert lib.tocvp_sizeof_tuning() == ctypes.sizeof(_lib.Tuning)

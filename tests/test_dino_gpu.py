@@ -4,6 +4,7 @@ test_stages_gpu.py: per-stage relative L2 error <= 1e-3 on identical stage input
 import pytest
 import torch
 
+from oracle import parity_log as PL
 from oracle import textocvp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -28,17 +29,17 @@ def dmodels(golden_dino, golden_dino_weights):
 def test_project(dmodels, golden_dino, golden_dino_weights):
     dino, _ = dmodels
     x = golden_dino_weights["feats"][:, 0].cuda()
-    assert O.rel_err(dino.project(x, want_f32=True), golden_dino["proj_feats"]) < STAGE_TOL
-    assert O.rel_err(dino.project(x).float(), golden_dino["proj_feats"]) < STAGE_TOL      # f16 pipeline format
+    PL.check(O.rel_err(dino.project(x, want_f32=True), golden_dino["proj_feats"]), STAGE_TOL, "dino.project(x, want_f32=True), golden_dino['proj_feats']")
+    PL.check(O.rel_err(dino.project(x).float(), golden_dino["proj_feats"]), STAGE_TOL      # f16 pipeline format, "dino.project(x).float(), golden_dino['proj_feats']")
 
 
 def test_slot_attention_10_slots(dmodels, golden_dino, golden_dino_weights):
     dino, _ = dmodels
     proj = golden_dino["proj_feats"].cuda()                       # identical stage input (reference features)
     init = golden_dino_weights["init"].cuda()
-    assert O.rel_err(dino.slot_attention(proj, init, step=0), golden_dino["sa_step0"]) < STAGE_TOL
-    assert O.rel_err(dino.slot_attention(proj, init, step=1), golden_dino["sa_step1"]) < STAGE_TOL
-    assert O.rel_err(dino.slot_attention(proj.half(), init, step=0), golden_dino["sa_step0"]) < STAGE_TOL
+    PL.check(O.rel_err(dino.slot_attention(proj, init, step=0), golden_dino["sa_step0"]), STAGE_TOL, "dino.slot_attention(proj, init, step=0), golden_dino['sa_step0']")
+    PL.check(O.rel_err(dino.slot_attention(proj, init, step=1), golden_dino["sa_step1"]), STAGE_TOL, "dino.slot_attention(proj, init, step=1), golden_dino['sa_step1']")
+    PL.check(O.rel_err(dino.slot_attention(proj.half(), init, step=0), golden_dino["sa_step0"]), STAGE_TOL, "dino.slot_attention(proj.half(), init, step=0), golden_dino['sa_step0']")
 
 
 def test_slot_attention_ragged(dmodels, golden_dino_weights):
@@ -52,7 +53,7 @@ def test_slot_attention_ragged(dmodels, golden_dino_weights):
         feats = torch.randn(B, N, 128, generator=g)
         init = torch.randn(B, 10, 128, generator=g)
         ref = O.slot_attention(sd, feats, init, 0, cfg)
-        assert O.rel_err(dino.slot_attention(feats.cuda(), init.cuda(), step=0), ref) < STAGE_TOL, (B, N)
+        PL.check(O.rel_err(dino.slot_attention(feats.cuda(), init.cuda(), step=0), ref), STAGE_TOL, "dino.slot_attention(feats.cuda(), init.cuda(), step=0), ref")
 
 
 def test_decomp(dmodels, golden_dino, golden_dino_weights):
@@ -62,8 +63,8 @@ def test_decomp(dmodels, golden_dino, golden_dino_weights):
                init_slots=golden_dino_weights["init"].cuda())
     sh = out["slot_history"]
     assert sh.shape == (m["B"], m["T"], 10, 128)
-    assert O.rel_err(sh[:, 0], golden_dino["slot_history"][:, 0]) < STAGE_TOL
-    assert O.rel_err(sh, golden_dino["slot_history"]) < 3 * STAGE_TOL
+    PL.check(O.rel_err(sh[:, 0], golden_dino["slot_history"][:, 0]), STAGE_TOL, "sh[:, 0], golden_dino['slot_history'][:, 0]")
+    PL.check(O.rel_err(sh, golden_dino["slot_history"]), 3 * STAGE_TOL, "sh, golden_dino['slot_history']")
     dino.chain_corrector = False                       # one library call per frame (first version): bit-identical
     try:
         ref = dino(mode="decomp", x=golden_dino_weights["feats"].cuda(), num_imgs=m["T"], decode=False,
@@ -80,10 +81,10 @@ def test_patch_decode(dmodels, golden_dino):
     assert out["recons_feats"].shape == golden_dino["pred_feats"].shape
     assert out["masks"].shape == golden_dino["pred_masks"].shape
     assert out["recons_imgs"].shape == golden_dino["pred_imgs"].shape
-    assert O.rel_err(out["masks"], golden_dino["pred_masks"]) < STAGE_TOL
-    assert O.rel_err(out["recons_feats"], golden_dino["pred_feats"]) < STAGE_TOL
+    PL.check(O.rel_err(out["masks"], golden_dino["pred_masks"]), STAGE_TOL, "out['masks'], golden_dino['pred_masks']")
+    PL.check(O.rel_err(out["recons_feats"], golden_dino["pred_feats"]), STAGE_TOL, "out['recons_feats'], golden_dino['pred_feats']")
     # 5 convolutions (K up to 9216) behind the MLP: one stage budget for the MLP + one for the CNN
-    assert O.rel_err(out["recons_imgs"], golden_dino["pred_imgs"]) < 2 * STAGE_TOL
+    PL.check(O.rel_err(out["recons_imgs"], golden_dino["pred_imgs"]), 2 * STAGE_TOL, "out['recons_imgs'], golden_dino['pred_imgs']")
 
 
 def test_patch_decode_336(golden_dino_weights):
@@ -99,8 +100,8 @@ def test_patch_decode_336(golden_dino_weights):
     ref = O.mlp_patch_decode(sd, slots, O.DinoCfg(img_size=336, num_patches=576))
     out = dino(mode="decode", slots=slots.cuda())
     assert out["recons_imgs"].shape == (1, 3, 336, 336)
-    assert O.rel_err(out["recons_feats"], ref["recons_feats"]) < STAGE_TOL
-    assert O.rel_err(out["recons_imgs"], ref["recons_imgs"]) < 2 * STAGE_TOL
+    PL.check(O.rel_err(out["recons_feats"], ref["recons_feats"]), STAGE_TOL, "out['recons_feats'], ref['recons_feats']")
+    PL.check(O.rel_err(out["recons_imgs"], ref["recons_imgs"]), 2 * STAGE_TOL, "out['recons_imgs'], ref['recons_imgs']")
 
 
 def test_dino_rollout(dmodels, golden_dino, golden_dino_weights):
@@ -110,7 +111,7 @@ def test_dino_rollout(dmodels, golden_dino, golden_dino_weights):
     sh = dino(mode="decomp", x=w["feats"].cuda(), num_imgs=m["T"], decode=False, init_slots=w["init"].cuda())["slot_history"]
     ps = pred(sh, text_embeddings=w["text"].cuda())
     assert ps.shape == (m["B"], m["num_preds"], 10, 128)
-    assert O.rel_err(ps, golden_dino["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(ps, golden_dino["pred_slots"]), 5e-3, "ps, golden_dino['pred_slots']")
     imgs = dino(mode="decode", slots=ps.reshape(-1, 10, 128))["recons_imgs"].clamp(0, 1)
     p = O.psnr(imgs.cpu(), golden_dino["pred_imgs"].clamp(0, 1))
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")

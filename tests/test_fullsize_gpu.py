@@ -13,6 +13,7 @@ recomputed there; instead:
 import pytest
 import torch
 
+from oracle import parity_log as PL
 from oracle import textocvp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -50,10 +51,10 @@ def test_golden_sequences_inside_full_batch(full, golden):
     out = full["out"]
     assert out["pred_imgs"].shape == (B, 19, 3, 64, 64)
     idx = list(POS)
-    assert O.rel_err(out["slot_history"][idx], golden["slot_history"]) < 3e-3
-    assert O.rel_err(out["pred_slots"][idx], golden["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(out["slot_history"][idx], golden["slot_history"]), 3e-3, "out['slot_history'][idx], golden['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"][idx], golden["pred_slots"]), 5e-3, "out['pred_slots'][idx], golden['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), golden["pred_imgs"])
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
 
 def test_oracle_spot_check_inside_full_batch(full, golden_weights):
@@ -61,9 +62,9 @@ def test_oracle_spot_check_inside_full_batch(full, golden_weights):
     ref = O.rollout(golden_weights["savi_sd"], golden_weights["pred_sd"], full["videos"][idx], full["text"][idx],
                     full["init"][idx], O.SAViCfg(), O.PredCfg(num_context=1, num_preds=19))
     out = full["out"]
-    assert O.rel_err(out["pred_slots"][idx], ref["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), 5e-3, "out['pred_slots'][idx], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), ref["pred_imgs"])
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
 
 def test_batch_order_and_sharding_are_bit_exact(full):
@@ -129,10 +130,10 @@ def test_cliport_oracle_spot_check_inside_full_batch(full_dino, golden_dino_weig
                          O.DinoCfg(img_size=m["img_size"], num_patches=m["N"]), O.PredCfg(num_context=1, num_preds=DPREDS))
     out = full_dino["out"]
     assert out["pred_imgs"].shape == (DB, DPREDS, 3, m["img_size"], m["img_size"])
-    assert O.rel_err(out["slot_history"][idx], ref["slot_history"]) < 3e-3
-    assert O.rel_err(out["pred_slots"][idx], ref["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(out["slot_history"][idx], ref["slot_history"]), 3e-3, "out['slot_history'][idx], ref['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), 5e-3, "out['pred_slots'][idx], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), ref["pred_imgs"])
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
 
 def test_cliport_batch_order_and_sharding(full_dino):
@@ -148,6 +149,6 @@ def test_cliport_batch_order_and_sharding(full_dino):
     for lo in (0, DB // 2):
         sh = full_dino["run"](torch.arange(lo, lo + DB // 2))
         assert torch.equal(sh["slot_history"], out["slot_history"][lo:lo + DB // 2]), lo
-        assert O.rel_err(sh["pred_slots"], out["pred_slots"][lo:lo + DB // 2]) < 2e-3
+        PL.check(O.rel_err(sh["pred_slots"], out["pred_slots"][lo:lo + DB // 2]), 2e-3, "sh['pred_slots'], out['pred_slots'][lo:lo + DB // 2]")
         p = O.psnr(sh["pred_imgs"].cpu(), out["pred_imgs"][lo:lo + DB // 2].cpu())
-        assert p.min() >= 50.0, (p.min(), p.mean())
+        PL.check_min(p.min(), 50.0, "frame PSNR vs reference (dB), min")

@@ -5,6 +5,7 @@ GEMM/conv operands are IEEE f16 (10-bit mantissa, same as TF32), fp32 accumulate
 import pytest
 import torch
 
+from oracle import parity_log as PL
 from oracle import textocvp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -26,23 +27,23 @@ def models(golden_weights):
 
 @pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4, 8])
 def test_encode(models, golden, golden_weights, enc_mode):
-    """tocvp_set_encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
+    """tocvp_tuning.encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
     into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass."""
     from textocvp_b200 import _lib as L
     savi, _ = models
     x = golden_weights["videos"][:, 0].cuda()
-    L.call("tocvp_set_encode_mode", L.c_int(enc_mode))
+    setattr(L.TUNING, "encode_mode", int(enc_mode))
     try:
         feats = savi.encode(x)                                   # fp32 features: the MLP runs as two GEMMs
         f16, _ = savi._encode_raw(x, x.shape[0], x[0].numel(), want_f32=False)   # pipeline format: fused MLP unless bit 2
         torch.cuda.synchronize()
     finally:
-        L.call("tocvp_set_encode_mode", L.c_int(0))
-    assert O.rel_err(f16.float(), O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())) < STAGE_TOL
+        setattr(L.TUNING, "encode_mode", int(0))
+    PL.check(O.rel_err(f16.float(), O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())), STAGE_TOL, "f16.float(), O.savi_encode(golden_weights['savi_sd'], golden_weights['videos'][:, 0], O.SA")
     ref = O.savi_encode(golden_weights["savi_sd"], golden_weights["videos"][:, 0], O.SAViCfg())
-    assert O.rel_err(feats, ref) < STAGE_TOL
+    PL.check(O.rel_err(feats, ref), STAGE_TOL, "feats, ref")
     st = golden["meta"]["feat_stride"]
-    assert O.rel_err(feats[:, ::st], golden["encode_feats_sub"]) < STAGE_TOL
+    PL.check(O.rel_err(feats[:, ::st], golden["encode_feats_sub"]), STAGE_TOL, "feats[:, ::st], golden['encode_feats_sub']")
 
 
 def test_slot_attention_iterations(models, golden, golden_weights):
@@ -54,12 +55,12 @@ def test_slot_attention_iterations(models, golden, golden_weights):
     for it in (1, 2, 3):
         sa.num_iters_first = it
         out = sa(feats.cuda(), init.cuda(), step=0)
-        assert O.rel_err(out, golden[f"sa_iter{it}"]) < STAGE_TOL, it
+        PL.check(O.rel_err(out, golden[f"sa_iter{it}"]), STAGE_TOL, "out, golden[f'sa_iter{it}']")
     sa.num_iters_first = 3
     out = sa(feats.cuda(), init.cuda(), step=1)
-    assert O.rel_err(out, golden["sa_step1"]) < STAGE_TOL
+    PL.check(O.rel_err(out, golden["sa_step1"]), STAGE_TOL, "out, golden['sa_step1']")
     out16 = sa(feats.cuda().half(), init.cuda(), step=0)                    # f16 features (the pipeline's format)
-    assert O.rel_err(out16, golden["sa_iter3"]) < STAGE_TOL
+    PL.check(O.rel_err(out16, golden["sa_iter3"]), STAGE_TOL, "out16, golden['sa_iter3']")
 
 
 def test_decomp_and_transition(models, golden, golden_weights):
@@ -68,9 +69,9 @@ def test_decomp_and_transition(models, golden, golden_weights):
     out = savi(mode="decomp", x=v, num_imgs=20, decode=False, init_slots=golden_weights["init"].cuda())
     sh = out["slot_history"]
     assert sh.shape == (2, 20, 8, 128)
-    assert O.rel_err(sh[:, 0], golden["slot_history"][:, 0]) < STAGE_TOL
+    PL.check(O.rel_err(sh[:, 0], golden["slot_history"][:, 0]), STAGE_TOL, "sh[:, 0], golden['slot_history'][:, 0]")
     # recurrent over 20 frames (encode -> correct -> transition): errors compound, allow 3x the single-stage budget
-    assert O.rel_err(sh, golden["slot_history"]) < 3 * STAGE_TOL
+    PL.check(O.rel_err(sh, golden["slot_history"]), 3 * STAGE_TOL, "sh, golden['slot_history']")
 
 
 def test_decomp_chained_matches_per_frame(models, golden_weights):
@@ -106,32 +107,32 @@ def test_predictor_step(models, golden, golden_weights):
     sh = golden["slot_history"].cuda()
     text = golden_weights["text"].cuda()
     out = pred.predictor(slots=sh[:, :10], text_embeddings=text)
-    assert O.rel_err(out, golden["pred_step_n10"]) < STAGE_TOL
+    PL.check(O.rel_err(out, golden["pred_step_n10"]), STAGE_TOL, "out, golden['pred_step_n10']")
     # the quantity the network adds (mlp_out branch) must itself be accurate, not just slots + small delta
     d_ref = golden["pred_step_n10"] - golden["slot_history"][:, 9]
     d_out = out.cpu() - golden["slot_history"][:, 9]
-    assert O.rel_err(d_out, d_ref) < 5e-3
+    PL.check(O.rel_err(d_out, d_ref), 5e-3, "d_out, d_ref")
     out1 = pred.predictor(slots=sh[:, :1], text_embeddings=text)
-    assert O.rel_err(out1, golden["pred_step_n1"]) < STAGE_TOL
+    PL.check(O.rel_err(out1, golden["pred_step_n1"]), STAGE_TOL, "out1, golden['pred_step_n1']")
 
 
 @pytest.mark.parametrize("fuse_layer1", [0, 1, 2, 4])
 def test_decode(models, golden, golden_weights, fuse_layer1):
-    """tocvp_set_decode_mode bit mask.  0 (default): separate layer-1 kernel, head conv with the 9 taps in N;
+    """tocvp_tuning.decode_mode bit mask.  0 (default): separate layer-1 kernel, head conv with the 9 taps in N;
     1: decoder layer 1 generated inside the layer-2 conv kernel; 2: first-version head conv (shifted windows, N = 16);
     4: first-version (image-stationary) layer-1 kernel."""
     from textocvp_b200 import _lib as L
     savi, _ = models
     slots = golden["pred_slots"][:1, -1].cuda()
-    L.call("tocvp_set_decode_mode", L.c_int(fuse_layer1))
+    setattr(L.TUNING, "decode_mode", int(fuse_layer1))
     try:
         out = savi(mode="decode", slots=slots)
         torch.cuda.synchronize()
     finally:
-        L.call("tocvp_set_decode_mode", L.c_int(0))
-    assert O.rel_err(out["recons"], golden["dec_recons"]) < STAGE_TOL
-    assert O.rel_err(out["masks"], golden["dec_masks"]) < STAGE_TOL
-    assert O.rel_err(out["recons_imgs"], golden["dec_img"]) < STAGE_TOL
+        setattr(L.TUNING, "decode_mode", int(0))
+    PL.check(O.rel_err(out["recons"], golden["dec_recons"]), STAGE_TOL, "out['recons'], golden['dec_recons']")
+    PL.check(O.rel_err(out["masks"], golden["dec_masks"]), STAGE_TOL, "out['masks'], golden['dec_masks']")
+    PL.check(O.rel_err(out["recons_imgs"], golden["dec_img"]), STAGE_TOL, "out['recons_imgs'], golden['dec_img']")
 
 
 def test_decode_chunk_pipeline_matches_serial(models, golden):
@@ -145,14 +146,14 @@ def test_decode_chunk_pipeline_matches_serial(models, golden):
     slots = (base + 0.3 * torch.randn(256 * 2 + 37, 8, 128, generator=g)).cuda()
     outs = {}
     for mode in (0, 8):
-        L.call("tocvp_set_decode_mode", L.c_int(mode))
+        setattr(L.TUNING, "decode_mode", int(mode))
         try:
             for _ in range(2):   # second call re-uses the side stream / events
                 o = savi(mode="decode", slots=slots)
             torch.cuda.synchronize()
             outs[mode] = {k: v.clone() for k, v in o.items()}
         finally:
-            L.call("tocvp_set_decode_mode", L.c_int(0))
+            setattr(L.TUNING, "decode_mode", int(0))
     for k in ("recons_imgs", "recons", "masks"):
         assert torch.equal(outs[0][k], outs[8][k]), k
     tail = savi(mode="decode", slots=slots[512:].contiguous())
@@ -190,9 +191,9 @@ def test_full_rollout_psnr(models, golden, golden_weights):
     ps = pred(sh, text_embeddings=text)
     assert ps.shape == (2, 19, 8, 128)
     imgs = savi(mode="decode", slots=ps.reshape(2 * 19, 8, 128))["recons_imgs"].view(2, 19, 3, 64, 64).clamp(0, 1)
-    assert O.rel_err(ps, golden["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(ps, golden["pred_slots"]), 5e-3, "ps, golden['pred_slots']")
     p = O.psnr(imgs.cpu(), golden["pred_imgs"])
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
 
 @pytest.mark.parametrize("B", [1, 3])
@@ -208,10 +209,10 @@ def test_rollout_small_and_odd_batches(models, golden_weights, B):
     out = rollout.forward_eval(savi, pred, videos.cuda(), text.cuda(), 1, 19, init_slots=init.cuda())
     ref = O.rollout(sd, golden_weights["pred_sd"], videos, text, init, O.SAViCfg(), O.PredCfg(num_context=1, num_preds=19))
     assert out["pred_imgs"].shape == (B, 19, 3, 64, 64)
-    assert O.rel_err(out["slot_history"], ref["slot_history"]) < 3e-3
-    assert O.rel_err(out["pred_slots"], ref["pred_slots"]) < 5e-3
+    PL.check(O.rel_err(out["slot_history"], ref["slot_history"]), 3e-3, "out['slot_history'], ref['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"], ref["pred_slots"]), 5e-3, "out['pred_slots'], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"].cpu(), ref["pred_imgs"])
-    assert p.min() >= 40.0, (p.min(), p.mean())
+    PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
     tgt = videos[:, 1:20].clamp(0, 1)
     assert (out["psnr"].cpu() - O.psnr(out["pred_imgs"].cpu(), tgt)).abs().max() < 1e-3
 
@@ -229,16 +230,16 @@ def test_predictor_step_folded_layernorm(models, golden, golden_weights):
     text = torch.randn(B, 32, 512, generator=g)
     ref = O.predictor_step(golden_weights["pred_sd"], slots, text, O.PredCfg())
     out = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())
-    assert O.rel_err(out, ref) < STAGE_TOL
+    PL.check(O.rel_err(out, ref), STAGE_TOL, "out, ref")
     d_ref, d_out = ref - slots[:, -1], out.cpu() - slots[:, -1]
-    assert O.rel_err(d_out, d_ref) < 5e-3
+    PL.check(O.rel_err(d_out, d_ref), 5e-3, "d_out, d_ref")
     ops.set_gemm_mode(1)
     try:
         out_unfolded = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())
         torch.cuda.synchronize()
     finally:
         ops.set_gemm_mode(0)
-    assert O.rel_err(out_unfolded, ref) < STAGE_TOL
+    PL.check(O.rel_err(out_unfolded, ref), STAGE_TOL, "out_unfolded, ref")
     print(f"folded-LN predictor step: rel err {O.rel_err(out, ref):.2e} (delta {O.rel_err(d_out, d_ref):.2e}); "
           f"unfolded {O.rel_err(out_unfolded, ref):.2e}")
 
@@ -256,13 +257,13 @@ def test_text_encoder(models):
     enc.load_state_dict(sd, strict=True)
     tokens, lengths = weights.synthetic_captions(m["B"], m["L"], seed=m["cap_seed"])
     out = enc(tokens.cuda(), lengths.cuda())
-    assert O.rel_err(out, g["out"]) < 1e-4
+    PL.check(O.rel_err(out, g["out"]), 1e-4, "out, g['out']")
     # through the wrapper's caption path (predictor_wrapper.py:90-127)
     emb = pred.encode_text_caption(caption_tokens=tokens, caption_lengths=lengths)
-    assert O.rel_err(emb, g["out"]) < 1e-4
+    PL.check(O.rel_err(emb, g["out"]), 1e-4, "emb, g['out']")
     # ragged: a longer batch with lengths down to 3 tokens
     tok2, len2 = weights.synthetic_captions(9, 50, seed=11)
-    assert O.rel_err(enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)) < 1e-4
+    PL.check(O.rel_err(enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)), 1e-4, "enc(tok2.cuda(), len2.cuda()), O.text_encoder(sd, tok2, len2)")
 
 
 @pytest.mark.parametrize("kind", ["VanillaTransformer", "OCVPSeq", "OCVPPar"])
@@ -281,14 +282,14 @@ def test_sibling_predictors(kind):
     pred.predictor.load_state_dict(sd, strict=True)
     pred = pred.cuda().eval()
     out = pred.predictor(slots=g["slots"].cuda())
-    assert O.rel_err(out, g[kind + "_step"]) < 1e-4
+    PL.check(O.rel_err(out, g[kind + "_step"]), 1e-4, "out, g[kind + '_step']")
     roll = pred(g["hist"].cuda())
     assert roll.shape == g[kind + "_rollout"].shape
-    assert O.rel_err(roll, g[kind + "_rollout"]) < 1e-4
+    PL.check(O.rel_err(roll, g[kind + "_rollout"]), 1e-4, "roll, g[kind + '_rollout']")
     # full 10-frame window of 8 slots (80 tokens, the kernel's maximum) against the oracle
     slots = torch.randn(2, 10, 8, 128, generator=torch.Generator().manual_seed(3))
     ref = O.ocvp_step(sd, slots, kind, max_len=m["input_buffer_size"])
-    assert O.rel_err(pred.predictor(slots=slots.cuda()), ref) < 1e-4
+    PL.check(O.rel_err(pred.predictor(slots=slots.cuda()), ref), 1e-4, "pred.predictor(slots=slots.cuda()), ref")
 
 
 def test_teacher_forcing_and_window(models, golden, golden_weights):
@@ -313,7 +314,7 @@ def test_teacher_forcing_and_window(models, golden, golden_weights):
         ref.append(cur)
     ref = torch.stack(ref, dim=1)
     assert out.shape == ref.shape == (2, 12, 8, 128)
-    assert O.rel_err(out, ref) < STAGE_TOL
+    PL.check(O.rel_err(out, ref), STAGE_TOL, "out, ref")
 
 
 def test_rollout_graph_matches_eager(models, golden, golden_weights):

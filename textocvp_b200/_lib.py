@@ -19,6 +19,22 @@ _lib = None
 _inited_devices = set()
 
 
+class Tuning(ctypes.Structure):
+    """tocvp_tuning (include/tocvp.h): per-call kernel-selection options.  The library holds no tuning state; the modules
+    attach a pointer to ONE caller-owned instance (``TUNING`` below) to every weights struct they pass, so tests and A/B
+    tools flip a field here and the next call sees it.  All-zero = defaults."""
+    _fields_ = [("gemm_mode", ctypes.c_int), ("gemm_no_wres", ctypes.c_int), ("conv_mode", ctypes.c_int),
+                ("encode_mode", ctypes.c_int), ("decode_mode", ctypes.c_int), ("corrector_mode", ctypes.c_int),
+                ("no_pdl", ctypes.c_int), ("no_tile_alternation", ctypes.c_int), ("reserved", ctypes.c_int * 8)]
+
+
+TUNING = Tuning()
+
+
+def tuning_ptr():
+    return ctypes.c_void_p(ctypes.addressof(TUNING))
+
+
 class TocvpError(RuntimeError):
     pass
 
@@ -31,8 +47,11 @@ def load() -> ctypes.CDLL:
                              "(there is no CPU / PyTorch fallback for this path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.tocvp_last_error.restype = ctypes.c_char_p
-        if _lib.tocvp_abi_version() != 1:
+        if _lib.tocvp_abi_version() != 2:
             raise TocvpError("libtocvp.so ABI version mismatch; rebuild")
+        _lib.tocvp_sizeof_tuning.restype = ctypes.c_size_t
+        if _lib.tocvp_sizeof_tuning() != ctypes.sizeof(Tuning):
+            raise TocvpError("struct tocvp_tuning: C size != ctypes size")
     return _lib
 
 
@@ -71,6 +90,20 @@ def stream():
 def call(name: str, *args):
     fn = getattr(load(), name)
     check(fn(*args))
+
+
+_probe = None
+
+
+def load_probe() -> ctypes.CDLL:
+    """Test-only hardware probes (tests/native/libtocvp_probe.so); not part of the product library."""
+    global _probe
+    if _probe is None:
+        path = os.path.join(os.path.dirname(_HERE), "tests", "native", "libtocvp_probe.so")
+        if not os.path.exists(path):
+            raise TocvpError(f"{path} not found: build it with `python -m textocvp_b200.build`")
+        _probe = ctypes.CDLL(path)
+    return _probe
 
 
 c_int = ctypes.c_int

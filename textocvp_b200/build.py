@@ -14,6 +14,9 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+# test-only native code (hardware probes): its own small library, NOT part of libtocvp.so or of include/tocvp.h
+TEST_NATIVE = os.path.join(HERE, "..", "tests", "native")
+TEST_LIB = os.path.join(TEST_NATIVE, "libtocvp_probe.so")
 
 
 def _deps_mtime():
@@ -53,7 +56,23 @@ def build(verbose: bool = False, force: bool = False, ptxas_v: bool = False) -> 
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_test_native(hdr_t, force)
     return LIB
+
+
+def build_test_native(hdr_t: float, force: bool = False) -> None:
+    """tests/native/*.cu -> tests/native/libtocvp_probe.so (linked with host_util.o for the tensor-map helpers)."""
+    srcs = sorted(glob.glob(os.path.join(TEST_NATIVE, "*.cu")))
+    if not srcs:
+        return
+    newest = max([hdr_t] + [os.path.getmtime(s) for s in srcs])
+    if not force and os.path.exists(TEST_LIB) and os.path.getmtime(TEST_LIB) >= newest:
+        return
+    cmd = [NVCC, *FLAGS, "-I", CSRC, "-shared", "-o", TEST_LIB, *srcs, os.path.join(OBJ, "host_util.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed for tests/native")
 
 
 if __name__ == "__main__":

@@ -226,11 +226,8 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
 #define MHA_LAUNCH(NTV, W, MB)                                                                                        \
   do {                                                                                                                \
     constexpr int smem_bytes = (2 * NTV * 8 + W * 16) * ATT_KS * 2;                                                   \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set && smem_bytes > 48 * 1024) {                                                                        \
-      TOCVP_CUDA(cudaFuncSetAttribute(mha_kernel<NTV, W, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
+    static SmemAttrOnce attr_once;                                                                                    \
+    if (smem_bytes > 48 * 1024) TOCVP_TRY(ensure_smem_attr(attr_once, mha_kernel<NTV, W, MB>, smem_bytes));           \
     TOCVP_CUDA(launch_pdl(mha_kernel<NTV, W, MB>, dim3(B * heads), dim3(warps * 32), smem_bytes, stream, q, ldq,      \
                           q_seq_rows, k, v, ldkv, Tq, Tk, heads, scale_log2e, out, ldo, rev));                        \
   } while (0)

@@ -563,12 +563,8 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
                         float ln_eps = 0.f) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP>, C::SMEM));
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmX, tmW;
   {
@@ -593,19 +589,15 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
   return TOCVP_OK;
 }
 
-static int g_conv_mode = 0;   // 0 = automatic (pair kernel when the tile count is even), 1 = single-CTA kernel only
+// tocvp_tuning.conv_mode (per call): 0 = automatic (pair kernel when the tile count is even), 1 = single-CTA kernel only
 
 template <int CIN, int COUT, int G, int KS, int EPI>
 static int launch_conv(const __half* x, const __half* wpacked, const float* bias, __half* out, float* out4, int n_img,
                        int H, int W, int relu, cudaStream_t stream) {
   using C = ConvCfg<CIN, COUT, G, KS>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, G, KS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, conv_tc_kernel<CIN, COUT, G, KS, EPI>, C::SMEM));
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmX, tmW;
   {
@@ -633,7 +625,7 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && wpacked && bias && out && n_img > 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const bool pair_ok = g_conv_mode == 0 && H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
+  const bool pair_ok = opts().conv_mode == 0 && H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
   if (cin == 64 && cout == 64) {
     if (pair_ok) return launch_conv2<64, 64, 4, 5>(x, wpacked, bias, out, n_img, H, W, relu, stream);
     return launch_conv<64, 64, 4, 5, 0>(x, wpacked, bias, out, nullptr, n_img, H, W, relu, stream);
@@ -683,14 +675,9 @@ int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, 
 
 }  // namespace tocvp
 
-extern "C" int tocvp_set_conv_mode(int mode) {
-  if (mode != 0 && mode != 1) return TOCVP_ERR_BAD_ARG;
-  tocvp::g_conv_mode = mode;
-  return TOCVP_OK;
-}
-
 extern "C" int tocvp_conv5x5_f16(const void* x, const void* w_packed, const float* bias, void* out, int n_img, int H,
-                                 int W, int cin, int cout, int relu, void* stream) {
+                                 int W, int cin, int cout, int relu, const tocvp_tuning* tuning, void* stream) {
+  tocvp::OptsScope scope(tuning);
   return tocvp::conv5x5_f16(static_cast<const __half*>(x), static_cast<const __half*>(w_packed), bias,
                             static_cast<__half*>(out), n_img, H, W, cin, cout, relu, static_cast<cudaStream_t>(stream));
 }

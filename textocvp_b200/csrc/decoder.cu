@@ -199,21 +199,17 @@ composite_kernel(const float4* __restrict__ maps, float* __restrict__ imgs, floa
 
 constexpr int DEC_CHUNK_FRAMES = 256;
 
-// tocvp_set_decode_mode: 1 = generate layer 1 inside the layer-2 conv, 0 = separate bandwidth kernel (default).
+// tocvp_tuning.decode_mode (per call), bit 0: 1 = generate layer 1 inside the layer-2 conv, 0 = separate bandwidth kernel (default).
 // Measured r1 (tools/ab_decode.py, same process): the fused layer-2 conv takes 1.86 ms instead of 1.44 ms per chunk -- the
 // generator warps share the shared-memory port and the issue slots the implicit GEMM is bound by -- which is more than the
 // 0.36 ms of dec_l1_kernel it removes, so the fused path is kept (tested, parity-green) but not the default.
-static int g_dec_fuse_l1 = 0;
-// bit 1 of tocvp_set_decode_mode: 0 = head conv3x3 with the 9 taps in the GEMM's N dimension (default), 1 = shifted-window
+// bit 1: 0 = head conv3x3 with the 9 taps in the GEMM's N dimension (default), 1 = shifted-window
 // kernel with N = 16 (first version, kept for A/B)
-static int g_dec_head_taps = 1;
 // bit 2: 0 = pixel-stationary layer-1 kernel (default), 1 = image-stationary first version
-static int g_dec_l1_pixel = 1;
 
 // bit 3: 0 = chunk-pipelined decode (default): layer 1 of chunk i+1 is written on a side stream while the convolutions of
 // chunk i run (the pixel-stationary kernel needs no shared memory / TMEM and 1 CTA per SM of registers, so it is
 // co-resident with the persistent conv CTAs and its 1 GiB write stream hides under tensor-bound time); 1 = serial.
-static int g_dec_overlap = 1;
 
 struct DecBuffers {
   __half* slots16;    // [n_frames*S, D]   (all chunks: the layer-1 front end runs once for the whole call)
@@ -280,14 +276,6 @@ using namespace tocvp;
 
 extern "C" size_t tocvp_sizeof_dec_weights(void) { return sizeof(tocvp_dec_weights); }
 
-extern "C" int tocvp_set_decode_mode(int mode) {
-  tocvp::g_dec_fuse_l1 = (mode & 1) ? 1 : 0;
-  tocvp::g_dec_head_taps = (mode & 2) ? 0 : 1;
-  tocvp::g_dec_l1_pixel = (mode & 4) ? 0 : 1;
-  tocvp::g_dec_overlap = (mode & 8) ? 0 : 1;
-  return TOCVP_OK;
-}
-
 extern "C" size_t tocvp_savi_decode_workspace_bytes(const tocvp_dec_weights* w, int n_frames) {
   if (!w || n_frames <= 0) return 0;
   return dec_carve(*w, n_frames, nullptr, nullptr);
@@ -298,6 +286,10 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
                                  void* const* conv_events, int n_conv_events) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && slots && recons_imgs && workspace && n_frames > 0);
+  OptsScope scope(w->tuning);
+  const int dmode = opts().decode_mode;
+  const bool g_dec_fuse_l1 = (dmode & 1) != 0, g_dec_head_taps = (dmode & 2) == 0, g_dec_l1_pixel = (dmode & 4) == 0,
+             g_dec_overlap = (dmode & 8) == 0;
   TOCVP_CHECK_ARG(w->hidden == 64 && w->slot_dim % 8 == 0 && w->H % 16 == 0 && w->W % 32 == 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   if (ws_bytes < dec_carve(*w, n_frames, nullptr, nullptr)) {
@@ -409,4 +401,19 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
     TOCVP_LAUNCHED();
   }
   return TOCVP_OK;
+}
+
+// Last layer of ConvDecoder.forward on its own (reference src/models/EncodersDecoders/decoders.py:104-108): conv3x3 64 -> 4,
+// no activation, on an NHWC f16 activation -> NHWC fp32 [n_img, H, W, 4] (RGB + mask logit per pixel).
+extern "C" int tocvp_conv3x3_head(const tocvp_dec_weights* w, const void* x_nhwc_f16, int n_img, float* out_nhwc4,
+                                  void* stream) {
+  TOCVP_CHECK_ARG(w && x_nhwc_f16 && out_nhwc4 && n_img > 0 && w->hidden == 64);
+  TOCVP_CHECK_ARG(w->H % 16 == 0 && w->W % 32 == 0);
+  OptsScope scope(w->tuning);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(opts().decode_mode & 2) && w->w_out_taps != nullptr)
+    return conv3x3_head_taps_f16(static_cast<const __half*>(x_nhwc_f16), static_cast<const __half*>(w->w_out_taps), w->b_out,
+                                 out_nhwc4, n_img, w->H, w->W, st);
+  return conv3x3_head_f16(static_cast<const __half*>(x_nhwc_f16), static_cast<const __half*>(w->w_out), w->b_out, out_nhwc4,
+                          n_img, w->H, w->W, st);
 }

@@ -241,11 +241,8 @@ int enc_mlp_f16(const __half* x, const __half* w1, const float* b1, const __half
                 cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && w1 && b1 && w2 && b2 && y && M > 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(enc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, enc_mlp_kernel, EM_SMEM));
   CUtensorMap tmX, tmW1, tmW2, tmY;
   {
     const uint64_t dims[2] = {uint64_t(EM_K1), uint64_t(M)};

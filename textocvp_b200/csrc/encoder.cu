@@ -25,9 +25,8 @@ int conv5x5_vp_f16(const __half* xp, const __half* wpacked, const float* bias, _
 int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
                    const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
 
-// tocvp_set_encode_mode: bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version),
+// tocvp_tuning.encode_mode (per call): bit 0 = first-version SIMT fp32 conv1, bit 1 = separate posemb + LayerNorm pass (first version),
 // bit 2 = the MLP as two separate GEMMs (first version), bit 3 = conv 1 over zero-padded channels (25 taps, second version)
-static int g_enc_mode = 0;
 
 // Frame -> tensor-core input of conv 1: NCHW fp32 [n,3,H,W] -> NHWC f16 [n,H,W,32] with channels 3..31 zero, so that conv 1
 // (3 -> 32, K = 75) runs on the same tcgen05 implicit-GEMM kernel as conv 2-4 with zero-padded input channels (ten times
@@ -157,38 +156,12 @@ static size_t enc_carve(const tocvp_enc_weights& w, int n, EncBuffers* eb, uint8
   return off;
 }
 
-}  // namespace tocvp
-
-using namespace tocvp;
-
-extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
-
-extern "C" int tocvp_set_encode_mode(int mode) {
-  tocvp::g_enc_mode = mode & 15;
-  return TOCVP_OK;
-}
-
-extern "C" size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img) {
-  if (!w || n_img <= 0) return 0;
-  return enc_carve(*w, n_img, nullptr, nullptr);
-}
-
-// frames: fp32, image i (3 x H x W, NCHW planes) at frames + i*img_stride floats; feats out: [n_img, H*W, feat_dim]
-extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img,
-                                 void* feats_f16, float* feats_f32, void* workspace, size_t ws_bytes, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  TOCVP_CHECK_ARG(w && frames && (feats_f16 || feats_f32) && workspace && n_img > 0);
-  TOCVP_CHECK_ARG(w->in_channels == 3 && w->hidden == 32 && w->feat_dim % 8 == 0);
-  TOCVP_CHECK_ARG(w->H % 16 == 0 && w->W % 32 == 0);
-  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
-  if (ws_bytes < enc_carve(*w, n_img, nullptr, nullptr)) {
-    set_last_error(__FILE__, __LINE__, "savi_encode: workspace too small");
-    return TOCVP_ERR_WORKSPACE;
-  }
-  EncBuffers eb;
-  enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
-  const int H = w->H, W = w->W, C = w->hidden, F = w->feat_dim;
-  const int M = n_img * H * W;
+// conv 1 .. conv 3 of SimpleConvEncoder (each + bias + ReLU): frames -> eb.actA (NHWC f16); conv 4 follows in the caller
+// (fused with the positional embedding + LayerNorm in SAVi.encode, plain in the stand-alone encoder forward).
+static int enc_convs_1_to_3(const tocvp_enc_weights& wr, EncBuffers& eb, const float* frames, size_t img_stride, int n_img,
+                            int g_enc_mode, cudaStream_t st) {
+  const tocvp_enc_weights* w = &wr;
+  const int H = w->H, W = w->W, C = w->hidden;
   if ((g_enc_mode & 1) || w->w_conv1_tc == nullptr) {
     const dim3 g1((H / E1_TH) * (W / E1_TW), n_img);
     enc_conv1_kernel<<<g1, 256, 0, st>>>(frames, img_stride, w->w_conv1, w->b_conv1, eb.actA, H, W);
@@ -206,6 +179,39 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   }
   TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], eb.actB, n_img, H, W, C, C, 1, st));
   TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv[1]), w->b_conv[1], eb.actA, n_img, H, W, C, C, 1, st));
+  return TOCVP_OK;
+}
+
+}  // namespace tocvp
+
+using namespace tocvp;
+
+extern "C" size_t tocvp_sizeof_enc_weights(void) { return sizeof(tocvp_enc_weights); }
+
+extern "C" size_t tocvp_savi_encode_workspace_bytes(const tocvp_enc_weights* w, int n_img) {
+  if (!w || n_img <= 0) return 0;
+  return enc_carve(*w, n_img, nullptr, nullptr);
+}
+
+// frames: fp32, image i (3 x H x W, NCHW planes) at frames + i*img_stride floats; feats out: [n_img, H*W, feat_dim]
+extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img,
+                                 void* feats_f16, float* feats_f32, void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TOCVP_CHECK_ARG(w && frames && (feats_f16 || feats_f32) && workspace && n_img > 0);
+  OptsScope scope(w->tuning);
+  const int g_enc_mode = opts().encode_mode & 15;
+  TOCVP_CHECK_ARG(w->in_channels == 3 && w->hidden == 32 && w->feat_dim % 8 == 0);
+  TOCVP_CHECK_ARG(w->H % 16 == 0 && w->W % 32 == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  if (ws_bytes < enc_carve(*w, n_img, nullptr, nullptr)) {
+    set_last_error(__FILE__, __LINE__, "savi_encode: workspace too small");
+    return TOCVP_ERR_WORKSPACE;
+  }
+  EncBuffers eb;
+  enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
+  const int H = w->H, W = w->W, C = w->hidden, F = w->feat_dim;
+  const int M = n_img * H * W;
+  TOCVP_TRY(enc_convs_1_to_3(*w, eb, frames, img_stride, n_img, g_enc_mode, st));
   const bool fuse_ln = !(g_enc_mode & 2) && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
   if (fuse_ln) {
     // conv 4 + positional embedding + LayerNorm(32) (eps 1e-5, SAVi.py:116) in one kernel: the LN input never leaves fp32
@@ -226,4 +232,24 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   TOCVP_TRY(gemm_f16(eb.mid16, F, static_cast<const __half*>(w->w_mlp2), F, M, F, F, w->b_mlp2, 0, nullptr, 0, 1, 0,
                      feats_f32, F, static_cast<__half*>(feats_f16), F, st));
   return TOCVP_OK;
+}
+
+// SimpleConvEncoder.forward on its own (reference src/models/EncodersDecoders/encoders.py:156-159): 4 x (conv5x5 + bias +
+// ReLU) -> NHWC f16 [n_img, H, W, 32] (no positional embedding, no LayerNorm, no MLP).  Same workspace as tocvp_savi_encode.
+extern "C" int tocvp_savi_conv_stack(const tocvp_enc_weights* w, const float* frames, size_t img_stride, int n_img,
+                                     void* out_nhwc_f16, void* workspace, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TOCVP_CHECK_ARG(w && frames && out_nhwc_f16 && workspace && n_img > 0);
+  TOCVP_CHECK_ARG(w->in_channels == 3 && w->hidden == 32 && w->H % 16 == 0 && w->W % 32 == 0);
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(out_nhwc_f16) & 15) == 0);
+  OptsScope scope(w->tuning);
+  if (ws_bytes < enc_carve(*w, n_img, nullptr, nullptr)) {
+    set_last_error(__FILE__, __LINE__, "savi_conv_stack: workspace too small");
+    return TOCVP_ERR_WORKSPACE;
+  }
+  EncBuffers eb;
+  enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
+  TOCVP_TRY(enc_convs_1_to_3(*w, eb, frames, img_stride, n_img, opts().encode_mode & 15, st));
+  return conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], static_cast<__half*>(out_nhwc_f16),
+                     n_img, w->H, w->W, w->hidden, w->hidden, 1, st);
 }

@@ -581,11 +581,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     TOCVP_TRY(encode_tmap(&tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.out32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   using S = G2Smem<BN, EWN, WRES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<BN, CONV, EWN, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, gemm2_f16_kernel<BN, CONV, EWN, WRES>, S::TOTAL));
   const int tiles_m = (g.M + 2 * G2_BM - 1) / (2 * G2_BM), tiles_n = (g.N + BN - 1) / BN;
   const int tiles = tiles_m * tiles_n;
   const int pairs = num_sms() / 2;
@@ -600,8 +597,6 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   count_launch();
   return TOCVP_OK;
 }
-
-int g_gemm2_wres = 1;   // tocvp_set_gemm_mode(258): W-resident variant off (A/B)
 
 // Tile width for the pair kernel, or 0 if the problem should stay on the single-CTA kernel.
 // cost model: waves of pair-tiles x tile width, with the narrower tile paying ~10% for its higher L2 traffic per FLOP
@@ -635,7 +630,7 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
     // W-resident variant: K <= 512 and a column-block-stationary schedule that needs no more rounds than round-robin
     const int pairs = num_sms() / 2;
     const int tiles_m = (M + 255) / 256, tiles_n = (N + 255) / 256;
-    if (g_gemm2_wres && K <= 512 && K % G2_BK == 0 && tiles_n <= pairs) {
+    if (!opts().gemm_no_wres && K <= 512 && K % G2_BK == 0 && tiles_n <= pairs) {
       int ppn = pairs / tiles_n;
       ppn = ppn < tiles_m ? ppn : tiles_m;
       const int rounds_w = (tiles_m + ppn - 1) / ppn, rounds_rr = (tiles_m * tiles_n + pairs - 1) / pairs;

@@ -292,11 +292,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, gemm_f16_kernel<BN, CONV>, S::TOTAL));
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   TOCVP_CUDA(launch_pdl(gemm_f16_kernel<BN, CONV>, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, tmA, tmB, g));
@@ -311,9 +308,12 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
 int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
                    int relu, float* out32, __half* out16, int ldo, cudaStream_t stream);
 
-// Tuning / test knob (tocvp_set_gemm_mode): 0 = automatic kernel choice, 1 = single-CTA kernel only,
+// tocvp_tuning.gemm_mode (per call): 0 = automatic kernel choice, 1 = single-CTA kernel only,
 // 128 / 256 = CTA-pair kernel with that tile width wherever it is applicable.
-static int g_gemm_mode = 0;
+static inline int gemm_mode() {
+  const int m = opts().gemm_mode;
+  return (m == 1 || m == 128 || m == 256) ? m : 0;
+}
 
 // Internal entry used by the stage drivers and by the public tocvp_gemm_f16.
 int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
@@ -327,10 +327,10 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   TOCVP_CHECK_ARG(out16 == nullptr || ld16 % 8 == 0);
   TOCVP_CHECK_ARG(residual == nullptr || ldr % 4 == 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  const int g_gemm_mode = gemm_mode();
   if (g_gemm_mode != 1) {
     // CTA-pair kernel (256-row tiles, half the L2 operand traffic) for everything large enough to fill the chip
-    const int bn2 = (g_gemm_mode >= 128 && N >= g_gemm_mode) ? g_gemm_mode
-                                                                                       : gemm2_pick_bn(M, N, 0);
+    const int bn2 = (g_gemm_mode >= 128 && N >= g_gemm_mode) ? g_gemm_mode : gemm2_pick_bn(M, N, 0);
     if (bn2 != 0)
       return gemm2_f16(bn2, A, lda, W, ldw, M, N, K, bias, relu, residual, ldr, res_div, res_mod, out32, ld32, out16, ld16,
                        stream, nullptr);
@@ -348,7 +348,7 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
   return launch_gemm<128, false>(tmA, tmB, g, stream);
 }
 
-bool gemm_ln_supported(int M, int N) { return g_gemm_mode != 1 && gemm2_pick_bn(M, N, 0) != 0 && N % 64 == 0; }
+bool gemm_ln_supported(int M, int N) { return gemm_mode() != 1 && gemm2_pick_bn(M, N, 0) != 0 && N % 64 == 0; }
 
 int gemm_f16_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const float* bias, int relu,
                 const float* residual, int ldr, float* out32, int ld32, __half* out16, int ld16, const GemmLn& ln,
@@ -356,7 +356,7 @@ int gemm_f16_ln(const __half* A, int lda, const __half* W, int ldw, int M, int N
   TOCVP_CHECK_ARG(A && W && gemm_ln_supported(M, N));
   TOCVP_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && (out32 || out16));
   // producers need the 128-wide tile (3 staging tiles per warp); consumers take the usual choice
-  const int bn = ln.stats_out != nullptr ? 128 : gemm2_pick_bn(M, N, g_gemm_mode >= 128 ? g_gemm_mode : 0);
+  const int bn = ln.stats_out != nullptr ? 128 : gemm2_pick_bn(M, N, gemm_mode() >= 128 ? gemm_mode() : 0);
   return gemm2_f16(bn, A, lda, W, ldw, M, N, K, bias, relu, residual, ldr, 1, 0, out32, ld32, out16, ld16, stream, &ln);
 }
 
@@ -370,6 +370,7 @@ int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const Conv
   const int M = int(M64), K = cm.taps * cm.cin;
   const bool phased = cm.tiles_per_phase != 0;     // each phase (cpp columns) has its own tap set: tiles must not straddle
   ConvMap cmx = cm;
+  const int g_gemm_mode = gemm_mode();
   if (g_gemm_mode != 1 && M >= 1024 && N >= 128) {
     int bn2 = 0;
     const int unit = phased ? cm.cpp : N;
@@ -394,21 +395,12 @@ int gemm_conv_f16(const __half* X, const __half* W, int n_img, int N, const Conv
 
 }  // namespace tocvp
 
-namespace tocvp { extern int g_gemm2_wres; }
-
-extern "C" int tocvp_set_gemm_mode(int mode) {
-  if (mode == 258 || mode == 259) {          // 258 / 259: W-resident variant of the 256-wide pair kernel off / on
-    tocvp::g_gemm2_wres = (mode == 259);
-    return TOCVP_OK;
-  }
-  if (mode != 0 && mode != 1 && mode != 128 && mode != 256) return TOCVP_ERR_BAD_ARG;
-  tocvp::g_gemm_mode = mode;
-  return TOCVP_OK;
-}
+extern "C" size_t tocvp_sizeof_tuning(void) { return sizeof(tocvp_tuning); }
 
 extern "C" int tocvp_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                               int relu, const float* residual, int ldr, float* out_f32, int ld32, void* out_f16,
-                              int ld16, void* stream) {
+                              int ld16, const tocvp_tuning* tuning, void* stream) {
+  tocvp::OptsScope scope(tuning);
   return tocvp::gemm_f16(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, M, N, K, bias, relu,
                          residual, ldr, 1, 0, out_f32, ld32, static_cast<__half*>(out_f16), ld16,
                          static_cast<cudaStream_t>(stream));

@@ -179,11 +179,8 @@ int conv3x3_head_taps_f16(const __half* x, const __half* w_taps, const float* bi
                           cudaStream_t stream) {
   TOCVP_CHECK_ARG(x && w_taps && bias && out4 && n_img > 0 && H % HD_TH == 0 && W % HD_TW == 0);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out4) & 15) == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(head3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, head3x3_kernel, HD_SMEM));
   CUtensorMap tmX, tmW;
   {
     const uint64_t dims[4] = {64, uint64_t(W), uint64_t(H), uint64_t(n_img)};

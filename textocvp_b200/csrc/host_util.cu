@@ -74,27 +74,34 @@ int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static std::atomic<int> g_pdl{1};
-bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
-void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
+// Options of the library call running on this thread (installed by OptsScope at the C-ABI boundary; caller-owned memory).
+static const tocvp_tuning g_default_tuning = {};
+static thread_local const tocvp_tuning* g_opts = nullptr;
+const tocvp_tuning& opts() { return g_opts ? *g_opts : g_default_tuning; }
+OptsScope::OptsScope(const tocvp_tuning* t) : saved_(g_opts) {
+  if (t != nullptr) g_opts = t;   // a nested call without options of its own inherits the caller's
+}
+OptsScope::~OptsScope() { g_opts = saved_; }
 
-static thread_local int g_next_rev = 0;
-static std::atomic<int> g_tile_alt{1};
-void set_next_tile_order(int reversed) { g_next_rev = (reversed && g_tile_alt.load(std::memory_order_relaxed)) ? 1 : 0; }
+bool pdl_enabled() { return opts().no_pdl == 0; }
+
+static thread_local int g_next_rev = 0;   // consumed by the next pair-GEMM / attention launch of this thread
+bool tile_order_alternation() { return opts().no_tile_alternation == 0; }
+void set_next_tile_order(int reversed) { g_next_rev = (reversed && tile_order_alternation()) ? 1 : 0; }
 int tile_order_reversed() {
   const int r = g_next_rev;
   g_next_rev = 0;
   return r;
 }
-bool tile_order_alternation() { return g_tile_alt.load(std::memory_order_relaxed) != 0; }
-void set_tile_alternation(int on) { g_tile_alt.store(on ? 1 : 0); }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];   // immutable device attribute, cached per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -116,18 +123,7 @@ extern "C" int tocvp_init(int device) {
     tocvp::set_last_error(__FILE__, __LINE__, msg);
     return TOCVP_ERR_ARCH;
   }
-  if (cudaSetDevice(device) != cudaSuccess) return TOCVP_ERR_CUDA;
-  return TOCVP_OK;
-}
-
-extern "C" int tocvp_set_tile_order(int alternate) {
-  tocvp::set_tile_alternation(alternate);
-  return TOCVP_OK;
-}
-
-extern "C" int tocvp_set_pdl(int on) {
-  tocvp::set_pdl(on);
-  return TOCVP_OK;
+  return TOCVP_OK;   // the current device is NOT changed: every call runs on the caller's current device
 }
 
 extern "C" int tocvp_abi_version(void) { return TOCVP_ABI_VERSION; }

@@ -53,9 +53,39 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const voi
 int encode_tmap_2d_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                        uint32_t box_rows, uint32_t box_cols);
 
-int num_sms();
+int num_sms();   // SM count of the CURRENT device (cached per device)
 
-// Programmatic dependent launch (tocvp_set_pdl, default on): the kernel may become resident while the previous kernel of
+// Per-call options.  The library keeps no process-wide tuning state: an entry point that accepts a `const tocvp_tuning*`
+// (directly or through its weights struct, include/tocvp.h) installs it for the duration of the call on the calling
+// thread; the kernel-selection code deeper in the library reads it through opts().  Without a scope opts() returns the
+// defaults (all zeros).
+const tocvp_tuning& opts();
+struct OptsScope {
+  explicit OptsScope(const tocvp_tuning* t);
+  ~OptsScope();
+  OptsScope(const OptsScope&) = delete;
+  OptsScope& operator=(const OptsScope&) = delete;
+ private:
+  const tocvp_tuning* saved_;
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: one flag per (kernel instantiation, device).  Two
+// threads racing on the same flag both set the attribute (idempotent).
+struct SmemAttrOnce {
+  unsigned long long done_mask = 0;   // bit d: set for device d
+};
+template <typename Fn>
+static inline int ensure_smem_attr(SmemAttrOnce& once, Fn* kernel, int bytes) {
+  int dev = 0;
+  TOCVP_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(&once.done_mask, __ATOMIC_ACQUIRE) & bit) return TOCVP_OK;
+  TOCVP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  __atomic_fetch_or(&once.done_mask, bit, __ATOMIC_RELEASE);
+  return TOCVP_OK;
+}
+
+// Programmatic dependent launch (tocvp_tuning.no_pdl, default on): the kernel may become resident while the previous kernel of
 // the stream drains; it runs its prologue (barrier init, TMEM allocation, descriptor prefetch, constant-weight loads) and
 // blocks in griddepcontrol.wait (pdl_wait(), ptx.cuh) until the previous grid has completed and flushed.  ONLY for kernels
 // that execute pdl_wait() before their first access to memory another kernel produces or consumes.
@@ -67,7 +97,7 @@ bool pdl_enabled();
 // streaming in the same order and missing on everything (LRU).  Results do not depend on the order.
 void set_next_tile_order(int reversed);
 int tile_order_reversed();          // reads and resets
-bool tile_order_alternation();      // tocvp_set_tile_order knob (default on)
+bool tile_order_alternation();      // !tocvp_tuning.no_tile_alternation (default on)
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

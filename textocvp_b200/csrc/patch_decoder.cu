@@ -215,6 +215,7 @@ extern "C" int tocvp_dino_project(const tocvp_proj_weights* w, const float* feat
                                   float* out_f32, void* workspace, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && feats && rows > 0 && (out_f16 || out_f32) && workspace);
+  OptsScope scope(w->tuning);
   TOCVP_CHECK_ARG(w->feat_dim % 8 == 0 && w->hidden_dim % 8 == 0 && w->slot_dim % 8 == 0 && w->feat_dim <= 1024);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   if (ws_bytes < proj_carve(*w, rows, nullptr, nullptr, nullptr)) {
@@ -245,6 +246,7 @@ extern "C" int tocvp_patch_decode(const tocvp_patch_weights* w, const float* slo
                                   float* recons_feats, float* masks, void* workspace, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && slots && workspace && n_frames > 0 && (recons_imgs || recons_feats || masks));
+  OptsScope scope(w->tuning);
   TOCVP_TRY(check_patch(*w));
   TOCVP_CHECK_ARG(!recons_imgs || w->reconstruct_images);
   TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);

@@ -322,6 +322,7 @@ extern "C" int tocvp_predictor_rollout(const tocvp_pred_weights* w, const float*
                                        float* pred_slots, void* workspace, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && slot_history && text && pred_slots && workspace && B > 0 && num_context >= 1 && num_preds >= 1);
+  OptsScope scope(w->tuning);
   TOCVP_TRY(check_weights(*w));
   if (ws_bytes < predictor_workspace_bytes(*w, B, L, num_context, num_preds)) {
     set_last_error(__FILE__, __LINE__, "predictor_rollout: workspace too small");
@@ -355,6 +356,7 @@ extern "C" int tocvp_predictor_forward(const tocvp_pred_weights* w, const float*
                                        int L, float* out, void* workspace, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TOCVP_CHECK_ARG(w && slots && text && out && workspace && B > 0 && n >= 1);
+  OptsScope scope(w->tuning);
   TOCVP_TRY(check_weights(*w));
   TOCVP_CHECK_ARG(n <= w->buffer_size);
   if (ws_bytes < predictor_workspace_bytes(*w, B, L, n, 1)) {

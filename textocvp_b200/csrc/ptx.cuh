@@ -282,14 +282,20 @@ __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t 
 }
 
 // ----------------------------------------------------------------------------- misc
+// two fp32 -> packed f16x2, SATURATING (|x| > 65504 -> +-65504 instead of +-inf; NaN stays NaN): every activation / operand
+// that enters a tensor-core kernel goes through one of these two.  IEEE f16 has the mantissa the 1e-3 contract needs but
+// only 5 exponent bits; a checkpoint whose activations leave that range must degrade to a clipped value, never to the
+// inf - inf = NaN a LayerNorm or softmax would make of it.  One F2FP instruction either way (SASS: F2FP.SATFINITE.F16.F32.PACK_AB
+// vs F2FP.F16.F32.PACK_AB), so saturation costs nothing.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-// two fp32 -> packed f16x2 with ReLU fused into the conversion (one instruction for convert + clamp of two values)
+// same with ReLU fused into the conversion (one instruction for convert + clamp of two values)
 __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   uint32_t r;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {

@@ -337,11 +337,10 @@ __device__ __forceinline__ void linear_T_mma(const float* __restrict__ Wt, const
 __device__ void linear_T_simt(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
                               const float* xs, float* ys, bool relu);
 
-__device__ int g_sa_update_simt = 0;   // tocvp_set_corrector_mode(1): first-version SIMT matvecs (A/B, tests)
-
-__device__ __forceinline__ void linear_T(const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
+// simt: tocvp_tuning.corrector_mode = 1 (per call): first-version SIMT matvecs (A/B, tests)
+__device__ __forceinline__ void linear_T(bool simt, const float* __restrict__ Wt, const float* __restrict__ bias, int IN, int OUT,
                                          const float* xs, float* ys, bool relu) {
-  if (g_sa_update_simt || (OUT != 128 && OUT != 256 && OUT != 384 && OUT != 512) || IN % 8 != 0) {
+  if (simt || (OUT != 128 && OUT != 256 && OUT != 384 && OUT != 512) || IN % 8 != 0) {
     linear_T_simt(Wt, bias, IN, OUT, xs, ys, relu);
     return;
   }
@@ -438,7 +437,8 @@ constexpr int UP_DO_A = 4;   // emit g / sg / cb for the next streaming pass (fr
 __global__ void __launch_bounds__(UP_THREADS, 1)
 sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags, const float* __restrict__ slots_in,
                  const float* __restrict__ partial, float* __restrict__ slots_out, int slots_out_stride /* per seq */,
-                 float* __restrict__ pred_out, float* __restrict__ gvec) {
+                 float* __restrict__ pred_out, float* __restrict__ gvec, int simt_i) {
+  const bool simt = simt_i != 0;
   extern __shared__ float sm[];
   float* cur = sm;                        // [128][R]  slots (prev, then new)
   float* t0 = cur + SA_D * UP_R;          // [128][R]
@@ -480,9 +480,9 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
       t0[f * UP_R + r] = val;
     }
     __syncthreads();
-    linear_T(w.wv_t, w.bv, D, D, t0, t1, false);                 // updates = Wv uhat + bv       -> t1
-    linear_T(w.w_ih_t, w.b_ih, D, 3 * D, t1, big0, false);       // gi                          -> big0 [384][R]
-    linear_T(w.w_hh_t, w.b_hh, D, 3 * D, cur, big1, false);      // gh (hidden = slots_prev)    -> big1
+    linear_T(simt, w.wv_t, w.bv, D, D, t0, t1, false);                 // updates = Wv uhat + bv       -> t1
+    linear_T(simt, w.w_ih_t, w.b_ih, D, 3 * D, t1, big0, false);       // gi                          -> big0 [384][R]
+    linear_T(simt, w.w_hh_t, w.b_hh, D, 3 * D, cur, big1, false);      // gh (hidden = slots_prev)    -> big1
     for (int e = tid; e < UP_R * D; e += UP_THREADS) {           // GRUCell, gate order r,z,n
       const int k = e / UP_R, r = e % UP_R;
       const float ir = big0[k * UP_R + r], iz = big0[(D + k) * UP_R + r], in_ = big0[(2 * D + k) * UP_R + r];
@@ -495,8 +495,8 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
     }
     __syncthreads();
     layernorm_T(cur, t0, w.ln_mlp_g, w.ln_mlp_b, w.ln_eps_sa, D);
-    linear_T(w.w1_t, w.b1, D, w.mlp_hidden, t0, big0, true);
-    linear_T(w.w2_t, w.b2, w.mlp_hidden, D, big0, t1, false);
+    linear_T(simt, w.w1_t, w.b1, D, w.mlp_hidden, t0, big0, true);
+    linear_T(simt, w.w2_t, w.b2, w.mlp_hidden, D, big0, t1, false);
     for (int e = tid; e < UP_R * D; e += UP_THREADS) cur[e] += t1[e];   // slots + MLP(LN(slots))
     __syncthreads();
     if (slots_out) {
@@ -510,9 +510,9 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
 
   if (flags & UP_DO_T) {
     // ---- post-norm TransformerBlock: y = LN(MHSA(x) + x); z = LN(MLP(y) + y)   (attention.py:387-395)
-    linear_T(w.t_wq_t, nullptr, D, D, cur, t0, false);           // q -> t0
-    linear_T(w.t_wk_t, nullptr, D, D, cur, t1, false);           // k -> t1
-    linear_T(w.t_wv_t, nullptr, D, D, cur, big0, false);         // v -> big0[0..127]
+    linear_T(simt, w.t_wq_t, nullptr, D, D, cur, t0, false);           // q -> t0
+    linear_T(simt, w.t_wk_t, nullptr, D, D, cur, t1, false);           // k -> t1
+    linear_T(simt, w.t_wv_t, nullptr, D, D, cur, big0, false);         // v -> big0[0..127]
     float* att = big1;                                           // attention output [128][R]
     float* sc = big1 + D * UP_R;                                 // scores [R][H][16]
     const int H = w.t_heads, dh = D / H;
@@ -552,12 +552,12 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
       }
     }
     __syncthreads();
-    linear_T(w.t_wo_t, nullptr, D, D, att, t0, false);
+    linear_T(simt, w.t_wo_t, nullptr, D, D, att, t0, false);
     for (int e = tid; e < UP_R * D; e += UP_THREADS) t0[e] += cur[e];
     __syncthreads();
     layernorm_T(t0, t1, w.t_ln1_g, w.t_ln1_b, w.ln_eps_tf, D);   // y -> t1
-    linear_T(w.t_w1_t, w.t_b1, D, w.t_hidden, t1, big0, true);
-    linear_T(w.t_w2_t, w.t_b2, w.t_hidden, D, big0, t0, false);
+    linear_T(simt, w.t_w1_t, w.t_b1, D, w.t_hidden, t1, big0, true);
+    linear_T(simt, w.t_w2_t, w.t_b2, w.t_hidden, D, big0, t0, false);
     for (int e = tid; e < UP_R * D; e += UP_THREADS) t0[e] += t1[e];
     __syncthreads();
     layernorm_T(t0, cur, w.t_ln2_g, w.t_ln2_b, w.ln_eps_tf, D);  // z -> cur
@@ -572,8 +572,8 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
   if (flags & UP_DO_A) {
     // ---- next pass: q = Wq LN(slots) + bq ; qt = Wk^T q ; g = scale*qt*gamma ; sg = sum g ; cb = scale*(qt.beta + q.bk)
     layernorm_T(cur, t0, w.ln_slot_g, w.ln_slot_b, w.ln_eps_sa, D);
-    linear_T(w.wq_t, w.bq, D, D, t0, t1, false);                 // q  -> t1
-    linear_T(w.wk, nullptr, D, D, t1, t0, false);                // qt -> t0  (Wk as stored [d][f] is "in-major" here)
+    linear_T(simt, w.wq_t, w.bq, D, D, t0, t1, false);                 // q  -> t1
+    linear_T(simt, w.wk, nullptr, D, D, t1, t0, false);                // qt -> t0  (Wk as stored [d][f] is "in-major" here)
     for (int e = tid; e < UP_R * D; e += UP_THREADS) {
       const int r = e / D, f = e % D;
       if (row0 + r < n_rows) {
@@ -608,15 +608,13 @@ constexpr int UP_SMEM = (3 * SA_D + 2 * 512) * UP_R * 4;   // 90112 B
 
 static int launch_update(const SaWeights& w, int S, int chunks, int B, int flags, const float* slots_in, const float* partial,
                          float* slots_out, int out_stride, float* pred_out, float* gvec, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, sa_update_kernel, UP_SMEM));
   const int rows = B * S;
   const int rpc = (UP_R / S) * S;
   sa_update_kernel<<<(rows + rpc - 1) / rpc, UP_THREADS, UP_SMEM, stream>>>(w, S, chunks, rows, flags, slots_in, partial,
-                                                                           slots_out, out_stride, pred_out, gvec);
+                                                                           slots_out, out_stride, pred_out, gvec,
+                                                                           opts().corrector_mode);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -774,12 +772,6 @@ int slot_attention_seq(const SaWeights& w, const void* feats, int feats_f16, siz
 
 extern "C" size_t tocvp_slot_attention_workspace_bytes(int B) { return tocvp::slot_attention_workspace_bytes(B); }
 
-extern "C" int tocvp_set_corrector_mode(int simt_update) {
-  const int v = simt_update ? 1 : 0;
-  if (cudaMemcpyToSymbol(tocvp::g_sa_update_simt, &v, sizeof(int)) != cudaSuccess) return TOCVP_ERR_CUDA;
-  return TOCVP_OK;
-}
-
 extern "C" int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats, int feats_f16,
                                     size_t feats_seq_stride, int B, int N,
                                     const float* slots_in, int iters, float* slots_out, int out_stride,
@@ -788,6 +780,7 @@ extern "C" int tocvp_slot_attention(const tocvp_sa_weights* w, const void* feats
     tocvp::set_last_error(__FILE__, __LINE__, "null weights");
     return TOCVP_ERR_BAD_ARG;
   }
+  tocvp::OptsScope scope(w->tuning);
   return tocvp::slot_attention(*w, feats, feats_f16, feats_seq_stride, B, N, slots_in, iters, slots_out, out_stride, pred_out, workspace,
                                ws_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -803,9 +796,23 @@ extern "C" int tocvp_slot_attention_seq(const tocvp_sa_weights* w, const void* f
     tocvp::set_last_error(__FILE__, __LINE__, "null weights");
     return TOCVP_ERR_BAD_ARG;
   }
+  tocvp::OptsScope scope(w->tuning);
   return tocvp::slot_attention_seq(*w, feats, feats_f16, feats_seq_stride, feats_frame_stride, B, N, n_frames,
                                    iters_first, iters, slots_in, slot_history, hist_seq_stride, hist_frame_stride,
                                    carry_out, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// TransformerBlock.forward, post-norm flavour = the SAVi transition module applied on its own (reference
+// src/models/Blocks/attention.py:387-395, called as `self.transition_module(slots)` at src/models/SAVi.py:193).
+extern "C" int tocvp_transition(const tocvp_sa_weights* w, const float* slots, int B, float* out, void* stream) {
+  using namespace tocvp;
+  TOCVP_CHECK_ARG(w && slots && out && B > 0);
+  const int S = w->num_slots;
+  TOCVP_CHECK_ARG(S >= 1 && S <= SA_MAX_S);
+  TOCVP_CHECK_ARG(w->t_heads > 0 && SA_D % w->t_heads == 0 && w->t_hidden % 256 == 0 && w->t_hidden <= 512);
+  TOCVP_CHECK_ARG(w->t_wq_t && w->t_wk_t && w->t_wv_t && w->t_wo_t && w->t_w1_t && w->t_w2_t);
+  OptsScope scope(w->tuning);
+  return launch_update(*w, S, 1, B, UP_DO_T, slots, nullptr, nullptr, 0, out, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t tocvp_sizeof_sa_weights(void) { return sizeof(tocvp_sa_weights); }

@@ -282,11 +282,8 @@ sa_stream_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
 int sa_stream_tc(const __half* feats, size_t seq_stride, int B, int N, const float* gvec, float* partial, float ln_eps,
                  float attn_eps, cudaStream_t stream) {
   TOCVP_CHECK_ARG(N % (SA_CHUNKS * ST_TILE) == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOCVP_CUDA(cudaFuncSetAttribute(sa_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  TOCVP_TRY(ensure_smem_attr(attr_once, sa_stream_tc_kernel, ST_SMEM));
   CUtensorMap tmX;
   const uint64_t dims[3] = {uint64_t(SA_D), uint64_t(N), uint64_t(B)};
   const uint64_t str[2] = {uint64_t(SA_D) * 2, uint64_t(seq_stride) * 2};

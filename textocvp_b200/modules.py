@@ -46,7 +46,7 @@ SaW = _struct("SaW", [
     "t_w1_t", "t_b1", "t_w2_t", "t_b2"],
     [("mlp_hidden", ctypes.c_int), ("t_heads", ctypes.c_int), ("t_hidden", ctypes.c_int),
      ("attn_eps", ctypes.c_float), ("ln_eps_sa", ctypes.c_float), ("ln_eps_tf", ctypes.c_float),
-     ("scale", ctypes.c_float), ("num_slots", ctypes.c_int)])
+     ("scale", ctypes.c_float), ("num_slots", ctypes.c_int), ("tuning", _f)])
 
 PredLayer = _struct("PredLayer", [
     "ln_q_g", "ln_q_b", "w_qkv", "w_o", "ln_cq_g", "ln_cq_b", "ln_ckv_g", "ln_ckv_b", "wc_q", "wc_kv", "wc_o", "bc_o",
@@ -59,23 +59,24 @@ PredW = type("PredW", (ctypes.Structure,), {"_fields_": [
     ("token_dim", ctypes.c_int), ("hidden_dim", ctypes.c_int), ("cross_hidden", ctypes.c_int),
     ("num_heads", ctypes.c_int), ("cross_heads", ctypes.c_int), ("buffer_size", ctypes.c_int),
     ("residual", ctypes.c_int), ("ln_eps", ctypes.c_float),
-    ("mlp_in_w", _f), ("mlp_in_b", _f), ("mlp_out_w", _f), ("mlp_out_b", _f), ("pe_flipped", _f)]})
+    ("mlp_in_w", _f), ("mlp_in_b", _f), ("mlp_out_w", _f), ("mlp_out_b", _f), ("pe_flipped", _f), ("tuning", _f)]})
 
 EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
     ("w_conv1", _f), ("b_conv1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("posemb", _f),
     ("ln_g", _f), ("ln_b", _f), ("w_mlp1", _f), ("b_mlp1", _f), ("w_mlp2", _f), ("b_mlp2", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("in_channels", ctypes.c_int), ("hidden", ctypes.c_int),
-    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f), ("w_conv1_vp", _f)]})
+    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f), ("w_conv1_vp", _f), ("tuning", _f)]})
 
 DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("slot_dim", ctypes.c_int), ("num_slots", ctypes.c_int),
-    ("hidden", ctypes.c_int), ("w_out_taps", _f)]})
+    ("hidden", ctypes.c_int), ("w_out_taps", _f), ("tuning", _f)]})
 
 
 ProjW = type("ProjW", (ctypes.Structure,), {"_fields_": [
     ("ln_g", _f), ("ln_b", _f), ("w1", _f), ("b1", _f), ("w2", _f), ("b2", _f),
-    ("feat_dim", ctypes.c_int), ("hidden_dim", ctypes.c_int), ("slot_dim", ctypes.c_int), ("ln_eps", ctypes.c_float)]})
+    ("feat_dim", ctypes.c_int), ("hidden_dim", ctypes.c_int), ("slot_dim", ctypes.c_int), ("ln_eps", ctypes.c_float),
+    ("tuning", _f)]})
 
 PATCH_MAX_MLP = PATCH_MAX_CNN = 6
 PatchW = type("PatchW", (ctypes.Structure,), {"_fields_": [
@@ -88,7 +89,7 @@ PatchW = type("PatchW", (ctypes.Structure,), {"_fields_": [
     ("n_mlp", ctypes.c_int), ("n_cnn", ctypes.c_int), ("out_cin", ctypes.c_int), ("out_up", ctypes.c_int),
     ("reconstruct_images", ctypes.c_int),
     ("num_slots", ctypes.c_int), ("slot_dim", ctypes.c_int), ("num_patches", ctypes.c_int), ("grid", ctypes.c_int),
-    ("feat_dim", ctypes.c_int), ("img_size", ctypes.c_int), ("ln_eps", ctypes.c_float)]})
+    ("feat_dim", ctypes.c_int), ("img_size", ctypes.c_int), ("ln_eps", ctypes.c_float), ("tuning", _f)]})
 
 
 def check_struct_sizes():
@@ -106,6 +107,26 @@ def _dp(t: torch.Tensor):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _on_device(fn):
+    """Run a forward with the device of its first CUDA tensor argument current: the library launches on the caller's
+    current device and stream (it never calls cudaSetDevice), so a model living on cuda:1 of a multi-GPU process must not
+    launch on cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class _Workspace:
     """Grow-only byte buffer owned by a module (the library never allocates)."""
 
@@ -119,6 +140,31 @@ class _Workspace:
         return ctypes.c_void_p(self.buf.data_ptr() + off), c_size_t(self.buf.numel() - off)
 
 
+_PACK_DEV = [None]      # target device of the _pack() call in progress (set by _Packed._ensure_packed)
+
+
+class _params_on_host:
+    """Weight packing runs on the CPU: for the duration of ``_pack`` every parameter / buffer of the module reads as a host
+    copy, so the packing arithmetic (LayerNorm / BatchNorm folding, tap re-ordering, conv1(posemb), casts) is plain CPU
+    tensor code and no cuBLAS / cuDNN / ATen device kernel is ever launched from this package; ``_f32`` / ``_f16`` / ``_tr``
+    upload the finished buffers.  (Packing happens once per ``load_state_dict`` / ``.to()``, not on the timed path.)"""
+
+    def __init__(self, module):
+        self.tensors = list(module.parameters()) + list(module.buffers())
+        extra = getattr(module, "_transition", None)
+        if extra is not None:
+            self.tensors += list(extra.parameters())
+
+    def __enter__(self):
+        self.saved = [t.data for t in self.tensors]
+        for t in self.tensors:
+            t.data = t.data.cpu()
+
+    def __exit__(self, *exc):
+        for t, d in zip(self.tensors, self.saved):
+            t.data = d
+
+
 class _Packed(nn.Module):
     """Mixin: device-side packed weight copies, rebuilt whenever a parameter changes (load_state_dict, .to())."""
 
@@ -126,28 +172,53 @@ class _Packed(nn.Module):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
 
     def _ensure_packed(self):
+        if getattr(self, "_is_replica", False):
+            # nn.DataParallel over SEVERAL devices re-creates replicas (parameter-less shallow copies that would share the
+            # original's device-0 buffers) on every forward.  The supported drive is the reference evaluator's wrapper with
+            # ONE visible device per process (CUDA_VISIBLE_DEVICES=<rank>, torchrun): DataParallel then calls the wrapped
+            # module directly (SURVEY 8(b) "Wrapping").
+            raise L.TocvpError("textocvp_b200 modules do not support multi-device nn.DataParallel replication; run one "
+                               "process per GPU (CUDA_VISIBLE_DEVICES=<rank>): with a single visible device the "
+                               "DataParallel wrapper is inert")
         sig = self._sig()
         if getattr(self, "_pack_sig", None) != sig:
-            dev = next(self.parameters()).device
+            params = list(self.parameters())
+            if not params:
+                raise L.TocvpError(f"{type(self).__name__} has no parameters to pack")
+            dev = params[0].device
             if dev.type != "cuda":
                 raise L.TocvpError("textocvp_b200 modules run on a CUDA (sm_100) device only; no CPU path exists")
             L.init(dev)
             check_struct_sizes()
-            with torch.no_grad():
-                self._pack(dev)
+            _PACK_DEV[0] = dev
+            try:
+                with torch.no_grad(), _params_on_host(self):
+                    self._pack(dev)
+            finally:
+                _PACK_DEV[0] = None
             self._pack_sig = sig
 
 
+def _upload(t):
+    dev = _PACK_DEV[0]
+    return t.to(dev) if dev is not None else t
+
+
 def _f32(t):
-    return t.detach().float().contiguous()
+    return _upload(t.detach().float().contiguous())
 
 
 def _f16(t):
-    return t.detach().half().contiguous()
+    """fp32 -> IEEE f16 operand copy.  A weight beyond the f16 range cannot be represented: refuse it at pack time."""
+    t = t.detach().float()
+    if t.numel() and not bool(torch.isfinite(t).all() and t.abs().max() <= 65504.0):
+        raise L.TocvpError("a weight tensor has entries that are not finite or exceed the IEEE f16 range (|w| > 65504); "
+                           "the tensor-core path cannot hold it")
+    return _upload(t.half().contiguous())
 
 
 def _tr(t):  # [out,in] -> [in,out] fp32
-    return t.detach().float().t().contiguous()
+    return _upload(t.detach().float().t().contiguous())
 
 
 
@@ -214,8 +285,19 @@ def fold_layernorm(w, ln_w, ln_b, bias=None):
     return wf.contiguous(), c.contiguous(), (d + bias.detach().float() if bias is not None else d).contiguous()
 
 
+class ClipTooShortError(IndexError, ValueError):
+    """``num_imgs`` exceeds the clip length.  The reference fails with an IndexError when it indexes frame t of a shorter
+    clip (src/models/SAVi.py:180); here the check runs before any library call (an out-of-range frame index would be an
+    out-of-bounds device read)."""
+
+
+def _check_clip(x, num_imgs, what):
+    if num_imgs < 1 or x.shape[1] < num_imgs:
+        raise ClipTooShortError(f"{what}: num_imgs = {num_imgs} but the clip has {x.shape[1]} frames")
+
+
 # =====================================================================================================
-# building blocks (parameter containers with the reference's names)
+# building blocks (the reference's sub-modules: same names, parameters and forward signatures)
 # =====================================================================================================
 def pack_conv1_vertical_pairs(w):
     """Encoder conv 1 (3 -> 32, 5x5) for the x-im2col input of `im2col_x_row_pairs`: weight [32, 3, 5, 5] ->
@@ -256,7 +338,13 @@ def build_grid(resolution):
     return torch.from_numpy(g).permute(0, 3, 1, 2).contiguous()
 
 
+def _no_standalone(name, where):
+    return NotImplementedError(f"{name}.forward is not a stand-alone kernel on the CUDA path: {where}")
+
+
 class SoftPositionEmbed(nn.Module):
+    """model_blocks.py:186-226.  forward(inputs [B,H,W,C], channels_last=True) -> inputs + projection(grid)."""
+
     def __init__(self, hidden_size, resolution, vmin=-1., vmax=1.):
         super().__init__()
         self.projection = nn.Conv2d(4, hidden_size, kernel_size=1)
@@ -264,14 +352,31 @@ class SoftPositionEmbed(nn.Module):
         self.resolution = tuple(resolution)
 
     def table(self) -> torch.Tensor:
-        """[H*W, C] fp32 = projection(grid): a 4 -> C affine map per pixel, batch independent."""
-        w = self.projection.weight.detach().float()
-        g = self.grid.to(w.device)[0].permute(1, 2, 0).reshape(-1, 4)          # [HW,4]
-        return (g @ w.reshape(w.shape[0], 4).t() + self.projection.bias.detach().float()).contiguous()
+        """[H*W, C] fp32 = projection(grid): a 4 -> C affine map per pixel, batch independent.  Computed on the host (fp64)."""
+        w = self.projection.weight.detach().cpu().double()
+        g = self.grid[0].permute(1, 2, 0).reshape(-1, 4).double()              # [HW,4]
+        return (g @ w.reshape(w.shape[0], 4).t() + self.projection.bias.detach().cpu().double()).float().contiguous()
+
+    @torch.no_grad()
+    def forward(self, inputs, channels_last=True):
+        H, W = self.resolution
+        C = self.projection.weight.shape[0]
+        x = inputs if channels_last else inputs.permute(0, 2, 3, 1)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (H, W, C):
+            raise ValueError(f"SoftPositionEmbed expects [B, {H}, {W}, {C}] (channels last), got {tuple(x.shape)}")
+        p = self.projection.weight
+        sig = (p.data_ptr(), p._version, self.projection.bias._version, str(p.device))
+        if getattr(self, "_tab_sig", None) != sig:
+            object.__setattr__(self, "_tab", self.table().to(p.device))
+            object.__setattr__(self, "_tab_sig", sig)
+        from . import ops
+        out = ops.add_table(x, self._tab, 1, H * W)
+        return out if channels_last else out.permute(0, 3, 1, 2)
 
 
 class ConvBlock(nn.Module):
-    """model_blocks.py:49-108 (conv - [BatchNorm] - ReLU); parameter container."""
+    """model_blocks.py:49-108 (conv - [BatchNorm] - ReLU).  forward(x NCHW) runs the kernel=5 / stride=1 / no-BatchNorm case
+    (the only one on the SAVi path) through the library's generic fp32 convolution."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=None, batch_norm=False, **kw):
         super().__init__()
@@ -281,6 +386,22 @@ class ConvBlock(nn.Module):
             layers.append(nn.BatchNorm2d(out_channels))
         layers.append(nn.ReLU())
         self.block = nn.Sequential(*layers)
+
+    @torch.no_grad()
+    def forward(self, x):
+        conv = self.block[0]
+        if len(self.block) != 2 or conv.kernel_size != (5, 5) or conv.stride != (1, 1) or conv.padding != (2, 2):
+            raise _no_standalone("ConvBlock", "only conv5x5 / stride 1 / no BatchNorm runs stand-alone; the BatchNorm + "
+                                 "Upsample blocks of MLPPatchDecoder are folded into tocvp_patch_decode")
+        x = x.float().contiguous()
+        n, ci, H, W = x.shape
+        out = torch.empty(n, conv.out_channels, H, W, device=x.device, dtype=torch.float32)
+        L.init(x.device)
+        with torch.cuda.device(x.device):
+            L.call("tocvp_conv5x5_generic", ptr(x), ptr(conv.weight.detach().float().contiguous()),
+                   ptr(conv.bias.detach().float().contiguous()), c_int(1), ptr(None), ptr(out), c_int(n), c_int(H), c_int(W),
+                   c_int(ci), c_int(conv.out_channels), stream())
+        return out
 
 
 class Upsample(nn.Module):
@@ -292,7 +413,32 @@ class Upsample(nn.Module):
         self.scale_factor = scale_factor
 
 
-class SimpleConvEncoder(nn.Module):
+def _pack_encoder_convs(enc, k, ew):
+    """encoder.encoder.{0..3}.block.0 -> tocvp_enc_weights conv fields (shared by SAVi._pack and SimpleConvEncoder._pack)."""
+    if len(enc) != 4 or enc[0].weight.shape[:2] != (32, 3) or any(m.weight.shape[:2] != (32, 32) for m in enc[1:]) \
+            or enc[0].weight.shape[-1] != 5:
+        raise L.TocvpError("encoder kernels are instantiated for 4 x conv5x5 (3->32->32->32->32)")
+    k["w_conv1"] = _f32(enc[0].weight.permute(2, 3, 1, 0).reshape(75, 32))
+    k["b_conv1"] = _f32(enc[0].bias)
+    w1p = torch.zeros(25, 32, 32)                                            # conv 1 for the tensor cores: cin 3 -> 32
+    w1p[:, :, :3] = enc[0].weight.detach().float().permute(2, 3, 0, 1).reshape(25, 32, 3)
+    k["w_conv1_tc"] = _f16(w1p)
+    k["w_conv1_vp"] = _f16(pack_conv1_vertical_pairs(enc[0].weight))           # conv 1 with the x-taps folded into K
+    for i in range(3):
+        k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
+        k[f"bc{i}"] = _f32(enc[i + 1].bias)
+    ew.w_conv1, ew.b_conv1 = k["w_conv1"].data_ptr(), k["b_conv1"].data_ptr()
+    for i in range(3):
+        ew.w_conv[i], ew.b_conv[i] = k[f"wc{i}"].data_ptr(), k[f"bc{i}"].data_ptr()
+    ew.w_conv1_tc = k["w_conv1_tc"].data_ptr()
+    ew.w_conv1_vp = k["w_conv1_vp"].data_ptr()
+    ew.in_channels, ew.hidden = 3, 32
+    ew.tuning = ctypes.addressof(L.TUNING)
+
+
+class SimpleConvEncoder(_Packed):
+    """encoders.py:99-159.  forward(x [B,3,H,W]) -> [B,32,H,W] (4 x conv5x5 + ReLU on the tensor cores)."""
+
     def __init__(self, in_channels=3, hidden_dims=(64, 64, 64, 64), kernel_size=5, **kw):
         super().__init__()
         mods, cin = [], in_channels
@@ -302,9 +448,59 @@ class SimpleConvEncoder(nn.Module):
         self.encoder = nn.Sequential(*mods)
         self.out_features = hidden_dims[-1]
         self.hidden_dims, self.kernel_size, self.in_channels = list(hidden_dims), kernel_size, in_channels
+        self._ws = _Workspace()
+
+    def _pack(self, dev):
+        k, ew = {}, EncW()
+        _pack_encoder_convs([m.block[0] for m in self.encoder], k, ew)
+        self._keep, self._w = k, ew
+
+    @_on_device
+    @torch.no_grad()
+    def forward(self, x):
+        self._ensure_packed()
+        lib = L.load()
+        x = x.float().contiguous()
+        n, ci, H, W = x.shape
+        if ci != 3 or H % 16 != 0 or W % 32 != 0:
+            raise ValueError(f"SimpleConvEncoder kernels need [B, 3, 16k, 32k] frames, got {tuple(x.shape)}")
+        self._w.H, self._w.W, self._w.feat_dim = H, W, 128
+        out = torch.empty(n, H, W, 32, device=x.device, dtype=torch.float16)
+        lib.tocvp_savi_encode_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_savi_encode_workspace_bytes(ctypes.byref(self._w), c_int(n)), x.device)
+        L.call("tocvp_savi_conv_stack", ctypes.byref(self._w), ptr(x), c_size_t(x[0].numel()), c_int(n), ptr(out), ws, wsb,
+               stream())
+        return out.float().permute(0, 3, 1, 2).contiguous()
 
 
-class ConvDecoder(nn.Module):
+def _pack_decoder_convs(convs, last, d, dw):
+    """decoder.decoder.{1..3}.block.0 and decoder.decoder.4 -> tocvp_dec_weights conv / head fields (shared by SAVi._pack
+    and ConvDecoder._pack)."""
+    if len(convs) != 4 or convs[0].weight.shape[0] != 64 or any(c.weight.shape[:2] != (64, 64) for c in convs[1:]) \
+            or last.weight.shape != (4, 64, 3, 3) or convs[1].weight.shape[-1] != 5:
+        raise L.TocvpError("decoder kernels are instantiated for conv5x5 D->64, 3 x conv5x5 64->64, conv3x3 64->4")
+    for i in range(3):
+        d[f"wc{i}"] = _f16(convs[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 64, 64))
+        d[f"bc{i}"] = _f32(convs[i + 1].bias)
+    wo = torch.zeros(9, 16, 64)                                              # N padded 4 -> 16 (UMMA minimum for M=128)
+    wo[:, :4] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
+    d["w_out"] = _f16(wo)
+    d["b_out"] = _f32(last.bias)
+    wt = torch.zeros(48, 64)                                                 # row (ky*3+kx)*4 + co: the 9 taps in N
+    wt[:36] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(36, 64)
+    d["w_out_taps"] = _f16(wt)
+    dw.w_out, dw.b_out, dw.w_out_taps = d["w_out"].data_ptr(), d["b_out"].data_ptr(), d["w_out_taps"].data_ptr()
+    for i in range(3):
+        dw.w_conv[i], dw.b_conv[i] = d[f"wc{i}"].data_ptr(), d[f"bc{i}"].data_ptr()
+    dw.hidden = 64
+    dw.tuning = ctypes.addressof(L.TUNING)
+
+
+class ConvDecoder(_Packed):
+    """decoders.py:52-125.  forward(x [B',Cin,H,W]) -> [B',4,H,W]: the reference's plain ``self.decoder(x)`` on a
+    MATERIALISED input (first layer: generic fp32 convolution; layers 2-4 and the head: the tcgen05 kernels).  SAVi.decode
+    does not go through here: it never builds the broadcast tensor (csrc/decoder.cu)."""
+
     def __init__(self, in_channels, hidden_dims, kernel_size=5, upsample=None, out_channels=4, **kw):
         super().__init__()
         if upsample is not None and upsample >= 2:
@@ -316,6 +512,33 @@ class ConvDecoder(nn.Module):
         mods.append(nn.Conv2d(hidden_dims[0], out_channels, kernel_size=3, stride=1, padding=1))
         self.decoder = nn.Sequential(*mods)
         self.hidden_dims, self.kernel_size, self.out_channels = list(hidden_dims), kernel_size, out_channels
+
+    def _pack(self, dev):
+        convs = [m.block[0] for m in list(self.decoder)[:-1]]
+        d, dw = {}, DecW()
+        _pack_decoder_convs(convs, self.decoder[-1], d, dw)
+        d["w1"], d["b1"] = _f32(convs[0].weight), _f32(convs[0].bias)          # torch layout [64, Cin, 5, 5], fp32
+        self._keep, self._w = d, dw
+
+    @_on_device
+    @torch.no_grad()
+    def forward(self, x):
+        from . import ops
+        self._ensure_packed()
+        x = x.float().contiguous()
+        n, ci, H, W = x.shape
+        d = self._keep
+        if ci != d["w1"].shape[1] or H % 16 != 0 or W % 32 != 0:
+            raise ValueError(f"ConvDecoder kernels need [B, {d['w1'].shape[1]}, 16k, 32k] inputs, got {tuple(x.shape)}")
+        a = torch.empty(n, H, W, 64, device=x.device, dtype=torch.float16)
+        L.call("tocvp_conv5x5_generic", ptr(x), ptr(d["w1"]), ptr(d["b1"]), c_int(1), ptr(a), ptr(None), c_int(n), c_int(H),
+               c_int(W), c_int(ci), c_int(64), stream())
+        for i in range(3):
+            a = ops.conv5x5_f16(a, d[f"wc{i}"], d[f"bc{i}"], relu=True)
+        self._w.H, self._w.W = H, W
+        maps = torch.empty(n, H, W, 4, device=x.device, dtype=torch.float32)
+        L.call("tocvp_conv3x3_head", ctypes.byref(self._w), ptr(a), c_int(n), ptr(maps), stream())
+        return maps.permute(0, 3, 1, 2).contiguous()
 
 
 class LearnedRandom(nn.Module):
@@ -342,7 +565,16 @@ class Learned(nn.Module):
         return self.slots.repeat(batch_size, 1, 1)
 
 
-class MultiHeadSelfAttention(nn.Module):
+def _mha_supported(dim_head, n_keys):
+    if dim_head != 64 or n_keys > 128:
+        raise _no_standalone("MultiHead*Attention", "the attention kernel is instantiated for 64-wide heads and <= 128 keys "
+                             "(the predictor's layers); the transition's 4 x 32 attention runs inside tocvp_transition")
+
+
+class MultiHeadSelfAttention(_Packed):
+    """attention.py:218-265.  forward(x [B,N,E]) -> [B,N,E] (fused QKV GEMM, fp32-softmax attention kernel, out-proj GEMM).
+    ``mask`` is not supported (no caller on the path passes one)."""
+
     def __init__(self, emb_dim, num_heads=8, dropout=0.):
         super().__init__()
         self.emb_dim, self.num_heads = emb_dim, num_heads
@@ -351,8 +583,29 @@ class MultiHeadSelfAttention(nn.Module):
         self.v = nn.Linear(emb_dim, emb_dim, bias=False)
         self.out_projection = nn.Sequential(nn.Linear(emb_dim, emb_dim, bias=False))
 
+    def _pack(self, dev):
+        self._keep = dict(w_qkv=_f16(torch.cat([self.q.weight, self.k.weight, self.v.weight], 0)),
+                          w_o=_f16(self.out_projection[0].weight))
 
-class MultiHeadCrossAttention(nn.Module):
+    @_on_device
+    @torch.no_grad()
+    def forward(self, x, **kwargs):
+        from . import ops
+        if kwargs.get("mask", None) is not None:
+            raise _no_standalone("MultiHeadSelfAttention", "attention masks are not implemented (unused on the rollout path)")
+        B, N, E = x.shape
+        _mha_supported(E // self.num_heads, N)
+        self._ensure_packed()
+        x16 = ops.cast_f16(x.reshape(B * N, E))
+        _, qkv = ops.gemm_f16(x16, self._keep["w_qkv"], out_f32=False, out_f16=True)
+        att = ops.mha_f16(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, N, N, self.num_heads)
+        y, _ = ops.gemm_f16(att, self._keep["w_o"])
+        return y.view(B, N, E)
+
+
+class MultiHeadCrossAttention(_Packed):
+    """attention.py:268-319.  forward(enc_embs [B,Lk,kv_dim], query_embs [B,Nq,E]) -> [B,Nq,E]."""
+
     def __init__(self, emb_dim, dim_head, kv_dim, num_heads=8, dropout=0.):
         super().__init__()
         inner = dim_head * num_heads
@@ -362,8 +615,31 @@ class MultiHeadCrossAttention(nn.Module):
         self.v = nn.Linear(kv_dim, inner, bias=False)
         self.out_projection = nn.Linear(inner, emb_dim)
 
+    def _pack(self, dev):
+        self._keep = dict(w_q=_f16(self.q.weight), w_kv=_f16(torch.cat([self.k.weight, self.v.weight], 0)),
+                          w_o=_f16(self.out_projection.weight), b_o=_f32(self.out_projection.bias))
+
+    @_on_device
+    @torch.no_grad()
+    def forward(self, enc_embs, query_embs, **kwargs):
+        from . import ops
+        B, Lk, _ = enc_embs.shape
+        Nq = query_embs.shape[1]
+        _mha_supported(self.dim_head, Lk)
+        self._ensure_packed()
+        inner = self.dim_head * self.num_heads
+        q16 = ops.cast_f16(query_embs.reshape(B * Nq, -1))
+        e16 = ops.cast_f16(enc_embs.reshape(B * Lk, -1))
+        _, q = ops.gemm_f16(q16, self._keep["w_q"], out_f32=False, out_f16=True)
+        _, kv = ops.gemm_f16(e16, self._keep["w_kv"], out_f32=False, out_f16=True)
+        att = ops.mha_f16(q, kv[:, :inner], kv[:, inner:], B, Nq, Lk, self.num_heads)
+        y, _ = ops.gemm_f16(att, self._keep["w_o"], bias=self._keep["b_o"])
+        return y.view(B, Nq, self.emb_dim)
+
 
 class TransformerDecoderBlock(nn.Module):
+    """attention.py:399-467 (cross-attention block of a predictor layer); runs fused inside tocvp_predictor_*."""
+
     def __init__(self, embed_dim, head_dim, kv_dim, num_heads, mlp_size):
         super().__init__()
         self.ln_mlp = nn.LayerNorm(embed_dim, eps=1e-6)
@@ -372,9 +648,16 @@ class TransformerDecoderBlock(nn.Module):
         self.ln_cross_att_kv = nn.LayerNorm(kv_dim, eps=1e-6)
         self.cross_attn = MultiHeadCrossAttention(embed_dim, head_dim, kv_dim, num_heads)
 
+    def forward(self, queries, feats):
+        raise _no_standalone("TransformerDecoderBlock", "a predictor layer (self-attention + this cross-attention block + "
+                             "MLP) is one fused kernel chain; call BaseTextOCVP.forward / PredictorWrapper.forward")
+
 
 class TransformerBlock(_Packed):
-    """attention.py:323-396.  Stand-alone forward is provided for the post-norm (transition) flavour."""
+    """attention.py:323-396.  forward(inputs [B,S,E]) -> [B,S,E].  The post-norm flavour (``pre_norm=False``: the SAVi
+    transition module, transition_models.py:26-31, called as ``self.transition_module(slots)`` at SAVi.py:193) runs
+    stand-alone through the same per-slot kernel the corrector chain uses (tocvp_transition).  The pre-norm flavour only
+    occurs as the base class of AdaptedEncoderBlock, whose forward is fused into the predictor."""
 
     def __init__(self, embed_dim, num_heads, mlp_size, pre_norm=True):
         super().__init__()
@@ -390,22 +673,81 @@ class TransformerBlock(_Packed):
                 elif p.dim() > 1:
                     nn.init.xavier_uniform_(p)
 
+    def _transition_fields(self, k):
+        """t_* fields of tocvp_sa_weights (shared with SlotAttention._pack, which chains the transition behind the corrector)."""
+        k["t_wq_t"], k["t_wk_t"], k["t_wv_t"] = _tr(self.attn.q.weight), _tr(self.attn.k.weight), _tr(self.attn.v.weight)
+        k["t_wo_t"] = _tr(self.attn.out_projection[0].weight)
+        k["t_ln1_g"], k["t_ln1_b"] = _f32(self.layernorm_query.weight), _f32(self.layernorm_query.bias)
+        k["t_ln2_g"], k["t_ln2_b"] = _f32(self.layernorm_mlp.weight), _f32(self.layernorm_mlp.bias)
+        k["t_w1_t"], k["t_b1"] = _tr(self.mlp[0].weight), _f32(self.mlp[0].bias)
+        k["t_w2_t"], k["t_b2"] = _tr(self.mlp[2].weight), _f32(self.mlp[2].bias)
+
+    def _pack(self, dev):
+        if self.embed_dim != 128 or self.mlp_size % 256 != 0 or self.mlp_size > 512 or 128 % self.num_heads != 0:
+            raise L.TocvpError("transition kernels are instantiated for 128-d slots and an MLP of 256 or 512 units")
+        k = {}
+        self._transition_fields(k)
+        w = SaW()
+        for n, v in k.items():
+            setattr(w, n, v.data_ptr())
+        w.t_heads, w.t_hidden, w.ln_eps_tf, w.mlp_hidden = self.num_heads, self.mlp_size, 1e-6, 256
+        w.tuning = ctypes.addressof(L.TUNING)
+        self._keep, self._w = k, w
+
+    @_on_device
+    @torch.no_grad()
+    def forward(self, inputs):
+        assert inputs.ndim == 3
+        if self.pre_norm:
+            raise _no_standalone("TransformerBlock(pre_norm=True)", "the pre-norm block only exists as the self-attention "
+                                 "half of a predictor layer (AdaptedEncoderBlock), which is fused into tocvp_predictor_*")
+        B, S, E = inputs.shape
+        if not 4 <= S <= 11:
+            raise L.TocvpError("transition kernels are instantiated for 4..11 slots")
+        self._ensure_packed()
+        x = inputs.float().contiguous()
+        out = torch.empty_like(x)
+        self._w.num_slots = S
+        L.call("tocvp_transition", ctypes.byref(self._w), ptr(x), c_int(B), ptr(out), stream())
+        return out
+
 
 class AdaptedEncoderBlock(TransformerBlock):
+    """attention.py:470-524: one predictor layer (parameter container; BaseTextOCVP runs all layers as one kernel chain)."""
+
     def __init__(self, embed_dim, num_heads, mlp_size, fusion_params):
         super().__init__(embed_dim=embed_dim, num_heads=num_heads, mlp_size=mlp_size)
         self.cross_attention = TransformerDecoderBlock(
             embed_dim=embed_dim, kv_dim=embed_dim, head_dim=fusion_params.get("head_dim"),
             num_heads=fusion_params.get("num_heads"), mlp_size=fusion_params.get("mlp_size"))
 
+    def _pack(self, dev):
+        raise _no_standalone("AdaptedEncoderBlock", "packed by BaseTextOCVP")
+
+    def forward(self, inputs, text_embeddings=None, **kwargs):
+        raise _no_standalone("AdaptedEncoderBlock", "a predictor layer is fused into the predictor's kernel chain; call "
+                             "BaseTextOCVP.forward(slots, text_embeddings) / PredictorWrapper.forward")
+
 
 class TemporalPositionalEncoding(nn.Module):
+    """model_blocks.py:293-379.  forward(x [B,n,S,T], batch_size, num_slots) -> x + flip(pe[:, :n], time) (dropout p = 0)."""
+
     def __init__(self, d_model, dropout=0.0, max_len=50, mode="learned"):
         super().__init__()
         if mode != "learned":
             raise NotImplementedError("only the learned PE is on the TextOCVP path (text_cond_OCVP.py:63-67)")
         self.d_model, self.max_len = d_model, max_len
         self.pe = nn.Parameter(d_model ** -0.5 * torch.randn(1, max_len, 1, d_model))
+
+    @torch.no_grad()
+    def forward(self, x, batch_size=None, num_slots=None):
+        from . import ops
+        B, n, S, T = x.shape
+        if n > self.max_len or T != self.d_model:
+            raise ValueError(f"TemporalPositionalEncoding: input {tuple(x.shape)} vs pe {tuple(self.pe.shape)}")
+        table = torch.flip(self.pe.detach()[0, :n, 0].cpu(), dims=(0,)).float().contiguous().to(x.device)   # [n, T], host flip
+        with torch.cuda.device(x.device):
+            return ops.add_table(x, table, S, n).view(B, n, S, T)
 
 
 # =====================================================================================================
@@ -450,12 +792,7 @@ class SlotAttention(_Packed):
         t = self._transition
         t_heads = t_hidden = 0
         if t is not None:
-            k["t_wq_t"], k["t_wk_t"], k["t_wv_t"] = _tr(t.attn.q.weight), _tr(t.attn.k.weight), _tr(t.attn.v.weight)
-            k["t_wo_t"] = _tr(t.attn.out_projection[0].weight)
-            k["t_ln1_g"], k["t_ln1_b"] = _f32(t.layernorm_query.weight), _f32(t.layernorm_query.bias)
-            k["t_ln2_g"], k["t_ln2_b"] = _f32(t.layernorm_mlp.weight), _f32(t.layernorm_mlp.bias)
-            k["t_w1_t"], k["t_b1"] = _tr(t.mlp[0].weight), _f32(t.mlp[0].bias)
-            k["t_w2_t"], k["t_b2"] = _tr(t.mlp[2].weight), _f32(t.mlp[2].bias)
+            t._transition_fields(k)
             t_heads, t_hidden = t.num_heads, t.mlp_size
         self._keep = k
         w = SaW()
@@ -464,12 +801,14 @@ class SlotAttention(_Packed):
         w.mlp_hidden, w.t_heads, w.t_hidden = self.mlp_hidden, t_heads, t_hidden
         w.attn_eps, w.ln_eps_sa, w.ln_eps_tf, w.scale = self.epsilon, 1e-3, 1e-6, self.scale
         w.num_slots = self.num_slots
+        w.tuning = ctypes.addressof(L.TUNING)
         self._w = w
 
     def _sig(self):
         extra = tuple((p.data_ptr(), p._version) for p in self._transition.parameters()) if self._transition is not None else ()
         return super()._sig() + extra
 
+    @_on_device
     def run(self, feats, feats_seq_stride, B, N, slots, iters, slots_out, out_stride, pred_out):
         """Raw call.  feats: f16/fp32 device tensor holding sequence b's [N,128] block at b*feats_seq_stride."""
         self._ensure_packed()
@@ -480,6 +819,7 @@ class SlotAttention(_Packed):
                c_size_t(feats_seq_stride), c_int(B), c_int(N), ptr(slots), c_int(iters), ptr(slots_out),
                c_int(out_stride), ptr(pred_out), ws, wsb, stream())
 
+    @_on_device
     def run_seq(self, feats, feats_seq_stride, feats_frame_stride, B, N, n_frames, first_step, slots, slot_history,
                 hist_seq_stride, hist_frame_stride, carry_out):
         """Raw call: the corrector + transition chain of forward_decomp (SAVi.py:178-204) over ``n_frames`` consecutive
@@ -495,6 +835,7 @@ class SlotAttention(_Packed):
                c_int(it_first), c_int(self.num_iters), ptr(slots), ptr(slot_history), c_size_t(hist_seq_stride),
                c_size_t(hist_frame_stride), ptr(carry_out), ws, wsb, stream())
 
+    @_on_device
     @torch.no_grad()
     def forward(self, inputs, slots, step=0, **kwargs):
         B, N, _ = inputs.shape
@@ -569,68 +910,32 @@ class SAVi(_Packed):
     # ------------------------------------------------------------------ packing
     def _pack(self, dev):
         H, W = self.encoder_pos_embedding.resolution
-        enc = [m.block[0] for m in self.encoder.encoder]
-        if len(enc) != 4 or enc[0].weight.shape[:2] != (32, 3) or any(m.weight.shape[:2] != (32, 32) for m in enc[1:]) \
-                or self.encoder.kernel_size != 5:
-            raise L.TocvpError("encoder kernels are instantiated for 4 x conv5x5 (3->32->32->32->32)")
-        k = {}
-        k["w_conv1"] = _f32(enc[0].weight.permute(2, 3, 1, 0).reshape(75, 32))
-        k["b_conv1"] = _f32(enc[0].bias)
-        w1p = torch.zeros(25, 32, 32, device=dev)                                # conv 1 for the tensor cores: cin 3 -> 32
-        w1p[:, :, :3] = enc[0].weight.detach().float().permute(2, 3, 0, 1).reshape(25, 32, 3)
-        k["w_conv1_tc"] = _f16(w1p)
-        k["w_conv1_vp"] = _f16(pack_conv1_vertical_pairs(enc[0].weight))           # conv 1 with the x-taps folded into K
-        for i in range(3):
-            k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
-            k[f"bc{i}"] = _f32(enc[i + 1].bias)
-        k["posemb"] = self.encoder_pos_embedding.table()
+        if self.encoder.kernel_size != 5 or self.decoder.kernel_size != 5:
+            raise L.TocvpError("SAVi kernels are instantiated for 5x5 convolutions (src/configs/models/SAVi.json)")
+        k, ew = {}, EncW()
+        _pack_encoder_convs([m.block[0] for m in self.encoder.encoder], k, ew)
+        k["posemb"] = _upload(self.encoder_pos_embedding.table())
         k["ln_g"], k["ln_b"] = _f32(self.encoder_mlp[0].weight), _f32(self.encoder_mlp[0].bias)
         k["w_mlp1"], k["b_mlp1"] = _f16(self.encoder_mlp[1].weight), _f32(self.encoder_mlp[1].bias)
         k["w_mlp2"], k["b_mlp2"] = _f16(self.encoder_mlp[3].weight), _f32(self.encoder_mlp[3].bias)
-        ew = EncW()
-        ew.w_conv1, ew.b_conv1, ew.posemb = k["w_conv1"].data_ptr(), k["b_conv1"].data_ptr(), k["posemb"].data_ptr()
-        for i in range(3):
-            ew.w_conv[i], ew.b_conv[i] = k[f"wc{i}"].data_ptr(), k[f"bc{i}"].data_ptr()
-        for n in ("ln_g", "ln_b", "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2"):
+        for n in ("posemb", "ln_g", "ln_b", "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2"):
             setattr(ew, n, k[n].data_ptr())
         ew.H, ew.W, ew.in_channels, ew.hidden, ew.feat_dim = H, W, self.in_channels, 32, self.mlp_encoder_dim
-        ew.w_conv1_tc = k["w_conv1_tc"].data_ptr()
-        ew.w_conv1_vp = k["w_conv1_vp"].data_ptr()
         self._enc_keep, self._enc_w = k, ew
 
         # ---- decoder
         dH, dW = self.decoder_resolution
         convs = [m.block[0] for m in list(self.decoder.decoder)[:-1]]
-        last = self.decoder.decoder[-1]
-        if len(convs) != 4 or convs[0].weight.shape[0] != 64 or any(c.weight.shape[:2] != (64, 64) for c in convs[1:]) \
-                or last.weight.shape != (4, 64, 3, 3) or self.decoder.kernel_size != 5:
-            raise L.TocvpError("decoder kernels are instantiated for conv5x5 D->64, 3 x conv5x5 64->64, conv3x3 64->4")
-        d = {}
+        d, dw = {}, DecW()
+        _pack_decoder_convs(convs, self.decoder.decoder[-1], d, dw)
         w1 = convs[0].weight.detach().float()                                   # [64, D, 5, 5]
         d["w1_taps"] = _f16(w1.permute(2, 3, 0, 1).reshape(25 * 64, self.slot_dim))
-        # P = conv1(posemb map) + b1 : batch-independent, computed once in fp32 (weight preparation, not the hot path)
+        # P = conv1(posemb map) + b1 : batch-independent, computed once on the host in fp64 (weight preparation)
         pos = self.decoder_pos_embedding.table().reshape(dH, dW, self.slot_dim).permute(2, 0, 1)[None]
-        prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
         p1 = torch.nn.functional.conv2d(pos.double(), w1.double(), convs[0].bias.detach().double(), padding=2)
-        torch.backends.cudnn.allow_tf32 = prev
-        d["p1"] = p1[0].permute(1, 2, 0).reshape(dH * dW, 64).float().contiguous()
-        for i in range(3):
-            d[f"wc{i}"] = _f16(convs[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 64, 64))
-            d[f"bc{i}"] = _f32(convs[i + 1].bias)
-        wo = torch.zeros(9, 16, 64, device=dev)                                  # N padded 4 -> 16 (UMMA minimum for M=128)
-        wo[:, :4] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(9, 4, 64)
-        d["w_out"] = _f16(wo)
-        d["b_out"] = _f32(last.bias)
-        wt = torch.zeros(48, 64, device=dev)                                     # row (ky*3+kx)*4 + co: the 9 taps in N
-        wt[:36] = last.weight.detach().float().permute(2, 3, 0, 1).reshape(36, 64)
-        d["w_out_taps"] = _f16(wt)
-        dw = DecW()
-        dw.w1_taps, dw.p1, dw.w_out, dw.b_out = (d[n].data_ptr() for n in ("w1_taps", "p1", "w_out", "b_out"))
-        dw.w_out_taps = d["w_out_taps"].data_ptr()
-        for i in range(3):
-            dw.w_conv[i], dw.b_conv[i] = d[f"wc{i}"].data_ptr(), d[f"bc{i}"].data_ptr()
-        dw.H, dw.W, dw.slot_dim, dw.num_slots, dw.hidden = dH, dW, self.slot_dim, self.num_slots, 64
+        d["p1"] = _f32(p1[0].permute(1, 2, 0).reshape(dH * dW, 64))
+        dw.w1_taps, dw.p1 = d["w1_taps"].data_ptr(), d["p1"].data_ptr()
+        dw.H, dw.W, dw.slot_dim, dw.num_slots = dH, dW, self.slot_dim, self.num_slots
         self._dec_keep, self._dec_w = d, dw
 
     # ------------------------------------------------------------------ forward API (SAVi.py:139-149)
@@ -641,6 +946,7 @@ class SAVi(_Packed):
             return self.decode(*args, **kwargs)
         raise NameError(f"mode = {mode!r} not recognized. Use ['decomp', 'decode']")
 
+    @_on_device
     def _encode_raw(self, frames: torch.Tensor, n_img: int, img_stride: int, want_f32: bool):
         """frames: fp32 device tensor; returns feats (f16 [n_img,N,F], fp32 or None)."""
         self._ensure_packed()
@@ -659,6 +965,9 @@ class SAVi(_Packed):
     @torch.no_grad()
     def encode(self, x):
         """x [B,3,H,W] -> [B, H*W, D] fp32 (SAVi.py:226-238)."""
+        H, W = self.encoder_pos_embedding.resolution
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self.in_channels, H, W):
+            raise ValueError(f"SAVi.encode expects [B, {self.in_channels}, {H}, {W}], got {tuple(x.shape)}")
         x = x.float().contiguous()
         _, f32 = self._encode_raw(x, x.shape[0], x[0].numel(), want_f32=True)
         return f32
@@ -667,9 +976,15 @@ class SAVi(_Packed):
     def forward_decomp(self, x, num_imgs=10, decode=True, init_slots=None, **kwargs):
         """SAVi.py:152-223.  ``init_slots`` (optional, not in the reference) injects the sampled initial slots so that
         parity runs do not depend on the device RNG."""
+        if x.dim() != 5:
+            raise ValueError(f"SAVi.forward_decomp expects videos [B, L, C, H, W], got {tuple(x.shape)}")
+        _check_clip(x, num_imgs, "SAVi.forward_decomp")
         B, T = x.shape[0], x.shape[1]
         S, D = self.num_slots, self.slot_dim
         H, W = self.encoder_pos_embedding.resolution
+        if tuple(x.shape[-2:]) != (H, W) or x.shape[2] != self.in_channels:
+            raise ValueError(f"SAVi.forward_decomp: frames are {tuple(x.shape[2:])}, the model was built for "
+                             f"({self.in_channels}, {H}, {W})")
         N = H * W
         x = x.float()
         init = (self.initializer(batch_size=B, **kwargs) if init_slots is None else init_slots).float()
@@ -715,6 +1030,7 @@ class SAVi(_Packed):
         empty = torch.zeros(0, num_imgs)                                          # torch.stack of empty tensors
         return {"recons_imgs": empty, "recons_objs": empty.clone(), "masks": empty.clone(), "slot_history": slot_history}
 
+    @_on_device
     @torch.no_grad()
     def decode(self, slots, only_imgs: bool = False, conv_events=None):
         """slots [B',S,D] -> recons_imgs [B',3,H,W], recons [B',S,3,H,W], masks [B',S,1,H,W] (SAVi.py:241-261)."""
@@ -838,8 +1154,10 @@ class MLPPatchDecoder(_Packed):
             setattr(w, n, k[n].data_ptr())
         w.slot_dim, w.num_patches, w.grid = self.in_dim, self.num_patches, self.patch_grid[0]
         w.feat_dim, w.img_size, w.ln_eps = self.out_dim - 1, int(self.image_size or 0) if self.reconstruct_images else 0, 1e-5
+        w.tuning = ctypes.addressof(L.TUNING)
         self._keep, self._w = k, w
 
+    @_on_device
     @torch.no_grad()
     def forward(self, slots, only_imgs: bool = False):
         self._ensure_packed()
@@ -931,6 +1249,7 @@ class ExtendedDINOSAUR(_Packed):
         for n, v in k.items():
             setattr(w, n, v.data_ptr())
         w.feat_dim, w.hidden_dim, w.slot_dim, w.ln_eps = p[1].weight.shape[1], p[1].weight.shape[0], self.slot_dim, 1e-5
+        w.tuning = ctypes.addressof(L.TUNING)
         self._keep, self._w = k, w
 
     def forward(self, mode="decomp", *args, **kwargs):
@@ -940,6 +1259,7 @@ class ExtendedDINOSAUR(_Packed):
             return self.decode(*args, **kwargs)
         raise NameError(f"mode = {mode!r} not recognized. Use ['decomp', 'decode']")
 
+    @_on_device
     @torch.no_grad()
     def project(self, feats, want_f32=False):
         """linear_feat_proj on patch features [..., F] -> [..., D] (f16 pipeline format, or fp32)."""
@@ -963,8 +1283,14 @@ class ExtendedDINOSAUR(_Packed):
             if bb is None:
                 raise L.TocvpError("ExtendedDINOSAUR got images but no ViT backbone is attached (set_backbone); the "
                                    "accelerated path starts at the patch features [B,T,N,F]")
+            _check_clip(x, num_imgs, "ExtendedDINOSAUR.forward_decomp")
             x = torch.stack([bb(x[:, t]) for t in range(num_imgs)], dim=1)
+        if x.dim() != 4:
+            raise ValueError(f"ExtendedDINOSAUR.forward_decomp expects patch features [B, T, N, F], got {tuple(x.shape)}")
+        _check_clip(x, num_imgs, "ExtendedDINOSAUR.forward_decomp")
         B, T, N, F = x.shape
+        if F != self.mlp_encoder_dim:
+            raise ValueError(f"patch features have {F} channels, the model was built for {self.mlp_encoder_dim}")
         S, D = self.num_slots, self.slot_dim
         feats_in = x[:, :num_imgs]
         proj = self.project(feats_in)                                             # [B,num_imgs,N,D] f16
@@ -1067,6 +1393,7 @@ class TransformerTextEncoder(_Packed):
         w.output_dim, w.vocab_size, w.context_length = self.output_dim, self.vocab_size, self.context_length
         self._keep, self._w = k, w
 
+    @_on_device
     @torch.no_grad()
     def forward(self, text, text_length):
         self._ensure_packed()
@@ -1161,6 +1488,7 @@ class _OCVPBase(_Packed):
         w.ffn_dim, w.num_heads, w.max_len, w.residual = self.hidden_dim, self.nhead, self.input_buffer_size, int(bool(self.residual))
         self._keep, self._w = keep, w
 
+    @_on_device
     @torch.no_grad()
     def forward(self, slots, **kwargs):
         self._ensure_packed()
@@ -1267,7 +1595,7 @@ class BaseTextOCVP(_Packed):
                 w_1=_f16(blk.mlp[0].weight), w_2=_f16(blk.mlp[2].weight), b_1=_f32(blk.mlp[0].bias), b_2=_f32(blk.mlp[2].bias))
             # LayerNorm folded into the consuming projection (include/tocvp.h, tocvp_pred_layer)
             def fold(w, ln, bias, names):
-                t[names[0]], t[names[1]], t[names[2]] = fold_layernorm(w, ln.weight, ln.bias, bias)
+                t[names[0]], t[names[1]], t[names[2]] = (_upload(x) for x in fold_layernorm(w, ln.weight, ln.bias, bias))
             fold(torch.cat([blk.attn.q.weight, blk.attn.k.weight, blk.attn.v.weight], 0), blk.layernorm_query, None,
                  ("w_qkv_f", "c_qkv", "d_qkv"))
             fold(c.cross_attn.q.weight, c.ln_cross_att_q, None, ("wc_q_f", "c_cq", "d_cq"))
@@ -1278,17 +1606,18 @@ class BaseTextOCVP(_Packed):
                 setattr(layers[i], n, v.data_ptr())
         nb = self.input_buffer_size
         pe = self.pe.pe.detach().float().reshape(-1, T)                       # [max_len, T]
-        pef = torch.zeros(nb, nb, T, device=dev)
+        pef = torch.zeros(nb, nb, T)
         for n in range(1, nb + 1):
             pef[n - 1, :n] = torch.flip(pe[:n], dims=(0,))                     # model_blocks.py:375-377
         g = dict(mlp_in_w=_f16(self.mlp_in.weight), mlp_in_b=_f32(self.mlp_in.bias), mlp_out_w=_f16(self.mlp_out.weight),
-                 mlp_out_b=_f32(self.mlp_out.bias), pe_flipped=pef.contiguous())
+                 mlp_out_b=_f32(self.mlp_out.bias), pe_flipped=_upload(pef.contiguous()))
         w = PredW()
         w.layers = ctypes.cast(layers, ctypes.POINTER(PredLayer))
         w.num_layers, w.slot_dim, w.token_dim, w.hidden_dim = self.num_layers, self.slot_dim, T, self.hidden_dim
         w.cross_hidden = self.fusion_params.get("mlp_size")
         w.num_heads, w.cross_heads = self.num_heads, self.fusion_params.get("num_heads")
         w.buffer_size, w.residual, w.ln_eps = nb, int(bool(self.residual)), 1e-6
+        w.tuning = ctypes.addressof(L.TUNING)
         for n, v in g.items():
             setattr(w, n, v.data_ptr())
         self._keep, self._layers, self._w = (keep, g), layers, w
@@ -1298,6 +1627,7 @@ class BaseTextOCVP(_Packed):
         self._w.num_slots = num_slots
         return self._w
 
+    @_on_device
     @torch.no_grad()
     def forward(self, slots, text_embeddings, **kwargs):
         B, n, S, D = slots.shape
@@ -1324,6 +1654,7 @@ class BaseTextOCVP(_Packed):
         L.call("tocvp_predictor_rollout", ctypes.byref(w), ptr(sh), c_size_t(seq_stride), ptr(text), c_int(B), c_int(Lt),
                c_int(num_context), c_int(num_preds), ptr(out), ws, wsb, stream())
 
+    @_on_device
     @torch.no_grad()
     def rollout(self, slot_history, text_embeddings, num_context, num_preds):
         """The whole autoregressive loop in one library call (all ~1300 kernels enqueued from C++).  With
@@ -1341,7 +1672,7 @@ class BaseTextOCVP(_Packed):
             out = torch.empty(B, num_preds, S, D, device=sh.device, dtype=torch.float32)
             self._rollout_eager(sh, sh.stride(0), text, B, S, D, Lt, num_context, num_preds, out)
             return out
-        key = (B, S, D, Lt, num_context, num_preds, str(sh.device), self._pack_sig)
+        key = (B, S, D, Lt, num_context, num_preds, str(sh.device), self._pack_sig, bytes(L.TUNING))   # kernel choice is baked in
         g = getattr(self, "_graph", None)
         ws_ptr = self._ws.buf.data_ptr() if self._ws.buf is not None else 0
         if g is None or g["key"] != key or g["ws_ptr"] != ws_ptr:   # the graph bakes in the workspace address
@@ -1379,6 +1710,42 @@ class TextOCVP_CustomTF(BaseTextOCVP):
                      if not n.startswith("text_encoder."))
 
 
+T5_SMALL_CONFIG = dict(vocab_size=32128, d_model=512, d_kv=64, d_ff=2048, num_layers=6, num_heads=8,
+                       relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.1,
+                       layer_norm_epsilon=1e-6, feed_forward_proj="relu", is_encoder_decoder=False, use_cache=False)
+
+
+class TextOCVP_T5(BaseTextOCVP):
+    """text_cond_OCVP.py:139-151: TextOCVP with a frozen T5 text encoder.  The encoder is the third-party ``transformers``
+    module (it runs once per rollout, before the path; SURVEY 8(f) row 2 asks for the HOOK): ``text_encoder`` is any module
+    with the HF encoder call signature ``(input_ids=, attention_mask=, return_dict=True) -> .last_hidden_state``.  Like the
+    reference this tries ``T5EncoderModel.from_pretrained("t5-small")``; without network access (or with
+    ``text_encoder_params["pretrained"] = False``) it builds the same architecture from the t5-small configuration with
+    random weights, to be filled by ``load_state_dict`` (the checkpoint holds ``text_encoder.*``).  A ready-made encoder
+    can be passed as ``text_encoder_params["module"]``."""
+
+    def _instantiate_text_encoder(self):
+        p = self.text_encoder_params or {}
+        enc = p.get("module", None)
+        if enc is None:
+            from transformers import T5Config, T5EncoderModel
+            if p.get("pretrained", True):
+                try:
+                    enc = T5EncoderModel.from_pretrained("t5-small", local_files_only=True)
+                except Exception:                                        # offline and not cached
+                    enc = None
+            if enc is None:
+                enc = T5EncoderModel(T5Config(**{**T5_SMALL_CONFIG, **p.get("config", {})}))
+        self.text_encoder = enc.eval()
+        for q in self.text_encoder.parameters():                         # freeze_params (text_cond_OCVP.py:149)
+            q.requires_grad_(False)
+        self.t5_token_dim = getattr(getattr(enc, "config", None), "d_model", 512)
+
+    def _sig(self):   # the text encoder is not packed; ignore its parameters
+        return tuple((p.data_ptr(), p._version, str(p.device)) for n, p in self.named_parameters()
+                     if not n.startswith("text_encoder."))
+
+
 class PredictorWrapper(nn.Module):
     """predictor_wrapper.py:18-153."""
 
@@ -1408,7 +1775,19 @@ class PredictorWrapper(nn.Module):
             if lengths is None:
                 raise KeyError("'caption_lengths' must be provided for CustomTF Pred.")
             return self.predictor.text_encoder(text=caption.to(device), text_length=lengths.to(device))
-        raise NotImplementedError("only the CustomTF text encoder is available offline (T5 weights need network)")
+        if "T5" in self.predictor_name:                            # predictor_wrapper.py:100-113
+            attention_mask = kwargs.get("attn_masks", None)
+            if attention_mask is None:
+                raise KeyError("'attn_masks' must be provided for T5 Predictor")
+            out_t5 = self.predictor.text_encoder(input_ids=caption.to(device), attention_mask=attention_mask.to(device),
+                                                 return_dict=True)
+            text_embeddings = out_t5.last_hidden_state
+            if self.predictor.token_dim != self.predictor.t5_token_dim:
+                # the reference calls an undefined `mlp_map_to_token_dim` here (predictor_wrapper.py:113)
+                raise L.TocvpError(f"T5 embeddings are {self.predictor.t5_token_dim}-d but token_dim is "
+                                   f"{self.predictor.token_dim}; the reference has no projection for this case")
+            return text_embeddings
+        return None
 
     @torch.no_grad()
     def forward(self, slot_history, num_preds=None, **kwargs):
@@ -1451,14 +1830,17 @@ def setup_predictor(exp_params: Dict):
     mp = exp_params["model"]["model_params"]
     if name == "TextOCVP_CustomTF":
         body = TextOCVP_CustomTF(slot_dim=mp["slot_dim"], **pp)
+    elif name == "TextOCVP_T5":                                        # setup_model.py:106-111
+        pp.setdefault("text_encoder_params", {})
+        body = TextOCVP_T5(slot_dim=mp["slot_dim"], **pp)
     elif name in ("VanillaTransformer", "OCVPSeq", "OCVPPar"):         # setup_model.py:83-99 (OCVPPar: OCVP.py:324, no
         cls = {"VanillaTransformer": VanillaTransformerPredictor, "OCVPSeq": OCVPSeq, "OCVPPar": OCVPPar}[name]   # factory entry in the reference)
         body = cls(num_slots=mp["num_slots"], slot_dim=mp["slot_dim"],
                    input_buffer_size=exp_params["prediction_params"]["input_buffer_size"],
                    **exp_params["predictor"]["predictor_params"])
     else:
-        raise NotImplementedError(f"predictor {name}: TextOCVP_T5 needs the T5 weights (network); available: "
-                                  "TextOCVP_CustomTF, VanillaTransformer, OCVPSeq")
+        raise NotImplementedError(f"predictor {name} is not recognized; available: TextOCVP_CustomTF, TextOCVP_T5, "
+                                  "VanillaTransformer, OCVPSeq, OCVPPar")
     return PredictorWrapper(exp_params=exp_params, predictor=body)
 
 

@@ -22,6 +22,10 @@ def frame_metrics(pred_imgs: torch.Tensor, videos: torch.Tensor, frame0: int, cl
     (unclamped) against videos[:, frame0:frame0+F] read in place; both are clamped to [0,1] inside the kernels.
     Returns dict of [B,F] tensors: mse, psnr, ssim."""
     B, F_, C, H, W = pred_imgs.shape
+    if videos.dim() != 5 or videos.shape[0] != B or tuple(videos.shape[2:]) != (C, H, W):
+        raise ValueError(f"frame_metrics: videos {tuple(videos.shape)} do not match predictions {tuple(pred_imgs.shape)}")
+    if frame0 < 0 or frame0 + F_ > videos.shape[1]:
+        raise ValueError(f"frame_metrics: frames [{frame0}, {frame0 + F_}) are outside the clip of {videos.shape[1]} frames")
     pred = pred_imgs.float().contiguous()
     vid = videos.float()
     if not vid.is_contiguous():
@@ -74,7 +78,8 @@ def forward_eval_dino(dino, pred, feats, text_embeddings, num_context, num_preds
     ps = pred(sh, text_embeddings=text_embeddings)
     dec = dino.decode(ps.reshape(B * num_preds, dino.num_slots, dino.slot_dim), only_imgs=only_imgs)
     I = dino.img_size
-    imgs = dec["recons_imgs"].view(B, num_preds, 3, I, I).clamp(0, 1)
+    imgs = dec["recons_imgs"].view(B, num_preds, 3, I, I)
+    L.call("tocvp_clamp01", L.ptr(imgs), L.c_size_t(imgs.numel()), L.stream())      # 05_evaluate_predictor.py:96
     return {"slot_history": sh, "pred_slots": ps, "pred_imgs": imgs, "recons_feats": dec["recons_feats"]}
 
 
@@ -96,7 +101,9 @@ def forward_eval(savi, pred, videos, text_embeddings, num_context, num_preds, in
     raw = dec["recons_imgs"].view(B, num_preds, C, H, W)
     # clamp + MSE / PSNR / SSIM in the metric kernels (targets = videos[:, num_context:num_context+num_preds], in place)
     m = frame_metrics(raw, videos, num_context, clamp=True, want_ssim=want_ssim)
-    pred_imgs = raw.clamp_(0, 1) if clamp_output else raw
+    if clamp_output:                                                     # 05_evaluate_predictor.py:96, in place, own kernel
+        L.call("tocvp_clamp01", L.ptr(raw), L.c_size_t(raw.numel()), L.stream())
+    pred_imgs = raw
     return {"slot_history": slot_history, "pred_slots": pred_slots, "pred_imgs": pred_imgs, "mse": m["mse"],
             "psnr": m["psnr"], "ssim": m["ssim"]}
 

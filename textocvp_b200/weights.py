@@ -351,3 +351,38 @@ def ocvp_state_dict(kind: str, seed: int = 19, slot_dim: int = 128, token_dim: i
         else:
             raise ValueError(kind)
     return sd
+
+
+T5_TEST_CONFIG = dict(vocab_size=200, d_model=512, d_kv=64, d_ff=1024, num_layers=2, num_heads=8)
+
+
+def t5_encoder(seed: int = 19, config: Optional[dict] = None):
+    """A ``transformers.T5EncoderModel`` of the t5-small family (d_model 512; depth / width reduced by ``config`` for
+    tests) with every parameter overwritten from a seeded CPU generator, so the same weights can be rebuilt anywhere
+    without depending on the library's init code: matrices 0.05 * randn, LayerNorm scales 1 + 0.05 * randn.
+    Used by the T5-hook golden vectors (oracle/make_golden_t5.py) and their tests."""
+    from transformers import T5Config, T5EncoderModel
+    from .modules import T5_SMALL_CONFIG
+    cfg = T5Config(**{**T5_SMALL_CONFIG, **(config if config is not None else T5_TEST_CONFIG)})
+    enc = T5EncoderModel(cfg).eval()
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in sorted(enc.named_parameters()):
+            if "layer_norm" in name:
+                p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    return enc
+
+
+def synthetic_t5_captions(B: int, L: int, vocab: int = 200, seed: int = 5):
+    """Token ids [B, L] int64 (0 = pad, 1 = eos as in T5) and attention masks [B, L] with ragged lengths."""
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(L // 3, L + 1, (B,), generator=g)
+    lengths[0] = L
+    ids = torch.randint(2, vocab, (B, L), generator=g)
+    pos = torch.arange(L)[None]
+    mask = (pos < lengths[:, None]).long()
+    ids = ids * mask
+    ids[torch.arange(B), lengths - 1] = 1
+    return ids, mask

@@ -22,10 +22,10 @@ def t(iters, nxt, n=10):
 outs = {}
 for rep in range(2):
     for mode in (1, 0):
-        L.call("tocvp_set_corrector_mode", L.c_int(mode))
+        setattr(L.TUNING, "corrector_mode", int(mode))
         a, b = t(3, None), t(1, nx)
         outs[mode] = (o.clone(), nx.clone())
         print(f"corrector update mode {mode}: 3 iterations {a*1e3:.0f} us, 1 iteration + transition {b*1e3:.0f} us", flush=True)
-L.call("tocvp_set_corrector_mode", L.c_int(0))
+setattr(L.TUNING, "corrector_mode", int(0))
 d0 = float((outs[0][0] - outs[1][0]).norm() / outs[1][0].norm()); d1 = float((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm())
 print(f"relative difference 3xTF32 vs fp32 SIMT: slots {d0:.2e}, transition {d1:.2e}")

@@ -1,4 +1,4 @@
-"""A/B of the decoder in one process (tocvp_set_decode_mode bits): 0 = default, 1 = layer 1 generated inside the layer-2
+"""A/B of the decoder in one process (tocvp_tuning.decode_mode bits): 0 = default, 1 = layer 1 generated inside the layer-2
 conv, 8 = serial chunks (no layer-1 / conv overlap), 2 = first-version head conv3x3 (shifted windows, N = 16) instead of the taps-in-N kernel;
 per-layer conv times from the event pairs tocvp_savi_decode records."""
 import os, sys
@@ -22,7 +22,7 @@ def t(n=3):
     return e0.elapsed_time(e1) / n, lay
 for rep in range(2):
     for mode in (0, 8, 0, 8):
-        L.call("tocvp_set_decode_mode", L.c_int(mode))
+        setattr(L.TUNING, "decode_mode", int(mode))
         ms, lay = t()
         print(f"decode mode {mode}: {ms:.1f} ms; conv layers 2/3/4: {lay[0]:.3f} {lay[1]:.3f} {lay[2]:.3f} ms", flush=True)
-L.call("tocvp_set_decode_mode", L.c_int(0))
+setattr(L.TUNING, "decode_mode", int(0))

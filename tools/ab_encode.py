@@ -1,4 +1,4 @@
-"""A/B of the encoder variants in one process (tocvp_set_encode_mode bits)."""
+"""A/B of the encoder variants in one process (tocvp_tuning.encode_mode bits)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,6 +16,6 @@ def t(n=3):
     return e0.elapsed_time(e1) / n
 for rep in range(2):
     for mode in (0, 8, 4, 0, 8):
-        L.call("tocvp_set_encode_mode", L.c_int(mode))
+        setattr(L.TUNING, "encode_mode", int(mode))
         print(f"encode mode {mode}: {t():.2f} ms", flush=True)
-L.call("tocvp_set_encode_mode", L.c_int(0))
+setattr(L.TUNING, "encode_mode", int(0))

@@ -1,4 +1,4 @@
-"""A/B: predictor rollout with / without programmatic dependent launch (tocvp_set_pdl), same process, graph replay;
+"""A/B: predictor rollout with / without programmatic dependent launch (tocvp_tuning.no_pdl), same process, graph replay;
 also checks that both give bit-identical predictions."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,15 +20,15 @@ def t(n=5):
 outs = {}
 for rep in range(3):
     for on in (0, 1):
-        L.call("tocvp_set_pdl", L.c_int(on))
+        setattr(L.TUNING, "no_pdl", int(not (on)))
         object.__setattr__(pred.predictor, "_graph", None)      # re-capture with the new launch attribute
         ms, o = t()
         outs[on] = o
         print(f"predict PDL={'on' if on else 'off'}: {ms:.2f} ms", flush=True)
 print("bit-identical:", torch.equal(outs[0], outs[1]), flush=True)
 for on in (0, 1):                                                # eager (no graph) as well
-    L.call("tocvp_set_pdl", L.c_int(on))
+    setattr(L.TUNING, "no_pdl", int(not (on)))
     pred.predictor.use_cuda_graph = False
     ms, o = t()
     print(f"eager predict PDL={'on' if on else 'off'}: {ms:.2f} ms; equal to graph: {torch.equal(o, outs[1])}", flush=True)
-L.call("tocvp_set_pdl", L.c_int(1))
+setattr(L.TUNING, "no_pdl", int(not (1)))

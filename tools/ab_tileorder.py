@@ -1,4 +1,4 @@
-"""A/B: predictor rollout with / without alternating tile traversal (tocvp_set_tile_order), same process, graph replay;
+"""A/B: predictor rollout with / without alternating tile traversal (tocvp_tuning.no_tile_alternation), same process, graph replay;
 checks bit-identical predictions."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,10 +20,10 @@ def t(n=5):
 outs = {}
 for rep in range(4):
     for on in (0, 1):
-        L.call("tocvp_set_tile_order", L.c_int(on))
+        setattr(L.TUNING, "no_tile_alternation", int(not (on)))
         object.__setattr__(pred.predictor, "_graph", None)      # re-capture
         ms, o = t()
         outs[on] = o
         print(f"predict alternating tile order={'on' if on else 'off'}: {ms:.2f} ms", flush=True)
 print("bit-identical:", torch.equal(outs[0], outs[1]), flush=True)
-L.call("tocvp_set_tile_order", L.c_int(1))
+setattr(L.TUNING, "no_tile_alternation", int(not (1)))

@@ -6,9 +6,9 @@ from textocvp_b200 import rollout, weights
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 NP = int(sys.argv[2]) if len(sys.argv) > 2 else 29
-if len(sys.argv) > 3:                     # optional: tocvp_set_pdl(0|1)
+if len(sys.argv) > 3:                     # optional: PDL on (1) or off (0)
     from textocvp_b200 import _lib as L
-    L.call("tocvp_set_pdl", L.c_int(int(sys.argv[3])))
+    setattr(L.TUNING, "no_pdl", int(not (int(sys.argv[3]))))
 dev = torch.device("cuda:0")
 dino, pred, _ = rollout.build_dino_models(dev, num_preds=NP)
 feats, text, noise = weights.synthetic_dino_inputs(B, NP + 1, 81, L=16, seed=0)

@@ -18,7 +18,7 @@ fn = {"decode": lambda: savi.decode(ps, only_imgs=True),
       "predict": lambda: pred(sh, text_embeddings=text),
       "decomp": lambda: savi(mode="decomp", x=videos, num_imgs=20, decode=False, init_slots=init),
       "eval": lambda: rollout.forward_eval(savi, pred, videos, text, 1, 19, init_slots=init)}[stage]
-if len(sys.argv) > 2:                      # optional: tocvp_set_gemm_mode(<mode>) before the run (e.g. 260 / 261)
+if len(sys.argv) > 2:                      # optional: ops.set_gemm_mode(<mode>) before the run (e.g. 260 / 261)
     from textocvp_b200 import ops
     ops.set_gemm_mode(int(sys.argv[2]))
 for _ in range(3): fn()
