@@ -30,7 +30,7 @@ def test_project(dmodels, golden_dino, golden_dino_weights):
     dino, _ = dmodels
     x = golden_dino_weights["feats"][:, 0].cuda()
     PL.check(O.rel_err(dino.project(x, want_f32=True), golden_dino["proj_feats"]), STAGE_TOL, "dino.project(x, want_f32=True), golden_dino['proj_feats']")
-    PL.check(O.rel_err(dino.project(x).float(), golden_dino["proj_feats"]), STAGE_TOL      # f16 pipeline format, "dino.project(x).float(), golden_dino['proj_feats']")
+    PL.check(O.rel_err(dino.project(x).float(), golden_dino["proj_feats"]), STAGE_TOL, "f16 pipeline format: dino.project(x), golden_dino['proj_feats']")
 
 
 def test_slot_attention_10_slots(dmodels, golden_dino, golden_dino_weights):
