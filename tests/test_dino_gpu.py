@@ -64,7 +64,7 @@ def test_decomp(dmodels, golden_dino, golden_dino_weights):
     sh = out["slot_history"]
     assert sh.shape == (m["B"], m["T"], 10, 128)
     PL.check(O.rel_err(sh[:, 0], golden_dino["slot_history"][:, 0]), STAGE_TOL, "sh[:, 0], golden_dino['slot_history'][:, 0]")
-    PL.check(O.rel_err(sh, golden_dino["slot_history"]), 3 * STAGE_TOL, "sh, golden_dino['slot_history']")
+    PL.check(O.rel_err(sh, golden_dino["slot_history"]), STAGE_TOL, "sh, golden_dino['slot_history']")
     dino.chain_corrector = False                       # one library call per frame (first version): bit-identical
     try:
         ref = dino(mode="decomp", x=golden_dino_weights["feats"].cuda(), num_imgs=m["T"], decode=False,
@@ -83,8 +83,8 @@ def test_patch_decode(dmodels, golden_dino):
     assert out["recons_imgs"].shape == golden_dino["pred_imgs"].shape
     PL.check(O.rel_err(out["masks"], golden_dino["pred_masks"]), STAGE_TOL, "out['masks'], golden_dino['pred_masks']")
     PL.check(O.rel_err(out["recons_feats"], golden_dino["pred_feats"]), STAGE_TOL, "out['recons_feats'], golden_dino['pred_feats']")
-    # 5 convolutions (K up to 9216) behind the MLP: one stage budget for the MLP + one for the CNN
-    PL.check(O.rel_err(out["recons_imgs"], golden_dino["pred_imgs"]), 2 * STAGE_TOL, "out['recons_imgs'], golden_dino['pred_imgs']")
+    # MLP + 5 convolutions (K up to 9216) chained: measured 4e-4 (profiles/parity_r2.md), inside ONE stage budget
+    PL.check(O.rel_err(out["recons_imgs"], golden_dino["pred_imgs"]), STAGE_TOL, "out['recons_imgs'], golden_dino['pred_imgs']")
 
 
 def test_patch_decode_336(golden_dino_weights):
@@ -101,7 +101,7 @@ def test_patch_decode_336(golden_dino_weights):
     out = dino(mode="decode", slots=slots.cuda())
     assert out["recons_imgs"].shape == (1, 3, 336, 336)
     PL.check(O.rel_err(out["recons_feats"], ref["recons_feats"]), STAGE_TOL, "out['recons_feats'], ref['recons_feats']")
-    PL.check(O.rel_err(out["recons_imgs"], ref["recons_imgs"]), 2 * STAGE_TOL, "out['recons_imgs'], ref['recons_imgs']")
+    PL.check(O.rel_err(out["recons_imgs"], ref["recons_imgs"]), STAGE_TOL, "out['recons_imgs'], ref['recons_imgs']")
 
 
 def test_dino_rollout(dmodels, golden_dino, golden_dino_weights):
@@ -111,7 +111,7 @@ def test_dino_rollout(dmodels, golden_dino, golden_dino_weights):
     sh = dino(mode="decomp", x=w["feats"].cuda(), num_imgs=m["T"], decode=False, init_slots=w["init"].cuda())["slot_history"]
     ps = pred(sh, text_embeddings=w["text"].cuda())
     assert ps.shape == (m["B"], m["num_preds"], 10, 128)
-    PL.check(O.rel_err(ps, golden_dino["pred_slots"]), 5e-3, "ps, golden_dino['pred_slots']")
+    PL.check(O.rel_err(ps, golden_dino["pred_slots"]), STAGE_TOL, "ps, golden_dino['pred_slots']")
     imgs = dino(mode="decode", slots=ps.reshape(-1, 10, 128))["recons_imgs"].clamp(0, 1)
     p = O.psnr(imgs.cpu(), golden_dino["pred_imgs"].clamp(0, 1))
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")

@@ -3,7 +3,7 @@ size-independent properties the path offers.  The oracle needs ~1 s per sequence
 recomputed there; instead:
 
   * the two golden sequences (pinned against the REAL reference, tests/golden/cater_b2.pt) are embedded at tile-unaligned
-    positions of the batch and must come out as the reference's frames (>= 40 dB, slot error <= 5e-3);
+    positions of the batch and must come out as the reference's frames (>= 40 dB, slot error <= 2e-3 after 19 recurrent steps);
   * two more sequences are re-computed by the CPU oracle as a B = 2 job and compared the same way;
   * no op of the path mixes batch elements, so the batch-256 job must be BIT-identical to (a) the same job
     with the batch order reversed and (b) the two batch-128 jobs a 2-GPU shard would run -- the multi-GPU result is then
@@ -17,6 +17,9 @@ from oracle import parity_log as PL
 from oracle import textocvp_oracle as O
 
 pytestmark = pytest.mark.gpu
+STAGE_TOL = 1e-3         # the north star's per-stage tolerance (here: the whole 20-frame decomp stays inside ONE stage budget)
+ROLLOUT_TOL = 2e-3       # slots after 19 / 29 RECURRENT predictor steps (each <= 1e-3 on identical inputs); measured 5.5-6.4e-4.
+                         # The rollout contract proper is the >= 40 dB frame PSNR checked beside it (measured 68-76 dB).
 B = 256
 POS = (37, 201)          # where the golden sequences sit in the batch
 SPOT = (5, 255)          # sequences re-computed by the CPU oracle
@@ -51,8 +54,8 @@ def test_golden_sequences_inside_full_batch(full, golden):
     out = full["out"]
     assert out["pred_imgs"].shape == (B, 19, 3, 64, 64)
     idx = list(POS)
-    PL.check(O.rel_err(out["slot_history"][idx], golden["slot_history"]), 3e-3, "out['slot_history'][idx], golden['slot_history']")
-    PL.check(O.rel_err(out["pred_slots"][idx], golden["pred_slots"]), 5e-3, "out['pred_slots'][idx], golden['pred_slots']")
+    PL.check(O.rel_err(out["slot_history"][idx], golden["slot_history"]), STAGE_TOL, "out['slot_history'][idx], golden['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"][idx], golden["pred_slots"]), ROLLOUT_TOL, "out['pred_slots'][idx], golden['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), golden["pred_imgs"])
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
@@ -62,7 +65,7 @@ def test_oracle_spot_check_inside_full_batch(full, golden_weights):
     ref = O.rollout(golden_weights["savi_sd"], golden_weights["pred_sd"], full["videos"][idx], full["text"][idx],
                     full["init"][idx], O.SAViCfg(), O.PredCfg(num_context=1, num_preds=19))
     out = full["out"]
-    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), 5e-3, "out['pred_slots'][idx], ref['pred_slots']")
+    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), ROLLOUT_TOL, "out['pred_slots'][idx], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), ref["pred_imgs"])
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
@@ -130,8 +133,8 @@ def test_cliport_oracle_spot_check_inside_full_batch(full_dino, golden_dino_weig
                          O.DinoCfg(img_size=m["img_size"], num_patches=m["N"]), O.PredCfg(num_context=1, num_preds=DPREDS))
     out = full_dino["out"]
     assert out["pred_imgs"].shape == (DB, DPREDS, 3, m["img_size"], m["img_size"])
-    PL.check(O.rel_err(out["slot_history"][idx], ref["slot_history"]), 3e-3, "out['slot_history'][idx], ref['slot_history']")
-    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), 5e-3, "out['pred_slots'][idx], ref['pred_slots']")
+    PL.check(O.rel_err(out["slot_history"][idx], ref["slot_history"]), STAGE_TOL, "out['slot_history'][idx], ref['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"][idx], ref["pred_slots"]), ROLLOUT_TOL, "out['pred_slots'][idx], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"][idx].cpu(), ref["pred_imgs"])
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
@@ -149,6 +152,6 @@ def test_cliport_batch_order_and_sharding(full_dino):
     for lo in (0, DB // 2):
         sh = full_dino["run"](torch.arange(lo, lo + DB // 2))
         assert torch.equal(sh["slot_history"], out["slot_history"][lo:lo + DB // 2]), lo
-        PL.check(O.rel_err(sh["pred_slots"], out["pred_slots"][lo:lo + DB // 2]), 2e-3, "sh['pred_slots'], out['pred_slots'][lo:lo + DB // 2]")
+        PL.check(O.rel_err(sh["pred_slots"], out["pred_slots"][lo:lo + DB // 2]), STAGE_TOL, "sh['pred_slots'], out['pred_slots'][lo:lo + DB // 2]")
         p = O.psnr(sh["pred_imgs"].cpu(), out["pred_imgs"][lo:lo + DB // 2].cpu())
         PL.check_min(p.min(), 50.0, "frame PSNR vs reference (dB), min")

@@ -110,8 +110,8 @@ def test_stock_init_rollout_is_finite(golden_weights):
     ref = O.rollout(ssd, psd, videos, text, init, O.SAViCfg(), O.PredCfg())
     PL.check_min(float(ref["pred_slots"][:, -1].std()), 10.0, "stock init: oracle slot std at step 19 (range reached)")
     p = O.psnr(out["pred_imgs"].cpu(), ref["pred_imgs"])
-    PL.check_min(p.min(), 20.0, "stock-init rollout: frame PSNR vs fp32 oracle (dB), min")
-    PL.check(O.rel_err(out["pred_slots"], ref["pred_slots"]), 5e-2, "stock-init rollout: pred_slots rel err")
+    PL.check_min(p.min(), 40.0, "stock-init rollout: frame PSNR vs fp32 oracle (dB), min")
+    PL.check(O.rel_err(out["pred_slots"], ref["pred_slots"]), 5e-3, "stock-init rollout: pred_slots rel err (slot std 266)")
 
 
 def test_out_of_range_activations_saturate(models):
@@ -158,7 +158,7 @@ def test_conv_decoder_forward(models):
     out = savi.decoder(x.cuda())
     assert out.shape == (2, 4, 64, 64)
     ref = _conv_ref(x, list(savi.decoder.decoder))
-    PL.check(O.rel_err(out, ref), 2 * STAGE_TOL, "ConvDecoder.forward (5 convolutions) vs torch fp32")
+    PL.check(O.rel_err(out, ref), STAGE_TOL, "ConvDecoder.forward (5 convolutions) vs torch fp32")
 
 
 def test_conv_decoder_forward_equals_fused_decode(models, golden):
@@ -173,7 +173,7 @@ def test_conv_decoder_forward_equals_fused_decode(models, golden):
     img = (recons * masks).sum(1)
     fused = savi(mode="decode", slots=slots)
     PL.check(O.rel_err(img, fused["recons_imgs"]), STAGE_TOL, "materialised ConvDecoder route vs fused decode")
-    PL.check(O.rel_err(img, golden["dec_img"]), 2 * STAGE_TOL, "materialised ConvDecoder route vs golden dec_img")
+    PL.check(O.rel_err(img, golden["dec_img"]), STAGE_TOL, "materialised ConvDecoder route vs golden dec_img")
 
 
 def test_conv_encoder_forward(models, golden_weights):
@@ -220,13 +220,13 @@ def test_attention_modules(models):
     W = lambda lin: lin.weight.detach().cpu().double()
     xd = x.double()
     ref = attn(xd @ W(sa.q).t(), xd @ W(sa.k).t(), xd @ W(sa.v).t(), 8) @ W(sa.out_projection[0]).t()
-    PL.check(O.rel_err(sa(x.cuda()), ref), 2 * STAGE_TOL, "MultiHeadSelfAttention.forward vs fp64 (3 chained f16 stages)")
+    PL.check(O.rel_err(sa(x.cuda()), ref), STAGE_TOL, "MultiHeadSelfAttention.forward vs fp64 (3 chained f16 stages)")
     ca = blk.cross_attention.cross_attn
     txt = torch.randn(3, 32, 512, generator=g)
     td = txt.double()
     ref = attn(xd @ W(ca.q).t(), td @ W(ca.k).t(), td @ W(ca.v).t(), 8) @ W(ca.out_projection).t() \
         + ca.out_projection.bias.detach().cpu().double()
-    PL.check(O.rel_err(ca(txt.cuda(), x.cuda()), ref), 2 * STAGE_TOL, "MultiHeadCrossAttention.forward vs fp64")
+    PL.check(O.rel_err(ca(txt.cuda(), x.cuda()), ref), STAGE_TOL, "MultiHeadCrossAttention.forward vs fp64")
 
 
 # ------------------------------------------------------------------------------------------------ evaluator drive (b)
@@ -294,10 +294,10 @@ def test_dino_576_decomp_and_rollout():
     sh_ref = O.dino_decomp(dsd, feats, T, dcfg, init)
     sh = dino(mode="decomp", x=feats.cuda(), num_imgs=T, decode=False, init_slots=init.cuda())["slot_history"]
     PL.check(O.rel_err(sh[:, 0], sh_ref[:, 0]), STAGE_TOL, "N=576 decomp frame 0 (3 iterations)")
-    PL.check(O.rel_err(sh, sh_ref), 3 * STAGE_TOL, "N=576 decomp, 3 frames (recurrent)")
+    PL.check(O.rel_err(sh, sh_ref), STAGE_TOL, "N=576 decomp, 3 frames (recurrent)")
     ps_ref = O.predictor_rollout(psd, sh_ref[:, :1], text, O.PredCfg(num_preds=npred))
     ps = pred(sh[:, :1].contiguous(), text_embeddings=text.cuda(), num_preds=npred)
-    PL.check(O.rel_err(ps, ps_ref), 5 * STAGE_TOL, "N=576 3-step rollout slots")
+    PL.check(O.rel_err(ps, ps_ref), STAGE_TOL, "N=576 3-step rollout slots")
 
 
 # ------------------------------------------------------------------------------------------------ T5 hook (f2)
@@ -322,6 +322,6 @@ def test_t5_hook_rollout():
     PL.check(O.rel_err(text, g["text_embeddings"]), 1e-4, "T5 hook: text embeddings vs reference wrapper")
     sh = torch.randn(m["B"], 1 + m["num_preds"], 8, 128, generator=torch.Generator().manual_seed(m["hist_seed"]))
     out = pred(sh.cuda(), caption_tokens=ids, attn_masks=mask, caption=["a"] * m["B"])
-    PL.check(O.rel_err(out, g["pred_slots"]), 3 * STAGE_TOL, "T5 hook: 3-step rollout vs reference wrapper")
+    PL.check(O.rel_err(out, g["pred_slots"]), STAGE_TOL, "T5 hook: 3-step rollout vs reference wrapper")
     with pytest.raises(KeyError):
         pred(sh.cuda(), caption_tokens=ids)

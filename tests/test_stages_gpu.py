@@ -9,7 +9,10 @@ from oracle import parity_log as PL
 from oracle import textocvp_oracle as O
 
 pytestmark = pytest.mark.gpu
-STAGE_TOL = 1e-3
+STAGE_TOL = 1e-3      # north star: per-stage relative L2 error vs the fp32 reference on identical stage inputs
+ROLLOUT_TOL = 2e-3    # slots after 19 RECURRENT predictor steps (measured 6.0e-4); the rollout contract proper is >= 40 dB PSNR
+DELTA_TOL = 2e-3      # error of the small mlp_out BRANCH alone (out - last slots: a derived quantity ~10x smaller than the
+                      # stage output, so ~10x the relative error of the output itself; measured 7.3-7.6e-4)
 
 
 @pytest.fixture(scope="module")
@@ -70,8 +73,8 @@ def test_decomp_and_transition(models, golden, golden_weights):
     sh = out["slot_history"]
     assert sh.shape == (2, 20, 8, 128)
     PL.check(O.rel_err(sh[:, 0], golden["slot_history"][:, 0]), STAGE_TOL, "sh[:, 0], golden['slot_history'][:, 0]")
-    # recurrent over 20 frames (encode -> correct -> transition): errors compound, allow 3x the single-stage budget
-    PL.check(O.rel_err(sh, golden["slot_history"]), 3 * STAGE_TOL, "sh, golden['slot_history']")
+    # recurrent over 20 frames (encode -> correct -> transition): measured 2.9e-4, inside ONE stage budget
+    PL.check(O.rel_err(sh, golden["slot_history"]), STAGE_TOL, "sh, golden['slot_history']")
 
 
 def test_decomp_chained_matches_per_frame(models, golden_weights):
@@ -111,7 +114,7 @@ def test_predictor_step(models, golden, golden_weights):
     # the quantity the network adds (mlp_out branch) must itself be accurate, not just slots + small delta
     d_ref = golden["pred_step_n10"] - golden["slot_history"][:, 9]
     d_out = out.cpu() - golden["slot_history"][:, 9]
-    PL.check(O.rel_err(d_out, d_ref), 5e-3, "d_out, d_ref")
+    PL.check(O.rel_err(d_out, d_ref), DELTA_TOL, "d_out, d_ref")
     out1 = pred.predictor(slots=sh[:, :1], text_embeddings=text)
     PL.check(O.rel_err(out1, golden["pred_step_n1"]), STAGE_TOL, "out1, golden['pred_step_n1']")
 
@@ -191,7 +194,7 @@ def test_full_rollout_psnr(models, golden, golden_weights):
     ps = pred(sh, text_embeddings=text)
     assert ps.shape == (2, 19, 8, 128)
     imgs = savi(mode="decode", slots=ps.reshape(2 * 19, 8, 128))["recons_imgs"].view(2, 19, 3, 64, 64).clamp(0, 1)
-    PL.check(O.rel_err(ps, golden["pred_slots"]), 5e-3, "ps, golden['pred_slots']")
+    PL.check(O.rel_err(ps, golden["pred_slots"]), ROLLOUT_TOL, "ps, golden['pred_slots']")
     p = O.psnr(imgs.cpu(), golden["pred_imgs"])
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
 
@@ -209,8 +212,8 @@ def test_rollout_small_and_odd_batches(models, golden_weights, B):
     out = rollout.forward_eval(savi, pred, videos.cuda(), text.cuda(), 1, 19, init_slots=init.cuda())
     ref = O.rollout(sd, golden_weights["pred_sd"], videos, text, init, O.SAViCfg(), O.PredCfg(num_context=1, num_preds=19))
     assert out["pred_imgs"].shape == (B, 19, 3, 64, 64)
-    PL.check(O.rel_err(out["slot_history"], ref["slot_history"]), 3e-3, "out['slot_history'], ref['slot_history']")
-    PL.check(O.rel_err(out["pred_slots"], ref["pred_slots"]), 5e-3, "out['pred_slots'], ref['pred_slots']")
+    PL.check(O.rel_err(out["slot_history"], ref["slot_history"]), STAGE_TOL, "out['slot_history'], ref['slot_history']")
+    PL.check(O.rel_err(out["pred_slots"], ref["pred_slots"]), ROLLOUT_TOL, "out['pred_slots'], ref['pred_slots']")
     p = O.psnr(out["pred_imgs"].cpu(), ref["pred_imgs"])
     PL.check_min(p.min(), 40.0, "frame PSNR vs reference (dB), min")
     tgt = videos[:, 1:20].clamp(0, 1)
@@ -232,7 +235,7 @@ def test_predictor_step_folded_layernorm(models, golden, golden_weights):
     out = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())
     PL.check(O.rel_err(out, ref), STAGE_TOL, "out, ref")
     d_ref, d_out = ref - slots[:, -1], out.cpu() - slots[:, -1]
-    PL.check(O.rel_err(d_out, d_ref), 5e-3, "d_out, d_ref")
+    PL.check(O.rel_err(d_out, d_ref), DELTA_TOL, "d_out, d_ref")
     ops.set_gemm_mode(1)
     try:
         out_unfolded = pred.predictor(slots=slots.cuda(), text_embeddings=text.cuda())

@@ -80,6 +80,13 @@ static inline int ensure_smem_attr(SmemAttrOnce& once, Fn* kernel, int bytes) {
   TOCVP_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ull << (dev & 63);
   if (__atomic_load_n(&once.done_mask, __ATOMIC_ACQUIRE) & bit) return TOCVP_OK;
+  if (bytes < 0) {   // "as much as the device allows": the opt-in maximum minus the kernel's static shared memory
+    cudaFuncAttributes fa;
+    TOCVP_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    int optin = 0;
+    TOCVP_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    bytes = optin - int(fa.sharedSizeBytes);
+  }
   TOCVP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   __atomic_fetch_or(&once.done_mask, bit, __ATOMIC_RELEASE);
   return TOCVP_OK;

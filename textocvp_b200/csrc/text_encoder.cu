@@ -87,7 +87,7 @@ extern "C" int tocvp_text_encode(const tocvp_text_weights* w, const long long* t
   const size_t smem = size_t(TE_MAXL) * (D + (F > ldq ? F : ldq) + D) * sizeof(float);
   TOCVP_CHECK_ARG(smem <= 220 * 1024);
   static SmemAttrOnce attr_once;   // opt in to the device maximum once per device; the launch passes the actual size
-  TOCVP_TRY(ensure_smem_attr(attr_once, text_encoder_kernel, 227 * 1024));
+  TOCVP_TRY(ensure_smem_attr(attr_once, text_encoder_kernel, -1));
   text_encoder_kernel<<<B, TE_THREADS, smem, st>>>(*w, tokens, lengths, L, out);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
