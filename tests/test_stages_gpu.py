@@ -119,11 +119,11 @@ def test_predictor_step(models, golden, golden_weights):
     PL.check(O.rel_err(out1, golden["pred_step_n1"]), STAGE_TOL, "out1, golden['pred_step_n1']")
 
 
-@pytest.mark.parametrize("fuse_layer1", [0, 1, 2, 4])
+@pytest.mark.parametrize("fuse_layer1", [0, 1, 2, 4, 16])
 def test_decode(models, golden, golden_weights, fuse_layer1):
     """tocvp_tuning.decode_mode bit mask.  0 (default): separate layer-1 kernel, head conv with the 9 taps in N;
     1: decoder layer 1 generated inside the layer-2 conv kernel; 2: first-version head conv (shifted windows, N = 16);
-    4: first-version (image-stationary) layer-1 kernel."""
+    4: first-version (image-stationary) layer-1 kernel; 16: separate compositing kernel (default: fused into the head conv)."""
     from textocvp_b200 import _lib as L
     savi, _ = models
     slots = golden["pred_slots"][:1, -1].cuda()
@@ -136,6 +136,29 @@ def test_decode(models, golden, golden_weights, fuse_layer1):
     PL.check(O.rel_err(out["recons"], golden["dec_recons"]), STAGE_TOL, "out['recons'], golden['dec_recons']")
     PL.check(O.rel_err(out["masks"], golden["dec_masks"]), STAGE_TOL, "out['masks'], golden['dec_masks']")
     PL.check(O.rel_err(out["recons_imgs"], golden["dec_img"]), STAGE_TOL, "out['recons_imgs'], golden['dec_img']")
+
+
+def test_decode_fused_composite_is_bit_identical(models, golden):
+    """Compositing in the head convolution's epilogue (default) against head conv -> fp32 map -> composite_kernel
+    (decode_mode bit 4): same arithmetic in the same order, so every output must be bit-identical; also with
+    only_imgs (recons / masks not requested) and over several chunks."""
+    from textocvp_b200 import _lib as L
+    savi, _ = models
+    g = torch.Generator().manual_seed(6)
+    slots = (golden["pred_slots"][:1, -1] + 0.3 * torch.randn(256 + 19, 8, 128, generator=g)).cuda()
+    outs = {}
+    for mode in (0, 16):
+        setattr(L.TUNING, "decode_mode", mode)
+        try:
+            o = savi(mode="decode", slots=slots)
+            oi = savi.decode(slots, only_imgs=True)
+            torch.cuda.synchronize()
+            outs[mode] = ({k: v.clone() for k, v in o.items()}, oi["recons_imgs"].clone())
+        finally:
+            setattr(L.TUNING, "decode_mode", 0)
+    for k in ("recons_imgs", "recons", "masks"):
+        assert torch.equal(outs[0][0][k], outs[16][0][k]), k
+    assert torch.equal(outs[0][1], outs[16][1]) and torch.equal(outs[0][1], outs[0][0]["recons_imgs"])
 
 
 def test_decode_chunk_pipeline_matches_serial(models, golden):

@@ -26,6 +26,8 @@ int conv5x5_f16(const __half* x, const __half* wpacked, const float* bias, __hal
                 int cout, int relu, cudaStream_t stream);
 int conv3x3_head_f16(const __half* x, const __half* wpacked, const float* bias, float* out4, int n_img, int H, int W,
                      cudaStream_t stream);
+int conv3x3_head_composite_f16(const __half* x, const __half* w_taps, const float* bias, int n_frames, int S, int H, int W,
+                               float* imgs, float* recons, float* masks, cudaStream_t stream);
 int conv3x3_head_taps_f16(const __half* x, const __half* w_taps, const float* bias, float* out4, int n_img, int H, int W,
                           cudaStream_t stream);
 int conv5x5_gen_f16(const float* P, const float* S, const __half* x_dummy, const __half* wpacked, const float* bias,
@@ -388,16 +390,23 @@ extern "C" int tocvp_savi_decode(const tocvp_dec_weights* w, const float* slots,
     }
     if (overlap) TOCVP_CUDA(cudaEventRecord(sd->conv_done[ci & 1], st));
     // conv3x3 64 -> 4 head on the tensor cores (N padded to 16), then softmax-over-slots compositing
+    const size_t npix = size_t(nf) * plane;
+    float* imgs_c = recons_imgs + size_t(f0) * 3 * plane;
+    float* recons_c = recons ? recons + size_t(f0) * S * 3 * plane : nullptr;
+    float* masks_c = masks ? masks + size_t(f0) * S * plane : nullptr;
+    if (g_dec_head_taps && w->w_out_taps != nullptr && !(dmode & 16) && S <= 11) {
+      // head conv with the slot-softmax compositing in its epilogue (SAVi.py:251-255): no fp32 map round trip, no extra launch
+      TOCVP_TRY(conv3x3_head_composite_f16(db.actB, static_cast<const __half*>(w->w_out_taps), w->b_out, nf, S, H, W, imgs_c,
+                                           recons_c, masks_c, st));
+      continue;
+    }
     if (g_dec_head_taps && w->w_out_taps != nullptr) {
       TOCVP_TRY(conv3x3_head_taps_f16(db.actB, static_cast<const __half*>(w->w_out_taps), w->b_out, db.maps4, nsi, H, W, st));
     } else {
       TOCVP_TRY(conv3x3_head_f16(db.actB, static_cast<const __half*>(w->w_out), w->b_out, db.maps4, nsi, H, W, st));
     }
-    const size_t npix = size_t(nf) * plane;
-    composite_kernel<<<int((npix + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(db.maps4), recons_imgs + size_t(f0) * 3 * plane,
-        recons ? recons + size_t(f0) * S * 3 * plane : nullptr, masks ? masks + size_t(f0) * S * plane : nullptr, S,
-        int(plane), nf);
+    composite_kernel<<<int((npix + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(db.maps4), imgs_c, recons_c,
+                                                              masks_c, S, int(plane), nf);
     TOCVP_LAUNCHED();
   }
   return TOCVP_OK;

@@ -12,6 +12,9 @@ ssd = weights.savi_state_dict(14)
 init = (ssd["initializer.slots_mu"] + ssd["initializer.slots_sigma"] * noise).to(dev)
 sh = torch.randn(B, 20, 8, 128, device=dev)
 ps = torch.randn(B * 19, 8, 128, device=dev)
+if os.environ.get("TOCVP_TUNING"):          # e.g. TOCVP_TUNING=decode_mode=16,no_pdl=1
+    from textocvp_b200 import ops
+    ops.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in os.environ["TOCVP_TUNING"].split(","))})
 for _ in range(reps):
     if stage == "predict": pred(sh, text_embeddings=text)
     elif stage == "decode": savi.decode(ps)

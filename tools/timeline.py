@@ -21,6 +21,9 @@ fn = {"decode": lambda: savi.decode(ps, only_imgs=True),
 if len(sys.argv) > 2:                      # optional: ops.set_gemm_mode(<mode>) before the run (e.g. 260 / 261)
     from textocvp_b200 import ops
     ops.set_gemm_mode(int(sys.argv[2]))
+if os.environ.get("TOCVP_TUNING"):          # e.g. TOCVP_TUNING=decode_mode=16,no_pdl=1
+    from textocvp_b200 import ops
+    ops.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in os.environ["TOCVP_TUNING"].split(","))})
 for _ in range(3): fn()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
