@@ -70,7 +70,8 @@ typedef struct tocvp_tuning {
                          bit 3 = serial chunks (default: chunk-pipelined, layer 1 of chunk i+1 on an internal side stream
                          under the convolutions of chunk i), bit 4 = separate compositing kernel (default: fused into the
                          head convolution's epilogue) */
-  int corrector_mode; /* 1 = first-version fp32 SIMT loops in the per-slot update kernel (default: 3xTF32 mma.sync) */
+  int corrector_mode; /* per-slot update kernel: 0 = 3xTF32 mma.sync with the weights streamed through a shared-memory ring
+                         (default), 2 = first tensor-core version (weight fragments read from L2), 1 = fp32 SIMT loops */
   int no_pdl;         /* 1 = plain stream order (default: programmatic dependent launch, bit-identical results) */
   int no_tile_alternation; /* 1 = every predictor kernel walks its row blocks ascending (default: alternating, so a
                          consumer starts with the rows its producer wrote last; bit-identical results) */
@@ -131,6 +132,14 @@ typedef struct tocvp_sa_weights {
   float attn_eps, ln_eps_sa, ln_eps_tf, scale; /* 1e-8, 1e-3, 1e-6, dim_feats^-0.5 */
   int num_slots;                               /* 4..11: 8 (SAVi.json) and 10 (ExtendedDINOSAUR.json) are the named ones */
   const tocvp_tuning* tuning;                  /* NULL = defaults */
+  /* Second copies of the matrices above for the streaming update kernel (csrc/slot_attention_update.cu).  Each in-major
+   * matrix W[K][N] is split into two IEEE f16 planes, hi = f16(W), lo = f16((W - hi) * 2048), and stored in mma.m16n8k16
+   * B-fragment order: for k-step ks (16 rows), column tile nt (8 columns), lane l = g*4 + t: four 32-bit words
+   * {b0_hi, b1_hi, b0_lo, b1_lo} with b0 = (W[ks*16 + 2t][nt*8 + g], W[ks*16 + 2t + 1][..]) (element 0 in the low half)
+   * and b1 the same 8 rows further down: K * N words per matrix (modules._stream states it in torch).  Matrices are
+   * concatenated in consumption order: stream_c = wv_t | w_ih_t | w_hh_t | w1_t | w2_t;  stream_t = t_wq_t | t_wk_t |
+   * t_wv_t | t_wo_t | t_w1_t | t_w2_t;  stream_a = wq_t | wk.  NULL = not provided (the first-version kernel is used). */
+  const float *stream_c, *stream_t, *stream_a;
 } tocvp_sa_weights;
 
 size_t tocvp_sizeof_sa_weights(void);

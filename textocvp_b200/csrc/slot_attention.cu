@@ -183,7 +183,7 @@ template <typename T, int S>
 __global__ void __launch_bounds__(256)
 sa_stream_generic_kernel(const T* __restrict__ feats, size_t seq_stride, int N, int chunks, const float* __restrict__ gvec,
                          float* __restrict__ partial, float ln_eps, float attn_eps) {
-  constexpr int PART = S * SA_D + 2 * S;
+  constexpr int PART = sa_part(S);
   __shared__ __align__(16) float s_red[8][S][SA_D];
   __shared__ float s_am[8][2][S];
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -450,7 +450,7 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
   const int row0 = blockIdx.x * RPC;
   const int tid = threadIdx.x;
   const int D = SA_D;
-  const int PART = S * D + 2 * S;
+  const int PART = sa_part(S);
   n_rows = min(n_rows, row0 + RPC);   // rows of the next CTA are not ours
 
   // load slots_in [rows][D] -> cur[D][R]
@@ -606,15 +606,24 @@ sa_update_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags
 
 constexpr int UP_SMEM = (3 * SA_D + 2 * 512) * UP_R * 4;   // 90112 B
 
+int launch_update2(const SaWeights& w, int S, int chunks, int B, int flags, const float* slots_in, const float* partial,
+                   float* slots_out, int out_stride, float* pred_out, float* gvec, cudaStream_t stream);
+bool update2_supported(const SaWeights& w, int flags);
+
+// tocvp_tuning.corrector_mode: 0 (default) = second-version update kernel (weights streamed through a shared-memory ring,
+// slot_attention_update.cu); 2 = first tensor-core version (B fragments read from L2 inside the MMA loop); 1 = first-version
+// fp32 SIMT loops.  All three compute the same thing at fp32-level accuracy.
 static int launch_update(const SaWeights& w, int S, int chunks, int B, int flags, const float* slots_in, const float* partial,
                          float* slots_out, int out_stride, float* pred_out, float* gvec, cudaStream_t stream) {
+  if (opts().corrector_mode == 0 && update2_supported(w, flags))
+    return launch_update2(w, S, chunks, B, flags, slots_in, partial, slots_out, out_stride, pred_out, gvec, stream);
   static SmemAttrOnce attr_once;
   TOCVP_TRY(ensure_smem_attr(attr_once, sa_update_kernel, UP_SMEM));
   const int rows = B * S;
   const int rpc = (UP_R / S) * S;
   sa_update_kernel<<<(rows + rpc - 1) / rpc, UP_THREADS, UP_SMEM, stream>>>(w, S, chunks, rows, flags, slots_in, partial,
                                                                            slots_out, out_stride, pred_out, gvec,
-                                                                           opts().corrector_mode);
+                                                                           opts().corrector_mode == 1 ? 1 : 0);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -622,7 +631,7 @@ static int launch_update(const SaWeights& w, int S, int chunks, int B, int flags
 constexpr int SA_MAX_S = 11;   // generic path: cross-warp reduction buffer [8][S][128] floats must fit static smem
 
 size_t slot_attention_workspace_bytes(int B) {   // sized for the largest supported slot count
-  constexpr size_t part = SA_MAX_S * SA_D + 2 * SA_MAX_S;
+  constexpr size_t part = sa_part(SA_MAX_S);
   return (size_t(B) * part + size_t(B) * SA_CHUNKS * part + size_t(B) * SA_MAX_S * SA_D) * sizeof(float);
 }
 
@@ -693,7 +702,7 @@ int slot_attention(const SaWeights& w, const void* feats, int feats_f16, size_t 
   // everything else (10 slots over 81 / 576 patch tokens for ExtendedDINOSAUR) takes the generic kernel
   const bool fast = (S == SA_S) && (N % (SA_CHUNKS * 128) == 0);
   const int chunks = fast ? SA_CHUNKS : (N >= 1024 ? 4 : (N >= 256 ? 2 : 1));
-  const int part = S * SA_D + 2 * S;
+  const int part = sa_part(S);
   float* gvec = static_cast<float*>(workspace);
   float* partial = gvec + size_t(B) * part;
   float* tmp_slots = partial + size_t(B) * chunks * part;   // [B,S,128] intermediate iterates
@@ -739,7 +748,7 @@ int slot_attention_seq(const SaWeights& w, const void* feats, int feats_f16, siz
   }
   const bool fast = (S == SA_S) && (N % (SA_CHUNKS * 128) == 0);
   const int chunks = fast ? SA_CHUNKS : (N >= 1024 ? 4 : (N >= 256 ? 2 : 1));
-  const int part = S * SA_D + 2 * S;
+  const int part = sa_part(S);
   float* gvec = static_cast<float*>(workspace);
   float* partial = gvec + size_t(B) * part;
   float* tmp_slots = partial + size_t(B) * chunks * part;

@@ -46,7 +46,8 @@ SaW = _struct("SaW", [
     "t_w1_t", "t_b1", "t_w2_t", "t_b2"],
     [("mlp_hidden", ctypes.c_int), ("t_heads", ctypes.c_int), ("t_hidden", ctypes.c_int),
      ("attn_eps", ctypes.c_float), ("ln_eps_sa", ctypes.c_float), ("ln_eps_tf", ctypes.c_float),
-     ("scale", ctypes.c_float), ("num_slots", ctypes.c_int), ("tuning", _f)])
+     ("scale", ctypes.c_float), ("num_slots", ctypes.c_int), ("tuning", _f), ("stream_c", _f), ("stream_t", _f),
+     ("stream_a", _f)])
 
 PredLayer = _struct("PredLayer", [
     "ln_q_g", "ln_q_b", "w_qkv", "w_o", "ln_cq_g", "ln_cq_b", "ln_ckv_g", "ln_ckv_b", "wc_q", "wc_kv", "wc_o", "bc_o",
@@ -220,6 +221,27 @@ def _f16(t):
 def _tr(t):  # [out,in] -> [in,out] fp32
     return _upload(t.detach().float().t().contiguous())
 
+
+def split_f16_fragments(m):
+    """In-major fp32 matrix W[K][N] -> the streaming update kernel's operand format (csrc/slot_attention_update.cu): two IEEE
+    f16 planes hi = f16(W), lo = f16((W - hi) * 2048) laid out in mma.m16n8k16 B-fragment order -- index
+    [k-step ks][column tile nt][lane = g*4 + t][b0_hi, b1_hi, b0_lo, b1_lo][element e] with k = ks*16 + h8*8 + 2t + e
+    (h8 = 0 for b0, 1 for b1) and n = nt*8 + g -- returned as int16 [K*N*2] (K*N 32-bit words)."""
+    m = m.detach().float()
+    K, N = m.shape
+    assert K % 16 == 0 and N % 8 == 0
+    hi = m.half()
+    lo = ((m - hi.float()) * 2048.0).half()
+    planes = torch.stack([hi, lo])                                            # [plane, K, N]
+    v = planes.view(2, K // 16, 2, 4, 2, N // 8, 8)                           # [plane, ks, h8, t, e, nt, g]
+    v = v.permute(1, 5, 6, 3, 0, 2, 4).contiguous()                           # [ks, nt, g, t, plane, h8, e]
+    return v.view(torch.int16).reshape(-1)
+
+
+def _stream(mats):
+    """Concatenate `split_f16_fragments` of the given in-major matrices in (consumption) order -> one fp32-typed buffer."""
+    parts = [split_f16_fragments(m) for m in mats]
+    return _upload(torch.cat(parts).contiguous().view(torch.float32))
 
 
 # =====================================================================================================
@@ -681,6 +703,9 @@ class TransformerBlock(_Packed):
         k["t_ln2_g"], k["t_ln2_b"] = _f32(self.layernorm_mlp.weight), _f32(self.layernorm_mlp.bias)
         k["t_w1_t"], k["t_b1"] = _tr(self.mlp[0].weight), _f32(self.mlp[0].bias)
         k["t_w2_t"], k["t_b2"] = _tr(self.mlp[2].weight), _f32(self.mlp[2].bias)
+        a = self.attn
+        k["stream_t"] = _stream([a.q.weight.t(), a.k.weight.t(), a.v.weight.t(), a.out_projection[0].weight.t(),
+                                 self.mlp[0].weight.t(), self.mlp[2].weight.t()])
 
     def _pack(self, dev):
         if self.embed_dim != 128 or self.mlp_size % 256 != 0 or self.mlp_size > 512 or 128 % self.num_heads != 0:
@@ -789,6 +814,9 @@ class SlotAttention(_Packed):
         k["b_ih"], k["b_hh"] = _f32(self.gru.bias_ih), _f32(self.gru.bias_hh)
         k["w1_t"], k["b1"] = _tr(self.mlp[0].weight), _f32(self.mlp[0].bias)
         k["w2_t"], k["b2"] = _tr(self.mlp[2].weight), _f32(self.mlp[2].bias)
+        k["stream_c"] = _stream([self.to_v.weight.t(), self.gru.weight_ih.t(), self.gru.weight_hh.t(), self.mlp[0].weight.t(),
+                                 self.mlp[2].weight.t()])
+        k["stream_a"] = _stream([self.to_q.weight.t(), self.to_k.weight])      # to_k as stored [d][f]: in-major for q -> W_k^T q
         t = self._transition
         t_heads = t_hidden = 0
         if t is not None:
