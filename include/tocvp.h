@@ -80,9 +80,9 @@ typedef struct tocvp_tuning {
 size_t tocvp_sizeof_tuning(void);
 
 /* ------------------------------------------------------------------------------------------
- * Dense projection: C[M,N] = A[M,K] . W[N,K]^T (+bias) (ReLU) (+residual), tcgen05 / TMEM / TMA.
- * A, W: f16, K innermost (W is torch.nn.Linear.weight as stored).  bias fp32[N] or NULL.
- * residual fp32 [M, ldr] or NULL (added after ReLU).  Writes out_f32 and/or out_f16 (either may
+ * Dense projection: C[M,N] = A[M,K] . W[N,K]^T (+bias) (activation) (+residual), tcgen05 / TMEM / TMA.
+ * A, W: f16, K innermost (W is torch.nn.Linear.weight as stored).  bias fp32[N] or NULL.  relu: activation code, 0 = none,
+ * 1 = ReLU, 2 = exact (erf) GELU.  residual fp32 [M, ldr] or NULL (added after the activation).  Writes out_f32 and/or out_f16 (either may
  * be NULL, not both).  N, K, lda, ldw multiples of 8.
  * Replaces nn.Linear -> cuBLAS at src/models/Blocks/attention.py:167-175, 296-300, 352-356,
  * src/models/Predictors/text_cond_OCVP.py:47-48, src/models/SAVi.py:117-119.
@@ -414,6 +414,48 @@ size_t tocvp_sizeof_ocvp_weights(void);
  * slots + b*seq_stride (floats) -> out [B, S, slot_dim].  n * S <= 80 tokens, token_dim <= 128. */
 int tocvp_ocvp_forward(const tocvp_ocvp_weights* w, const float* slots, size_t seq_stride, int B, int n, float* out,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frozen ViT front-end of ExtendedDINOSAUR: ViTEncoder.forward (src/models/EncodersDecoders/timm_encoders.py:58-69) around a
+ * timm VisionTransformer (vit_base_patch14_dinov2, timm_encoders.py:232-254: patch 14, 768-d, 12 pre-norm blocks with
+ * LayerScale, 12 heads, GELU MLP): normalise -> patch embedding -> cat(cls) + pos_embed -> blocks -> drop the class token.
+ * timm is a third-party dependency that is not vendored: the block structure restates its published definition (PARITY
+ * UNPINNED against timm itself; tests compare with a plain-torch restatement).  f16 matrices are torch Linear weights
+ * [out, in]; w_patch is patch_embed.proj.weight [E, 3, p, p] flattened to [E, 3*p*p] and zero-padded to k_pad columns.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tocvp_vit_block {
+  const float *ln1_g, *ln1_b;  /* norm1 */
+  const void* w_qkv;           /* f16 [3E, E]  attn.qkv */
+  const float* b_qkv;
+  const void* w_proj;          /* f16 [E, E]   attn.proj */
+  const float* b_proj;
+  const float* ls1;            /* [E] ls1.gamma */
+  const float *ln2_g, *ln2_b;  /* norm2 */
+  const void* w_fc1;           /* f16 [Hm, E]  mlp.fc1 */
+  const float* b_fc1;
+  const void* w_fc2;           /* f16 [E, Hm]  mlp.fc2 */
+  const float* b_fc2;
+  const float* ls2;            /* [E] ls2.gamma */
+} tocvp_vit_block;
+
+typedef struct tocvp_vit_weights {
+  const tocvp_vit_block* blocks; /* HOST array of num_blocks entries */
+  int num_blocks, embed_dim, num_heads, mlp_dim, patch, img_h, img_w, grid_h, grid_w, k_pad;
+  const void* w_patch;           /* f16 [E, k_pad] */
+  const float* b_patch;          /* [E] */
+  const float* cls_pos0;         /* [E] = cls_token + pos_embed[0] */
+  const float* pos;              /* [N, E] = pos_embed[1:]  (N = grid_h * grid_w) */
+  float mean[3], inv_std[3];     /* input normalisation (timm_encoders.py:82-96) */
+  float ln_eps;                  /* 1e-6 */
+  const tocvp_tuning* tuning;
+} tocvp_vit_weights;
+
+size_t tocvp_sizeof_vit_weights(void);
+size_t tocvp_sizeof_vit_block(void);
+size_t tocvp_vit_workspace_bytes(const tocvp_vit_weights* w, int n_img);
+/* images fp32: image i = 3 planes of img_h x img_w at images + i*img_stride (floats) -> patch features fp32 [n_img, N, E]. */
+int tocvp_vit_forward(const tocvp_vit_weights* w, const float* images, size_t img_stride, int n_img, float* feats,
+                      void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone forwards of the reference's sub-modules.  The fused stage entry points above never call these; they exist

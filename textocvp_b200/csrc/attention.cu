@@ -202,6 +202,153 @@ mha_kernel(const __half* __restrict__ q, int ldq, int q_seq_rows, const __half* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long sequences (> 128 keys: the ViT front-end at the reference JSON's 336 x 336 / 577-token geometry).  Same fragment
+// scheme, but the keys stream through shared memory in blocks of 64 (cp.async, double-buffered) with a running
+// (max, sum) per query row -- the standard online softmax -- so any Tk fits.  One CTA = 64 queries of one (sequence, head),
+// 4 warps x 16 query rows.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int AL_BQ = 64, AL_BK = 64;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(128, 3)
+mha_long_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, const __half* __restrict__ v, int ldkv,
+                int Tq, int Tk, int heads, float scale_log2e, __half* __restrict__ out, int ldo) {
+  __shared__ __align__(16) __half sQ[AL_BQ * ATT_KS];
+  __shared__ __align__(16) __half sK[2][AL_BK * ATT_KS];
+  __shared__ __align__(16) __half sV[2][AL_BK * ATT_KS];
+  const int b = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int q0 = blockIdx.x * AL_BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const __half* kb = k + size_t(b) * Tk * ldkv + h * ATT_DH;
+  const __half* vb = v + size_t(b) * Tk * ldkv + h * ATT_DH;
+  const __half* qb = q + size_t(b) * Tq * ldq + h * ATT_DH;
+  __half* ob = out + size_t(b) * Tq * ldo + h * ATT_DH;
+  pdl_wait();
+  pdl_trigger();
+  auto load_kv = [&](int blk, int buf) {
+    for (int e = threadIdx.x; e < AL_BK * 8; e += 128) {
+      const int r = e >> 3, c = e & 7;
+      const int key = blk * AL_BK + r;
+      const bool ok = key < Tk;                                  // keys past the end are zero rows, masked below
+      cp_async16(&sK[buf][r * ATT_KS + c * 8], ok ? kb + size_t(key) * ldkv + c * 8 : kb, ok);
+      cp_async16(&sV[buf][r * ATT_KS + c * 8], ok ? vb + size_t(key) * ldkv + c * 8 : vb, ok);
+    }
+  };
+  for (int e = threadIdx.x; e < AL_BQ * 8; e += 128) {
+    const int r = e >> 3, c = e & 7;
+    const bool ok = q0 + r < Tq;
+    cp_async16(&sQ[r * ATT_KS + c * 8], ok ? qb + size_t(q0 + r) * ldq + c * 8 : qb, ok);
+  }
+  load_kv(0, 0);
+  cp_async_commit();
+  const int n_blk = (Tk + AL_BK - 1) / AL_BK;
+  __half* sQw = sQ + warp * 16 * ATT_KS;
+  uint32_t qa[4][4];
+  float o[ATT_DH / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < ATT_DH / 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;           // running max (raw scores) and sum of rows g, g + 8
+  for (int blk = 0; blk < n_blk; ++blk) {
+    const int buf = blk & 1;
+    if (blk + 1 < n_blk) load_kv(blk + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait_group<1>();                                    // block `blk` (and Q) have landed
+    __syncthreads();
+    if (blk == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        ldmatrix_x4(qa[ks], sQw + ((lane & 7) + ((lane >> 3) & 1) * 8) * ATT_KS + ks * 16 + (lane >> 4) * 8);
+    }
+    float s[AL_BK / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < AL_BK / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __half* kr = &sK[buf][(nt * 8 + (lane & 7)) * ATT_KS + ((lane >> 3) << 3)];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t kb4[4];
+        ldmatrix_x4(kb4, kr + p * 32);
+        mma_16816(s[nt], qa[2 * p], kb4[0], kb4[1]);
+        mma_16816(s[nt], qa[2 * p + 1], kb4[2], kb4[3]);
+      }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < AL_BK / 8; ++nt) {
+      const int c = blk * AL_BK + nt * 8 + 2 * t;
+      if (c >= Tk) s[nt][0] = s[nt][2] = -1e30f;
+      if (c + 1 >= Tk) s[nt][1] = s[nt][3] = -1e30f;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = ex2_ftz((m0 - mx0) * scale_log2e), c1 = ex2_ftz((m1 - mx1) * scale_log2e);   // rescale of the past
+    m0 = mx0; m1 = mx1;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < AL_BK / 8; ++nt) {
+      s[nt][0] = ex2_ftz((s[nt][0] - mx0) * scale_log2e);
+      s[nt][1] = ex2_ftz((s[nt][1] - mx0) * scale_log2e);
+      s[nt][2] = ex2_ftz((s[nt][2] - mx1) * scale_log2e);
+      s[nt][3] = ex2_ftz((s[nt][3] - mx1) * scale_log2e);
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    l0 = l0 * c0 + sum0;
+    l1 = l1 * c1 + sum1;
+#pragma unroll
+    for (int nd = 0; nd < ATT_DH / 8; ++nd) {
+      o[nd][0] *= c0; o[nd][1] *= c0; o[nd][2] *= c1; o[nd][3] *= c1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < AL_BK / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const __half* vrow = &sV[buf][(kk * 16 + (lane & 15)) * ATT_KS + ((lane >> 4) << 3)];
+#pragma unroll
+      for (int nd2 = 0; nd2 < ATT_DH / 16; ++nd2) {
+        uint32_t vb4[4];
+        ldmatrix_x4_trans(vb4, vrow + nd2 * 16);
+        mma_16816(o[2 * nd2], pa, vb4[0], vb4[1]);
+        mma_16816(o[2 * nd2 + 1], pa, vb4[2], vb4[3]);
+      }
+    }
+    __syncthreads();                                             // every warp is done with this K / V buffer
+  }
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+#pragma unroll
+  for (int nd = 0; nd < ATT_DH / 8; ++nd) {
+    const int c = nd * 8 + 2 * t;
+    *reinterpret_cast<__half2*>(sQw + g * ATT_KS + c) = __floats2half2_rn(o[nd][0] * inv0, o[nd][1] * inv0);
+    *reinterpret_cast<__half2*>(sQw + (g + 8) * ATT_KS + c) = __floats2half2_rn(o[nd][2] * inv1, o[nd][3] * inv1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 3) + 4 * i, c = lane & 7;
+    const int row = q0 + warp * 16 + r;
+    if (row < Tq) *reinterpret_cast<uint4*>(ob + size_t(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(sQw + r * ATT_KS + c * 8);
+  }
+}
+
+// Self-attention over sequences of any length (head dim 64): the short kernel for Tk <= 128, the streaming one above beyond.
+int mha_f16_any(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk, int heads,
+                __half* out, int ldo, cudaStream_t stream);
+
 int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk,
                 int heads, __half* out, int ldo, cudaStream_t stream);
 
@@ -245,11 +392,24 @@ int mha_f16_sub(const __half* q, int ldq, int q_seq_rows, const __half* k, const
   return TOCVP_OK;
 }
 
+int mha_f16_any(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int Tq, int Tk, int heads,
+                __half* out, int ldo, cudaStream_t stream) {
+  if (Tk <= ATT_MAXK) return mha_f16(q, ldq, k, v, ldkv, B, Tq, Tk, heads, out, ldo, stream);
+  TOCVP_CHECK_ARG(q && k && v && out && B > 0 && Tq > 0 && heads > 0 && B * heads <= 65535);
+  TOCVP_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;
+  (void)tile_order_reversed();
+  TOCVP_CUDA(launch_pdl(mha_long_kernel, dim3((Tq + AL_BQ - 1) / AL_BQ, B * heads), dim3(128), 0, stream, q, ldq, k, v, ldkv,
+                        Tq, Tk, heads, scale_log2e, out, ldo));
+  count_launch();
+  return TOCVP_OK;
+}
+
 }  // namespace tocvp
 
 extern "C" int tocvp_mha_f16(const void* q, int ldq, const void* k, const void* v, int ldkv, int B, int Tq, int Tk,
                              int heads, void* out, int ldo, void* stream) {
-  return tocvp::mha_f16(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
-                        static_cast<const __half*>(v), ldkv, B, Tq, Tk, heads, static_cast<__half*>(out), ldo,
-                        static_cast<cudaStream_t>(stream));
+  return tocvp::mha_f16_any(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
+                            static_cast<const __half*>(v), ldkv, B, Tq, Tk, heads, static_cast<__half*>(out), ldo,
+                            static_cast<cudaStream_t>(stream));
 }

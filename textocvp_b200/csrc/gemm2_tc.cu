@@ -357,10 +357,13 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[4 * j4] += bb.x; f[4 * j4 + 1] += bb.y; f[4 * j4 + 2] += bb.z; f[4 * j4 + 3] += bb.w;
             }
           }
-          const bool relu_in_cvt = g.relu && g.out32 == nullptr && g.residual == nullptr;   // f16-only output: fused
-          if (g.relu && !relu_in_cvt) {
+          const bool relu_in_cvt = g.relu == 1 && g.out32 == nullptr && g.residual == nullptr;   // f16-only output: fused
+          if (g.relu == 1 && !relu_in_cvt) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (g.relu == 2) {          // exact GELU (ViT MLP)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           }
           if (g.residual != nullptr && !tma_res) {
 #pragma unroll
@@ -517,9 +520,12 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
-              if (g.relu) {
+              if (g.relu == 1) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              } else if (g.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
               }
               // column n -> (phase, channel); a 4-column group never straddles a phase (cpp % 4 == 0)
 #pragma unroll

@@ -230,9 +230,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
-              if (g.relu) {
+              if (g.relu == 1) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              } else if (g.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
               }
               if (res_row != nullptr) {
                 const float4 r0 = rbuf[c & 1][j8 * 2], r1 = rbuf[c & 1][j8 * 2 + 1];

@@ -298,6 +298,9 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// exact (erf) GELU, the nn.GELU default: activation code 2 of the GEMM epilogues (1 = ReLU)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -151,10 +151,7 @@ class _params_on_host:
     upload the finished buffers.  (Packing happens once per ``load_state_dict`` / ``.to()``, not on the timed path.)"""
 
     def __init__(self, module):
-        self.tensors = list(module.parameters()) + list(module.buffers())
-        extra = getattr(module, "_transition", None)
-        if extra is not None:
-            self.tensors += list(extra.parameters())
+        self.tensors = module._host_tensors()
 
     def __enter__(self):
         self.saved = [t.data for t in self.tensors]
@@ -171,6 +168,10 @@ class _Packed(nn.Module):
 
     def _sig(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+
+    def _host_tensors(self):
+        """Tensors ``_pack`` reads (they are presented as host copies while it runs).  Default: every parameter and buffer."""
+        return list(self.parameters()) + list(self.buffers())
 
     def _ensure_packed(self):
         if getattr(self, "_is_replica", False):
@@ -836,6 +837,9 @@ class SlotAttention(_Packed):
         extra = tuple((p.data_ptr(), p._version) for p in self._transition.parameters()) if self._transition is not None else ()
         return super()._sig() + extra
 
+    def _host_tensors(self):
+        return super()._host_tensors() + (list(self._transition.parameters()) if self._transition is not None else [])
+
     @_on_device
     def run(self, feats, feats_seq_stride, B, N, slots, iters, slots_out, out_stride, pred_out):
         """Raw call.  feats: f16/fp32 device tensor holding sequence b's [N,128] block at b*feats_seq_stride."""
@@ -1204,6 +1208,183 @@ class MLPPatchDecoder(_Packed):
         return {"recons_imgs": imgs if imgs is not None else torch.tensor([]), "recons_feats": feats, "masks": masks}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Frozen ViT front-end (timm VisionTransformer behind the reference's ViTEncoder wrapper)
+# ---------------------------------------------------------------------------------------------------------------------
+VitBlockW = _struct("VitBlockW", ["ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "ls1", "ln2_g", "ln2_b", "w_fc1",
+                                  "b_fc1", "w_fc2", "b_fc2", "ls2"], [])
+VitW = type("VitW", (ctypes.Structure,), {"_fields_": [
+    ("blocks", ctypes.POINTER(VitBlockW)),
+    ("num_blocks", ctypes.c_int), ("embed_dim", ctypes.c_int), ("num_heads", ctypes.c_int), ("mlp_dim", ctypes.c_int),
+    ("patch", ctypes.c_int), ("img_h", ctypes.c_int), ("img_w", ctypes.c_int), ("grid_h", ctypes.c_int),
+    ("grid_w", ctypes.c_int), ("k_pad", ctypes.c_int),
+    ("w_patch", _f), ("b_patch", _f), ("cls_pos0", _f), ("pos", _f),
+    ("mean", ctypes.c_float * 3), ("inv_std", ctypes.c_float * 3), ("ln_eps", ctypes.c_float), ("tuning", _f)]})
+
+IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+VIT_VARIANTS = {   # timm_encoders.py:101-254: name -> (patch, embed_dim, depth, heads)
+    "vit_small_patch16_224_dino": (16, 384, 12, 6), "vit_small_patch8_224_dino": (8, 384, 12, 6),
+    "vit_base_patch16_224_dino": (16, 768, 12, 12), "vit_base_patch8_224_dino": (8, 768, 12, 12),
+    "vit_small_patch14_dinov2": (14, 384, 12, 6), "vit_base_patch14_dinov2": (14, 768, 12, 12)}
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, embed_dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, embed_dim, kernel_size=patch, stride=patch)
+
+
+class _ViTAttention(nn.Module):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _ViTMlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
+
+
+class _LayerScale(nn.Module):
+    def __init__(self, dim, init_values):
+        super().__init__()
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+
+class _ViTBlock(nn.Module):
+    """timm.models.vision_transformer.Block (pre-norm, LayerScale): parameter container with timm's names."""
+
+    def __init__(self, dim, num_heads, mlp_ratio, init_values):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _ViTAttention(dim, num_heads)
+        self.ls1 = _LayerScale(dim, init_values) if init_values else nn.Identity()
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _ViTMlp(dim, int(dim * mlp_ratio))
+        self.ls2 = _LayerScale(dim, init_values) if init_values else nn.Identity()
+
+
+class VisionTransformer(nn.Module):
+    """Parameter container with the state_dict keys of timm's VisionTransformer as the reference instantiates it
+    (num_classes=0, class token, learned pos_embed of 1 + (img/patch)^2 rows, no register tokens)."""
+
+    def __init__(self, img_size, patch_size=14, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, init_values=1e-5):
+        super().__init__()
+        hw = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
+        self.img_size, self.patch_size, self.embed_dim, self.num_heads = hw, patch_size, embed_dim, num_heads
+        self.grid = (hw[0] // patch_size, hw[1] // patch_size)
+        self.patch_embed = _PatchEmbed(patch_size, embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, 1 + self.grid[0] * self.grid[1], embed_dim) * .02)
+        self.blocks = nn.Sequential(*[_ViTBlock(embed_dim, num_heads, mlp_ratio, init_values) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)     # exists in timm's model; the wrapper never applies it
+        self.default_cfg = {"mean": IMAGENET_DEFAULT_MEAN, "std": IMAGENET_DEFAULT_STD}
+        with torch.no_grad():
+            nn.init.normal_(self.cls_token, std=1e-6)
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.trunc_normal_(m.weight, std=.02)
+                    nn.init.zeros_(m.bias)
+
+
+class ViTEncoder(_Packed):
+    """timm_encoders.py:18-96: wrapper that normalises the images, runs patch embedding + positional embedding + the first
+    ``num_blocks`` transformer blocks of a timm VisionTransformer and drops the class token.
+    forward(x [B,3,H,W] or [B,T,3,H,W]) -> [B(,T), N, embed_dim].  The backbone is frozen.
+
+    ``reference_std`` (default True) reproduces the reference's normalisation exactly: it divides by the MEAN
+    (``self.std`` is set from ``default_cfg["mean"]``, timm_encoders.py:54-56) -- a checkpoint trained behind the reference
+    has seen exactly that input scaling.  False uses the ImageNet standard deviation."""
+
+    def __init__(self, vit_backbone, num_blocks=None, reference_std=True):
+        if not isinstance(vit_backbone, VisionTransformer):
+            raise TypeError("ViT must be a 'timm' VisionTransfromer")
+        if num_blocks is not None and (len(vit_backbone.blocks) < num_blocks or num_blocks < 0):
+            raise ValueError(f"num_blocks = {num_blocks} must be in [0, {len(vit_backbone.blocks)}]")
+        super().__init__()
+        self.vit_backbone, self.num_blocks = vit_backbone, num_blocks
+        if num_blocks is not None:
+            self.vit_backbone.blocks = self.vit_backbone.blocks[:num_blocks]
+        for p_ in self.parameters():
+            p_.requires_grad_(False)                                     # freeze_params (timm_encoders.py:50)
+        cfg = vit_backbone.default_cfg
+        self.mean = torch.tensor(cfg["mean"]).view(1, 1, 3, 1, 1)
+        self.std = torch.tensor(cfg["mean"] if reference_std else cfg["std"]).view(1, 1, 3, 1, 1)
+        self._ws = _Workspace()
+
+    def _pack(self, dev):
+        vb = self.vit_backbone
+        E, p = vb.embed_dim, vb.patch_size
+        if E % 64 != 0 or E // vb.num_heads != 64:
+            raise L.TocvpError("ViT kernels are instantiated for 64-wide heads (ViT-S / ViT-B)")
+        k_real = 3 * p * p
+        k_pad = (k_real + 63) // 64 * 64
+        wp = torch.zeros(E, k_pad)
+        wp[:, :k_real] = vb.patch_embed.proj.weight.detach().float().reshape(E, k_real)
+        keep = dict(w_patch=_f16(wp), b_patch=_f32(vb.patch_embed.proj.bias),
+                    cls_pos0=_f32(vb.cls_token[0, 0] + vb.pos_embed[0, 0]), pos=_f32(vb.pos_embed[0, 1:]))
+        blocks = (VitBlockW * max(1, len(vb.blocks)))()
+        per = []
+        for i, b in enumerate(vb.blocks):
+            one = torch.ones(E)
+            t = dict(ln1_g=_f32(b.norm1.weight), ln1_b=_f32(b.norm1.bias), w_qkv=_f16(b.attn.qkv.weight),
+                     b_qkv=_f32(b.attn.qkv.bias), w_proj=_f16(b.attn.proj.weight), b_proj=_f32(b.attn.proj.bias),
+                     ls1=_f32(b.ls1.gamma if isinstance(b.ls1, _LayerScale) else one),
+                     ln2_g=_f32(b.norm2.weight), ln2_b=_f32(b.norm2.bias), w_fc1=_f16(b.mlp.fc1.weight),
+                     b_fc1=_f32(b.mlp.fc1.bias), w_fc2=_f16(b.mlp.fc2.weight), b_fc2=_f32(b.mlp.fc2.bias),
+                     ls2=_f32(b.ls2.gamma if isinstance(b.ls2, _LayerScale) else one))
+            for n, v in t.items():
+                setattr(blocks[i], n, v.data_ptr())
+            per.append(t)
+        w = VitW()
+        w.blocks = ctypes.cast(blocks, ctypes.POINTER(VitBlockW))
+        w.num_blocks, w.embed_dim, w.num_heads, w.mlp_dim = len(vb.blocks), E, vb.num_heads, vb.blocks[0].mlp.fc1.out_features \
+            if len(vb.blocks) else 4 * E
+        w.patch, w.img_h, w.img_w, w.grid_h, w.grid_w, w.k_pad = p, vb.img_size[0], vb.img_size[1], vb.grid[0], vb.grid[1], k_pad
+        for n in ("w_patch", "b_patch", "cls_pos0", "pos"):
+            setattr(w, n, keep[n].data_ptr())
+        for c in range(3):
+            w.mean[c] = float(self.mean.reshape(3)[c])
+            w.inv_std[c] = 1.0 / float(self.std.reshape(3)[c])
+        w.ln_eps = 1e-6
+        w.tuning = ctypes.addressof(L.TUNING)
+        self._keep, self._blocks, self._w = (keep, per), blocks, w
+
+    @_on_device
+    @torch.no_grad()
+    def forward(self, x):
+        self._ensure_packed()
+        lib = L.load()
+        vb = self.vit_backbone
+        if x.dim() not in (4, 5):
+            raise ValueError(f"Weird x.shape = {tuple(x.shape)}. It should be either 4- or 5-dim")
+        lead = x.shape[:-3]
+        if tuple(x.shape[-3:]) != (3, vb.img_size[0], vb.img_size[1]):
+            raise ValueError(f"ViTEncoder was built for images (3, {vb.img_size[0]}, {vb.img_size[1]}), got {tuple(x.shape[-3:])}")
+        x = x.float().contiguous().reshape(-1, 3, vb.img_size[0], vb.img_size[1])
+        n, N = x.shape[0], vb.grid[0] * vb.grid[1]
+        out = torch.empty(n, N, vb.embed_dim, device=x.device, dtype=torch.float32)
+        lib.tocvp_vit_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws.get(lib.tocvp_vit_workspace_bytes(ctypes.byref(self._w), c_int(n)), x.device)
+        L.call("tocvp_vit_forward", ctypes.byref(self._w), ptr(x), c_size_t(x[0].numel()), c_int(n), ptr(out), ws, wsb,
+               stream())
+        return out.reshape(*lead, N, vb.embed_dim)
+
+
+def get_vit_encoder(encoder, img_size, reference_std=True):
+    """encoders.py:50-92 for the ViT names: VisionTransformer of the named geometry at ``img_size`` behind ViTEncoder."""
+    name = encoder["encoder_name"]
+    if name not in VIT_VARIANTS:
+        raise ValueError(f"Unknwon encoder_name = {name}. Use one of {sorted(VIT_VARIANTS)}")
+    patch, dim, depth, heads = VIT_VARIANTS[name]
+    init_values = 1e-5 if "dinov2" in name else None
+    backbone = VisionTransformer(img_size, patch, dim, depth, heads, 4, init_values)
+    return ViTEncoder(backbone, num_blocks=encoder.get("encoder_params", {}).get("num_blocks"), reference_std=reference_std)
+
+
 class ExtendedDINOSAUR(_Packed):
     """src/models/ExtendedDINOSAUR.py.  forward(mode="decomp"|"decode", ...).  The frozen ViT backbone
     (timm vit_base_patch14_dinov2, third-party and weight-gated) is NOT part of the accelerated path: ``x`` carries its
@@ -1234,7 +1415,14 @@ class ExtendedDINOSAUR(_Packed):
             raise KeyError("'img_size' must be provided in model parameters in order to instanciate ViT-based image encoder.")
         if encoder is not None and "vit" not in encoder.get("encoder_name", "vit"):
             raise NameError("Extended-DINOSAUR expects a ViT-Based encoder...")
-        self.encoder = nn.Identity()
+        # The frozen ViT backbone (reference: get_encoder(...) -> timm model behind ViTEncoder, ExtendedDINOSAUR.py:83-93).
+        # Default: nn.Identity -- ``x`` then carries the backbone's OUTPUT, patch features [B,T,N,768] (BASELINE.json north
+        # star: synthetic inputs of the named shape).  ``build_backbone=True`` instantiates the ViT on the CUDA path
+        # (state_dict keys encoder.vit_backbone.* as in the reference) and forward_decomp accepts images [B,T,3,H,W].
+        if kwargs.get("build_backbone", False):
+            self.encoder = get_vit_encoder(encoder, img_size)
+        else:
+            self.encoder = nn.Identity()
         self.linear_feat_proj = nn.Sequential(nn.LayerNorm(mlp_encoder_dim), nn.Linear(mlp_encoder_dim, mlp_encoder_dim),
                                               nn.ReLU(), nn.Linear(mlp_encoder_dim, slot_dim))
         if decoder["decoder_name"] != "MLPPatchDecoder":
@@ -1268,6 +1456,9 @@ class ExtendedDINOSAUR(_Packed):
 
     def _sig(self):   # only the projection is packed here (sub-modules pack themselves)
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.linear_feat_proj.parameters())
+
+    def _host_tensors(self):
+        return list(self.linear_feat_proj.parameters())
 
     def _pack(self, dev):
         p = self.linear_feat_proj
@@ -1307,12 +1498,16 @@ class ExtendedDINOSAUR(_Packed):
     def forward_decomp(self, x, num_imgs=10, decode=True, init_slots=None, **kwargs):
         """ExtendedDINOSAUR.py:139-214.  x: patch features [B,T,N,F] (or images [B,T,3,H,W] with a backbone attached)."""
         if x.dim() == 5:
-            bb = getattr(self, "_backbone", None)
-            if bb is None:
-                raise L.TocvpError("ExtendedDINOSAUR got images but no ViT backbone is attached (set_backbone); the "
-                                   "accelerated path starts at the patch features [B,T,N,F]")
             _check_clip(x, num_imgs, "ExtendedDINOSAUR.forward_decomp")
-            x = torch.stack([bb(x[:, t]) for t in range(num_imgs)], dim=1)
+            bb = getattr(self, "_backbone", None)
+            if isinstance(self.encoder, ViTEncoder):
+                x = self.encoder(x[:, :num_imgs])                          # all frames in one call: [B, num_imgs, N, F]
+            elif bb is not None:
+                x = torch.stack([bb(x[:, t]) for t in range(num_imgs)], dim=1)
+            else:
+                raise L.TocvpError("ExtendedDINOSAUR got images but has no ViT backbone (construct it with "
+                                   "build_backbone=True or attach one with set_backbone); without one the path starts at "
+                                   "the patch features [B,T,N,F]")
         if x.dim() != 4:
             raise ValueError(f"ExtendedDINOSAUR.forward_decomp expects patch features [B, T, N, F], got {tuple(x.shape)}")
         _check_clip(x, num_imgs, "ExtendedDINOSAUR.forward_decomp")
@@ -1603,6 +1798,9 @@ class BaseTextOCVP(_Packed):
 
     def _instantiate_text_encoder(self):
         raise NotImplementedError("'BaseTextOCVP' does not implement '_instantiate_text_encoder'...")
+
+    def _host_tensors(self):   # the text encoder is not packed here
+        return [p for n, p in self.named_parameters() if not n.startswith("text_encoder.")]
 
     def _pack(self, dev, num_slots=None):
         T, keep, layers = self.token_dim, [], (PredLayer * self.num_layers)()

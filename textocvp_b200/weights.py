@@ -386,3 +386,33 @@ def synthetic_t5_captions(B: int, L: int, vocab: int = 200, seed: int = 5):
     ids = ids * mask
     ids[torch.arange(B), lengths - 1] = 1
     return ids, mask
+
+
+def vit_state_dict(seed: int = 23, img_size: int = 128, patch: int = 14, embed_dim: int = 768, depth: int = 12,
+                   mlp_ratio: int = 4, prefix: str = "vit_backbone.", ls_range=(0.05, 1.0)) -> Dict[str, Tensor]:
+    """timm VisionTransformer parameters (the reference's vit_base_patch14_dinov2 geometry by default) from a seeded CPU
+    generator: trunc-normal-like 0.02 matrices, LayerNorm (1, 0) + jitter, LayerScale gammas drawn from ``ls_range`` (trained
+    DINOv2 checkpoints carry O(0.1 - 1) gammas; the 1e-5 initial value would make every block a no-op in a parity test)."""
+    g = torch.Generator().manual_seed(seed)
+    E, H = embed_dim, embed_dim * mlp_ratio
+    N = (img_size // patch) ** 2
+    sd: Dict[str, Tensor] = {}
+    rn = lambda *s, std=0.02: std * torch.randn(*s, generator=g)
+    sd[prefix + "cls_token"] = rn(1, 1, E, std=0.5)
+    sd[prefix + "pos_embed"] = rn(1, 1 + N, E, std=0.5)
+    sd[prefix + "patch_embed.proj.weight"] = rn(E, 3, patch, patch, std=0.05)
+    sd[prefix + "patch_embed.proj.bias"] = rn(E, std=0.1)
+    for i in range(depth):
+        p = f"{prefix}blocks.{i}."
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"] = 1.0 + 0.05 * torch.randn(E, generator=g)
+            sd[p + n + ".bias"] = 0.05 * torch.randn(E, generator=g)
+        sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"] = rn(3 * E, E, std=0.04), rn(3 * E, std=0.02)
+        sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"] = rn(E, E, std=0.04), rn(E, std=0.02)
+        sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"] = rn(H, E, std=0.04), rn(H, std=0.02)
+        sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"] = rn(E, H, std=0.04), rn(E, std=0.02)
+        lo, hi = ls_range
+        sd[p + "ls1.gamma"] = lo + (hi - lo) * torch.rand(E, generator=g)
+        sd[p + "ls2.gamma"] = lo + (hi - lo) * torch.rand(E, generator=g)
+    sd[prefix + "norm.weight"], sd[prefix + "norm.bias"] = torch.ones(E), torch.zeros(E)
+    return sd
