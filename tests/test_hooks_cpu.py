@@ -147,3 +147,27 @@ def test_packing_runs_on_the_host():
     assert set(seen) == {"cpu"} and k["w_conv1_vp"].dtype == torch.float16
     with pytest.raises(M.L.TocvpError, match="f16 range"):
         M._f16(torch.tensor([1.0e5]))
+
+
+def test_modules_copy_and_pickle_without_packed_state():
+    """deepcopy / pickle drop the derived packed state (ctypes structs with device pointers cannot be pickled)."""
+    import copy, io, ctypes
+    from textocvp_b200 import modules as M
+    ep = M.default_exp_params()
+    savi, pred = M.setup_model(ep["model"]), M.setup_predictor(ep)
+    # simulate a packed module: attach what a forward would have left behind
+    savi._w = M.SaW(); savi._keep = {"x": torch.zeros(1)}; savi._pack_sig = ("stale",)
+    savi.slot_attention._w = M.SaW(); savi.slot_attention._pack_sig = ("stale",)
+    c = copy.deepcopy(savi)
+    assert not hasattr(c, "_w") and not hasattr(c.slot_attention, "_pack_sig")
+    assert c.slot_attention._transition is c.transition_module          # the unregistered link follows the copy
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), savi.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(savi, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert not hasattr(r, "_w") and r.slot_attention._transition is r.transition_module
+    buf = io.BytesIO()
+    torch.save(pred, buf)
+    buf.seek(0)
+    assert torch.load(buf, weights_only=False).predictor.token_dim == 512

@@ -325,3 +325,19 @@ def test_t5_hook_rollout():
     PL.check(O.rel_err(out, g["pred_slots"]), STAGE_TOL, "T5 hook: 3-step rollout vs reference wrapper")
     with pytest.raises(KeyError):
         pred(sh.cuda(), caption_tokens=ids)
+
+
+def test_deepcopy_and_save_after_forward(models, golden):
+    """A module that has run (and therefore holds packed device state) can still be deep-copied and torch.save'd; the copy
+    re-packs on its first forward and gives the same result."""
+    import copy, io
+    savi, _ = models
+    slots = golden["pred_slots"][:1, -1].cuda()
+    ref = savi(mode="decode", slots=slots)["recons_imgs"]
+    c = copy.deepcopy(savi)
+    assert torch.equal(c(mode="decode", slots=slots)["recons_imgs"], ref)
+    buf = io.BytesIO()
+    torch.save(savi, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert torch.equal(r(mode="decode", slots=slots)["recons_imgs"], ref)

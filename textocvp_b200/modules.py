@@ -163,8 +163,40 @@ class _params_on_host:
             t.data = d
 
 
+_TRANSIENT = ("_w", "_keep", "_pack_sig", "_blocks", "_layers", "_graph", "_enc_w", "_enc_keep", "_dec_w", "_dec_keep",
+              "_tab", "_tab_sig", "_backbone")
+
+
 class _Packed(nn.Module):
-    """Mixin: device-side packed weight copies, rebuilt whenever a parameter changes (load_state_dict, .to())."""
+    """Mixin: device-side packed weight copies, rebuilt whenever a parameter changes (load_state_dict, .to()).
+
+    The packed state (ctypes structs with raw device pointers, packed tensors, captured CUDA graphs, workspaces) is derived
+    data: it is dropped by ``copy.deepcopy`` / ``pickle`` / ``torch.save(model)`` and rebuilt on the next forward, so whole
+    modules can be copied and saved like the reference's."""
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in _TRANSIENT:
+            state.pop(k, None)
+        for k, v in list(state.items()):
+            if isinstance(v, _Workspace):
+                state[k] = _Workspace()
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        tr = getattr(self, "_transition", None)          # SlotAttention's unregistered link to the transition module
+        if tr is not None and "_transition" in self.__dict__:
+            new.__dict__["_transition"] = copy.deepcopy(tr, memo)
+        return new
 
     def _sig(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
@@ -993,6 +1025,17 @@ class SAVi(_Packed):
         L.call("tocvp_savi_encode", ctypes.byref(self._enc_w), ptr(frames), c_size_t(img_stride), c_int(n_img),
                ptr(f16), ptr(f32), ws, wsb, stream())
         return f16, f32
+
+    @_on_device
+    def _encode_into(self, frames: torch.Tensor, n_img: int, img_stride: int, f16_out: torch.Tensor):
+        """Raw call into a caller-owned f16 feature buffer [n_img, N, F] (no allocation: measurement tools)."""
+        self._ensure_packed()
+        lib = L.load()
+        lib.tocvp_savi_encode_workspace_bytes.restype = ctypes.c_size_t
+        ws, wsb = self._ws_enc.get(lib.tocvp_savi_encode_workspace_bytes(ctypes.byref(self._enc_w), c_int(n_img)),
+                                   frames.device)
+        L.call("tocvp_savi_encode", ctypes.byref(self._enc_w), ptr(frames), c_size_t(img_stride), c_int(n_img),
+               ptr(f16_out), ptr(None), ws, wsb, stream())
 
     @torch.no_grad()
     def encode(self, x):
