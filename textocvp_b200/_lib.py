@@ -12,7 +12,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtocvp.so")
+LIB_PATH = os.environ.get("TOCVP_LIB") or os.path.join(_HERE, "libtocvp.so")   # TOCVP_LIB: A/B of two builds (dev tools)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tocvp.h")
 
 _lib = None

@@ -21,6 +21,13 @@
 //  3. The weight layout.  The host packs the split weights in MMA-fragment order (tocvp_sa_weights.stream_*): per 16 x 8
 //     block 32 lanes x 16 bytes = {b0_hi, b1_hi, b0_lo, b1_lo}, so a lane's whole B operand is ONE conflict-free LDS.128 and
 //     no split arithmetic is spent on weights in the kernel.  Bytes per weight stay 4.
+//  4. What did NOT help (measured, B = 256, C|T|A launch, CUPTI): the same stream fetched ONCE per cluster of 2 / 4 CTAs by
+//     multicast bulk copies (UBLKCP.S.G.MULTICAST, remote `empty` arrives): 65 / 63 us against 59 us without clusters --
+//     a quarter of the L2 -> SM bytes buys nothing, the cluster barriers cost a little; an evict_last L2 policy on the
+//     weight stream and a fourth ring slot: +-1 us.  The ncu stall profile of this version is flat (wait 24 %, long
+//     scoreboard 18 %, barrier 15 %, short scoreboard 13 %, L2 throughput 4 %): with 8 warps per SM the kernel is a
+//     latency chain per chunk (LDS -> split -> dependent HMMAs -> barrier), ~1 us per 32 KB chunk, not a bandwidth problem.
+//     The multicast path is kept behind U2_CLUSTER (1 = off, the default).
 // Activations are row-major fp32 [16][K + 8] (conflict-free 64-bit A loads), split per k-step in registers.
 #include "host_util.h"
 #include "ptx.cuh"
@@ -35,7 +42,8 @@ constexpr int U2_THREADS = 256;
 constexpr int U2_WARPS = U2_THREADS / 32;
 constexpr int U2_LDA = SA_D + 8;         // 136: row pitch of the [16][128] activation buffers (pitch = 8 mod 32 words: the
 constexpr int U2_LDB = 512 + 8;          // 520: 64-bit A-fragment loads and C stores of a half-warp hit 32 distinct banks)
-constexpr int U2_STAGES = 3;
+constexpr int U2_STAGES = 4;             // ring depth: three chunks in flight while one is consumed
+constexpr int U2_CLUSTER = 1;            // > 1: CTAs of a cluster share one weight stream by multicast (measured slower, see 4.)
 constexpr int U2_SLOT_FLOATS = 64 * 128;         // 8192 words = 32 KB: largest chunk (rows x N x 4 bytes)
 constexpr int U2_MAX_SEGS = 16;
 constexpr int U2_DO_C = 1, U2_DO_T = 2, U2_DO_A = 4;   // same flags as sa_update_kernel
@@ -48,20 +56,44 @@ struct U2Seg {
 // weight rows per ring slot: 32 KB (N = 128, 256, 512) or 24 KB (N = 384) of payload
 __host__ __device__ constexpr int u2_chunk_rows(int N) { return N <= 128 ? 64 : (N <= 256 ? 32 : 16); }
 
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// L2 eviction-priority policy for the weight stream: evict_last.  Between two update launches the streaming pass reads
+// 268 MB of features through the 126 MB L2; without the hint every launch found its 1.8 MB of weights evicted and paid DRAM
+// latency on the first touch of every chunk (2 us per 32 KB chunk with two chunks of look-ahead = the kernel's whole time).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// one copy, delivered to the same shared-memory offset of every CTA in `cta_mask`, completing `bytes` on the mbarrier at
+// the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask,
+                                                   uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, "
+      "[%3], %4, %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 struct U2Pipe {
   const U2Seg* segs;   // shared memory
   int n_segs;
   float* ring;         // shared memory: U2_STAGES slots of U2_SLOT_FLOATS floats
-  uint64_t* full;      // shared memory: [U2_STAGES]
+  uint64_t* full;      // shared memory: [U2_STAGES]  data of the slot has landed (this CTA)
+  uint64_t* empty;     // shared memory: [U2_STAGES]  every CTA of the cluster has released the slot (waited on by the issuer)
   int cidx;            // chunks consumed so far (uniform over the CTA)
   int pseg, pk, pidx;  // producer cursor: next chunk to request (used by warp 0 only, uniform there)
+  int n_chunks;        // chunks in the whole schedule
+  uint32_t rank;       // CTA rank in the cluster
+  uint32_t ewaits;     // bit s: parity of the next wait on empty[s] (issuer side)
+  uint64_t policy;     // L2 evict_last policy of the weight stream
 };
 
 // warp 0 (converged): request the next chunk of the schedule, if any, into ring slot pidx % STAGES
@@ -73,8 +105,16 @@ __device__ __forceinline__ void u2_issue(U2Pipe& p, int lane) {
   float* dst = p.ring + slot * U2_SLOT_FLOATS;
   if (lane == 0) {
     const uint32_t bytes = uint32_t(rows) * uint32_t(sg.N) * 4u;
-    mbar_expect_tx(&p.full[slot], bytes);
-    bulk_g2s(dst, sg.w + size_t(p.pk) * sg.N, bytes, &p.full[slot]);
+    mbar_expect_tx(&p.full[slot], bytes);                       // every CTA expects the chunk on its own barrier
+    if constexpr (U2_CLUSTER == 1) {
+      bulk_g2s(dst, sg.w + size_t(p.pk) * sg.N, bytes, &p.full[slot], p.policy);
+    } else if (uint32_t(p.pidx % U2_CLUSTER) == p.rank) {       // ... one CTA fetches it for the whole cluster
+      if (p.pidx >= U2_STAGES) {                                // refill: all CTAs must have released the slot
+        mbar_wait_cluster(&p.empty[slot], (p.ewaits >> slot) & 1u);
+        p.ewaits ^= 1u << slot;
+      }
+      bulk_g2s_multicast(dst, sg.w + size_t(p.pk) * sg.N, bytes, &p.full[slot], uint16_t((1u << U2_CLUSTER) - 1), p.policy);
+    }
   }
   p.pk += rows;
   p.pidx += 1;
@@ -102,7 +142,7 @@ __device__ __forceinline__ void u2_mma(float (&d)[4], const uint32_t (&a)[4], ui
 // ys[r][n] = act(bias[n] + sum_k xs[r][k] W[k][n]) (+ add[r][n]) with W = the NEXT segment of the schedule (K x N, N = 64 NT).
 // Warp w owns the 8-column tiles w, w + 8, ..., w + 8 (NT - 1).  Ends with a CTA barrier (ys complete, xs reusable).
 template <int NT>
-__device__ __forceinline__ void u2_linear(U2Pipe& p, int K, const float* xs, int ldx, const float* __restrict__ bias,
+__device__ __noinline__ void u2_linear(U2Pipe& p, int K, const float* xs, int ldx, const float* __restrict__ bias,
                                           float* ys, int ldy, bool relu, const float* add, int ldadd) {
   constexpr int N = NT * 64;
   constexpr int rows = u2_chunk_rows(N);
@@ -140,8 +180,17 @@ __device__ __forceinline__ void u2_linear(U2Pipe& p, int K, const float* xs, int
         u2_mma(cor[i], al, bw[i].x, bw[i].y);      // lo . hi
       }
     }
+    __syncthreads();                         // every warp of this CTA is done with the slot
+    if (U2_CLUSTER > 1 && warp == 0) {
+      // release the slot towards the CTA that will refill it (chunk cidx + STAGES), if that chunk exists
+      const int nxt = p.cidx + U2_STAGES;
+      // relaxed: the arrive publishes no data; this CTA's reads of the slot have completed (their values fed the MMAs above
+      // and every warp passed the barrier).  A release here compiles to MEMBAR + ERRBAR on the one lane the whole CTA then
+      // waits for at the next barrier: 26 % of the kernel's stall samples in the first cluster version (ncu r2).
+      if (lane == 0 && nxt < p.n_chunks)
+        mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&p.empty[slot]), uint32_t(nxt % U2_CLUSTER)));
+    }
     p.cidx += 1;
-    __syncthreads();                         // every warp is done with this slot: it can be refilled
     if (warp == 0) u2_issue(p, lane);
   }
 #pragma unroll
@@ -189,7 +238,7 @@ __device__ __forceinline__ void u2_layernorm(const float* xs, int ldx, float* ys
 }
 
 constexpr int U2_SMEM_FLOATS = 3 * U2_R * U2_LDA + 2 * U2_R * U2_LDB + U2_STAGES * U2_SLOT_FLOATS + 64;
-constexpr int U2_SMEM = U2_SMEM_FLOATS * 4 + U2_MAX_SEGS * 16 + U2_STAGES * 8 + 64;
+constexpr int U2_SMEM = U2_SMEM_FLOATS * 4 + U2_MAX_SEGS * 16 + 2 * U2_STAGES * 8 + 64;
 
 __global__ void __launch_bounds__(U2_THREADS, 1)
 sa_update2_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flags, const float* __restrict__ slots_in,
@@ -205,6 +254,7 @@ sa_update2_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flag
   float* s_am = ring + U2_STAGES * U2_SLOT_FLOATS;   // [16][2] A, Mw per row (+ padding)
   U2Seg* segs = reinterpret_cast<U2Seg*>(s_am + 64);
   uint64_t* full = reinterpret_cast<uint64_t*>(segs + U2_MAX_SEGS);
+  uint64_t* empty = full + U2_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = SA_D;
@@ -243,18 +293,30 @@ sa_update2_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flag
       push(b, D, D);                 // wq_t
       push(b, D, D);                 // wk (as stored: in-major for q -> qt)
     }
+    int nch = 0;
+    for (int i = 0; i < n; ++i) nch += segs[i].K / u2_chunk_rows(segs[i].N);
     s_am[62] = __int_as_float(n);
-    for (int s = 0; s < U2_STAGES; ++s) mbar_init(&full[s], 1);
+    s_am[63] = __int_as_float(nch);
+    for (int s = 0; s < U2_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], U2_CLUSTER);      // one release per CTA of the cluster
+    }
     fence_barrier_init();
   }
-  __syncthreads();
+  if (U2_CLUSTER > 1) cluster_sync_all();    // barriers of every CTA are initialised before any peer copies / arrives
+  else __syncthreads();
   U2Pipe p;
   p.segs = segs;
   p.n_segs = __float_as_int(s_am[62]);
   p.ring = ring;
   p.full = full;
+  p.empty = empty;
   p.cidx = 0;
   p.pseg = 0; p.pk = 0; p.pidx = 0;
+  p.n_chunks = __float_as_int(s_am[63]);
+  p.rank = U2_CLUSTER > 1 ? cluster_ctarank() : 0;
+  p.ewaits = 0;
+  p.policy = l2_policy_evict_last();
   if (warp == 0) {
     for (int s = 0; s < U2_STAGES; ++s) u2_issue(p, lane);      // the weights do not depend on the previous kernel
   }
@@ -419,6 +481,7 @@ sa_update2_kernel(SaWeights w, int S, int chunks, int n_rows /* B*S */, int flag
       }
     }
   }
+  if (U2_CLUSTER > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its ring / arrive on its barriers
 }
 
 int launch_update2(const SaWeights& w, int S, int chunks, int B, int flags, const float* slots_in, const float* partial,
@@ -427,9 +490,23 @@ int launch_update2(const SaWeights& w, int S, int chunks, int B, int flags, cons
   TOCVP_TRY(ensure_smem_attr(attr_once, sa_update2_kernel, U2_SMEM));
   const int rows = B * S;
   const int rpc = (U2_R / S) * S;
-  sa_update2_kernel<<<(rows + rpc - 1) / rpc, U2_THREADS, U2_SMEM, stream>>>(w, S, chunks, rows, flags, slots_in, partial,
-                                                                            slots_out, out_stride, pred_out, gvec);
-  TOCVP_LAUNCHED();
+  int grid = (rows + rpc - 1) / rpc;
+  grid = (grid + U2_CLUSTER - 1) / U2_CLUSTER * U2_CLUSTER;   // padding CTAs own no rows but take part in the weight pipeline
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(U2_THREADS);
+  cfg.dynamicSmemBytes = U2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = U2_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TOCVP_CUDA(cudaLaunchKernelEx(&cfg, sa_update2_kernel, w, S, chunks, rows, flags, slots_in, partial, slots_out, out_stride,
+                                pred_out, gvec));
+  count_launch();
   return TOCVP_OK;
 }
 
