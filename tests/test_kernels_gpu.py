@@ -158,3 +158,19 @@ def test_frame_metrics(B, F, H, W, T, f0):
     assert _rel(m["mse"].cpu(), mse) < 1e-4
     assert (m["psnr"].cpu() - O.psnr(p, t)).abs().max() < 1e-3
     assert (m["ssim"].cpu() - O.ssim(p, t)).abs().max() < 1e-4
+
+
+def test_lpips_hook_feeds_metric_sums():
+    """LPIPS is a hook (its AlexNet weights cannot be fetched offline): any callable on the clamped frames flows into the
+    accumulators the way piqa's LPIPS does in the reference (lib/metrics.py:266-298)."""
+    from textocvp_b200 import rollout
+    g = torch.Generator().manual_seed(9)
+    pred = (torch.rand(3, 4, 3, 64, 64, generator=g) * 1.4 - 0.2).cuda()
+    vid = torch.rand(3, 6, 3, 64, 64, generator=g).cuda()
+    fake = lambda a, b: (a - b).abs().flatten(1).mean(1)
+    m = rollout.frame_metrics(pred, vid, 1, lpips_fn=fake)
+    ref = (pred.clamp(0, 1) - vid[:, 1:5].clamp(0, 1)).abs().flatten(2).mean(2)
+    assert m["lpips"].shape == (3, 4) and torch.allclose(m["lpips"], ref, atol=1e-6)
+    sums = rollout.MetricSums(4, pred.device)
+    sums.accumulate(m["psnr"], m["mse"], m["ssim"], m["lpips"])
+    assert abs(sums.results()["lpips_mean"] - float(ref.mean())) < 1e-5

@@ -17,10 +17,15 @@ from . import weights
 
 
 @torch.no_grad()
-def frame_metrics(pred_imgs: torch.Tensor, videos: torch.Tensor, frame0: int, clamp: bool = True, want_ssim: bool = True):
+def frame_metrics(pred_imgs: torch.Tensor, videos: torch.Tensor, frame0: int, clamp: bool = True, want_ssim: bool = True,
+                  lpips_fn=None):
     """Evaluator metrics on the device (05_evaluate_predictor.py:96-103, lib/metrics.py:181-270): pred_imgs [B,F,C,H,W]
     (unclamped) against videos[:, frame0:frame0+F] read in place; both are clamped to [0,1] inside the kernels.
-    Returns dict of [B,F] tensors: mse, psnr, ssim."""
+    Returns dict of [B,F] tensors: mse, psnr, ssim (+ lpips when ``lpips_fn`` is given).
+
+    LPIPS (lib/metrics.py:266-298 -> piqa.LPIPS, AlexNet) needs pretrained weights that cannot be obtained offline, so it is
+    a HOOK: ``lpips_fn(pred [n,C,H,W] in [0,1], target [n,C,H,W] in [0,1]) -> [n]`` (e.g. ``piqa.LPIPS(reduction="none")``
+    on the same device) is called on the clamped frames and its values flow into MetricSums like the reference's."""
     B, F_, C, H, W = pred_imgs.shape
     if videos.dim() != 5 or videos.shape[0] != B or tuple(videos.shape[2:]) != (C, H, W):
         raise ValueError(f"frame_metrics: videos {tuple(videos.shape)} do not match predictions {tuple(pred_imgs.shape)}")
@@ -37,7 +42,12 @@ def frame_metrics(pred_imgs: torch.Tensor, videos: torch.Tensor, frame0: int, cl
     L.call("tocvp_frame_metrics", L.ptr(pred), L.ptr(vid), L.c_size_t(vid.stride(0)), L.c_int(F_), L.c_int(frame0),
            L.c_int(n), L.c_int(C), L.c_int(H), L.c_int(W), L.c_int(int(clamp)), L.ptr(mse), L.ptr(psnr), L.ptr(ssim),
            L.stream())
-    return {"mse": mse, "psnr": psnr, "ssim": ssim}
+    out = {"mse": mse, "psnr": psnr, "ssim": ssim}
+    if lpips_fn is not None:
+        tgt = vid[:, frame0:frame0 + F_].reshape(n, C, H, W)
+        p01, t01 = (pred.reshape(n, C, H, W).clamp(0, 1), tgt.clamp(0, 1)) if clamp else (pred.reshape(n, C, H, W), tgt)
+        out["lpips"] = lpips_fn(p01, t01).reshape(B, F_).float()
+    return out
 
 
 def build_models(device, savi_seed=14, pred_seed=15, mlp_out_scale=0.1, num_context=1, num_preds=19,
