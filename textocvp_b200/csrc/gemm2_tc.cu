@@ -242,7 +242,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // fp32 residual + fp32 output with two chunks per warp (the N = 512 projections of the predictor): the residual
     // tiles are TMA-LOADED into the staging tiles while the main loop of the tile runs, the accumulator is added in
     // place and the same tile is TMA-stored -- both directions in full 128-byte lines instead of 16 bytes per row
-    const bool tma_res = !CONV && S::STG_TILES == 3 && g.residual != nullptr && g.res_mod == 0 && g.out32 != nullptr;
+    // (a producer whose fp32 result nobody reads -- only its f16 copy + statistics -- passes out32 = nullptr: no store)
+    const bool tma_res = !CONV && S::STG_TILES == 3 && g.residual != nullptr && g.res_mod == 0 &&
+                         (g.out32 != nullptr || g.stats_out != nullptr);
     const uint32_t sw = uint32_t(lane & 7);
     int mb, nb;
     for (int it = 0; tile_at(it, mb, nb); ++it) {
@@ -381,13 +383,17 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float4* sp = reinterpret_cast<float4*>(dst + ((uint32_t(j4) ^ sw) << 4));
               const float4 r = *sp;
               f[4 * j4] += r.x; f[4 * j4 + 1] += r.y; f[4 * j4 + 2] += r.z; f[4 * j4 + 3] += r.w;
-              *sp = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              if (g.out32 != nullptr) *sp = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmC32, stg + c * 4096, n0, trow);
-              bulk_commit();
+            if (g.out32 != nullptr) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmC32, stg + c * 4096, n0, trow);
+                bulk_commit();
+              }
+            } else {
+              __syncwarp();                              // every lane has read the residual tile before it is reloaded
             }
             if (g.stats_out != nullptr) {
 #pragma unroll
@@ -623,7 +629,7 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
               cudaStream_t stream, const GemmLn* ln) {
   // the fused f16 copy + row statistics live on the TMA-residual path: 128-wide tiles, plain residual rows, fp32 output
   if (ln != nullptr && ln->stats_out != nullptr)
-    TOCVP_CHECK_ARG(bn == 128 && residual != nullptr && res_mod == 0 && out32 != nullptr && N % 128 == 0);
+    TOCVP_CHECK_ARG(bn == 128 && residual != nullptr && res_mod == 0 && (out32 != nullptr || out16 != nullptr) && N % 128 == 0);
   if (ln != nullptr && ln->stats != nullptr) TOCVP_CHECK_ARG(ln->slots >= 2 && ln->slots % 2 == 0);
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, G2_BM, G2_BK));

@@ -202,7 +202,7 @@ static int predictor_step(const tocvp_pred_weights& w, const PredBuffers& pb, in
                             0, nullptr, 0, pb.mid16, w.cross_hidden, c, st));
       set_next_tile_order(0);
       TOCVP_TRY(gemm_f16_ln(pb.mid16, w.cross_hidden, static_cast<const __half*>(ly.wc_2), w.cross_hidden, Mr, T,
-                            w.cross_hidden, ly.bc_2, 0, pb.z32, T, pb.z32, T, pb.h16, T, prod, st));
+                            w.cross_hidden, ly.bc_2, 0, pb.z32, T, nullptr, 0, pb.h16, T, prod, st));   // fp32 z is dead: the skip below is y
       // ---- out = y + MLP(LN(z))   (skip is y, attention.py:521-523)
       const GemmLn c2{pb.stats, slots, ly.c_1, inv_t, w.ln_eps, nullptr};
       set_next_tile_order(1);
