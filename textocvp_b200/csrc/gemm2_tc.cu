@@ -60,13 +60,13 @@ struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;       // 16 KB (BN = 256) / 8 KB (BN = 128)
   static constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int STAGES = WRES ? 3 : ((BN == 256) ? 4 : 5);
+  static constexpr int STAGES = WRES ? 4 : ((BN == 256) ? 4 : 5);
   static constexpr int W_KB = 8;                             // k-blocks held by the resident W half (K <= 512)
   static constexpr int W_BYTES = WRES ? W_KB * B_BYTES : 0;
   static constexpr int EW = EWN;
   static constexpr int STG_TILES = WRES ? 1 : ((BN == 128) ? 3 : (EWN == 16 ? 1 : 2));   // staging tiles per epilogue warp
   static constexpr int STG_BYTES = EW * STG_TILES * 4096;
-  static constexpr int BAR_BYTES = 512 + 4 * BN * 4;        // barriers, then [2 buffers][bias | ln_c][BN] floats
+  static constexpr int BAR_BYTES = 512;                     // barriers (bias / ln_c are read through L1, not staged)
   static constexpr int OFF_W = STAGES * STAGE_BYTES;
   static constexpr int OFF_STG = OFF_W + W_BYTES;
   static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
@@ -86,7 +86,12 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, bool CONV, int EWN, bool WRES>
+// EPI = 2 is the producer side (fp32 residual in and out through TMA, f16 copy + row statistics; 128-wide tiles), EPI = 0
+// the general epilogue.
+// EPI = 1 specialises the epilogue for the consumer of a folded LayerNorm with f16-only output (QKV / cross-q / MLP up
+// projections of the predictor: no residual, no fp32 output, ReLU or nothing): the other variants' code and registers
+// are compiled out (ncu r2: the all-in-one epilogue spilled and took instruction-cache misses on its branch-over code).
+template <int BN, bool CONV, int EWN, bool WRES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EWN), 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
@@ -103,7 +108,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint64_t* resbar = tempty + 4;                                                      // [8 warps][2]: residual tiles landed
   uint64_t* wfull = resbar + 16;                                                      // WRES, leader: resident W landed
-  float* sbias = reinterpret_cast<float*>(stage_base + S::OFF_BAR + 512);             // [2][2][BN]: bias, ln_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -233,8 +237,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;
     const int q = warp & 3;               // TMEM lane quarter
     const int half = ew >> 2;             // which column slice of the tile (BN / (EW/4) columns each)
-    const int et = threadIdx.x - 64;      // 0 .. 32*EW-1
-    constexpr int ETH = 32 * S::EW;
     constexpr int CW = BN / (S::EW / 4);  // columns per warp: 64 (two 32-column chunks)
     constexpr int NCH = CW / 32;
     uint8_t* stg = stg_base + ew * (S::STG_TILES * 4096);  // this warp's staging tiles
@@ -243,25 +245,41 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // tiles are TMA-LOADED into the staging tiles while the main loop of the tile runs, the accumulator is added in
     // place and the same tile is TMA-stored -- both directions in full 128-byte lines instead of 16 bytes per row
     // (a producer whose fp32 result nobody reads -- only its f16 copy + statistics -- passes out32 = nullptr: no store)
-    const bool tma_res = !CONV && S::STG_TILES == 3 && g.residual != nullptr && g.res_mod == 0 &&
-                         (g.out32 != nullptr || g.stats_out != nullptr);
+    constexpr bool E1 = EPI == 1, E2 = EPI == 2;
+    const bool has_res = E2 || (!E1 && g.residual != nullptr);
+    const bool has_out32 = !E1 && g.out32 != nullptr;
+    const bool has_out16 = E1 || g.out16 != nullptr;
+    const bool has_ln = E1 || (!E2 && g.ln_stats != nullptr);
+    const bool has_bias = E1 || g.bias != nullptr;
+    const int act = E1 ? (g.relu & 1) : (E2 ? 0 : g.relu);
+    const bool tma_res = E2 || (!E1 && !CONV && S::STG_TILES == 3 && has_res && g.res_mod == 0 &&
+                                (has_out32 || g.stats_out != nullptr));
+    const bool reg_res = has_res && !tma_res;        // residual rows through registers
     const uint32_t sw = uint32_t(lane & 7);
+    // Row statistics of a folded LayerNorm (consumer): [sum, sumsq] partials -> rstd, -mu * rstd of this thread's row.
+    // With the predictor's 8 partial pairs per row the NEXT tile's are fetched while the last chunk of the current tile
+    // is processed, so their L2 latency is off the per-tile critical path (ncu r2: ~1000 clk per tile exposed before).
+    const bool ln_pf = has_ln && g.ln_slots == 8;
+    auto ln_finish = [&](float sm, float sq, float& rstd, float& nmr) {
+      const float mu = sm * g.ln_inv_k;
+      rstd = rsqrtf(fmaxf(sq * g.ln_inv_k - mu * mu, 0.f) + g.ln_eps);
+      nmr = -mu * rstd;
+    };
+    auto tile_row = [&](int mbx) { return mbx * 2 * G2_BM + int(rank) * G2_BM + q * 32 + lane; };
+    float nx_rstd = 1.f, nx_nmr = 0.f;
     int mb, nb;
+    if (ln_pf && tile_at(0, mb, nb)) {
+      const int row0 = tile_row(mb);
+      if (row0 < g.M) {
+        const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + size_t(row0) * 16);
+        const float4 a0 = __ldg(sp), a1 = __ldg(sp + 1), a2 = __ldg(sp + 2), a3 = __ldg(sp + 3);
+        ln_finish((a0.x + a0.z) + (a1.x + a1.z) + (a2.x + a2.z) + (a3.x + a3.z),
+                  (a0.y + a0.w) + (a1.y + a1.w) + (a2.y + a2.w) + (a3.y + a3.w), nx_rstd, nx_nmr);
+      }
+    }
     for (int it = 0; tile_at(it, mb, nb); ++it) {
       const int b = it & 1;
       const uint32_t bph = (it >> 1) & 1;
-      if (g.bias != nullptr) {
-        for (int e = et; e < BN; e += ETH) {
-          const int n = nb * BN + e;
-          sbias[(b * 2) * BN + e] = (n < g.N) ? __ldg(g.bias + n) : 0.f;
-        }
-      }
-      if (g.ln_c != nullptr) {
-        for (int e = et; e < BN; e += ETH) {
-          const int n = nb * BN + e;
-          sbias[(b * 2 + 1) * BN + e] = (n < g.N) ? __ldg(g.ln_c + n) : 0.f;
-        }
-      }
       const int row = mb * 2 * G2_BM + int(rank) * G2_BM + q * 32 + lane;
       bool row_ok = row < g.M;
       const int ncol0 = nb * BN + half * CW;
@@ -275,12 +293,12 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int sc = g.cm.up ? 2 : 1;
         cbase = (size_t(img) * g.cm.Hop + size_t((yp - 1) * sc + g.cm.pad)) * g.cm.Wop + size_t((xp - 1) * sc + g.cm.pad);
       }
-      if (g.residual != nullptr && row_ok) {
+      if (has_res && row_ok) {
         const int rr = g.res_mod ? (row / g.res_div) % g.res_mod : row;
         res_row = g.residual + size_t(rr) * g.ldr;
       }
-      float ln_rstd = 1.f, ln_nmr = 0.f;      // consumer of a folded LayerNorm: rstd and -mu*rstd of this thread's row
-      if (g.ln_stats != nullptr && row < g.M) {
+      float ln_rstd = nx_rstd, ln_nmr = nx_nmr;   // consumer of a folded LayerNorm: rstd and -mu*rstd of this thread's row
+      if (has_ln && !ln_pf && row < g.M) {
         const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + size_t(row) * 2 * g.ln_slots);
         float sm = 0.f, sq = 0.f;
         for (int i = 0; i < g.ln_slots / 2; ++i) {
@@ -288,10 +306,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sm += v4.x + v4.z;
           sq += v4.y + v4.w;
         }
-        const float mu = sm * g.ln_inv_k;
-        ln_rstd = rsqrtf(fmaxf(sq * g.ln_inv_k - mu * mu, 0.f) + g.ln_eps);
-        ln_nmr = -mu * ln_rstd;
+        ln_finish(sm, sq, ln_rstd, ln_nmr);
       }
+      float4 pf0, pf1, pf2, pf3;              // next tile's statistics in flight (ln_pf)
+      bool pf_ok = false;
       float st_sum = 0.f, st_sq = 0.f;        // producer: row statistics of the fp32 output
       float4 rbuf[2][8];
       auto load_res = [&](int c, float4 (&dst)[8]) {
@@ -313,10 +331,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
-      } else {
+      } else if (reg_res) {
         load_res(0, rbuf[0]);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");   // bias staged (epilogue warps only)
       mbar_wait(&tfull[b], bph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * BN + half * CW);
@@ -328,12 +345,23 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();                                            // chunk c is in v[c & 1]
         if (c + 1 < NCH) {
           tmem_ld32(t_addr + uint32_t((c + 1) * 32), v[(c + 1) & 1]);   // next chunk in flight while this one is stored
-          if (!tma_res) load_res(c + 1, rbuf[(c + 1) & 1]);
+          if (reg_res) load_res(c + 1, rbuf[(c + 1) & 1]);
         } else {
           // all accumulator columns of this warp are in registers: hand the TMEM buffer back to the leader's MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tempty[b]), 0));
+          if (ln_pf) {                           // the second accumulator buffer's registers are free from here on
+            int mb2, nb2;
+            if (tile_at(it + 1, mb2, nb2)) {
+              const int row2 = tile_row(mb2);
+              if (row2 < g.M) {
+                const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + size_t(row2) * 16);
+                pf0 = __ldg(sp); pf1 = __ldg(sp + 1); pf2 = __ldg(sp + 2); pf3 = __ldg(sp + 3);
+                pf_ok = true;
+              }
+            }
+          }
         }
         const int n0 = ncol0 + c * 32;
         if constexpr (!CONV) {
@@ -341,33 +369,38 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[c & 1][j]);
-          if (g.ln_stats != nullptr) {
+          // bias / c_n / d_n come straight from global memory: the same 16 bytes for every lane (one L1 broadcast hit),
+          // which needs neither a staging pass nor an epilogue-wide barrier per tile
+          auto col4 = [&](const float* p, int n) {
+            return n < g.N ? __ldg(reinterpret_cast<const float4*>(p + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          if (has_ln) {
             // y = rstd * (acc - mu * c_n) + d_n
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 dd = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j4 * 4]);
-              const float4 cc = *reinterpret_cast<const float4*>(&sbias[(b * 2 + 1) * BN + half * CW + c * 32 + j4 * 4]);
+              const float4 dd = col4(g.bias, n0 + j4 * 4);
+              const float4 cc = col4(g.ln_c, n0 + j4 * 4);
               f[4 * j4] = fmaf(ln_rstd, f[4 * j4], fmaf(ln_nmr, cc.x, dd.x));
               f[4 * j4 + 1] = fmaf(ln_rstd, f[4 * j4 + 1], fmaf(ln_nmr, cc.y, dd.y));
               f[4 * j4 + 2] = fmaf(ln_rstd, f[4 * j4 + 2], fmaf(ln_nmr, cc.z, dd.z));
               f[4 * j4 + 3] = fmaf(ln_rstd, f[4 * j4 + 3], fmaf(ln_nmr, cc.w, dd.w));
             }
-          } else if (g.bias != nullptr) {
+          } else if (has_bias) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j4 * 4]);
+              const float4 bb = col4(g.bias, n0 + j4 * 4);
               f[4 * j4] += bb.x; f[4 * j4 + 1] += bb.y; f[4 * j4 + 2] += bb.z; f[4 * j4 + 3] += bb.w;
             }
           }
-          const bool relu_in_cvt = g.relu == 1 && g.out32 == nullptr && g.residual == nullptr;   // f16-only output: fused
-          if (g.relu == 1 && !relu_in_cvt) {
+          const bool relu_in_cvt = act == 1 && !has_out32 && !has_res;   // f16-only output: fused into the conversion
+          if (act == 1 && !relu_in_cvt) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          } else if (g.relu == 2) {          // exact GELU (ViT MLP)
+          } else if (act == 2) {             // exact GELU (ViT MLP)
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           }
-          if (g.residual != nullptr && !tma_res) {
+          if (reg_res) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 r = rbuf[c & 1][j4];
@@ -430,7 +463,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             }
-          } else if (g.out32 != nullptr) {
+          } else if (has_out32) {
             if (lane == 0) {                             // the store that last read this staging tile has drained
               if (S::STG_TILES >= 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
             }
@@ -448,7 +481,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (S::STG_TILES >= 2) sbuf ^= 1;
           }
-          if (g.out16 != nullptr && !tma_res) {
+          if (has_out16 && !tma_res) {
             // two 32-column chunks make one 64-column (128 B) staging row: the even chunk waits in registers
             uint4 p[4];
             if (relu_in_cvt) {
@@ -468,7 +501,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 p[j8].w = pack_half2(f[8 * j8 + 6], f[8 * j8 + 7]);
               }
             }
-            if (NCH == 4 && S::STG_TILES == 2 && g.out32 == nullptr) {
+            if (NCH == 4 && S::STG_TILES == 2 && !has_out32) {
               // f16-only output of a 256-wide tile: the warp's 128 columns fill exactly its two staging tiles, so ONE
               // proxy fence and one bulk group per tile cover both TMA stores (the fence, not the math, is what an
               // epilogue warp waits on: r1 A/B in profiles/gemm2_r1_summary.md)
@@ -521,8 +554,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c & 1][j8 * 8 + j]);
               if (g.bias != nullptr) {
-                const float4 b0 = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j8 * 8]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&sbias[(b * 2) * BN + half * CW + c * 32 + j8 * 8 + 4]);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));        // n + 8 <= N (N % 8 == 0)
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
@@ -556,6 +589,12 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (ln_pf) {
+        nx_rstd = 1.f; nx_nmr = 0.f;
+        if (pf_ok)
+          ln_finish((pf0.x + pf0.z) + (pf1.x + pf1.z) + (pf2.x + pf2.z) + (pf3.x + pf3.z),
+                    (pf0.y + pf0.w) + (pf1.y + pf1.w) + (pf2.y + pf2.w) + (pf3.y + pf3.w), nx_rstd, nx_nmr);
+      }
     }
     if (lane == 0) bulk_wait_read<0>();   // staging tiles must outlive the TMA stores that read them
     __syncwarp();
@@ -569,8 +608,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, bool CONV, int EWN, bool WRES = false>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
+template <int BN, bool CONV, int EWN, bool WRES, int EPI>
+static int launch_gemm2_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
   // output maps for the TMA-store epilogue: 32-row x 128-byte boxes (64 f16 / 32 fp32 columns), 128B swizzle
   CUtensorMap tmC16 = tmA, tmC32 = tmA, tmR = tmA;     // placeholders when absent (never dereferenced)
   if (!CONV && g.residual != nullptr && g.res_mod == 0) {
@@ -594,7 +633,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   }
   using S = G2Smem<BN, EWN, WRES>;
   static SmemAttrOnce attr_once;
-  TOCVP_TRY(ensure_smem_attr(attr_once, gemm2_f16_kernel<BN, CONV, EWN, WRES>, S::TOTAL));
+  TOCVP_TRY(ensure_smem_attr(attr_once, gemm2_f16_kernel<BN, CONV, EWN, WRES, EPI>, S::TOTAL));
   const int tiles_m = (g.M + 2 * G2_BM - 1) / (2 * G2_BM), tiles_n = (g.N + BN - 1) / BN;
   const int tiles = tiles_m * tiles_n;
   const int pairs = num_sms() / 2;
@@ -604,10 +643,25 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     ppn = ppn < tiles_m ? ppn : tiles_m;
     grid = 2 * tiles_n * ppn;
   }
-  TOCVP_CUDA(launch_pdl(gemm2_f16_kernel<BN, CONV, EWN, WRES>, dim3(grid), dim3(g2_threads(EWN)), S::TOTAL, stream, tmA,
+  TOCVP_CUDA(launch_pdl(gemm2_f16_kernel<BN, CONV, EWN, WRES, EPI>, dim3(grid), dim3(g2_threads(EWN)), S::TOTAL, stream, tmA,
                         tmB, tmC16, tmC32, tmR, g));
   count_launch();
   return TOCVP_OK;
+}
+
+template <int BN, bool CONV, int EWN, bool WRES = false>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
+  if constexpr (!CONV) {
+    if (g.ln_stats != nullptr && g.ln_c != nullptr && g.bias != nullptr && g.residual == nullptr && g.out32 == nullptr &&
+        g.out16 != nullptr && g.relu != 2 && g.stats_out == nullptr)
+      return launch_gemm2_epi<BN, CONV, EWN, WRES, 1>(tmA, tmB, g, stream);
+    if constexpr (BN == 128 && !WRES) {
+      if (g.ln_stats == nullptr && g.residual != nullptr && g.res_mod == 0 && g.relu == 0 &&
+          (g.out32 != nullptr || g.stats_out != nullptr))
+        return launch_gemm2_epi<BN, CONV, EWN, WRES, 2>(tmA, tmB, g, stream);
+    }
+  }
+  return launch_gemm2_epi<BN, CONV, EWN, WRES, 0>(tmA, tmB, g, stream);
 }
 
 // Tile width for the pair kernel, or 0 if the problem should stay on the single-CTA kernel.
@@ -631,6 +685,8 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
   if (ln != nullptr && ln->stats_out != nullptr)
     TOCVP_CHECK_ARG(bn == 128 && residual != nullptr && res_mod == 0 && (out32 != nullptr || out16 != nullptr) && N % 128 == 0);
   if (ln != nullptr && ln->stats != nullptr) TOCVP_CHECK_ARG(ln->slots >= 2 && ln->slots % 2 == 0);
+  // bias / c_n are read as float4 by the epilogue
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (ln == nullptr || (reinterpret_cast<uintptr_t>(ln->c) & 15) == 0));
   CUtensorMap tmA, tmB;
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, A, M, K, lda, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, ldw, bn / 2, G2_BK));
@@ -656,6 +712,7 @@ int gemm2_f16(int bn, const __half* A, int lda, const __half* W, int ldw, int M,
 int gemm2_conv_f16(int bn, const __half* X, const __half* W, int M, int N, int K, const ConvMap& cm, const float* bias,
                    int relu, float* out32, __half* out16, int ldo, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   TOCVP_TRY(encode_tmap_2d_f16(&tmA, X, M, cm.cin, cm.cin, G2_BM, G2_BK));
   TOCVP_TRY(encode_tmap_2d_f16(&tmB, W, N, K, K, bn / 2, G2_BK));
   Gemm2Args g{M, N, K, bias, nullptr, 0, 1, 0, relu, out32, ldo, out16, ldo, cm, nullptr, 0, nullptr, 0.f, 0.f, nullptr, 0};
