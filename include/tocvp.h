@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TOCVP_ABI_VERSION 2
+#define TOCVP_ABI_VERSION 3
 
 #define TOCVP_OK 0
 #define TOCVP_ERR_BAD_ARG (-1)   /* bad shape / null or misaligned pointer / unsupported size */
@@ -63,7 +63,8 @@ typedef struct tocvp_tuning {
   int encode_mode;    /* bit mask: bit 0 = first-version fp32 SIMT conv 1, bit 1 = separate posemb + LayerNorm pass
                          (default: fused into conv 4's epilogue), bit 2 = the 32 -> 128 -> 128 MLP as two GEMMs (default:
                          one kernel with two chained tcgen05 GEMMs when only f16 features are requested), bit 3 = conv 1 as
-                         25 taps over zero-padded channels (default: x-taps folded into K, 3 taps) */
+                         25 taps over zero-padded channels (default: x-taps folded into K, 3 taps), bit 4 = the 32 -> 32
+                         layers on the 25-tap N = 32 kernel (default: pixel-pair kernel, N = 64, when w_conv_xp is set) */
   int decode_mode;    /* bit mask: bit 0 = decoder layer 1 generated inside the layer-2 convolution kernel (default:
                          separate bandwidth kernel), bit 1 = first-version head conv3x3 (shifted windows, N = 16; default:
                          nine taps in the GEMM's N dimension), bit 2 = first-version (image-stationary) layer-1 kernel,
@@ -249,6 +250,9 @@ typedef struct tocvp_enc_weights {
   const void* w_conv1_vp;    /* f16 [3,32,32]: conv 1 with the 5 x-taps x 3 channels of two filter rows folded into K = 32
                                 (k = half*16 + kx*3 + c), three vertical taps two rows apart; null = use w_conv1_tc */
   const tocvp_tuning* tuning; /* NULL = defaults */
+  const void* w_conv_xp[3];  /* f16 [30,64,32] = [(ky, u)][parity*32 + co][ci]: the 32 -> 32 layers for the pixel-pair kernel
+                                (one MMA row = pixels 2j, 2j+1; u = 0..5 horizontal input shifts; block (ky, u) holds
+                                w[co][ci][ky][u - parity] or zeros).  NULL = the 25-tap kernel on w_conv.  ABI 3. */
 } tocvp_enc_weights;
 
 size_t tocvp_sizeof_enc_weights(void);

@@ -11,7 +11,7 @@ def test_library_exports_all_declared_symbols():
     assert "tocvp_gemm_f16" in names and "tocvp_init" in names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.tocvp_abi_version() == 2
+    assert lib.tocvp_abi_version() == 3
     assert not [n for n in names if n.startswith("tocvp_set_") or "probe" in n], "no process-wide knobs in the product ABI"
 
 

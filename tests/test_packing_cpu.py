@@ -108,3 +108,26 @@ def test_conv1_vertical_pair_packing():
         rows = Pz[:, 2 * j + 1:2 * j + 1 + H]                                    # stored row (y + 2j - 2) + 1, offset by the pad 2
         out = out + torch.einsum("nyxk,ok->nyxo", rows, wp[j])
     assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-4, rtol=1e-4)
+
+
+def test_conv_x_pair_packing():
+    """Encoder 32 -> 32 layers in pixel-pair form (conv5x5_tc.cu, XP): with one MMA row = pixels (2j, 2j+1) and the six input
+    shifts u = 0..5 of a filter row, block (ky, u) of modules.pack_conv_x_pairs applied to input pixel 2j + u - 2 and summed
+    over (ky, u) gives both pixels of the pair of the zero-padded 5x5 convolution."""
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(32, 32, 5, 5, generator=g)
+    x = torch.randn(2, 32, 16, 64, generator=g)
+    ref = F.conv2d(x, w, padding=2)
+    wp = M.pack_conv_x_pairs(w)
+    assert wp.shape == (30, 64, 32)
+    assert (wp[0::6, 32:] == 0).all() and (wp[5::6, :32] == 0).all()           # the taps that do not exist are zero blocks
+    n, c, H, W = x.shape
+    xz = F.pad(x, (2, 4, 2, 2))                                                 # columns -2 .. W+3 (TMA zero fill)
+    out = torch.zeros(n, 32, H, W)
+    for ky in range(5):
+        for u in range(6):
+            inp = xz[:, :, ky:ky + H, u:u + W:2]                                # input pixel 2j + u - 2 of row y + ky - 2
+            res = torch.einsum("oc,nchw->nohw", wp[ky * 6 + u], inp)            # [n, 64, H, W/2]
+            out[:, :, :, 0::2] += res[:, :32]
+            out[:, :, :, 1::2] += res[:, 32:]
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4)

@@ -47,7 +47,7 @@ def load() -> ctypes.CDLL:
                              "(there is no CPU / PyTorch fallback for this path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.tocvp_last_error.restype = ctypes.c_char_p
-        if _lib.tocvp_abi_version() != 2:
+        if _lib.tocvp_abi_version() != 3:
             raise TocvpError("libtocvp.so ABI version mismatch; rebuild")
         _lib.tocvp_sizeof_tuning.restype = ctypes.c_size_t
         if _lib.tocvp_sizeof_tuning() != ctypes.sizeof(Tuning):

@@ -246,10 +246,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // to 4 KB + 1 KB per SM -- the smem read port is what bounds the single-CTA kernel at N = 64 (ncu, profiles/) -- and
 // the per-SM L2 traffic for weights halves as well.
 // ------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int G, int KS, bool GEN = false>
+//
+// XP ("x pairs", the encoder's 32 -> 32 layers): a 32-channel MMA with N = 32 is bound by the A-operand fetch (128 rows x
+// 32 B per instruction, ~50 clocks for 16 clocks of math).  The NHWC activation is therefore read as PIXEL PAIRS -- one
+// 128-byte row = pixels (2j, 2j+1) x 32 channels, which is the same memory -- and one instruction computes BOTH pixels of
+// the pair: N = 64 = [32 outputs of pixel 2j | 32 outputs of pixel 2j+1].  Output 2j needs inputs 2j-2 .. 2j+2 and output
+// 2j+1 inputs 2j-1 .. 2j+3, so a filter row becomes KS + 1 horizontal shifts u = 0..5 of one input pixel (32 channels =
+// two k-steps, at byte (u & 1) * 64 of pair row u >> 1) against a [64 x 32] weight block that holds tap u for the even
+// pixel and tap u - 1 for the odd one (zeros where the tap does not exist; packed by the host).  30 x 2 instructions per
+// 256 pixels instead of 25 x 2 per 128: 0.6 x the instruction count for 1.2 x the flops.  With CIN = COUT = 64 as template
+// arguments the halo tile, the TMEM layout and the store addressing are exactly the 64-channel kernel's.
+template <int CIN, int COUT, int G, int KS, bool GEN = false, bool XP = false>
 struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
   using Base = ConvCfg<CIN, COUT, G, KS>;
-  static constexpr int W_HALF = (COUT / 2) * Base::KB;
+  static_assert(!XP || (CIN == 64 && COUT == 64 && !GEN), "XP is the 32-channel layer seen as 64-wide pixel pairs");
+  static constexpr int WKB = XP ? 64 : Base::KB;            // bytes per weight row = K extent of one tap
+  static constexpr int WLAYOUT = (WKB == 128) ? 2 : 4;
+  static constexpr int KSTEPS2 = WKB / 32;
+  static constexpr int NTAPS = XP ? KS * (KS + 1) : Base::TAPS;
+  static constexpr int W_HALF = (COUT / 2) * WKB;
   // 5 (not 6) stages at 64 channels: 230912 + 1024 static + 1024 reserved bytes per CTA left no room for the 1 KB a second,
   // shared-memory-free CTA needs on the SM, so the decoder's layer-1 kernel (chunk pipeline, decoder.cu) could never be
   // co-resident with this kernel (r1 timeline: the convolution waited ~250 us per chunk for layer-1 CTAs to exit).
@@ -274,11 +289,13 @@ __device__ __forceinline__ int border_pat(int v, int n) { return v < 2 ? v : (v 
 // VP ("vertical pairs", encoder conv 1): the input rows already hold an x-im2col of TWO image rows (encoder.cu,
 // enc_pack_vp_kernel), so the filter collapses to (KS+1)/2 vertical taps two rows apart, all at the centre column; the
 // packed tensor has one extra row on top (stored row r = image row r-1).
-template <int CIN, int COUT, int G, int KS, bool GEN, bool VP = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEN ? 320 : 192, ConvCfg2<CIN, COUT, G, KS, GEN>::CTAS_PER_SM)
+template <int CIN, int COUT, int G, int KS, bool GEN, bool VP = false, bool XP = false>
+__global__ void __cluster_dims__(2, 1, 1)
+__launch_bounds__((GEN || XP) ? 320 : 192, ConvCfg2<CIN, COUT, G, KS, GEN, XP>::CTAS_PER_SM)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvArgs a, ConvGen gen) {
-  using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
-  constexpr int NTAPS = VP ? (KS + 1) / 2 : C::TAPS;
+  using C = ConvCfg2<CIN, COUT, G, KS, GEN, XP>;
+  constexpr int NTAPS = VP ? (KS + 1) / 2 : C::NTAPS;
+  constexpr int HALO_X = XP ? 1 : KS / 2;               // XP: the halo starts one pixel PAIR left of the tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();     // swizzled TMA / UMMA tiles need 1024-byte alignment
@@ -311,7 +328,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_init(&a_full[b], GEN ? 8 : 1);     // GEN: one arrival per generator warp of both CTAs
       mbar_init(&a_empty[b], 1);
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 8);
+      mbar_init(&t_empty[b], XP ? 16 : 8);   // epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -332,7 +349,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int y0 = (r / tiles_x) * C::TILE_H, x0 = (r % tiles_x) * C::TILE_W;
         mbar_wait(&a_empty[buf], ph ^ 1);
         if (rank == 0) mbar_expect_tx(&a_full[buf], 2 * C::A_BYTES);
-        tma_load_4d_pair(&tmX, mapa_rank(smem_u32(&a_full[buf]), 0), sA + buf * C::A_STRIDE, 0, x0 - KS / 2,
+        tma_load_4d_pair(&tmX, mapa_rank(smem_u32(&a_full[buf]), 0), sA + buf * C::A_STRIDE, 0, x0 - HALO_X,
                          y0 - KS / 2 + (VP ? 1 : 0), img);
       };
       int s = 0;
@@ -371,16 +388,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t d_base = tmem_u + uint32_t(buf * C::ACC_COLS);
 #pragma unroll 1
         for (int tap = 0; tap < NTAPS; ++tap) {
-          const int ty = VP ? 2 * tap : tap / KS, tx = VP ? KS / 2 : tap % KS;
+          // XP: tap = (ty, u), u = 0..KS: input pixel u of the row = pair row u >> 1, byte (u & 1) * 64
+          const int ty = VP ? 2 * tap : (XP ? tap / (KS + 1) : tap / KS);
+          const int tx = VP ? KS / 2 : (XP ? (tap % (KS + 1)) >> 1 : tap % KS);
+          const uint32_t sub = XP ? uint32_t((tap % (KS + 1)) & 1) * 64u : 0u;
           mbar_wait(&w_full[s], wph);
           tc_fence_after();
-          const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_HALF), 8 * C::KB, C::LAYOUT);
+          const uint64_t db = make_desc_kmajor(smem_u32(sW + s * C::W_HALF), 8 * C::WKB, C::WLAYOUT);
 #pragma unroll
           for (int j = 0; j < G; ++j) {
-            const uint32_t a_addr = a_base + uint32_t((ty * C::WBUF + tx + 8 * j) * C::KB);
+            const uint32_t a_addr = a_base + uint32_t((ty * C::WBUF + tx + 8 * j) * C::KB) + sub;
             const uint64_t da = make_desc_kmajor(a_addr, SBO, C::LAYOUT);
 #pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k)
+            for (int k = 0; k < C::KSTEPS2; ++k)
               umma_f16_pair(d_base + uint32_t(j * COUT), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (tap | k) != 0,
                             leader);
           }
@@ -456,6 +476,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else {
     // ---------------------------------------------------------------- epilogue (own tile)
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;     // XP: 0 = warps 2-5, 1 = warps 6-9
     const int m = q * 32 + lane;
     const int pr = m >> 3, pc = m & 7;
     int it = 0;
@@ -468,62 +489,67 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int x0 = (r % tiles_x) * C::TILE_W + pc;
       mbar_wait(&t_full[buf], ph);
       tc_fence_after();
+      // the tile's (sub-tile j, 32-column slice c) pieces; XP runs two epilogue warps per TMEM lane quarter (warps 2-5
+      // take the even pixel of the pair, warps 6-9 the odd one): with one warp per scheduler the LayerNorm epilogue of
+      // encoder conv 4 was a dependent-issue chain longer than the tile's MMAs
+      constexpr int HP = COUT / 32, NIT = G * HP;
+      const size_t pix0 = size_t(y) * a.W + x0;
+      bool with_ln = false;
+      if constexpr (COUT == 32 || XP) with_ln = a.ln_g != nullptr;
 #pragma unroll 1
-      for (int j = 0; j < G; ++j) {
-        __half* o = a.out + (size_t(img) * a.H * a.W + size_t(y) * a.W + (x0 + 8 * j)) * COUT;
-        if constexpr (COUT == 32) {
-          if (a.ln_g != nullptr) {
-            // ---- relu(conv + b) + posemb -> LayerNorm over the pixel's 32 channels, all in this thread's registers
-            uint32_t v[32];
-            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT), v);
-            tmem_ld_wait();
-            const float* pe = a.ln_posemb + (size_t(y) * a.W + (x0 + 8 * j)) * COUT;
-            float f[32];
-            float sum = 0.f;
+      for (int i = XP ? part : 0; i < NIT; i += XP ? 2 : 1) {
+        const int j = i / HP, c = i % HP;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
+        tmem_ld_wait();
+        __half* o = a.out + (size_t(img) * a.H * a.W + pix0 + size_t(8 * j)) * COUT + c * 32;
+        const float* bias = a.bias + (XP ? 0 : c * 32);            // XP: both pixels of the pair share the 32 biases
+        if (with_ln) {
+          // ---- relu(conv + b) + posemb -> LayerNorm over the pixel's 32 channels, all in this thread's registers
+          const float* pe = a.ln_posemb + (pix0 + size_t(8 * j)) * COUT + c * 32;
+          float f[32];
+          float sum = 0.f;
+          float4 pv[8];
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias) + e4);
-              const float4 pp = __ldg(reinterpret_cast<const float4*>(pe) + e4);
-              f[4 * e4 + 0] = fmaxf(__uint_as_float(v[4 * e4 + 0]) + bb.x, 0.f) + pp.x;
-              f[4 * e4 + 1] = fmaxf(__uint_as_float(v[4 * e4 + 1]) + bb.y, 0.f) + pp.y;
-              f[4 * e4 + 2] = fmaxf(__uint_as_float(v[4 * e4 + 2]) + bb.z, 0.f) + pp.z;
-              f[4 * e4 + 3] = fmaxf(__uint_as_float(v[4 * e4 + 3]) + bb.w, 0.f) + pp.w;
-              sum += (f[4 * e4] + f[4 * e4 + 1]) + (f[4 * e4 + 2] + f[4 * e4 + 3]);
-            }
-            const float mean = sum * (1.f / 32.f);
-            float var = 0.f;
+          for (int e8 = 0; e8 < 4; ++e8) ldg_nc_256(pe + 8 * e8, pv[2 * e8], pv[2 * e8 + 1]);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              f[e] -= mean;
-              var = fmaf(f[e], f[e], var);
-            }
-            const float rstd = rsqrtf(var * (1.f / 32.f) + a.ln_eps);
-#pragma unroll
-            for (int e8 = 0; e8 < 4; ++e8) {
-              float g[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                g[e] = f[8 * e8 + e] * rstd * __ldg(a.ln_g + 8 * e8 + e) + __ldg(a.ln_b + 8 * e8 + e);
-              uint4 p;
-              p.x = pack_half2(g[0], g[1]);
-              p.y = pack_half2(g[2], g[3]);
-              p.z = pack_half2(g[4], g[5]);
-              p.w = pack_half2(g[6], g[7]);
-              *reinterpret_cast<uint4*>(o + 8 * e8) = p;
-            }
-            continue;
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + e4);
+            const float4 pp = pv[e4];
+            f[4 * e4 + 0] = fmaxf(__uint_as_float(v[4 * e4 + 0]) + bb.x, 0.f) + pp.x;
+            f[4 * e4 + 1] = fmaxf(__uint_as_float(v[4 * e4 + 1]) + bb.y, 0.f) + pp.y;
+            f[4 * e4 + 2] = fmaxf(__uint_as_float(v[4 * e4 + 2]) + bb.z, 0.f) + pp.z;
+            f[4 * e4 + 3] = fmaxf(__uint_as_float(v[4 * e4 + 3]) + bb.w, 0.f) + pp.w;
+            sum += (f[4 * e4] + f[4 * e4 + 1]) + (f[4 * e4 + 2] + f[4 * e4 + 3]);
           }
-        }
+          const float mean = sum * (1.f / 32.f);
+          float var = 0.f;
 #pragma unroll
-        for (int c = 0; c < COUT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * C::ACC_COLS + j * COUT + c * 32), v);
-          tmem_ld_wait();
+          for (int e = 0; e < 32; ++e) {
+            f[e] -= mean;
+            var = fmaf(f[e], f[e], var);
+          }
+          const float rstd = rsqrtf(var * (1.f / 32.f) + a.ln_eps);
+          uint4 pk[4];
+#pragma unroll
+          for (int e8 = 0; e8 < 4; ++e8) {
+            float g[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              g[e] = f[8 * e8 + e] * rstd * __ldg(a.ln_g + 8 * e8 + e) + __ldg(a.ln_b + 8 * e8 + e);
+            pk[e8].x = pack_half2(g[0], g[1]);
+            pk[e8].y = pack_half2(g[2], g[3]);
+            pk[e8].z = pack_half2(g[4], g[5]);
+            pk[e8].w = pack_half2(g[6], g[7]);
+          }
+          stg_256(o, pk[0], pk[1]);
+          stg_256(o + 16, pk[2], pk[3]);
+        } else {
+          uint4 pk[4];
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            const int n = c * 32 + j8 * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + j8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + j8 * 8 + 4);
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j8 * 8 + e]);
@@ -533,13 +559,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
-            uint4 p;
-            p.x = pack_half2(f[0], f[1]);
-            p.y = pack_half2(f[2], f[3]);
-            p.z = pack_half2(f[4], f[5]);
-            p.w = pack_half2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(o + n) = p;
+            pk[j8].x = pack_half2(f[0], f[1]);
+            pk[j8].y = pack_half2(f[2], f[3]);
+            pk[j8].z = pack_half2(f[4], f[5]);
+            pk[j8].w = pack_half2(f[6], f[7]);
           }
+          stg_256(o, pk[0], pk[1]);
+          stg_256(o + 16, pk[2], pk[3]);
         }
       }
       tc_fence_before();
@@ -556,15 +582,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-template <int CIN, int COUT, int G, int KS, bool GEN = false, bool VP = false>
+template <int CIN, int COUT, int G, int KS, bool GEN = false, bool VP = false, bool XP = false>
 static int launch_conv2(const __half* x, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
                         int relu, cudaStream_t stream, ConvGen gen = ConvGen{nullptr, nullptr},
                         const float* ln_posemb = nullptr, const float* ln_g = nullptr, const float* ln_b = nullptr,
                         float ln_eps = 0.f) {
-  using C = ConvCfg2<CIN, COUT, G, KS, GEN>;
+  using C = ConvCfg2<CIN, COUT, G, KS, GEN, XP>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
   static SmemAttrOnce attr_once;
-  TOCVP_TRY(ensure_smem_attr(attr_once, conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP>, C::SMEM));
+  TOCVP_TRY(ensure_smem_attr(attr_once, conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP, XP>, C::SMEM));
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmX, tmW;
   {
@@ -575,16 +601,18 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
     TOCVP_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, str, box, sw));
   }
   {
-    const uint64_t dims[2] = {uint64_t(CIN), uint64_t((VP ? (KS + 1) / 2 : C::TAPS) * COUT)};
-    const uint64_t str[1] = {uint64_t(CIN) * 2};
-    const uint32_t box[2] = {uint32_t(CIN), uint32_t(COUT / 2)};
-    TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box, sw));
+    constexpr int WK = C::WKB / 2;                        // K extent of one tap's weight rows (XP: 32 of the 64 'channels')
+    const uint64_t dims[2] = {uint64_t(WK), uint64_t((VP ? (KS + 1) / 2 : C::NTAPS) * COUT)};
+    const uint64_t str[1] = {uint64_t(WK) * 2};
+    const uint32_t box[2] = {uint32_t(WK), uint32_t(COUT / 2)};
+    TOCVP_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wpacked, dims, str, box,
+                          C::WKB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   }
   const int num_ptiles = n_img * (H / C::TILE_H) * (W / C::TILE_W) / 2;
   const int pairs = (num_sms() / 2) * C::CTAS_PER_SM;
   const int grid = 2 * (num_ptiles < pairs ? num_ptiles : pairs);
   ConvArgs a{n_img, H, W, bias, out, nullptr, relu, ln_posemb, ln_g, ln_b, ln_eps};
-  conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP><<<grid, GEN ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
+  conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP, XP><<<grid, (GEN || XP) ? 320 : 192, C::SMEM, stream>>>(tmX, tmW, a, gen);
   TOCVP_LAUNCHED();
   return TOCVP_OK;
 }
@@ -645,6 +673,18 @@ int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, co
   TOCVP_CHECK_ARG(H % 16 == 0 && W % 32 == 0 && ((n_img * (H / 16) * (W / 32)) % 2 == 0));
   return launch_conv2<32, 32, 4, 5>(x, wpacked, bias, out, n_img, H, W, 1, stream, ConvGen{nullptr, nullptr}, posemb, ln_g,
                                     ln_b, ln_eps);
+}
+
+// Encoder 32 -> 32 layers in pixel-pair form (XP, see ConvCfg2).  x / out: f16 NHWC [n_img, H, W, 32] (W % 64 == 0);
+// wxp: f16 [30, 64, 32] = [(ky, u)][pixel parity * 32 + cout][cin] with W[ky][u - parity] or zeros (host-packed).
+// With ln_g != null the epilogue also adds the positional embedding and applies LayerNorm(32) (encoder conv 4).
+int conv5x5_xp_f16(const __half* x, const __half* wxp, const float* bias, const float* posemb, const float* ln_g,
+                   const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream) {
+  TOCVP_CHECK_ARG(x && wxp && bias && out && n_img > 0);
+  TOCVP_CHECK_ARG(H % 16 == 0 && W % 64 == 0 && ((n_img * (H / 16) * (W / 64)) % 2 == 0));
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  return launch_conv2<64, 64, 4, 5, false, false, true>(x, wxp, bias, out, n_img, H, W / 2, 1, stream, ConvGen{nullptr, nullptr},
+                                                        posemb, ln_g, ln_b, ln_eps);
 }
 
 // Encoder conv 1 on the x-im2col packed input (encoder.cu): xp f16 [n_img, H+1, W, 32], wpacked f16 [3, 32, 32].

@@ -22,6 +22,8 @@ int enc_mlp_f16(const __half* x, const __half* w1, const float* b1, const __half
                 cudaStream_t stream);
 int conv5x5_vp_f16(const __half* xp, const __half* wpacked, const float* bias, __half* out, int n_img, int H, int W,
                    cudaStream_t stream);
+int conv5x5_xp_f16(const __half* x, const __half* wxp, const float* bias, const float* posemb, const float* ln_g,
+                   const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
 int conv5x5_ln_f16(const __half* x, const __half* wpacked, const float* bias, const float* posemb, const float* ln_g,
                    const float* ln_b, float ln_eps, __half* out, int n_img, int H, int W, cudaStream_t stream);
 
@@ -158,6 +160,12 @@ static size_t enc_carve(const tocvp_enc_weights& w, int n, EncBuffers* eb, uint8
 
 // conv 1 .. conv 3 of SimpleConvEncoder (each + bias + ReLU): frames -> eb.actA (NHWC f16); conv 4 follows in the caller
 // (fused with the positional embedding + LayerNorm in SAVi.encode, plain in the stand-alone encoder forward).
+// pixel-pair kernel for 32 -> 32 layer i (conv5x5_tc.cu, XP): full-width 16 x 64 tiles, an even tile count
+static bool enc_xp_ok(const tocvp_enc_weights& w, int i, int n_img) {
+  return !(opts().encode_mode & 16) && w.w_conv_xp[i] != nullptr && w.W % 64 == 0 && w.H % 16 == 0 &&
+         ((n_img * (w.H / 16) * (w.W / 64)) % 2 == 0);
+}
+
 static int enc_convs_1_to_3(const tocvp_enc_weights& wr, EncBuffers& eb, const float* frames, size_t img_stride, int n_img,
                             int g_enc_mode, cudaStream_t st) {
   const tocvp_enc_weights* w = &wr;
@@ -177,9 +185,17 @@ static int enc_convs_1_to_3(const tocvp_enc_weights& wr, EncBuffers& eb, const f
     TOCVP_LAUNCHED();
     TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv1_tc), w->b_conv1, eb.actA, n_img, H, W, C, C, 1, st));
   }
-  TOCVP_TRY(conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[0]), w->b_conv[0], eb.actB, n_img, H, W, C, C, 1, st));
-  TOCVP_TRY(conv5x5_f16(eb.actB, static_cast<const __half*>(w->w_conv[1]), w->b_conv[1], eb.actA, n_img, H, W, C, C, 1, st));
-  return TOCVP_OK;
+  __half* src = eb.actA;
+  __half* dst = eb.actB;
+  for (int i = 0; i < 2; ++i) {
+    if (enc_xp_ok(wr, i, n_img))
+      TOCVP_TRY(conv5x5_xp_f16(src, static_cast<const __half*>(w->w_conv_xp[i]), w->b_conv[i], nullptr, nullptr, nullptr, 0.f,
+                               dst, n_img, H, W, st));
+    else
+      TOCVP_TRY(conv5x5_f16(src, static_cast<const __half*>(w->w_conv[i]), w->b_conv[i], dst, n_img, H, W, C, C, 1, st));
+    __half* t = src; src = dst; dst = t;
+  }
+  return TOCVP_OK;      // conv 3's output is back in eb.actA
 }
 
 }  // namespace tocvp
@@ -213,7 +229,11 @@ extern "C" int tocvp_savi_encode(const tocvp_enc_weights* w, const float* frames
   const int M = n_img * H * W;
   TOCVP_TRY(enc_convs_1_to_3(*w, eb, frames, img_stride, n_img, g_enc_mode, st));
   const bool fuse_ln = !(g_enc_mode & 2) && ((n_img * (H / 16) * (W / 32)) % 2 == 0);
-  if (fuse_ln) {
+  if (fuse_ln && enc_xp_ok(*w, 2, n_img)) {
+    TOCVP_TRY(conv5x5_xp_f16(eb.actA, static_cast<const __half*>(w->w_conv_xp[2]), w->b_conv[2], w->posemb, w->ln_g, w->ln_b,
+                             1e-5f, eb.actB, n_img, H, W, st));
+    eb.h16 = eb.actB;
+  } else if (fuse_ln) {
     // conv 4 + positional embedding + LayerNorm(32) (eps 1e-5, SAVi.py:116) in one kernel: the LN input never leaves fp32
     TOCVP_TRY(conv5x5_ln_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], w->posemb, w->ln_g, w->ln_b,
                              1e-5f, eb.actB, n_img, H, W, st));
@@ -250,6 +270,9 @@ extern "C" int tocvp_savi_conv_stack(const tocvp_enc_weights* w, const float* fr
   EncBuffers eb;
   enc_carve(*w, n_img, &eb, static_cast<uint8_t*>(workspace));
   TOCVP_TRY(enc_convs_1_to_3(*w, eb, frames, img_stride, n_img, opts().encode_mode & 15, st));
+  if (enc_xp_ok(*w, 2, n_img))
+    return conv5x5_xp_f16(eb.actA, static_cast<const __half*>(w->w_conv_xp[2]), w->b_conv[2], nullptr, nullptr, nullptr, 0.f,
+                          static_cast<__half*>(out_nhwc_f16), n_img, w->H, w->W, st);
   return conv5x5_f16(eb.actA, static_cast<const __half*>(w->w_conv[2]), w->b_conv[2], static_cast<__half*>(out_nhwc_f16),
                      n_img, w->H, w->W, w->hidden, w->hidden, 1, st);
 }

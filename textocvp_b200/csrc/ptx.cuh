@@ -299,6 +299,19 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   return r;
 }
 // exact (erf) GELU, the nn.GELU default: activation code 2 of the GEMM epilogues (1 = ReLU)
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256; 32-byte aligned).  One lane = one full 32-byte sector: for the
+// epilogues whose lanes own whole rows (16-byte pieces at a row stride) this halves the L1 wavefront count.
+__device__ __forceinline__ void ldg_nc_256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -66,7 +66,7 @@ EncW = type("EncW", (ctypes.Structure,), {"_fields_": [
     ("w_conv1", _f), ("b_conv1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("posemb", _f),
     ("ln_g", _f), ("ln_b", _f), ("w_mlp1", _f), ("b_mlp1", _f), ("w_mlp2", _f), ("b_mlp2", _f),
     ("H", ctypes.c_int), ("W", ctypes.c_int), ("in_channels", ctypes.c_int), ("hidden", ctypes.c_int),
-    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f), ("w_conv1_vp", _f), ("tuning", _f)]})
+    ("feat_dim", ctypes.c_int), ("w_conv1_tc", _f), ("w_conv1_vp", _f), ("tuning", _f), ("w_conv_xp", _f * 3)]})
 
 DecW = type("DecW", (ctypes.Structure,), {"_fields_": [
     ("w1_taps", _f), ("p1", _f), ("w_conv", _f * 3), ("b_conv", _f * 3), ("w_out", _f), ("b_out", _f),
@@ -370,6 +370,20 @@ def pack_conv1_vertical_pairs(w):
     return wp
 
 
+def pack_conv_x_pairs(w):
+    """A 32 -> 32 conv5x5 for the pixel-pair kernel (conv5x5_tc.cu, XP): weight [32, 32, 5, 5] -> [30, 64, 32] with block
+    (ky, u), u = 0..5, row parity*32 + co, column ci = w[co, ci, ky, u - parity] where that tap exists, else 0:
+    out[y, 2j + parity] = sum_{ky, u} block(ky, u)[parity] . in[y + ky - 2, 2j + u - 2]."""
+    co, ci, kh, kw = w.shape
+    assert (co, ci, kh, kw) == (32, 32, 5, 5)
+    wf = w.detach().float()
+    wp = torch.zeros(kh, kw + 1, 2, co, ci, dtype=torch.float32, device=w.device)
+    for par in range(2):
+        for kx in range(kw):
+            wp[:, kx + par, par] = wf[:, :, :, kx].permute(2, 0, 1)              # [ky, co, ci]
+    return wp.reshape(kh * (kw + 1), 2 * co, ci)
+
+
 def im2col_x_row_pairs(x):
     """Reference (torch) statement of what enc_pack_vp_kernel writes: frames [n, 3, H, W] -> [n, H+1, W, 32] where stored row
     r stands for image row y' = r - 1 and holds, per pixel, the 5 x 3 x-neighbourhood of image row y' (k = kx*3 + c) and of
@@ -482,6 +496,8 @@ def _pack_encoder_convs(enc, k, ew):
     for i in range(3):
         k[f"wc{i}"] = _f16(enc[i + 1].weight.permute(2, 3, 0, 1).reshape(25, 32, 32))
         k[f"bc{i}"] = _f32(enc[i + 1].bias)
+        k[f"wxp{i}"] = _f16(pack_conv_x_pairs(enc[i + 1].weight))
+        ew.w_conv_xp[i] = k[f"wxp{i}"].data_ptr()
     ew.w_conv1, ew.b_conv1 = k["w_conv1"].data_ptr(), k["b_conv1"].data_ptr()
     for i in range(3):
         ew.w_conv[i], ew.b_conv[i] = k[f"wc{i}"].data_ptr(), k[f"bc{i}"].data_ptr()
