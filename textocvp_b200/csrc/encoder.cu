@@ -78,11 +78,9 @@ enc_pack_vp_kernel(const float* __restrict__ x, size_t img_stride, __half* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[half * 8 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + idx * 32);
-  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  o[2] = make_uint4(w[8], w[9], w[10], w[11]);
-  o[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  __half* o = out + idx * 32;                    // 64 bytes per thread: two full 32-byte sectors (256-bit stores)
+  stg_256(o, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+  stg_256(o + 16, make_uint4(w[8], w[9], w[10], w[11]), make_uint4(w[12], w[13], w[14], w[15]));
 }
 
 constexpr int E1_TH = 8, E1_TW = 32, E1_CO = 32;

@@ -40,6 +40,9 @@ constexpr int HD_D_BYTES = HD_MT * 128 * HD_DS * 4;
 constexpr int HD_SMEM = 2 * HD_A_STRIDE + HD_W_BYTES + HD_D_BYTES + 256 + 1024;
 constexpr int HD_MAX_SLOTS = 11;
 constexpr int HD_COMP_BYTES = HD_TH * HD_TW * 16;   // per slot: float4 per pixel of the tile
+constexpr int HD_THREADS = 320;                 // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int HD_ETH = HD_THREADS - 64;         // epilogue threads = pixels of the 8 x 32 tile
+static_assert(HD_ETH == HD_TH * HD_TW, "one epilogue thread per output pixel");
 constexpr int HD_TMEM_COLS = 512;                // 2 x 3 x 48 = 288 columns used (two accumulator sets)
 
 __device__ __forceinline__ uint64_t hd_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, dense 128-byte rows
@@ -63,7 +66,7 @@ struct HeadComposite {
 // on the ONE epilogue warp each scheduler has, every S-th tile -- more than the two-deep accumulator pipeline can hide
 // (first fused version: 343 us per 2048 slot-images against 293 + 30 us for the separate kernels).
 template <bool COMPOSITE, int S_CT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(HD_THREADS, 1)
 head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int n_img, int H, int W,
                const float* __restrict__ bias, float* __restrict__ out4, HeadComposite hc) {
   extern __shared__ uint8_t smem_raw[];
@@ -115,7 +118,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(&a_full[b], 1);
       mbar_init(&a_empty[b], 1);
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 4);
+      mbar_init(&t_empty[b], HD_ETH / 32);
     }
     fence_barrier_init();
   }
@@ -164,8 +167,10 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       umma_commit(&t_full[buf], leader);
     }
   } else {
-    const int q = warp & 3;
-    const int et = threadIdx.x - 64;                         // 0..127
+    // 8 epilogue warps: with 4 (one per scheduler) the epilogue was a dependent-issue chain and the kernel's pace (ncu r1 /
+    // r2); warps q and q + 4 share a TMEM lane quarter and split its M-tiles, then every thread owns one pixel of the tile
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                         // 0..255
     const float4 b4 = *reinterpret_cast<const float4*>(bias);
     int img, y0, x0, slot;
     const size_t plane = size_t(H) * W;
@@ -176,7 +181,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_after();
       // ---- phase 1: accumulators -> shared memory, D[halo pixel][tap*4 + co]
 #pragma unroll 1
-      for (int mt = 0; mt < HD_MT; ++mt) {
+      for (int mt = part; mt < HD_MT; mt += 2) {
         uint32_t v[32], v4[4];
         const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * HD_MT * HD_N + mt * HD_N);
         tmem_ld32(ta, v);
@@ -192,12 +197,10 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);             // this accumulator set is free for the MMAs of tile it+2
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // D complete
-      // ---- phase 2: shift-and-add over the 9 taps; thread -> column x, rows y = (et >> 5) + 4 i
-      const int px = et & 31;
-#pragma unroll 1
-      for (int i = 0; i < HD_TH / 4; ++i) {
-        const int py = (et >> 5) + 4 * i;
+      asm volatile("bar.sync 1, %0;" ::"n"(HD_ETH) : "memory");   // D complete
+      // ---- phase 2: shift-and-add over the 9 taps; thread -> pixel (row et >> 5, column et & 31)
+      const int px = et & 31, py = et >> 5;
+      {
         float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -218,9 +221,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (slot == S - 1) {
           // softmax over the slot axis + weighted RGB sum (SAVi.py:252-255); same arithmetic, same order as composite_kernel
           const int frame = img / S;
-#pragma unroll 1
-          for (int i = 0; i < HD_TH / 4; ++i) {
-            const int py = (et >> 5) + 4 * i;
+          {
             const float4* m = sM + py * HD_TW + px;
             float mx = -1e30f;
 #pragma unroll
@@ -244,7 +245,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // everyone is done reading D
+      asm volatile("bar.sync 1, %0;" ::"n"(HD_ETH) : "memory");   // everyone is done reading D
     }
   }
 
@@ -279,18 +280,18 @@ static int launch_head(const __half* x, const __half* w_taps, const float* bias,
     if (hc->S == 8) {                                    // SAVi.json: 8 slots
       static SmemAttrOnce attr_once;
       TOCVP_TRY(ensure_smem_attr(attr_once, head3x3_kernel<true, 8>, HD_SMEM + 8 * HD_COMP_BYTES));
-      head3x3_kernel<true, 8><<<grid, 192, smem, stream>>>(tmX, tmW, n_img, H, W, bias, nullptr, *hc);
+      head3x3_kernel<true, 8><<<grid, HD_THREADS, smem, stream>>>(tmX, tmW, n_img, H, W, bias, nullptr, *hc);
     } else {
       static SmemAttrOnce attr_once;
       TOCVP_TRY(ensure_smem_attr(attr_once, head3x3_kernel<true, 0>, HD_SMEM + HD_MAX_SLOTS * HD_COMP_BYTES));
-      head3x3_kernel<true, 0><<<grid, 192, smem, stream>>>(tmX, tmW, n_img, H, W, bias, nullptr, *hc);
+      head3x3_kernel<true, 0><<<grid, HD_THREADS, smem, stream>>>(tmX, tmW, n_img, H, W, bias, nullptr, *hc);
     }
   } else {
     TOCVP_CHECK_ARG(out4 != nullptr && (reinterpret_cast<uintptr_t>(out4) & 15) == 0);
     static SmemAttrOnce attr_once;
     TOCVP_TRY(ensure_smem_attr(attr_once, head3x3_kernel<false, 1>, HD_SMEM));
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    head3x3_kernel<false, 1><<<grid, 192, HD_SMEM, stream>>>(tmX, tmW, n_img, H, W, bias, out4, HeadComposite{1, nullptr, nullptr, nullptr});
+    head3x3_kernel<false, 1><<<grid, HD_THREADS, HD_SMEM, stream>>>(tmX, tmW, n_img, H, W, bias, out4, HeadComposite{1, nullptr, nullptr, nullptr});
   }
   TOCVP_LAUNCHED();
   return TOCVP_OK;
