@@ -48,10 +48,11 @@ def parse():
 
 # provenance of roofline.traffic (an ncu --set full capture cannot run inside the timed bench; the number is per launch
 # of the dominant kernel over 2048 slot-images, like roofline.achieved)
-TRAFFIC = {"bytes_per_launch": 2.096e9, "algorithmic_bytes_per_launch": 2.147e9,
-           "metric": "dram__bytes_read.sum + dram__bytes_write.sum", "file": "profiles/conv64_pair_r1_summary.md",
-           "captured": "2026-10-18 (round 1, ncu --set full --clock-control none, gpurun_out/conv64_r1_final.ncu-rep); the "
-                       "kernel source has not changed since"}
+TRAFFIC = {"bytes_per_launch": 2.101e9, "algorithmic_bytes_per_launch": 2.147e9,
+           "metric": "dram__bytes_read.sum + dram__bytes_write.sum", "file": "profiles/conv64_r2_summary.md",
+           "captured": "2026-10-18 (round 2, ncu --set full --clock-control none -k regex:conv_tc2_kernel --launch-skip 20 "
+                       "--launch-count 2 python tools/run_stage.py decode 256 1): 1.074 GB read + 1.027 GB written per launch "
+                       "of 2048 slot-images; round 1 measured 2.096 GB on the previous epilogue"}
 # The CPU arm times the ORACLE PORT (oracle/textocvp_oracle.py), because /root/reference cannot travel to the GPU box.  Port
 # and reference modules were timed side by side in the build container (8 threads, B = 1): reference 11.1 frames/s, port
 # 14.8 frames/s -- the port is 1.33x FASTER than the reference's own modules, so GPU / CPU ratios quoted against it are
