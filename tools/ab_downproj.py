@@ -23,6 +23,15 @@ def run(label, mode, **kw):
     us = e0.elapsed_time(e1) * 1e3 / n
     print(f"{label:40s} mode {mode:3d}: {us:7.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s")
 
+if os.environ.get("TOCVP_TUNING"):
+    ops.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in os.environ["TOCVP_TUNING"].split(","))})
+# correctness of the producer form at both widths against fp32 torch
+ref = As[0].float() @ w.float().t() + b + res
+for mode in (128, 256):
+    ops.set_gemm_mode(mode)
+    o32, o16 = ops.gemm_f16(As[0], w, bias=b, residual=res, out_f32=True, out_f16=True)
+    torch.cuda.synchronize()
+    print(f"mode {mode}: max |out32 - ref| = {(o32 - ref).abs().max().item():.3e}, |out16 - ref| = {(o16.float() - ref).abs().max().item():.3e}")
 for mode in (128, 256):
     run("f16 out only", mode, out_f32=False, out_f16=True)
     run("fp32 residual in, fp32 out", mode, residual=res, out_f32=True)
