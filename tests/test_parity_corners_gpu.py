@@ -185,6 +185,27 @@ def test_conv_encoder_forward(models, golden_weights):
     PL.check(O.rel_err(out, ref), STAGE_TOL, "SimpleConvEncoder.forward (4 convolutions) vs torch fp32")
 
 
+@pytest.mark.parametrize("shape, enc_mode", [((2, 32, 128), 0), ((3, 16, 64), 0), ((1, 48, 192), 0), ((2, 64, 64), 16),
+                                             ((5, 16, 96), 0)])
+def test_conv_encoder_shapes(models, shape, enc_mode):
+    """The encoder convolutions away from the 64 x 64 benchmark frame: the pixel-pair kernel with several 64-pixel tiles per
+    row (its halo starts one pair left of a tile that is not at the image border), an odd tile count and a width that is
+    not a multiple of 64 (both fall back to the 25-tap kernel), and the 25-tap kernel forced by encode_mode bit 4."""
+    from textocvp_b200 import _lib as L
+    savi, _ = models
+    n, H, W = shape
+    x = torch.rand(n, 3, H, W, generator=torch.Generator().manual_seed(11 + H + W))
+    setattr(L.TUNING, "encode_mode", int(enc_mode))
+    try:
+        out = savi.encoder(x.cuda())
+        torch.cuda.synchronize()
+    finally:
+        setattr(L.TUNING, "encode_mode", 0)
+    assert out.shape == (n, 32, H, W)
+    ref = _conv_ref(x.float(), list(savi.encoder.encoder))
+    PL.check(O.rel_err(out, ref), STAGE_TOL, f"SimpleConvEncoder.forward {n}x3x{H}x{W}, encode_mode {enc_mode}, vs torch fp32")
+
+
 def test_positional_modules(models):
     savi, pred = models
     x = torch.randn(3, 64, 64, 32, generator=torch.Generator().manual_seed(2))

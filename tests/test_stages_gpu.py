@@ -28,10 +28,11 @@ def models(golden_weights):
     return savi.cuda().eval(), pred.cuda().eval()
 
 
-@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4, 8])
+@pytest.mark.parametrize("enc_mode", [0, 1, 2, 3, 4, 8, 16, 18])
 def test_encode(models, golden, golden_weights, enc_mode):
     """tocvp_tuning.encode_mode bits: 0 (default) = tensor-core conv 1 (zero-padded input channels) + posemb/LayerNorm fused
-    into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass."""
+    into conv 4's epilogue; bit 0 = fp32 SIMT conv 1; bit 1 = separate posemb + LayerNorm pass; bit 4 = the 32 -> 32 layers on
+    the 25-tap N = 32 kernel instead of the pixel-pair kernel."""
     from textocvp_b200 import _lib as L
     savi, _ = models
     x = golden_weights["videos"][:, 0].cuda()
