@@ -88,9 +88,9 @@ __device__ __forceinline__ void bulk_wait_read() {
 
 // EPI = 2 is the producer side (fp32 residual in and out through TMA, f16 copy + row statistics; 128-wide tiles), EPI = 0
 // the general epilogue.
-// EPI = 1 specialises the epilogue for the consumer of a folded LayerNorm with f16-only output (QKV / cross-q / MLP up
-// projections of the predictor: no residual, no fp32 output, ReLU or nothing): the other variants' code and registers
-// are compiled out (ncu r2: the all-in-one epilogue spilled and took instruction-cache misses on its branch-over code).
+// EPI = 1 specialises the epilogue for f16-only output without a residual (ReLU or nothing; with or without a folded
+// LayerNorm: the QKV / cross-q / MLP up projections of the predictor, the hoisted text K|V projection): the other variants'
+// code and registers are compiled out (ncu r2: the all-in-one epilogue spilled and took instruction-cache misses on its branch-over code).
 template <int BN, bool CONV, int EWN, bool WRES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EWN), 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -249,8 +249,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_res = E2 || (!E1 && g.residual != nullptr);
     const bool has_out32 = !E1 && g.out32 != nullptr;
     const bool has_out16 = E1 || g.out16 != nullptr;
-    const bool has_ln = E1 || (!E2 && g.ln_stats != nullptr);
-    const bool has_bias = E1 || g.bias != nullptr;
+    const bool has_ln = !E2 && g.ln_stats != nullptr;
+    const bool has_bias = g.bias != nullptr;
     const int act = E1 ? (g.relu & 1) : (E2 ? 0 : g.relu);
     const bool tma_res = E2 || (!E1 && !CONV && S::STG_TILES == 3 && has_res && g.res_mod == 0 &&
                                 (has_out32 || g.stats_out != nullptr));
@@ -652,8 +652,8 @@ static int launch_gemm2_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 template <int BN, bool CONV, int EWN, bool WRES = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& g, cudaStream_t stream) {
   if constexpr (!CONV) {
-    if (g.ln_stats != nullptr && g.ln_c != nullptr && g.bias != nullptr && g.residual == nullptr && g.out32 == nullptr &&
-        g.out16 != nullptr && g.relu != 2 && g.stats_out == nullptr)
+    const bool ln_ok = g.ln_stats == nullptr || (g.ln_c != nullptr && g.bias != nullptr);
+    if (ln_ok && g.residual == nullptr && g.out32 == nullptr && g.out16 != nullptr && g.relu != 2 && g.stats_out == nullptr)
       return launch_gemm2_epi<BN, CONV, EWN, WRES, 1>(tmA, tmB, g, stream);
     if constexpr (BN == 128 && !WRES) {
       if (g.ln_stats == nullptr && g.residual != nullptr && g.res_mod == 0 && g.relu == 0 &&

@@ -38,11 +38,11 @@ def bench_gemm():
             ops.set_gemm_mode(mode)
             ms = timeit(lambda: ops.gemm_f16(a, w, out_f32=False, out_f16=True))
             res.append(f"mode{mode}: {ms*1e3:7.1f} us {2*M*N*K/ms/1e9:7.1f} TF")
-        ops.set_gemm_mode(258)                                   # 256-wide tiles without the W-resident variant
-        ops.set_gemm_mode(256)
+        ops.set_gemm_mode(256)                                   # 256-wide tiles without the W-resident variant
+        ops.set_tuning(gemm_no_wres=1)
         ms = timeit(lambda: ops.gemm_f16(a, w, out_f32=False, out_f16=True))
         res.append(f"256/noWres: {ms*1e3:7.1f} us {2*M*N*K/ms/1e9:7.1f} TF")
-        ops.set_gemm_mode(259)
+        ops.set_tuning(gemm_no_wres=0)
         ops.set_gemm_mode(0)
         ms_t = timeit(lambda: a @ w.t())
         print(f"gemm {M}x{N}x{K}: " + " | ".join(res) + f" | cuBLAS {2*M*N*K/ms_t/1e9:.1f}", flush=True)
