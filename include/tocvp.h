@@ -107,7 +107,8 @@ int tocvp_layernorm(const void* x, int x_is_f16, int ldx, const float* add, int 
  * 5x5 stride-1 zero-padded convolution + bias (+ReLU) as a tcgen05 implicit GEMM.
  * x: f16 NHWC [n_img,H,W,cin]; w_packed: f16 [25,cout,cin] (tap-major, tap = ky*5+kx, i.e.
  * torch weight[co,ci,ky,kx] permuted); bias fp32[cout]; out: f16 NHWC [n_img,H,W,cout].
- * H % 16 == 0, W % 32 == 0; (cin,cout) in {(64,64),(32,32)}.
+ * H % 16 == 0, W % 32 == 0; (cin,cout) in {(64,64),(32,32)}; x 16-byte and out 32-byte aligned (the CTA-pair
+ * kernel stores with 256-bit accesses).
  * Replaces nn.Conv2d -> cuDNN at src/models/Blocks/model_blocks.py:83-91 as used by
  * src/models/EncodersDecoders/decoders.py:96-108 and encoders.py:141-153.
  * ------------------------------------------------------------------------------------------ */

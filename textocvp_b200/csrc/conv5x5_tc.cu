@@ -589,6 +589,8 @@ static int launch_conv2(const __half* x, const __half* wpacked, const float* bia
                         float ln_eps = 0.f) {
   using C = ConvCfg2<CIN, COUT, G, KS, GEN, XP>;
   TOCVP_CHECK_ARG(H % C::TILE_H == 0 && W % C::TILE_W == 0);
+  // the epilogue stores each lane's 64 bytes with 256-bit accesses (and reads the positional embedding the same way)
+  TOCVP_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (reinterpret_cast<uintptr_t>(ln_posemb) & 31) == 0);
   static SmemAttrOnce attr_once;
   TOCVP_TRY(ensure_smem_attr(attr_once, conv_tc2_kernel<CIN, COUT, G, KS, GEN, VP, XP>, C::SMEM));
   const CUtensorMapSwizzle sw = (C::KB == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
