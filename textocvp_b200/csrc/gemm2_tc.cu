@@ -670,6 +670,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
 int gemm2_pick_bn(int M, int N, int force) {
   if (force == 128 || force == 256) return force;
   if (M < 1024 || N < 128) return 0;   // ragged N is fine: TMA zero-fills W rows >= N and clips the stores
+  // wide outputs: 256-wide tiles at every row count the rollout meets (r2 sweep, tools/ab_bn_sweep.py: the wave model below
+  // picked 128 at M = 8192 / 10240 and lost 17-21 % there once the 256-wide epilogue had been specialised)
+  if (N >= 1024 && N % 256 == 0 && M >= 2048) return 256;
   const int pairs = num_sms() / 2;
   const int tm = (M + 255) / 256;
   auto waves = [&](int bn) { return (tm * ((N + bn - 1) / bn) + pairs - 1) / pairs; };
