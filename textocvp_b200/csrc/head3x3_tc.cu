@@ -91,22 +91,29 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // t = group * S + slot with groups handed out round-robin (gridDim.x groups per round).
   const int S = !COMPOSITE ? 1 : (S_CT > 0 ? S_CT : hc.S);
   const int num_groups = num_tiles / S;
+  // every thread of every role decodes every item: with run-time divisors these four divisions were 16 M of the kernel's
+  // 60 M instructions (ncu r2); tile counts are powers of two for every frame size the decoder is built for
+  const bool pow2 = (tiles_per_img & (tiles_per_img - 1)) == 0 && (tiles_x & (tiles_x - 1)) == 0;
+  const int sh_img = 31 - __clz(tiles_per_img), sh_x = 31 - __clz(tiles_x);
   auto item = [&](int it, int& img, int& y0, int& x0, int& slot) -> bool {
     const int g = int(blockIdx.x) + (it / S) * int(gridDim.x);
     if (g >= num_groups) return false;
     const int gr = num_groups - 1 - g;      // last groups first: layer 4 wrote them last, ~100 MB of them are still in L2
     slot = it % S;
-    int r;
-    if (COMPOSITE) {
-      const int frame = gr / tiles_per_img;
-      r = gr % tiles_per_img;
-      img = frame * S + slot;
+    int q, r, ry;
+    if (pow2) {
+      q = gr >> sh_img;
+      r = gr & (tiles_per_img - 1);
+      ry = r >> sh_x;
+      x0 = (r & (tiles_x - 1)) * HD_TW;
     } else {
-      img = gr / tiles_per_img;
-      r = gr % tiles_per_img;
+      q = gr / tiles_per_img;
+      r = gr - q * tiles_per_img;
+      ry = r / tiles_x;
+      x0 = (r - ry * tiles_x) * HD_TW;
     }
-    y0 = (r / tiles_x) * HD_TH;
-    x0 = (r % tiles_x) * HD_TW;
+    img = COMPOSITE ? q * S + slot : q;
+    y0 = ry * HD_TH;
     return true;
   };
 
@@ -212,7 +219,7 @@ head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         } else {
           sM[slot * (HD_TH * HD_TW) + py * HD_TW + px] = make_float4(a0, a1, a2, a3);   // thread-private column
           if (hc.recons != nullptr) {
-            float* o = hc.recons + size_t(img) * 3 * plane + size_t(y0 + py) * W + (x0 + px);
+            float* o = hc.recons + size_t(img) * 3 * plane + uint32_t((y0 + py) * W + (x0 + px));
             o[0] = a0; o[plane] = a1; o[2 * plane] = a2;
           }
         }
