@@ -272,7 +272,8 @@ struct ConvCfg2 : ConvCfg<CIN, COUT, G, KS> {
   static constexpr int GEN_BYTES = GEN ? 25 * CIN * 4 : 0;   // this tile's 5x5 border-pattern sums, fp32
   // no alignment slack: the dynamic shared array is declared __align__(1024) and checked at run time.  The 32-channel
   // configuration (111104 B, 161 registers x 192 threads, 256 TMEM columns) then fits TWO CTAs per SM.
-  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + 512;
+  static constexpr int LN_BYTES = XP ? 512 : 0;             // XP: bias | gamma | beta of the fused LayerNorm epilogue (3 x 32 floats)
+  static constexpr int SMEM = 2 * Base::A_STRIDE + WSTAGES * W_HALF + GEN_BYTES + LN_BYTES + 512;
   static constexpr int CTAS_PER_SM = (2 * (SMEM + 2048) <= 233472 && 2 * Base::TMEM_COLS <= 512 && !GEN) ? 2 : 1;
 };
 
@@ -308,7 +309,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* t_full = a_empty + 2;                                                 // per CTA
   uint64_t* t_empty = t_full + 2;                                                 // leader: 4 warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* sS = reinterpret_cast<float*>(sW + C::WSTAGES * C::W_HALF + 512);        // GEN: [25][CIN]
+  float* sS = reinterpret_cast<float*>(sW + C::WSTAGES * C::W_HALF + 512);        // GEN: [25][CIN]; XP: [3][32] LN vectors
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -333,6 +334,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+  if constexpr (XP) {
+    // the fused LayerNorm epilogue reads bias / gamma / beta for every pixel: as 64 + 8 scalar global loads per pixel they
+    // throttled the load / store queue (48 % of the kernel's stall samples, ncu r2); staged once, they are broadcast LDS.128
+    if (a.ln_g != nullptr && threadIdx.x >= 64 && threadIdx.x < 64 + 96) {
+      const int e = threadIdx.x - 64;
+      sS[e] = e < 32 ? a.bias[e] : (e < 64 ? a.ln_g[e - 32] : a.ln_b[e - 64]);
+    }
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -506,6 +515,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const float* bias = a.bias + (XP ? 0 : c * 32);            // XP: both pixels of the pair share the 32 biases
         if (with_ln) {
           // ---- relu(conv + b) + posemb -> LayerNorm over the pixel's 32 channels, all in this thread's registers
+          // (requesting the next piece's embedding ahead of the current one's arithmetic measured no gain: 1.267 vs 1.256 ms)
           const float* pe = a.ln_posemb + (pix0 + size_t(8 * j)) * COUT + c * 32;
           float f[32];
           float sum = 0.f;
@@ -514,7 +524,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int e8 = 0; e8 < 4; ++e8) ldg_nc_256(pe + 8 * e8, pv[2 * e8], pv[2 * e8 + 1]);
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + e4);
+            const float4 bb = XP ? reinterpret_cast<const float4*>(sS)[e4] : __ldg(reinterpret_cast<const float4*>(bias) + e4);
             const float4 pp = pv[e4];
             f[4 * e4 + 0] = fmaxf(__uint_as_float(v[4 * e4 + 0]) + bb.x, 0.f) + pp.x;
             f[4 * e4 + 1] = fmaxf(__uint_as_float(v[4 * e4 + 1]) + bb.y, 0.f) + pp.y;
@@ -533,10 +543,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           uint4 pk[4];
 #pragma unroll
           for (int e8 = 0; e8 < 4; ++e8) {
-            float g[8];
+            float g[8], gam[8], bet[8];
+            if constexpr (XP) {
+              const float4 g0 = reinterpret_cast<const float4*>(sS + 32)[2 * e8], g1 = reinterpret_cast<const float4*>(sS + 32)[2 * e8 + 1];
+              const float4 b0 = reinterpret_cast<const float4*>(sS + 64)[2 * e8], b1 = reinterpret_cast<const float4*>(sS + 64)[2 * e8 + 1];
+              gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+              bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              g[e] = f[8 * e8 + e] * rstd * __ldg(a.ln_g + 8 * e8 + e) + __ldg(a.ln_b + 8 * e8 + e);
+              for (int e = 0; e < 8; ++e) { gam[e] = __ldg(a.ln_g + 8 * e8 + e); bet[e] = __ldg(a.ln_b + 8 * e8 + e); }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = f[8 * e8 + e] * rstd * gam[e] + bet[e];
             pk[e8].x = pack_half2(g[0], g[1]);
             pk[e8].y = pack_half2(g[2], g[3]);
             pk[e8].z = pack_half2(g[4], g[5]);
