@@ -65,8 +65,12 @@ struct HeadComposite {
 // their shared loads / exponentials issue back to back; as run-time loops they were a ~1000-clock dependent chain per pixel
 // on the ONE epilogue warp each scheduler has, every S-th tile -- more than the two-deep accumulator pipeline can hide
 // (first fused version: 343 us per 2048 slot-images against 293 + 30 us for the separate kernels).
+// Register cap: the decoder's next-chunk layer-1 kernel (256 threads x 128 registers) is meant to run CO-RESIDENT with
+// this kernel (decoder.cu chunk pipeline).  An SM sub-partition has 16 K registers and gets up to 3 of this kernel's 10
+// warps + 2 of layer 1's 8: 3 x 32 x R + 2 x 4096 <= 16384 needs R <= 85.  At 86 registers (one build of round 2) layer 1
+// silently stopped overlapping and ran under the next convolution instead: +0.18 ms per chunk (same-box A/B of two builds).
 template <bool COMPOSITE, int S_CT>
-__global__ void __launch_bounds__(HD_THREADS, 1)
+__global__ void __maxnreg__(80)
 head3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int n_img, int H, int W,
                const float* __restrict__ bias, float* __restrict__ out4, HeadComposite hc) {
   extern __shared__ uint8_t smem_raw[];
